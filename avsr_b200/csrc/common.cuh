@@ -1,0 +1,105 @@
+// Shared helpers for all avsr_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define AVSR_OK 0
+#define AVSR_ERR_CUDA -1
+#define AVSR_ERR_ARG -2
+#define AVSR_ERR_UNSUPPORTED -3
+
+// Implemented in capi.cu
+void avsr_set_error(const char* fmt, ...);
+
+#define AVSR_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            avsr_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,               \
+                           cudaGetErrorString(_e));                                             \
+            return AVSR_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define AVSR_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            avsr_set_error(__VA_ARGS__);                                                        \
+            return AVSR_ERR_ARG;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define AVSR_LAUNCH_CHECK()                                                                     \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            avsr_set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,               \
+                           cudaGetErrorString(_e));                                             \
+            return AVSR_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide reductions; `red` is a shared array of >= 32 floats. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// Epilogue descriptor shared by the tcgen05 GEMM and the fp32 SIMT GEMM (mirrored by ctypes in _lib.py).
+//   v = acc (+ bias[col] | bias[row]) ; v = act(v) ; v += residual[row, col] ; store bf16 and/or fp32.
+struct AvsrEpilogue {
+    const float* bias;       // nullptr = none
+    int bias_mode;           // 1 = per output column, 2 = per output row
+    int act;                 // 0 none, 1 GELU(erf), 2 ReLU, 3 PReLU (per-column slope)
+    const float* prelu;      // [N] slopes when act == 3
+    const void* residual;    // nullptr = none
+    int res_dtype;           // 0 fp32, 1 bf16
+    long long ldr;           // residual leading dimension (elements)
+    void* out_bf16;          // nullptr = skip
+    long long ld_bf16;
+    float* out_f32;          // nullptr = skip
+    long long ld_f32;
+    const int* row_mask;     // optional [M]: rows with mask==0 are stored as zero (padded conv layouts)
+};
+
+enum { AVSR_ACT_NONE = 0, AVSR_ACT_GELU = 1, AVSR_ACT_RELU = 2, AVSR_ACT_PRELU = 3 };
+
+__device__ __forceinline__ float avsr_apply_act(float v, int act, float slope) {
+    if (act == AVSR_ACT_GELU) return gelu_erf(v);
+    if (act == AVSR_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == AVSR_ACT_PRELU) return v >= 0.f ? v : v * slope;
+    return v;
+}
