@@ -1,0 +1,301 @@
+"""Joint CTC/attention beam search on B200 with the hypothesis state resident on the device.
+
+Drop-in for the object returned by the reference's ``get_beam_search_decoder``
+(/root/reference/src/avhubert_avsr/avhubert_avsr_model.py:12-36), i.e. ``BatchBeamSearch``
+(src/nets/batch_beam_search.py:26-349, src/nets/beam_search.py:33-105,330-406): ``search(x[T,1024]) -> List[Hypothesis]``
+sorted best first, each with ``.yseq`` (int64, starts with sos and ends with eos), ``.score``,
+``.scores{"decoder","ctc"}`` and ``.asdict()``.  Semantics kept: weights {decoder: 1-ctc_weight, ctc: ctc_weight},
+pre-beam on the decoder scores with ``int(1.5*beam)`` candidates, ``maxlen = T``, eos appended after the last step,
+no length normalisation, ``end_detect`` with M=3 / D_end=-10.
+
+Beyond the reference, ``decode_batch`` runs many utterances (mixed lengths) at once; every utterance evolves exactly as
+its own B=1 run (per-utterance maxlen, top-k, early exit).  One decode step is a fixed sequence of
+kernel launches that read the step index and liveness from device memory, so it is captured once into a CUDA graph and
+replayed; the host only polls an "any utterance still running" flag every few steps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, NamedTuple, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .weights import DecoderWeights
+
+
+class Hypothesis(NamedTuple):
+    """Same fields as the reference's Hypothesis (src/nets/beam_search.py:13-27)."""
+
+    yseq: torch.Tensor
+    score: Union[float, torch.Tensor] = 0
+    scores: Dict[str, Union[float, torch.Tensor]] = dict()
+    states: Dict[str, object] = dict()
+
+    def asdict(self) -> dict:
+        return self._replace(
+            yseq=self.yseq.tolist(),
+            score=float(self.score),
+            scores={k: float(v) for k, v in self.scores.items()},
+        )._asdict()
+
+
+D_END = math.log(1 * math.exp(-10))      # e2e_asr_common.py:18
+
+
+class BatchedBeamSearch:
+    POLL_EVERY = 16
+
+    def __init__(self, weights: DecoderWeights, beam_size: int = 3, ctc_weight: float = 0.1, pre_beam_ratio: float = 1.5,
+                 token_list: Optional[Sequence[str]] = None, device="cuda:0", use_graph: bool = True):
+        self.w = weights
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("avsr_b200 beam search needs a CUDA device (no CPU fallback)")
+        if not (1 <= beam_size <= 8):
+            raise RuntimeError("beam_size must be in [1, 8]")
+        if ctc_weight in (0.0, 1.0):
+            raise RuntimeError("ctc_weight 0.0 / 1.0 (single-scorer search) is not wired yet; use 0 < ctc_weight < 1")
+        if token_list is not None and len(token_list) != weights.V:
+            raise RuntimeError(f"token_list has {len(token_list)} entries, model vocabulary is {weights.V}")
+        self.beam_size = beam_size
+        self.pre_beam_size = int(pre_beam_ratio * beam_size)        # beam_search.py:91
+        self.n_vocab = weights.V
+        self.sos, self.eos = weights.sos, weights.eos
+        self.token_list = token_list
+        self.weights = {"decoder": 1.0 - ctc_weight, "ctc": ctc_weight, "lm": 0.0, "length_bonus": 0.0}
+        self.w_dec = float(np.float32(1.0 - ctc_weight))
+        self.w_ctc = float(np.float32(ctc_weight))
+        self.use_graph = use_graph
+        self._sessions = {}
+        L.load()
+
+    # ------------------------------------------------------------------------------------------ session buffers
+    def _session(self, B: int, tmax: int, F: int):
+        key = (B, tmax, F)
+        s = self._sessions.get(key)
+        if s is not None:
+            return s
+        if len(self._sessions) > 4:
+            self._sessions.clear()
+        dev, beam, S, V = self.device, self.beam_size, self.pre_beam_size, self.n_vocab
+        R = B * beam
+        nl = self.w.n_layers
+        lmax = tmax + 1
+        i32 = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=dev)
+        f32 = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
+        s["utt_T"], s["utt_off"] = i32(B), i32(B)
+        s["step"], s["any_running"] = i32(1), i32(1)
+        s["n_run"], s["row_active"], s["last_tok"], s["rprev_idx"] = i32(B), i32(R), i32(R), i32(R)
+        for k in ("score", "dec_sc", "ctc_sc", "s_prev", "rsum_last"):
+            s[k] = f32(R)
+        s["anc"] = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
+        s["hist_tok"], s["hist_prev"], s["run2j"] = i32(B, tmax, beam), i32(B, tmax, beam), i32(B, tmax, beam)
+        cap = beam * (tmax + 1)
+        s["cap"] = cap
+        s["n_ended"], s["done"], s["overflow"] = i32(B), i32(B), i32(1)
+        s["end_step"], s["end_j"], s["end_len"] = i32(B, cap), i32(B, cap), i32(B, cap)
+        s["end_score"], s["end_dec"], s["end_ctc"] = f32(B, cap), f32(B, cap), f32(B, cap)
+        s["best_len"], s["best_all"] = f32(B, tmax + 4), f32(B)
+        # activations of one decoder step
+        s["x"], s["a"], s["att"], s["q2"] = f32(R, 1024), f32(R, 1024), f32(R, 1024), f32(R, 1024)
+        s["qkv"], s["ffn"] = f32(R, 3072), f32(R, 3072)
+        s["dec_logp"] = f32(R, V)
+        s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
+        s["kc"] = torch.empty(nl, lmax, R, 1024, dtype=torch.float32, device=dev)
+        s["vc"] = torch.empty(nl, lmax, R, 1024, dtype=torch.float32, device=dev)
+        s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
+        lib = L.load()
+        ns = max(lib.avsr_sgemm_skinny_splits(R, n, k) for n, k in ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024)))
+        s["part"] = torch.empty(ns * R * max(3072, V), dtype=torch.float32, device=dev)
+        # per-utterance precomputed tensors
+        s["logp"] = torch.empty(F, V, dtype=torch.float32, device=dev)
+        s["ckv"] = torch.empty(F, nl * 2 * 1024, dtype=torch.float32, device=dev)
+        st = L.BeamState()
+        st.B, st.beam, st.S, st.V, st.lmax, st.tmax = B, beam, S, V, lmax, tmax
+        st.blank, st.eos, st.cap = self.w.blank, self.eos, cap
+        for name in ("utt_T", "step", "n_run", "row_active", "last_tok", "score", "dec_sc", "ctc_sc", "s_prev", "rprev_idx", "anc",
+                     "hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j", "end_score", "end_dec", "end_ctc", "end_len",
+                     "best_len", "best_all", "done", "overflow"):
+            setattr(st, name, s[name].data_ptr())
+        st.d_end = D_END
+        s["state"] = st
+        s["graph"] = None
+        self._sessions[key] = s
+        return s
+
+    # ------------------------------------------------------------------------------------------ one decode step
+    def _skinny(self, s, a, w, N, K):
+        lib = L.load()
+        R = s["R"]
+        ns = lib.avsr_sgemm_skinny_splits(R, N, K)
+        L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(a.stride(0)), L.ptr(w), L.ll(K), R, N, K, L.ptr(s["part"]), ns, L.stream()),
+                "avsr_sgemm_skinny")
+        return ns
+
+    def _epi(self, s, ns, N, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, ln_out=None):
+        lib = L.load()
+        g, b = (ln if ln is not None else (None, None))
+        L.check(lib.avsr_splitk_epilogue(L.ptr(s["part"]), ns, s["R"], N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
+                                         L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(ln_out), L.ll(1024),
+                                         L.ptr(s["row_active"]), L.stream()), "avsr_splitk_epilogue")
+
+    def _step(self, s):
+        """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
+        lib = L.load()
+        w = self.w
+        R, beam, S, V, lmax = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab, s["lmax"]
+        st = L.stream
+        l0 = w.layers[0]
+        L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
+                                      L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), L.ptr(s["a"]), st()),
+                "avsr_dec_embed_ln")
+        nl = w.n_layers
+        kvld = nl * 2 * 1024
+        for li, lay in enumerate(w.layers):
+            # self-attention (decoder_layer.py:82-93)
+            ns = self._skinny(s, s["a"], lay["wqkv"], 3072, 1024)
+            self._epi(s, ns, 3072, lay["bqkv"], out=s["qkv"])
+            L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
+                                           lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
+                                           L.ptr(s["att"]), lmax, L.ll(0), st()), "avsr_dec_attn_step(self)")
+            ns = self._skinny(s, s["att"], lay["wo"], 1024, 1024)
+            self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), ln_out=s["a"])
+            # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
+            ns = self._skinny(s, s["a"], lay["wq2"], 1024, 1024)
+            self._epi(s, ns, 1024, lay["bq2"], out=s["q2"])
+            ck = s["ckv"][:, li * 2048:]
+            cv = s["ckv"][:, li * 2048 + 1024:]
+            L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
+                                           L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), L.ptr(s["att"]),
+                                           s["tmax"], L.ll(kvld), st()), "avsr_dec_attn_step(src)")
+            ns = self._skinny(s, s["att"], lay["wo2"], 1024, 1024)
+            self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), ln_out=s["a"])
+            # feed-forward (decoder_layer.py:112-116)
+            ns = self._skinny(s, s["a"], lay["w1"], 3072, 1024)
+            self._epi(s, ns, 3072, lay["b1"], act=L.ACT_RELU, out=s["ffn"])
+            ns = self._skinny(s, s["ffn"], lay["w2"], 1024, 3072)
+            nxt = (w.layers[li + 1]["n1_g"], w.layers[li + 1]["n1_b"]) if li + 1 < nl else (w.after_g, w.after_b)
+            self._epi(s, ns, 1024, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, ln_out=s["a"])
+        # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
+        ns = self._skinny(s, s["a"], w.out_w, V, 1024)
+        L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
+                                             L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
+        # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
+        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
+                                            beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
+                                            L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
+                "avsr_ctc_prefix_prebeam")
+        # fusion, top-k, hypothesis bookkeeping, end detection (batch_beam_search.py:222-349)
+        L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
+                                                L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc), st()),
+                "avsr_beam_fuse_topk_advance")
+        L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
+                "avsr_beam_step_advance")
+
+    # ------------------------------------------------------------------------------------------ public API
+    def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int]):
+        """CTC posteriors (scorers/ctc.py:87-99) and the once-per-utterance cross-attention K/V projection."""
+        w, V = self.w, self.n_vocab
+        F = x_packed.shape[0]
+        L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
+        lib = L.load()
+        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(V), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
+        n = w.ckv_w.shape[0]
+        L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+        B, beam = s["B"], self.beam_size
+        offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
+        s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))
+        s["utt_off"].copy_(torch.from_numpy(offs))
+        for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev"):
+            s[k].zero_()
+        s["n_run"].fill_(1)
+        s["row_active"].zero_()
+        s["row_active"].view(B, beam)[:, 0] = 1
+        s["last_tok"].fill_(self.sos)
+        s["best_len"].fill_(float("-inf"))
+        s["best_all"].fill_(float("-inf"))
+
+    def decode_batch(self, x_packed: torch.Tensor, lengths: Sequence[int], max_steps: Optional[int] = None) -> List[List[Hypothesis]]:
+        """x_packed [sum(T),1024] fp32 encoder outputs (utterances back to back) -> n-best list per utterance."""
+        L.require_cuda(x_packed, torch.float32, "encoder output")
+        lengths = [int(t) for t in lengths]
+        if x_packed.dim() != 2 or x_packed.shape[1] != 1024 or x_packed.shape[0] != sum(lengths) or min(lengths) < 1:
+            raise RuntimeError(f"bad decode input: x {tuple(x_packed.shape)}, lengths {lengths}")
+        B, tmax, F = len(lengths), max(lengths), x_packed.shape[0]
+        s = self._session(B, tmax, F)
+        self.prepare(s, x_packed, lengths)
+        n_steps = tmax if max_steps is None else min(tmax, max_steps)
+        self._step(s)                                   # position 0 eagerly (also warms every kernel up)
+        done_steps = 1
+        if n_steps > 1:
+            if self.use_graph and s["graph"] is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                # capture runs no kernels; state is untouched
+                with torch.cuda.graph(g):
+                    self._step(s)
+                s["graph"] = g
+            while done_steps < n_steps:
+                n = min(self.POLL_EVERY, n_steps - done_steps)
+                for _ in range(n):
+                    if self.use_graph:
+                        s["graph"].replay()
+                    else:
+                        self._step(s)
+                done_steps += n
+                if int(s["any_running"].item()) == 0:
+                    break
+        if int(s["overflow"].item()) != 0:
+            raise RuntimeError("ended-hypothesis table overflowed")
+        return self._collect(s, lengths, truncated=max_steps is not None)
+
+    def _collect(self, s, lengths, truncated=False) -> List[List[Hypothesis]]:
+        """Backtrace the ended hypotheses on the host (one D2H at the end instead of the reference's per-step syncs)."""
+        tok = s["hist_tok"].cpu().numpy()
+        prev = s["hist_prev"].cpu().numpy()
+        r2j = s["run2j"].cpu().numpy()
+        n_end = s["n_ended"].cpu().numpy()
+        e_step, e_j, e_len = s["end_step"].cpu().numpy(), s["end_j"].cpu().numpy(), s["end_len"].cpu().numpy()
+        e_sc, e_dec, e_ctc = s["end_score"].cpu(), s["end_dec"].cpu(), s["end_ctc"].cpu()
+        out = []
+        for b in range(s["B"]):
+            hyps = []
+            for e in range(int(n_end[b])):
+                i, j = int(e_step[b, e]), int(e_j[b, e])
+                toks = []
+                ii, jj = i, j
+                while True:
+                    toks.append(int(tok[b, ii, jj]))
+                    if ii == 0:
+                        break
+                    p = int(prev[b, ii, jj])
+                    jj = int(r2j[b, ii - 1, p])
+                    ii -= 1
+                yseq = [self.sos] + toks[::-1]
+                if int(e_len[b, e]) == len(yseq) + 1:        # eos appended at the last position (batch_beam_search.py:321-337)
+                    yseq.append(self.eos)
+                hyps.append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e],
+                                       scores={"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}, states={}))
+            hyps.sort(key=lambda h: float(h.score), reverse=True)     # stable, like sorted() in beam_search.py:378
+            out.append(hyps)
+        return out
+
+    def forward(self, x: torch.Tensor, maxlenratio: float = 0.0, minlenratio: float = 0.0) -> List[Hypothesis]:
+        """Reference entry point: x [T, 1024] -> n-best (beam_search.py:330-406)."""
+        if maxlenratio != 0.0 or minlenratio != 0.0:
+            raise RuntimeError("only maxlenratio=0.0 / minlenratio=0.0 (what script/evaluation.py uses) are supported")
+        x = x.to(self.device, torch.float32).contiguous()
+        return self.decode_batch(x, [x.shape[0]])[0]
+
+    __call__ = forward
+
+
+def get_beam_search_decoder(model, token_list, ctc_weight=0.1, beam_size=3):
+    """Same signature as the reference factory (src/avhubert_avsr/avhubert_avsr_model.py:12-36); ``model`` is an
+    ``avsr_b200.model.AVSRCocktailB200`` (exposes ``.decoder_weights``, ``.sos``, ``.eos``)."""
+    return BatchedBeamSearch(model.decoder_weights, beam_size=beam_size, ctc_weight=ctc_weight, token_list=token_list,
+                             device=model.device)

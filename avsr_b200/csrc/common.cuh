@@ -5,10 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define AVSR_OK 0
-#define AVSR_ERR_CUDA -1
-#define AVSR_ERR_ARG -2
-#define AVSR_ERR_UNSUPPORTED -3
+#include "../../include/avsr_b200.h"
 
 // Implemented in capi.cu
 void avsr_set_error(const char* fmt, ...);
@@ -77,25 +74,6 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-
-// Epilogue descriptor shared by the tcgen05 GEMM and the fp32 SIMT GEMM (mirrored by ctypes in _lib.py).
-//   v = acc (+ bias[col] | bias[row]) ; v = act(v) ; v += residual[row, col] ; store bf16 and/or fp32.
-struct AvsrEpilogue {
-    const float* bias;       // nullptr = none
-    int bias_mode;           // 1 = per output column, 2 = per output row
-    int act;                 // 0 none, 1 GELU(erf), 2 ReLU, 3 PReLU (per-column slope)
-    const float* prelu;      // [N] slopes when act == 3
-    const void* residual;    // nullptr = none
-    int res_dtype;           // 0 fp32, 1 bf16
-    long long ldr;           // residual leading dimension (elements)
-    void* out_bf16;          // nullptr = skip
-    long long ld_bf16;
-    float* out_f32;          // nullptr = skip
-    long long ld_f32;
-    const int* row_mask;     // optional [M]: rows with mask==0 are stored as zero (padded conv layouts)
-};
-
-enum { AVSR_ACT_NONE = 0, AVSR_ACT_GELU = 1, AVSR_ACT_RELU = 2, AVSR_ACT_PRELU = 3 };
 
 __device__ __forceinline__ float avsr_apply_act(float v, int act, float slope) {
     if (act == AVSR_ACT_GELU) return gelu_erf(v);

@@ -1,0 +1,261 @@
+// Memory-bound helper kernels of the encoder: LayerNorm, im2col gathers that feed the tcgen05 GEMM (3D-conv frontend,
+// ResNet 3x3 / 1x1 convs, grouped positional conv), max/avg pooling, casts and transposes.
+// Reference ops: src/nets/backend/backbones/resnet.py:30-164, avhubert.py:187-198,486-502,698-734 and HF
+// Wav2Vec2PositionalConvEmbedding (transformers/models/wav2vec2/modeling_wav2vec2.py:326-379).
+// All activations are channels-last bf16 ([frames, H, W, C]); frames of all utterances are packed back to back and
+// frame_t / frame_T give each frame's index inside its utterance and that utterance's length, so that temporal
+// zero padding never crosses an utterance boundary.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm (fp32 in, bf16 and/or fp32 out)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, int N, const float* __restrict__ g, const float* __restrict__ b,
+                 float eps, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16, float* __restrict__ out_f32, long long ld_f32) {
+    extern __shared__ float rowbuf[];
+    __shared__ float red[32];
+    const long long row = blockIdx.x;
+    const float* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + c);
+        *reinterpret_cast<float4*>(rowbuf + c) = v;
+        s += v.x + v.y + v.z + v.w;
+    }
+    const float mean = block_sum(s, red) / (float)N;
+    float q = 0.f;
+    for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(rowbuf + c);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    const float rstd = rsqrtf(block_sum(q, red) / (float)N + eps);
+    for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(rowbuf + c);
+        const float4 gg = *reinterpret_cast<const float4*>(g + c);
+        const float4 bb = *reinterpret_cast<const float4*>(b + c);
+        const float o0 = (v.x - mean) * rstd * gg.x + bb.x, o1 = (v.y - mean) * rstd * gg.y + bb.y;
+        const float o2 = (v.z - mean) * rstd * gg.z + bb.z, o3 = (v.w - mean) * rstd * gg.w + bb.w;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + c) = make_float4(o0, o1, o2, o3);
+        if (out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(out_bf16 + row * ld_bf16 + c) = pk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ frontend 3D conv im2col
+// video fp32 [F,88,88] (packed frames) -> A [F*44*44, 256] bf16, k = (dt*7 + dy)*7 + dx for the 5x7x7 patch
+// (stride 1x2x2, pad 2x3x3), columns 245..255 zero.  One CTA per (frame, output row).
+__global__ void __launch_bounds__(256)
+im2col_frontend_kernel(const float* __restrict__ video, const int* __restrict__ frame_t, const int* __restrict__ frame_T,
+                       __nv_bfloat16* __restrict__ out, int f0) {
+    __shared__ float rows[5][7][96];       // [dt][dy][x + 3], x in [-3, 91)
+    const int f = f0 + blockIdx.x / 44, oy = blockIdx.x % 44;
+    const int t = frame_t[f], T = frame_T[f];
+    for (int i = threadIdx.x; i < 5 * 7 * 96; i += blockDim.x) {
+        const int dt = i / (7 * 96), dy = (i / 96) % 7, xx = i % 96;
+        const int tt = t + dt - 2, y = oy * 2 + dy - 3, x = xx - 3;
+        float v = 0.f;
+        if (tt >= 0 && tt < T && y >= 0 && y < 88 && x >= 0 && x < 88) v = video[((long long)(f + dt - 2) * 88 + y) * 88 + x];
+        rows[dt][dy][xx] = v;
+    }
+    __syncthreads();
+    __nv_bfloat16* o = out + ((long long)(blockIdx.x) * 44) * 256;
+    for (int i = threadIdx.x; i < 44 * 128; i += blockDim.x) {
+        const int ox = i / 128, k = (i % 128) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (k < 245) { const int dt = k / 49, dy = (k / 7) % 7, dx = k % 7; v0 = rows[dt][dy][ox * 2 + dx]; }
+        if (k + 1 < 245) { const int k1 = k + 1; const int dt = k1 / 49, dy = (k1 / 7) % 7, dx = k1 % 7; v1 = rows[dt][dy][ox * 2 + dx]; }
+        __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+        *reinterpret_cast<__nv_bfloat162*>(o + (long long)ox * 256 + k) = p;
+    }
+}
+
+// ------------------------------------------------------------------ 2D conv im2col (NHWC bf16)
+// in [F,H,W,C] -> out [F*Ho*Wo, ks*ks*C], k = (ky*ks + kx)*C + c; pad = ks/2; 8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256)
+im2col2d_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total_vec, int H, int W, int C,
+                int Ho, int Wo, int ks, int stride) {
+    const int cv = C / 8;
+    const int pad = ks / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
+        const int kx = (int)(r % ks); r /= ks;
+        const int ky = (int)(r % ks); r /= ks;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const long long f = r / Ho;
+        const int y = oy * stride + ky - pad, x = ox * stride + kx - pad;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const uint4*>(in + (((f * H + y) * W + x) * C + c8 * 8));
+        *reinterpret_cast<uint4*>(out + i * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------ max pool 3x3 s2 p1 (NHWC bf16), 8 channels/thread
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total_vec, int H, int W, int C,
+                    int Ho, int Wo) {
+    const int cv = C / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        long long r = i / cv;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const long long f = r / Ho;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = oy * 2 + dy - 1;
+            if (y < 0 || y >= H) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int x = ox * 2 + dx - 1;
+                if (x < 0 || x >= W) continue;
+                const uint4 v = *reinterpret_cast<const uint4*>(in + (((f * H + y) * W + x) * C + c8 * 8));
+                const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __bfloat162float(e[j]));
+            }
+        }
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(m[j]);
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// ------------------------------------------------------------------ global average pool: [F, HW, C] bf16 -> [F, C] bf16
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long F, int HW, int C) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= F * C) return;
+    const long long f = i / C;
+    const int c = (int)(i % C);
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(in[(f * HW + p) * C + c]);
+    out[i] = __float2bfloat16_rn(s / (float)HW);
+}
+
+// ------------------------------------------------------------------ audio [B,104,T] fp32 -> packed [F,104] bf16
+__global__ void __launch_bounds__(256)
+audio_pack_kernel(const float* __restrict__ audio, __nv_bfloat16* __restrict__ out, const int* __restrict__ frame_b,
+                  const int* __restrict__ frame_t, long long F, int Cin, int Tpad) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= F * Cin) return;
+    const long long f = i / Cin;
+    const int c = (int)(i % Cin);
+    out[i] = __float2bfloat16_rn(audio[((long long)frame_b[f] * Cin + c) * Tpad + frame_t[f]]);
+}
+
+// ------------------------------------------------------------------ positional-conv im2col
+// x bf16 [F,1024] -> out [16][F][128*64], out[g][f][j*64 + c] = x[f + j - 64][g*64 + c] if the source frame lies in
+// the same utterance, else 0 (k=128, pad=64, last output dropped).  8 channels per thread.
+__global__ void __launch_bounds__(256)
+posconv_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const int* __restrict__ frame_t,
+                      const int* __restrict__ frame_T, long long F, int g0, int ng) {
+    const long long per_g = F * 128 * 8;                    // uint4 vectors per group
+    const long long total = per_g * ng;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % 8);
+        long long r = i / 8;
+        const int j = (int)(r % 128); r /= 128;
+        const long long f = r % F;
+        const int g = (int)(r / F);
+        const int tt = frame_t[f] + j - 64;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tt >= 0 && tt < frame_T[f]) v = *reinterpret_cast<const uint4*>(x + (f + j - 64) * 1024 + (g0 + g) * 64 + c8 * 8);
+        *reinterpret_cast<uint4*>(out + i * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 cast (2D with leading dims)
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out, long long ldo, long long rows, int cols) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    out[r * ldo + c] = __float2bfloat16_rn(in[r * ldi + c]);
+}
+
+}  // namespace
+
+#define GRID1D(total) ((int)(((total) + 255) / 256 > 148 * 64 ? 148 * 64 : ((total) + 255) / 256))
+
+extern "C" int avsr_layernorm(const float* x, long long ldx, long long rows, int N, const float* gamma, const float* beta, float eps,
+                              void* out_bf16, long long ld_bf16, float* out_f32, long long ld_f32, cudaStream_t stream) {
+    AVSR_REQUIRE(x && gamma && beta && rows > 0 && N > 0 && (N & 3) == 0 && (ldx & 3) == 0 && N * 4 <= 48 * 1024,
+                 "avsr_layernorm: bad arguments (rows=%lld N=%d)", rows, N);
+    AVSR_REQUIRE(out_bf16 || out_f32, "avsr_layernorm: no output");
+    layernorm_kernel<<<(unsigned)rows, 256, (size_t)N * 4, stream>>>(x, ldx, N, gamma, beta, eps, (__nv_bfloat16*)out_bf16, ld_bf16,
+                                                                    out_f32, ld_f32);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+// Frames [f0, f0+nf) of the packed video -> out [nf*1936, 256] bf16.
+extern "C" int avsr_im2col_frontend(const float* video, const int* frame_t, const int* frame_T, int f0, int nf, void* out,
+                                    cudaStream_t stream) {
+    AVSR_REQUIRE(video && frame_t && frame_T && out && nf > 0, "avsr_im2col_frontend: bad arguments");
+    im2col_frontend_kernel<<<nf * 44, 256, 0, stream>>>(video, frame_t, frame_T, (__nv_bfloat16*)out, f0);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_im2col2d(const void* in, void* out, long long F, int H, int W, int C, int ks, int stride, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && F > 0 && (C & 7) == 0 && (ks == 1 || ks == 3) && (stride == 1 || stride == 2),
+                 "avsr_im2col2d: bad arguments");
+    const int pad = ks / 2;
+    const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+    const long long total = F * Ho * Wo * ks * ks * (C / 8);
+    im2col2d_kernel<<<GRID1D(total), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C, Ho, Wo, ks, stride);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_maxpool3x3s2(const void* in, void* out, long long F, int H, int W, int C, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && F > 0 && (C & 7) == 0, "avsr_maxpool3x3s2: bad arguments");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = F * Ho * Wo * (C / 8);
+    maxpool3x3s2_kernel<<<GRID1D(total), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C, Ho, Wo);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_avgpool(const void* in, void* out, long long F, int HW, int C, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && F > 0, "avsr_avgpool: bad arguments");
+    avgpool_kernel<<<cdiv(F * C, 256), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, F, HW, C);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_audio_pack(const float* audio, void* out, const int* frame_b, const int* frame_t, long long F, int Cin, int Tpad,
+                               cudaStream_t stream) {
+    AVSR_REQUIRE(audio && out && frame_b && frame_t && F > 0, "avsr_audio_pack: bad arguments");
+    audio_pack_kernel<<<cdiv(F * Cin, 256), 256, 0, stream>>>(audio, (__nv_bfloat16*)out, frame_b, frame_t, F, Cin, Tpad);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_posconv_im2col(const void* x, void* out, const int* frame_t, const int* frame_T, long long F, int g0, int ng,
+                                   cudaStream_t stream) {
+    AVSR_REQUIRE(x && out && frame_t && frame_T && F > 0 && g0 >= 0 && ng > 0 && g0 + ng <= 16, "avsr_posconv_im2col: bad arguments");
+    const long long total = F * 128 * 8 * ng;
+    posconv_im2col_kernel<<<GRID1D(total), 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, frame_t, frame_T, F, g0, ng);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_cast_bf16(const float* in, long long ldi, void* out, long long ldo, long long rows, int cols, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && rows > 0 && cols > 0, "avsr_cast_bf16: bad arguments");
+    cast_bf16_kernel<<<cdiv(rows * cols, 256), 256, 0, stream>>>(in, ldi, (__nv_bfloat16*)out, ldo, rows, cols);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}

@@ -1,0 +1,328 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05) for the AV-HuBERT encoder:
+//     C[M,N] = epilogue( A[M,K] * B[N,K]^T )        A, B bf16 K-major, fp32 accumulation in TMEM.
+// This single kernel carries every dense op of the encoder: the QKV/out/FFN projections of the 24
+// transformer layers (reference: HF Wav2Vec2Attention/FeedForward called from
+// src/nets/backend/backbones/avhubert.py:747-768), the modality projections and post_extract_proj
+// (avhubert.py:187-198,486-502), the grouped positional conv and the ResNet-18 / 3D-conv frontend as im2col GEMMs
+// (src/nets/backend/backbones/resnet.py:30-164).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor 2D loads of 128x64 (A) and BNx64 (B) bf16 tiles, 128B swizzle
+//   warp 1   : MMA issuer    - one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block; owns the TMEM allocation
+//   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator (double-buffered in TMEM), fused bias / activation /
+//                              residual / row-mask, bf16 and/or fp32 stores
+// Pipelines: smem ring full[]/empty[] (TMA <-> MMA) and TMEM tfull[]/tempty[] (MMA <-> epilogue), all mbarriers.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, int col0, int M, int N, const uint32_t (&r)[32]) {
+    if (row >= M) return;
+    const int ncols = min(32, N - col0);
+    if (ncols <= 0) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (ep.bias != nullptr) {
+        if (ep.bias_mode == 2) {
+            const float b = ep.bias[row];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += b;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __ldg(ep.bias + col0 + j);
+        }
+    }
+    if (ep.act != AVSR_ACT_NONE && !ep.act_after_residual) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float s = (ep.act == AVSR_ACT_PRELU && j < ncols) ? __ldg(ep.prelu + col0 + j) : 0.f;
+            v[j] = avsr_apply_act(v[j], ep.act, s);
+        }
+    }
+    if (ep.residual != nullptr) {
+        if (ep.res_dtype == 0) {
+            const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col0;
+            if (ncols == 32 && (ep.ldr & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(rp + j);
+                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) v[j] += rp[j];
+            }
+        } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __bfloat162float(rp[j]);
+        }
+    }
+    if (ep.act != AVSR_ACT_NONE && ep.act_after_residual) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float s = (ep.act == AVSR_ACT_PRELU && j < ncols) ? __ldg(ep.prelu + col0 + j) : 0.f;
+            v[j] = avsr_apply_act(v[j], ep.act, s);
+        }
+    }
+    if (ep.row_mask != nullptr && ep.row_mask[row] == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    if (ep.out_f32 != nullptr) {
+        float* op = ep.out_f32 + (long long)row * ep.ld_f32 + col0;
+        if (ncols == 32 && (ep.ld_f32 & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) op[j] = v[j];
+        }
+    }
+    if (ep.out_bf16 != nullptr) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out_bf16) + (long long)row * ep.ld_bf16 + col0;
+        if (ncols == 32 && (ep.ld_bf16 & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(op + j) = pk;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < ncols) op[j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               const AvsrEpilogue ep) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int tiles_m = (M + BM - 1) / BM;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull[a], 1);
+            tc::mbar_init(&tempty[a], 4);
+        }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tc::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
+                    tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t adesc = tc::umma_desc_sw128(sa);
+                    const uint64_t bdesc = tc::umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc::umma_commit(&empty[stage]);     // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(&tfull[acc]);           // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            tc::tc_fence_after();
+            const int row = m0 + quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(taddr + c * 32, r);
+                tc::tmem_ld_wait();
+                epilogue_chunk(ep, row, n0 + c * 32, M, N, r);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+int g_sm_count = 0;
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, cudaStream_t stream) {
+    using C = Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = cdiv(M, BM) * cdiv(N, BN);
+    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+    gemm_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+}  // namespace
+
+namespace tc {
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                      uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        avsr_set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+        return AVSR_ERR_CUDA;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld_elems * 2) & 15) != 0) {
+        avsr_set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (base=%p ld=%llu)", base,
+                       (unsigned long long)ld_elems);
+        return AVSR_ERR_ARG;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        avsr_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows, box_cols);
+        return AVSR_ERR_CUDA;
+    }
+    return AVSR_OK;
+}
+}  // namespace tc
+
+// C[M,N] = epilogue(A[M,K] * B[N,K]^T); A, B bf16 row-major with leading dimensions lda/ldb (elements, multiples of 8).
+// bn_hint: 0 = choose the N tile automatically, else 64 / 128 / 256.
+extern "C" int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                 const AvsrEpilogue* ep, int bn_hint, cudaStream_t stream) {
+    AVSR_REQUIRE(A && B && ep, "avsr_gemm_bf16_tc: null operand");
+    AVSR_REQUIRE(M > 0 && N > 0 && K > 0, "avsr_gemm_bf16_tc: bad shape %dx%dx%d", M, N, K);
+    AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_gemm_bf16_tc: no output buffer");
+    if (g_sm_count == 0) {
+        int dev = 0;
+        AVSR_CHECK_CUDA(cudaGetDevice(&dev));
+        AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int bn = bn_hint;
+    if (bn == 0) {
+        if (N <= 64) bn = 64;
+        else if (N <= 128) bn = 128;
+        else bn = (cdiv(M, BM) * cdiv(N, 256) >= 2 * g_sm_count) ? 256 : 128;
+    }
+    AVSR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "avsr_gemm_bf16_tc: bad bn_hint %d", bn_hint);
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (rc != AVSR_OK) return rc;
+    rc = tc::make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)bn, BK);
+    if (rc != AVSR_OK) return rc;
+    if (bn == 64) return launch<64>(ta, tb, M, N, K, *ep, stream);
+    if (bn == 128) return launch<128>(ta, tb, M, N, K, *ep, stream);
+    return launch<256>(ta, tb, M, N, K, *ep, stream);
+}

@@ -1,0 +1,238 @@
+// fp32 CUDA-core GEMM for the decode side of the hot path, where token-identical beam search needs fp32 weights and
+// fp32 accumulation (hard part 1):
+//     C[M,N] = epilogue( A[M,K] * W[N,K]^T )     A, W fp32 row-major (K contiguous).
+// Used for: decoder step projections (reference src/nets/backend/transformer/decoder_layer.py:58-121,
+// attention.py:38-106, positionwise_feed_forward.py:11-30, decoder.py:176-181), the once-per-utterance
+// cross-attention K/V projection of the encoder memory (attention.py:50-52 hoisted out of the step loop) and the
+// CTC head (src/nets/backend/ctc.py:163-170).
+//
+// Two tilings: a 128x128x16 register-tiled kernel for tall operands (M = frames) and a 96x64x16 split-K kernel for the
+// skinny per-step operands (M = utterances x beam <= ~192 rows), whose deterministic partial sums are combined by
+// avsr_splitk_epilogue (fixed summation order -> run-to-run identical tokens).
+#include "common.cuh"
+
+namespace {
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ W, long long ldw, float* __restrict__ part,
+                int M, int N, int K, int k_per_split, const AvsrEpilogue ep, int direct) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int PAD = 4;
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Ws[2][BK][BN + PAD];
+    constexpr int A_F4 = BM * BK / 4, W_F4 = BN * BK / 4;
+    constexpr int A_PER = (A_F4 + NT - 1) / NT, W_PER = (W_F4 + NT - 1) / NT;
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    const int num_kt = (kend - kbeg + BK - 1) / BK;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[A_PER], rw[W_PER];
+    auto gload = [&](int kt) {
+        const int k0 = kbeg + kt * BK;
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int f = tid + i * NT;
+            const int r = f / (BK / 4), kq = (f % (BK / 4)) * 4;
+            ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < A_F4 && m0 + r < M && k0 + kq < kend) ra[i] = *reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + kq);
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER; ++i) {
+            const int f = tid + i * NT;
+            const int r = f / (BK / 4), kq = (f % (BK / 4)) * 4;
+            rw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < W_F4 && n0 + r < N && k0 + kq < kend) rw[i] = *reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ldw + k0 + kq);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int f = tid + i * NT;
+            if (f < A_F4) {
+                const int r = f / (BK / 4), kq = (f % (BK / 4)) * 4;
+                As[buf][kq + 0][r] = ra[i].x; As[buf][kq + 1][r] = ra[i].y; As[buf][kq + 2][r] = ra[i].z; As[buf][kq + 3][r] = ra[i].w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER; ++i) {
+            const int f = tid + i * NT;
+            if (f < W_F4) {
+                const int r = f / (BK / 4), kq = (f % (BK / 4)) * 4;
+                Ws[buf][kq + 0][r] = rw[i].x; Ws[buf][kq + 1][r] = rw[i].y; Ws[buf][kq + 2][r] = rw[i].z; Ws[buf][kq + 3][r] = rw[i].w;
+            }
+        }
+    };
+
+    if (num_kt > 0) {
+        gload(0);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int kt = 0; kt < num_kt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < num_kt) gload(kt + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], w[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 2) {
+                const float2 t = *reinterpret_cast<const float2*>(&As[buf][k][ty * TM + i]);
+                a[i] = t.x; a[i + 1] = t.y;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * TN + j]);
+                w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        if (kt + 1 < num_kt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    if (!direct) {
+        float* p = part + (long long)blockIdx.z * M * N;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int row = m0 + ty * TM + i;
+            if (row >= M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int col = n0 + tx * TN + j;
+                if (col < N) p[(long long)row * N + col] = acc[i][j];
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int row = m0 + ty * TM + i;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int col = n0 + tx * TN + j;
+            if (col >= N) continue;
+            float v = acc[i][j];
+            if (ep.bias) v += (ep.bias_mode == 2) ? ep.bias[row] : ep.bias[col];
+            if (!ep.act_after_residual) v = avsr_apply_act(v, ep.act, ep.act == AVSR_ACT_PRELU ? ep.prelu[col] : 0.f);
+            if (ep.residual) {
+                v += ep.res_dtype == 0 ? reinterpret_cast<const float*>(ep.residual)[(long long)row * ep.ldr + col]
+                                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.residual)[(long long)row * ep.ldr + col]);
+            }
+            if (ep.act_after_residual) v = avsr_apply_act(v, ep.act, ep.act == AVSR_ACT_PRELU ? ep.prelu[col] : 0.f);
+            if (ep.out_f32) ep.out_f32[(long long)row * ep.ld_f32 + col] = v;
+            if (ep.out_bf16) reinterpret_cast<__nv_bfloat16*>(ep.out_bf16)[(long long)row * ep.ld_bf16 + col] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// One CTA per output row: v = sum_z part[z][row][:] + bias ; act ; + residual -> out (fp32);
+// optionally a LayerNorm of the finished row -> ln_out (fp32), which is the input of the next projection.
+__global__ void __launch_bounds__(256)
+splitk_epilogue_kernel(const float* __restrict__ part, int nsplit, int M, int N, const float* __restrict__ bias, int act,
+                       const float* __restrict__ residual, long long ldr, float* __restrict__ out, long long ldo,
+                       const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, float* __restrict__ ln_out,
+                       long long ld_ln, const int* __restrict__ row_active) {
+    extern __shared__ float rowbuf[];
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    if (row_active != nullptr && row_active[row] == 0) return;
+    float lsum = 0.f;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        float v = 0.f;
+        for (int z = 0; z < nsplit; ++z) v += part[((long long)z * M + row) * N + c];
+        if (bias) v += bias[c];
+        if (act == AVSR_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == AVSR_ACT_GELU) v = gelu_erf(v);
+        if (residual) v += residual[(long long)row * ldr + c];
+        if (out) out[(long long)row * ldo + c] = v;
+        if (ln_out) { rowbuf[c] = v; lsum += v; }
+    }
+    if (ln_out == nullptr) return;
+    const float mean = block_sum(lsum, red) / (float)N;
+    float lvar = 0.f;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) {
+        const float d = rowbuf[c] - mean;
+        lvar += d * d;
+    }
+    const float var = block_sum(lvar, red) / (float)N;
+    const float rstd = rsqrtf(var + ln_eps);
+    for (int c = threadIdx.x; c < N; c += blockDim.x)
+        ln_out[(long long)row * ld_ln + c] = (rowbuf[c] - mean) * rstd * ln_g[c] + ln_b[c];
+}
+
+int g_sms = 0;
+int sm_count() {
+    if (g_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sms;
+}
+
+}  // namespace
+
+// Tall fp32 GEMM with the fused epilogue (no split-K).
+extern "C" int avsr_sgemm(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K,
+                          const AvsrEpilogue* ep, cudaStream_t stream) {
+    AVSR_REQUIRE(A && W && ep, "avsr_sgemm: null operand");
+    AVSR_REQUIRE(M > 0 && N > 0 && K > 0 && (K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0,
+                 "avsr_sgemm: bad shape/stride M=%d N=%d K=%d lda=%lld ldw=%lld", M, N, K, lda, ldw);
+    dim3 grid(cdiv(N, 128), cdiv(M, 128), 1);
+    sgemm_tn_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, stream>>>(A, lda, W, ldw, nullptr, M, N, K, K, *ep, 1);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+// Number of K splits avsr_sgemm_skinny will use (the caller sizes the partial-sum workspace: nsplit*M*N floats).
+extern "C" int avsr_sgemm_skinny_splits(int M, int N, int K) {
+    const int tiles = cdiv(N, 64) * cdiv(M, 96);
+    int ns = cdiv(2 * sm_count(), tiles);
+    const int max_ns = K / 64 > 0 ? K / 64 : 1;
+    if (ns > max_ns) ns = max_ns;
+    if (ns < 1) ns = 1;
+    return ns;
+}
+
+// Skinny fp32 GEMM: writes raw partial sums part[nsplit][M][N]; combine with avsr_splitk_epilogue.
+extern "C" int avsr_sgemm_skinny(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K, float* part,
+                                 int nsplit, cudaStream_t stream) {
+    AVSR_REQUIRE(A && W && part, "avsr_sgemm_skinny: null operand");
+    AVSR_REQUIRE(M > 0 && N > 0 && K > 0 && (K & 3) == 0 && (lda & 3) == 0 && (ldw & 3) == 0 && nsplit >= 1,
+                 "avsr_sgemm_skinny: bad shape/stride M=%d N=%d K=%d", M, N, K);
+    int kps = cdiv(K, nsplit);
+    kps = ((kps + 15) / 16) * 16;
+    AvsrEpilogue ep = {};
+    dim3 grid(cdiv(N, 64), cdiv(M, 96), nsplit);
+    sgemm_tn_kernel<96, 64, 16, 6, 4><<<grid, 256, 0, stream>>>(A, lda, W, ldw, part, M, N, K, kps, ep, 0);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
+                                    long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
+                                    float* ln_out, long long ld_ln, const int* row_active, cudaStream_t stream) {
+    AVSR_REQUIRE(part && M > 0 && N > 0 && nsplit >= 1, "avsr_splitk_epilogue: bad arguments");
+    AVSR_REQUIRE(out || ln_out, "avsr_splitk_epilogue: no output");
+    AVSR_REQUIRE(!ln_out || (ln_g && ln_b && N * 4 <= 48 * 1024), "avsr_splitk_epilogue: LayerNorm needs gamma/beta and N <= 12288");
+    const size_t smem = ln_out ? (size_t)N * 4 : 0;
+    splitk_epilogue_kernel<<<M, 256, smem, stream>>>(part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps,
+                                                     ln_out, ld_ln, row_active);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}

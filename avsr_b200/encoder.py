@@ -1,0 +1,222 @@
+"""AV-HuBERT-large encoder forward on B200: host orchestration of the sm_100a kernels.
+
+Drop-in for ``AVHubertModel.forward`` (/root/reference/src/nets/backend/backbones/avhubert.py:546-561): same call
+``encoder(input_features=audios[B,104,T], video=videos[B,1,T,88,88])`` and an output object with ``.last_hidden_state``
+``[B,T,1024]``.  Inference branch only (mask=False, features_only=True), see SURVEY.md 3.2.  Beyond the reference it
+takes ``lengths`` (frames per utterance) so mixed-length batches give exactly the per-utterance B=1 results: frames are
+packed back to back and every temporal op (3D conv, positional conv, attention) stops at utterance boundaries.
+
+Every dense op is the tcgen05 GEMM (csrc/gemm_tc.cu) with a fused epilogue; attention is csrc/attn_tc.cu; the rest are
+the HBM-bound helpers of csrc/elementwise.cu.  The residual stream is kept in fp32, GEMM operands are bf16.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .weights import EncoderWeights
+
+
+@dataclass
+class EncoderOutput:
+    last_hidden_state: torch.Tensor
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+    packed: Optional[torch.Tensor] = None          # [sum(T), 1024] fp32, utterances back to back
+    lengths: Optional[List[int]] = None
+
+
+class Encoder:
+    CHUNK_FRAMES = 2048      # frames of the video frontend processed per pass (bounds the im2col workspace at ~2 GB)
+
+    def __init__(self, state_dict, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("avsr_b200.Encoder needs a CUDA device (no CPU fallback)")
+        L.load()
+        self.w = EncoderWeights(state_dict, self.device)
+        self._ws = {}
+
+    # ------------------------------------------------------------------ workspace
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    # ------------------------------------------------------------------ pieces
+    def _conv_gemm(self, col, w, M, N, K, **ep):
+        L.gemm_bf16(col, w, M, N, K, L.make_epilogue(**ep), lda=K, ldb=K)
+
+    def _basic_block(self, x, nf, H, C_in, blk, tag):
+        """x: [nf,H,H,C_in] bf16 -> [nf,Ho,Ho,C_out] bf16 (resnet.py:56-69)."""
+        lib = L.load()
+        s, C_out = blk["stride"], blk["cout"]
+        Ho = (H + 2 - 3) // s + 1
+        M = nf * Ho * Ho
+        col = self._buf("col", (M, 9 * C_in), torch.bfloat16)
+        L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(nf), H, H, C_in, 3, s, L.stream()), "avsr_im2col2d")
+        t1 = self._buf("blk_t1", (M, C_out), torch.bfloat16)
+        self._conv_gemm(col, blk["conv1_w"], M, C_out, 9 * C_in, bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"],
+                        out_bf16=t1, ld_bf16=C_out)
+        if "down_w" in blk:
+            colr = self._buf("col", (M, C_in), torch.bfloat16)
+            L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(colr), L.ll(nf), H, H, C_in, 1, s, L.stream()), "avsr_im2col2d")
+            res = self._buf("blk_res", (M, C_out), torch.bfloat16)
+            self._conv_gemm(colr, blk["down_w"], M, C_out, C_in, bias=blk["down_b"], out_bf16=res, ld_bf16=C_out)
+        else:
+            res = x.view(M, C_out)
+        col2 = self._buf("col", (M, 9 * C_out), torch.bfloat16)
+        L.check(lib.avsr_im2col2d(L.ptr(t1), L.ptr(col2), L.ll(nf), Ho, Ho, C_out, 3, 1, L.stream()), "avsr_im2col2d")
+        out = self._buf("blk_out_" + tag, (M, C_out), torch.bfloat16)
+        self._conv_gemm(col2, blk["conv2_w"], M, C_out, 9 * C_out, bias=blk["conv2_b"], act=L.ACT_PRELU, prelu=blk["prelu2"],
+                        residual=res, ldr=C_out, act_after_residual=True, out_bf16=out, ld_bf16=C_out)
+        return out.view(nf, Ho, Ho, C_out), Ho
+
+    def _video_frontend(self, video_packed, frame_t, frame_T, F, taps=None):
+        """[F,88,88] fp32 -> trunk features [F,512] bf16 (resnet.py:126-164)."""
+        lib = L.load()
+        w = self.w
+        feat = self._buf("trunk_out", (F, 512), torch.bfloat16)
+        for f0 in range(0, F, self.CHUNK_FRAMES):
+            nf = min(self.CHUNK_FRAMES, F - f0)
+            M0 = nf * 44 * 44
+            col = self._buf("col", (M0, 256), torch.bfloat16)
+            L.check(lib.avsr_im2col_frontend(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(col), L.stream()),
+                    "avsr_im2col_frontend")
+            c0 = self._buf("front_conv", (M0, 64), torch.bfloat16)
+            self._conv_gemm(col, w.front_w, M0, 64, 256, bias=w.front_b, act=L.ACT_PRELU, prelu=w.front_prelu, out_bf16=c0, ld_bf16=64)
+            x = self._buf("front_pool", (nf, 22, 22, 64), torch.bfloat16)
+            L.check(lib.avsr_maxpool3x3s2(L.ptr(c0), L.ptr(x), L.ll(nf), 44, 44, 64, L.stream()), "avsr_maxpool3x3s2")
+            if taps is not None:
+                taps.setdefault("frontend3d", []).append(x.clone())
+            H, Cc = 22, 64
+            for i, blk in enumerate(w.blocks):
+                x, H = self._basic_block(x, nf, H, Cc, blk, str(i & 1))
+                Cc = blk["cout"]
+            L.check(lib.avsr_avgpool(L.ptr(x), L.ptr(feat[f0:]), L.ll(nf), H * H, 512, L.stream()), "avsr_avgpool")
+        return feat
+
+    # ------------------------------------------------------------------ forward
+    def forward_packed(self, video_packed: torch.Tensor, audio: torch.Tensor, lengths: Sequence[int], taps=None) -> torch.Tensor:
+        """video_packed [F,88,88] fp32 (valid frames of all utterances back to back), audio [B,104,Tpad] fp32.
+        Returns the encoder output for the packed frames, [F,1024] fp32."""
+        lib = L.load()
+        w = self.w
+        dev = self.device
+        L.require_cuda(video_packed, torch.float32, "video")
+        L.require_cuda(audio, torch.float32, "audio")
+        B, Cin, Tpad = audio.shape
+        lengths = [int(t) for t in lengths]
+        F = sum(lengths)
+        if len(lengths) != B or video_packed.shape[0] != F or Cin != 104 or tuple(video_packed.shape[1:]) != (88, 88):
+            raise RuntimeError(f"bad encoder input shapes: video {tuple(video_packed.shape)}, audio {tuple(audio.shape)}, lengths {lengths}")
+        if min(lengths) < 1 or max(lengths) > Tpad:
+            raise RuntimeError("utterance lengths must be in [1, T]")
+        fb, ft, fT, offs = [], [], [], []
+        o = 0
+        for b, t in enumerate(lengths):
+            offs.append(o)
+            fb += [b] * t
+            ft += list(range(t))
+            fT += [t] * t
+            o += t
+        frame_b = torch.tensor(fb, dtype=torch.int32, device=dev)
+        frame_t = torch.tensor(ft, dtype=torch.int32, device=dev)
+        frame_T = torch.tensor(fT, dtype=torch.int32, device=dev)
+
+        # --- modality front-ends (avhubert.py:187-198) and concat-fusion (avhubert.py:486-502)
+        trunk = self._video_frontend(video_packed, frame_t, frame_T, F, taps)
+        if taps is not None:
+            taps["trunk"] = trunk.float()
+        feats = self._buf("feats", (F, 2048), torch.float32)
+        a16 = self._buf("audio16", (F, 104), torch.bfloat16)
+        L.check(lib.avsr_audio_pack(L.ptr(audio), L.ptr(a16), L.ptr(frame_b), L.ptr(frame_t), L.ll(F), 104, Tpad, L.stream()), "avsr_audio_pack")
+        L.gemm_bf16(a16, w.aproj_w, F, 1024, 104, L.make_epilogue(bias=w.aproj_b, out_f32=feats, ld_f32=2048), lda=104, ldb=104)
+        L.gemm_bf16(trunk, w.vproj_w, F, 1024, 512, L.make_epilogue(bias=w.vproj_b, out_f32=feats[:, 1024:], ld_f32=2048), lda=512, ldb=512)
+        fn = self._buf("feats_ln", (F, 2048), torch.bfloat16)
+        L.layernorm(feats, w.fuse_ln_g, w.fuse_ln_b, 1e-5, out_bf16=fn)
+        h = self._buf("h", (F, 1024), torch.float32)
+        hb = self._buf("h16", (F, 1024), torch.bfloat16)
+        L.gemm_bf16(fn, w.post_w, F, 1024, 2048, L.make_epilogue(bias=w.post_b, out_f32=h, ld_f32=1024, out_bf16=hb, ld_bf16=1024))
+        if taps is not None:
+            taps["fused"] = h.clone()
+
+        # --- positional conv (k=128, groups=16) + GELU + residual (avhubert.py:698-699)
+        pcol = self._buf("col", (16, F, 8192), torch.bfloat16)
+        L.check(lib.avsr_posconv_im2col(L.ptr(hb), L.ptr(pcol), L.ptr(frame_t), L.ptr(frame_T), L.ll(F), 0, 16, L.stream()), "avsr_posconv_im2col")
+        for g in range(16):
+            hg = h[:, g * 64:]
+            L.gemm_bf16(pcol[g], w.pos_w[g], F, 64, 8192,
+                        L.make_epilogue(bias=w.pos_b[g * 64:], act=L.ACT_GELU, residual=hg, ldr=1024, out_f32=hg, ld_f32=1024),
+                        lda=8192, ldb=8192, bn_hint=64)
+        if taps is not None:
+            taps["posconv"] = h.clone()
+
+        # --- 24 pre-LN transformer layers (avhubert.py:747-768)
+        work = [(offs[b], t, q0) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
+        work_off = torch.tensor([x[0] for x in work], dtype=torch.int32, device=dev)
+        work_T = torch.tensor([x[1] for x in work], dtype=torch.int32, device=dev)
+        work_q0 = torch.tensor([x[2] for x in work], dtype=torch.int32, device=dev)
+        Fld = (F + 7) // 8 * 8
+        a = self._buf("ln_out", (F, 1024), torch.bfloat16)
+        qk = self._buf("qk", (F, 2048), torch.bfloat16)
+        vt = self._buf("vt", (1024, Fld), torch.bfloat16)
+        ao = self._buf("attn_out", (F, 1024), torch.bfloat16)
+        ff = self._buf("ffn_mid", (F, 4096), torch.bfloat16)
+        for li, lay in enumerate(w.layers):
+            L.layernorm(h, lay["ln1_g"], lay["ln1_b"], 1e-5, out_bf16=a)
+            L.gemm_bf16(a, lay["wqk"], F, 2048, 1024, L.make_epilogue(bias=lay["bqk"], out_bf16=qk, ld_bf16=2048))
+            L.gemm_bf16(lay["wv"], a, 1024, F, 1024, L.make_epilogue(bias=lay["bv"], bias_mode=2, out_bf16=vt, ld_bf16=Fld))
+            L.check(lib.avsr_attention_varlen(L.ptr(qk), L.ptr(vt), L.ll(Fld), L.ptr(ao), L.ll(F), L.ptr(work_off), L.ptr(work_T),
+                                              L.ptr(work_q0), len(work), max(lengths), L.stream()), "avsr_attention_varlen")
+            L.gemm_bf16(ao, lay["wo"], F, 1024, 1024, L.make_epilogue(bias=lay["bo"], residual=h, ldr=1024, out_f32=h, ld_f32=1024))
+            L.layernorm(h, lay["ln2_g"], lay["ln2_b"], 1e-5, out_bf16=a)
+            L.gemm_bf16(a, lay["w1"], F, 4096, 1024, L.make_epilogue(bias=lay["b1"], act=L.ACT_GELU, out_bf16=ff, ld_bf16=4096))
+            L.gemm_bf16(ff, lay["w2"], F, 1024, 4096, L.make_epilogue(bias=lay["b2"], residual=h, ldr=1024, out_f32=h, ld_f32=1024))
+            if taps is not None and li == 0:
+                taps["enc_layer0"] = h.clone()
+        out = torch.empty(F, 1024, dtype=torch.float32, device=dev)
+        L.layernorm(h, w.final_ln_g, w.final_ln_b, 1e-5, out_f32=out)
+        return out
+
+    def __call__(self, input_features: torch.Tensor, attention_mask=None, video: torch.Tensor = None,
+                 lengths: Optional[Sequence[int]] = None, **kwargs) -> EncoderOutput:
+        """Reference signature (avhubert.py:546-552).  ``attention_mask`` must be None, as in script/evaluation.py:101
+        (the reference's masked branch raises under its own pinned-vs-installed transformers); pass
+        ``lengths`` for padded batches instead."""
+        if attention_mask is not None:
+            raise RuntimeError("attention_mask is not supported; pass lengths=[frames per utterance] for padded batches")
+        if video is None or input_features is None:
+            raise RuntimeError("both input_features (audio) and video are required (modality 'av')")
+        if video.dim() != 5 or video.shape[1] != 1:
+            raise RuntimeError(f"video must be [B,1,T,88,88], got {tuple(video.shape)}")
+        B, _, T = input_features.shape
+        if lengths is None:
+            lengths = [T] * B
+        video = video.to(self.device, torch.float32)
+        audio = input_features.to(self.device, torch.float32).contiguous()
+        if all(t == T for t in lengths):
+            vp = video.reshape(B * T, 88, 88).contiguous()
+        else:
+            vp = torch.cat([video[b, 0, :t] for b, t in enumerate(lengths)], 0).contiguous()
+        packed = self.forward_packed(vp, audio, lengths)
+        if all(t == T for t in lengths):
+            padded = packed.view(B, T, 1024)
+        else:
+            padded = torch.zeros(B, T, 1024, dtype=torch.float32, device=self.device)
+            o = 0
+            for b, t in enumerate(lengths):
+                padded[b, :t] = packed[o:o + t]
+                o += t
+        return EncoderOutput(last_hidden_state=padded, packed=packed, lengths=list(lengths))
+
+    forward = __call__

@@ -1,0 +1,150 @@
+/* libavsr_b200.so - C ABI of the B200-native AVSRCocktail inference hot path.
+ *
+ * The reference (quanpn90/avsr) is pure Python/PyTorch and has no FFI; each entry point below replaces a span of the
+ * reference's Python that today expands into ATen/cuBLAS/cuDNN library calls (file:line relative to /root/reference).
+ * Host code stays Python (avsr_b200/*.py) and binds these symbols with ctypes (avsr_b200/_lib.py); INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative AVSR_ERR_* code and records a message retrievable with
+ * avsr_last_error().  All pointers are DEVICE pointers unless stated otherwise; the library never allocates, frees or
+ * synchronises: buffers (including workspaces) belong to the caller (torch tensors), work is enqueued on `stream`.
+ * bf16 buffers are passed as void*.  Leading dimensions are in elements.
+ */
+#ifndef AVSR_B200_H
+#define AVSR_B200_H
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+typedef cudaStream_t avsr_stream_t;
+#else
+typedef void* avsr_stream_t;
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVSR_OK 0
+#define AVSR_ERR_CUDA -1
+#define AVSR_ERR_ARG -2
+#define AVSR_ERR_UNSUPPORTED -3
+
+enum { AVSR_ACT_NONE = 0, AVSR_ACT_GELU = 1, AVSR_ACT_RELU = 2, AVSR_ACT_PRELU = 3 };
+
+/* Fused GEMM epilogue:  v = acc (+ bias[col] | bias[row]); [v = act(v)]; v += residual[row,col];
+ * [v = act(v) if act_after_residual]; rows with row_mask == 0 become 0; store bf16 and/or fp32. */
+typedef struct AvsrEpilogue {
+    const float* bias;      /* NULL = none */
+    int bias_mode;          /* 1 = per output column, 2 = per output row */
+    int act;                /* AVSR_ACT_* */
+    const float* prelu;     /* [N] slopes when act == AVSR_ACT_PRELU */
+    const void* residual;   /* NULL = none */
+    int res_dtype;          /* 0 fp32, 1 bf16 */
+    long long ldr;
+    void* out_bf16;         /* NULL = skip */
+    long long ld_bf16;
+    float* out_f32;         /* NULL = skip */
+    long long ld_f32;
+    const int* row_mask;    /* optional [M] */
+    int act_after_residual;
+} AvsrEpilogue;
+
+/* Device-resident state of the batched joint CTC/attention beam search (one row = utterance * beam + slot).
+ * Replaces the Python Hypothesis / BatchHypothesis lists of src/nets/beam_search.py:13-27 and
+ * src/nets/batch_beam_search.py:12-84. */
+typedef struct AvsrBeamState {
+    int B, beam, S, V, lmax, tmax, blank, eos, cap, _pad;
+    const int* utt_T;       /* [B] frames per utterance (= maxlen, beam_search.py:349-350) */
+    const int* step;        /* current position i */
+    int* n_run;             /* [B] running hyps; 0 = utterance finished */
+    int* row_active;        /* [R] */
+    int* last_tok;          /* [R] */
+    float* score;           /* [R] fused score */
+    float* dec_sc;          /* [R] accumulated decoder log-prob */
+    float* ctc_sc;          /* [R] accumulated CTC score */
+    float* s_prev;          /* [R] log_psi of the prefix (CTC state) */
+    int* rprev_idx;         /* [R] chain index of the inherited CTC forward variables */
+    unsigned char* anc;     /* [2][R][lmax] self-attention cache ancestry */
+    int* hist_tok;          /* [B][tmax][beam] chosen token of candidate j at step i */
+    int* hist_prev;         /* [B][tmax][beam] its parent running index */
+    int* run2j;             /* [B][tmax][beam] running index (after step i) -> candidate j */
+    int* n_ended;           /* [B] */
+    int* end_step;          /* [B][cap] */
+    int* end_j;             /* [B][cap] */
+    float* end_score;       /* [B][cap] */
+    float* end_dec;         /* [B][cap] */
+    float* end_ctc;         /* [B][cap] */
+    int* end_len;           /* [B][cap] len(yseq) incl. sos and eos */
+    float* best_len;        /* [B][tmax+4] best ended score per yseq length, -inf = none */
+    float* best_all;        /* [B] */
+    int* done;              /* [B] */
+    int* overflow;          /* [1] set if an ended list overflowed */
+    double d_end;           /* end_detect threshold log(exp(-10)), e2e_asr_common.py:18 */
+} AvsrBeamState;
+
+const char* avsr_last_error(void);
+int avsr_abi_version(void);
+
+/* ---- dense encoder ops (tcgen05 tensor cores) --------------------------------------------------------------------
+ * C[M,N] = epilogue(A[M,K] * B[N,K]^T), A/B bf16 row-major.  Replaces every nn.Linear / Conv (as im2col GEMM) of the
+ * encoder: src/nets/backend/backbones/avhubert.py:187-198,486-502,747-768, resnet.py:30-164, and HF
+ * Wav2Vec2Attention/FeedForward/PositionalConvEmbedding (modeling_wav2vec2.py:326-573). */
+int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue* ep,
+                      int bn_hint, avsr_stream_t stream);
+/* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */
+int avsr_attention_varlen(const void* qk, const void* vt, long long ld_vt, void* out, long long F, const int* work_off,
+                          const int* work_T, const int* work_q0, int n_work, int max_T, avsr_stream_t stream);
+/* torch.nn.LayerNorm over the last dim (avhubert.py:495, 705, 734; HF encoder layers). */
+int avsr_layernorm(const float* x, long long ldx, long long rows, int N, const float* gamma, const float* beta, float eps,
+                   void* out_bf16, long long ld_bf16, float* out_f32, long long ld_f32, avsr_stream_t stream);
+/* Conv3d(1->64, 5x7x7, s 1x2x2, p 2x3x3) patches of packed frames (resnet.py:132). */
+int avsr_im2col_frontend(const float* video, const int* frame_t, const int* frame_T, int f0, int nf, void* out, avsr_stream_t stream);
+/* Conv2d 3x3 / 1x1 patches, channels-last bf16 (resnet.py:10-19). */
+int avsr_im2col2d(const void* in, void* out, long long F, int H, int W, int C, int ks, int stride, avsr_stream_t stream);
+/* MaxPool3d (1,3,3)/(1,2,2)/(0,1,1) (resnet.py:136) and AdaptiveAvgPool2d(1) (resnet.py:76). */
+int avsr_maxpool3x3s2(const void* in, void* out, long long F, int H, int W, int C, avsr_stream_t stream);
+int avsr_avgpool(const void* in, void* out, long long F, int HW, int C, avsr_stream_t stream);
+/* audio [B,104,Tpad] fp32 -> packed [F,104] bf16 (the transpose of avhubert.py:196). */
+int avsr_audio_pack(const float* audio, void* out, const int* frame_b, const int* frame_t, long long F, int Cin, int Tpad,
+                    avsr_stream_t stream);
+/* patches of the grouped positional Conv1d (k=128, pad=64, g=16), zero outside the utterance. */
+int avsr_posconv_im2col(const void* x, void* out, const int* frame_t, const int* frame_T, long long F, int g0, int ng,
+                        avsr_stream_t stream);
+int avsr_cast_bf16(const float* in, long long ldi, void* out, long long ldo, long long rows, int cols, avsr_stream_t stream);
+
+/* ---- fp32 decode-side ops ----------------------------------------------------------------------------------------- */
+/* CTC head / cross-attention K,V projection (src/nets/backend/ctc.py:163-170; transformer/attention.py:50-52). */
+int avsr_sgemm(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K, const AvsrEpilogue* ep,
+               avsr_stream_t stream);
+int avsr_sgemm_skinny_splits(int M, int N, int K);
+int avsr_sgemm_skinny(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K, float* part, int nsplit,
+                      avsr_stream_t stream);
+int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
+                         long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
+                         float* ln_out, long long ld_ln, const int* row_active, avsr_stream_t stream);
+int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_stream_t stream);
+/* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
+int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
+                      const float* gamma, const float* beta, float eps, float* x, float* a, avsr_stream_t stream);
+int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
+                       const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step, float* out,
+                       int max_keys, long long kv_ld, avsr_stream_t stream);
+int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
+                             int* part_ids, int S, avsr_stream_t stream);
+/* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes. */
+int avsr_ctc_prefix_prebeam(const float* logp, int V, int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam,
+                            int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx, float* r_buf, int tmax,
+                            const int* step, float* psi, float* rsum_last, avsr_stream_t stream);
+int avsr_ctc_prefix_full(const float* logp, int V, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
+                         int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
+                         const int* step, const float* s_prev, float* scores, avsr_stream_t stream);
+/* BatchBeamSearch.search fusion + batch_beam top-k + post_process + end_detect
+ * (src/nets/batch_beam_search.py:86-110,222-349; src/nets/e2e_asr_common.py:18-48). */
+int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,
+                                const float* rsum_last, float w_dec, float w_ctc, avsr_stream_t stream);
+int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, avsr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSR_B200_H */

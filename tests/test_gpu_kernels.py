@@ -1,0 +1,217 @@
+"""GPU: every kernel of libavsr_b200.so, called through the C ABI, against a plain PyTorch fp32 restatement of the op."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from avsr_b200 import _lib
+    _lib.load()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _lib
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 64, 128), (300, 256, 128, 256), (1000, 1024, 1024, 0),
+                                      (777, 200, 104, 0), (5000, 64, 576, 0), (12000, 4096, 1024, 0), (1024, 3001, 1024, 0)])
+def test_gemm_tc_plain(L, M, N, K, bn):
+    a, b = _rand(M, K, seed=1).bfloat16(), _rand(N, K, seed=2).bfloat16()
+    ld = (N + 7) // 8 * 8
+    out16 = torch.zeros(M, ld, dtype=torch.bfloat16, device="cuda")
+    out32 = torch.zeros(M, ld, dtype=torch.float32, device="cuda")
+    L.gemm_bf16(a, b, M, N, K, L.make_epilogue(out_bf16=out16, ld_bf16=ld, out_f32=out32, ld_f32=ld), bn_hint=bn)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    err = (out32[:, :N] - ref).abs().max().item()
+    assert err < 2e-3 * math.sqrt(K), f"fp32 out max-abs {err}"
+    assert (out16[:, :N].float() - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 1e-2
+    if ld > N:
+        assert out32[:, N:].abs().max().item() == 0.0      # nothing written past column N
+
+
+def test_gemm_tc_epilogues(L):
+    M, N, K = 900, 256, 192
+    a, b = _rand(M, K, seed=3).bfloat16(), _rand(N, K, seed=4, scale=0.1).bfloat16()
+    bias, slope = _rand(N, seed=5), torch.rand(N, device="cuda") * 0.3 + 0.1
+    res32, res16 = _rand(M, N, seed=6), _rand(M, N, seed=7).bfloat16()
+    acc = a.float() @ b.float().t()
+    out = torch.empty(M, N, device="cuda")
+    # bias + GELU, then residual (fp32)
+    L.gemm_bf16(a, b, M, N, K, L.make_epilogue(bias=bias, act=L.ACT_GELU, residual=res32, ldr=N, out_f32=out, ld_f32=N))
+    assert (out - (F.gelu(acc + bias) + res32)).abs().max().item() < 2e-3
+    # bias, bf16 residual, PReLU after the residual (ResNet block tail)
+    L.gemm_bf16(a, b, M, N, K, L.make_epilogue(bias=bias, act=L.ACT_PRELU, prelu=slope, residual=res16, ldr=N,
+                                               act_after_residual=True, out_f32=out, ld_f32=N))
+    ref = acc + bias + res16.float()
+    ref = torch.where(ref >= 0, ref, ref * slope)
+    assert (out - ref).abs().max().item() < 2e-3
+    # per-row bias (V^T projection), ReLU
+    rb = _rand(M, seed=8)
+    L.gemm_bf16(a, b, M, N, K, L.make_epilogue(bias=rb, bias_mode=2, act=L.ACT_RELU, out_f32=out, ld_f32=N))
+    assert (out - torch.relu(acc + rb[:, None])).abs().max().item() < 2e-3
+    # in-place residual stream update
+    h = res32.clone()
+    L.gemm_bf16(a, b, M, N, K, L.make_epilogue(bias=bias, residual=h, ldr=N, out_f32=h, ld_f32=N))
+    assert (h - (acc + bias + res32)).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(500, 333, 1024), (96, 3072, 1024), (3000, 5049, 1024)])
+def test_sgemm(L, M, N, K):
+    a, w, bias = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=0.03), _rand(N, seed=3)
+    out = torch.empty(M, N, device="cuda")
+    L.sgemm(a, w, M, N, K, L.make_epilogue(bias=bias, out_f32=out, ld_f32=N))
+    ref = (a.double() @ w.double().t() + bias.double()).float()
+    assert (out - ref).abs().max().item() < 2e-5 * math.sqrt(K)
+
+
+@pytest.mark.parametrize("R,N,K", [(96, 1024, 1024), (160, 3072, 1024), (96, 1024, 3072), (15, 5049, 1024), (3, 1024, 1024)])
+def test_sgemm_skinny_and_epilogue(L, R, N, K):
+    lib = L.load()
+    a, w, bias = _rand(R, K, seed=1), _rand(N, K, seed=2, scale=0.03), _rand(N, seed=3)
+    ns = lib.avsr_sgemm_skinny_splits(R, N, K)
+    part = torch.empty(ns, R, N, device="cuda")
+    L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(w), L.ll(K), R, N, K, L.ptr(part), ns, L.stream()), "skinny")
+    ref = (a.double() @ w.double().t()).float()
+    assert (part.sum(0) - ref).abs().max().item() < 2e-5 * math.sqrt(K)
+    if N == 1024:
+        res, g, b = _rand(R, N, seed=4), _rand(N, seed=5), _rand(N, seed=6)
+        act = torch.ones(R, dtype=torch.int32, device="cuda")
+        act[R // 2] = 0
+        out, ln = torch.zeros(R, N, device="cuda"), torch.zeros(R, N, device="cuda")
+        L.check(lib.avsr_splitk_epilogue(L.ptr(part), ns, R, N, L.ptr(bias), 0, L.ptr(res), L.ll(N), L.ptr(out), L.ll(N), L.ptr(g),
+                                         L.ptr(b), C.c_float(1e-12), L.ptr(ln), L.ll(N), L.ptr(act), L.stream()), "epilogue")
+        want = ref + bias + res
+        keep = act.bool()
+        assert (out[keep] - want[keep]).abs().max().item() < 1e-4
+        assert (ln[keep] - F.layer_norm(want, (N,), g, b, 1e-12)[keep]).abs().max().item() < 1e-4
+        assert out[~keep].abs().max().item() == 0.0
+
+
+def test_layernorm(L):
+    x, g, b = _rand(777, 2048, seed=1, scale=3.0), _rand(2048, seed=2), _rand(2048, seed=3)
+    o16 = torch.empty(777, 2048, dtype=torch.bfloat16, device="cuda")
+    o32 = torch.empty(777, 2048, device="cuda")
+    L.layernorm(x, g, b, 1e-5, out_bf16=o16, out_f32=o32)
+    ref = F.layer_norm(x, (2048,), g, b, 1e-5)
+    assert (o32 - ref).abs().max().item() < 1e-4
+    assert (o16.float() - ref).abs().max().item() < 0.05
+
+
+def test_im2col_pool_kernels(L):
+    lib = L.load()
+    # 2D im2col against F.unfold (channels-last k ordering (ky, kx, c))
+    for (H, Cc, ks, s) in ((22, 64, 3, 1), (22, 64, 3, 2), (11, 128, 1, 2), (6, 256, 3, 2), (3, 512, 3, 1)):
+        Fr = 5
+        x = _rand(Fr, H, H, Cc, seed=H).bfloat16()
+        pad = ks // 2
+        Ho = (H + 2 * pad - ks) // s + 1
+        out = torch.empty(Fr * Ho * Ho, ks * ks * Cc, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(out), L.ll(Fr), H, H, Cc, ks, s, L.stream()), "im2col2d")
+        u = F.unfold(x.float().permute(0, 3, 1, 2), ks, padding=pad, stride=s)          # [F, C*ks*ks, L]
+        u = u.view(Fr, Cc, ks * ks, Ho * Ho).permute(0, 3, 2, 1).reshape(Fr * Ho * Ho, ks * ks * Cc)
+        assert torch.equal(out.float(), u), (H, Cc, ks, s)
+    # max pool
+    x = _rand(4, 44, 44, 64, seed=9).bfloat16()
+    out = torch.empty(4, 22, 22, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_maxpool3x3s2(L.ptr(x), L.ptr(out), L.ll(4), 44, 44, 64, L.stream()), "maxpool")
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), ref)
+    # avg pool
+    x = _rand(7, 9, 512, seed=10).bfloat16()
+    out = torch.empty(7, 512, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_avgpool(L.ptr(x), L.ptr(out), L.ll(7), 9, 512, L.stream()), "avgpool")
+    assert (out.float() - x.float().mean(1)).abs().max().item() < 0.02
+
+
+def test_frontend_and_posconv_im2col(L):
+    lib = L.load()
+    lengths = [5, 3]
+    Fr = sum(lengths)
+    video = _rand(Fr, 88, 88, seed=11)
+    ft = torch.tensor([0, 1, 2, 3, 4, 0, 1, 2], dtype=torch.int32, device="cuda")
+    fT = torch.tensor([5] * 5 + [3] * 3, dtype=torch.int32, device="cuda")
+    out = torch.empty(Fr * 1936, 256, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_im2col_frontend(L.ptr(video), L.ptr(ft), L.ptr(fT), 0, Fr, L.ptr(out), L.stream()), "im2col_frontend")
+    # restatement: per utterance, pad time by 2 and space by 3, unfold 5x7x7 with stride (1,2,2)
+    o = 0
+    for T in lengths:
+        v = F.pad(video[o:o + T].bfloat16().float(), (3, 3, 3, 3, 2, 2))              # [T+4, 94, 94]
+        p = v.unfold(0, 5, 1).unfold(1, 7, 2).unfold(2, 7, 2)                          # [T,44,44,5,7,7]
+        ref = p.reshape(T * 1936, 245)
+        got = out[o * 1936:(o + T) * 1936].float()
+        assert torch.equal(got[:, :245], ref)
+        assert got[:, 245:].abs().max().item() == 0.0
+        o += T
+    # positional-conv patches
+    x = _rand(Fr, 1024, seed=12).bfloat16()
+    pc = torch.empty(16, Fr, 8192, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_posconv_im2col(L.ptr(x), L.ptr(pc), L.ptr(ft), L.ptr(fT), L.ll(Fr), 0, 16, L.stream()), "posconv_im2col")
+    o = 0
+    for T in lengths:
+        xp = F.pad(x[o:o + T].float(), (0, 0, 64, 64))                                  # [T+128, 1024]
+        for g in (0, 7, 15):
+            for t in range(T):
+                ref = xp[t:t + 128, g * 64:(g + 1) * 64].reshape(-1)
+                assert torch.equal(pc[g, o + t].float(), ref)
+        o += T
+
+
+@pytest.mark.parametrize("lengths", [[12], [30, 7], [375], [130, 257, 64], [700]])
+def test_attention_varlen(L, lengths):
+    lib = L.load()
+    Fr = sum(lengths)
+    Fld = (Fr + 7) // 8 * 8
+    qk = _rand(Fr, 2048, seed=21, scale=0.6).bfloat16()
+    v = _rand(Fr, 1024, seed=22).bfloat16()
+    vt = torch.zeros(1024, Fld, dtype=torch.bfloat16, device="cuda")
+    vt[:, :Fr] = v.t()
+    out = torch.zeros(Fr, 1024, dtype=torch.bfloat16, device="cuda")
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    work = [(int(offs[b]), t, q0) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
+    wo, wT, wq = (torch.tensor([w[i] for w in work], dtype=torch.int32, device="cuda") for i in range(3))
+    L.check(lib.avsr_attention_varlen(L.ptr(qk), L.ptr(vt), L.ll(Fld), L.ptr(out), L.ll(Fr), L.ptr(wo), L.ptr(wT), L.ptr(wq),
+                                      len(work), max(lengths), L.stream()), "attention")
+    torch.cuda.synchronize()
+    o = 0
+    for T in lengths:
+        q = qk[o:o + T, :1024].float().view(T, 16, 64).transpose(0, 1)
+        k = qk[o:o + T, 1024:].float().view(T, 16, 64).transpose(0, 1)
+        vv = v[o:o + T].float().view(T, 16, 64).transpose(0, 1)
+        ref = (torch.softmax(q @ k.transpose(1, 2), -1) @ vv).transpose(0, 1).reshape(T, 1024)     # scale pre-folded into q
+        err = (out[o:o + T].float() - ref).abs().max().item()
+        assert err < 0.03, (T, err)
+        o += T
+
+
+def test_log_softmax_and_logits_topk(L):
+    lib = L.load()
+    V, R, beam, S = 5049, 6, 3, 4
+    x = _rand(50, V, seed=31, scale=3.0)
+    ref = torch.log_softmax(x, -1)
+    L.check(lib.avsr_log_softmax_rows(L.ptr(x), L.ll(V), L.ll(50), V, L.stream()), "log_softmax")
+    assert (x - ref).abs().max().item() < 1e-5
+    part = _rand(2, R, V, seed=32)
+    bias = _rand(V, seed=33)
+    n_run = torch.tensor([3, 2], dtype=torch.int32, device="cuda")
+    logp = torch.zeros(R, V, device="cuda")
+    ids = torch.full((R, S), -1, dtype=torch.int32, device="cuda")
+    L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(part), 2, R, V, L.ptr(bias), L.ptr(n_run), beam, L.ptr(logp), L.ptr(ids), S, L.stream()), "lsm_topk")
+    want = torch.log_softmax(part.sum(0) + bias, -1)
+    for r in (0, 1, 2, 3, 4):
+        assert (logp[r] - want[r]).abs().max().item() < 1e-5
+        assert ids[r].tolist() == torch.topk(want[r], S)[1].tolist()
+    assert ids[5].tolist() == [-1] * S                       # dead row untouched

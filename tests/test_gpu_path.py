@@ -1,0 +1,193 @@
+"""GPU: the hot path through the public API (avsr_b200.model / encoder / beam_search -> C ABI) against (i) the golden
+vectors produced by the unmodified reference and (ii) the CPU oracle on the same seeded inputs.
+
+Tolerances: bf16 encoder vs fp32 reference: rel-RMSE <= 1.5e-2, max-abs <= 0.10, cosine >= 0.9999;
+decode: identical token sequences for every n-best entry with score > -1e8, |d score| <= 1e-3 * len.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from avsr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc_metrics(x, ref):
+    d = (x - ref).double()
+    return dict(max_abs=d.abs().max().item(), rel_rmse=(d.pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item(),
+                cos=torch.nn.functional.cosine_similarity(x.double().flatten(), ref.double().flatten(), dim=0).item())
+
+
+def _check_enc(x, ref, what):
+    m = _enc_metrics(x, ref)
+    assert m["max_abs"] <= 0.10 and m["rel_rmse"] <= 1.5e-2 and m["cos"] >= 0.9999, (what, m)
+
+
+@pytest.mark.parametrize("T,seed", [(12, 1234), (30, 1235)])
+def test_encoder_vs_reference_golden(gpu_model, golden, T, seed):
+    video, audio = synth.make_inputs(seed, T)
+    taps = {}
+    enc = gpu_model.encoder
+    x = enc.forward_packed(video[0, 0].cuda().contiguous(), audio.cuda(), [T], taps).cpu()
+    # stage by stage first, so that a failure names the kernel that broke
+    tr, tr_ref = taps["trunk"].cpu(), torch.from_numpy(golden[f"trunk_T{T}"])
+    assert (tr - tr_ref).abs().max().item() <= 0.02 * tr_ref.abs().max().item() + 0.02, ("trunk", _enc_metrics(tr, tr_ref))
+    for name in ("fused", "posconv", "enc_layer0"):
+        got, ref = taps[name].cpu(), torch.from_numpy(golden[f"{name}_T{T}"])
+        m = _enc_metrics(got, ref)
+        assert m["rel_rmse"] <= 1.5e-2, (name, m)
+    _check_enc(x, torch.from_numpy(golden[f"enc_T{T}"]), f"encoder T={T}")
+
+
+def _check_nbest(nbest, golden, T, beam):
+    yseq, score = golden[f"nbest_T{T}_b{beam}_yseq"], golden[f"nbest_T{T}_b{beam}_score"]
+    n = int((score > -1e8).sum())
+    assert len(nbest) >= n >= 1
+    for k in range(n):
+        assert nbest[k].yseq.tolist() == yseq[k].tolist(), (T, beam, k, nbest[k].yseq.tolist(), yseq[k].tolist())
+        ln = len(yseq[k])
+        assert abs(float(nbest[k].score) - score[k]) <= 1e-3 * ln
+        assert abs(float(nbest[k].scores["decoder"]) - golden[f"nbest_T{T}_b{beam}_dec"][k]) <= 1e-3 * ln
+        assert abs(float(nbest[k].scores["ctc"]) - golden[f"nbest_T{T}_b{beam}_ctc"][k]) <= 1e-2 * ln
+
+
+@pytest.mark.parametrize("T", [12, 30])
+@pytest.mark.parametrize("beam", [3, 5])
+@pytest.mark.parametrize("graph", [False, True])
+def test_beam_search_vs_reference_golden(state_dict, gpu_model, golden, T, beam, graph):
+    """Decode from the reference's own fp32 encoder output: token-identical n-best at beam 3 and 5."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam, use_graph=graph)
+    x = torch.from_numpy(golden[f"enc_T{T}"]).cuda()
+    nbest = bs(x)
+    _check_nbest(nbest, golden, T, beam)
+    h = nbest[0]
+    assert h.yseq.dtype == torch.int64 and h.yseq[0].item() == 5048 and h.yseq[-1].item() == 5048
+    d = h.asdict()
+    assert isinstance(d["yseq"], list) and isinstance(d["score"], float) and set(d["scores"]) == {"decoder", "ctc"}
+
+
+def test_batched_decode_equals_single_runs(gpu_model, golden):
+    """Mixed-length batch: every utterance must evolve exactly as its own B=1 run."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=3)
+    x12, x30 = torch.from_numpy(golden["enc_T12"]).cuda(), torch.from_numpy(golden["enc_T30"]).cuda()
+    out = bs.decode_batch(torch.cat([x30, x12, x30[:20].contiguous()], 0), [30, 12, 20])
+    _check_nbest(out[0], golden, 30, 3)
+    _check_nbest(out[1], golden, 12, 3)
+    single = bs(x30[:20].contiguous())
+    assert [h.yseq.tolist() for h in out[2]] == [h.yseq.tolist() for h in single]
+    assert all(abs(float(a.score) - float(b.score)) < 1e-4 for a, b in zip(out[2], single))
+
+
+def test_batched_encoder_equals_single_runs(gpu_model):
+    """Padded mixed-length batch == per-utterance runs (temporal conv / pos-conv / attention stop at utterance ends)."""
+    enc = gpu_model.encoder
+    v1, a1 = synth.make_inputs(7, 20)
+    v2, a2 = synth.make_inputs(8, 9)
+    video = torch.zeros(2, 1, 20, 88, 88)
+    audio = torch.zeros(2, 104, 20)
+    video[0], audio[0] = v1[0], a1[0]
+    video[1, :, :9], audio[1, :, :9] = v2[0], a2[0]
+    video[1, :, 9:] = 5.0                     # garbage in the padding must be invisible
+    audio[1, :, 9:] = -3.0
+    both = enc(input_features=audio.cuda(), video=video.cuda(), lengths=[20, 9]).last_hidden_state.cpu()
+    s1 = enc(input_features=a1.cuda(), video=v1.cuda()).last_hidden_state.cpu()[0]
+    s2 = enc(input_features=a2.cuda(), video=v2.cuda()).last_hidden_state.cpu()[0]
+    assert (both[0] - s1).abs().max().item() < 2e-2
+    assert (both[1, :9] - s2).abs().max().item() < 2e-2
+    assert both[1, 9:].abs().max().item() == 0.0
+
+
+def test_full_path_vs_oracle(state_dict, gpu_model):
+    """Encoder (bf16) -> beam search end to end through the evaluation-style call, against the CPU oracle."""
+    from oracle import avsr_oracle as O
+    T = 25
+    video, audio = synth.make_inputs(4321, T)
+    x_ref = O.encoder_forward(state_dict, audio, video)[0]
+    x = gpu_model.encoder(input_features=audio.cuda(), video=video.cuda()).last_hidden_state[0]
+    _check_enc(x.cpu(), x_ref, "encoder T=25")
+    ref = O.beam_search(state_dict, x_ref, 3, kv_cache=True)
+    nbest = gpu_model.beam_search(x_ref.cuda())
+    for a, b in zip(nbest, ref):
+        if b.score > -1e8:
+            assert a.yseq.tolist() == b.yseq
+            assert abs(float(a.score) - b.score) < 1e-3 * len(b.yseq)
+    # evaluation-style call (script/evaluation.py:96-108): token ids without sos
+    ids = gpu_model.inference(video.cuda(), audio.cuda())
+    assert isinstance(ids, list) and ids[-1] == 5048 and len(ids) == T + 1
+
+
+def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
+    """avsr_ctc_prefix_prebeam / avsr_ctc_prefix_full driven with the golden CTCPrefixScoreTH call sequences."""
+    from avsr_b200 import _lib as L
+    lib = L.load()
+    g = golden_ctc
+    LOGZERO = -1e10
+    for tag in ("small", "vocab"):
+        T, V, n_h, S = [int(v) for v in g[f"{tag}_shape"]]
+        gen = torch.Generator().manual_seed(77)
+        logp = torch.log_softmax(torch.randn(1, T, V, generator=gen) * 2.0, dim=-1)[0].cuda().contiguous()
+        beam, R = n_h, n_h
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")
+        utt_off, utt_T = i32([0]), i32([T])
+        for mode in ("prebeam", "full"):
+            Sk = S if mode == "prebeam" else 1
+            r_buf = torch.full((2, R * Sk, T, 2), LOGZERO, device="cuda")
+            rprev = i32([0] * R)
+            s_prev = torch.zeros(R, device="cuda")
+            n_hyp = 1
+            for step in range(4):
+                last = g[f"{tag}_{mode}_last{step}"].tolist()
+                n_run, last_tok, step_t = i32([n_hyp]), i32(last + [0] * (R - n_hyp)), i32([step])
+                ref = g[f"{tag}_{mode}_scores{step}"]
+                picks = g[f"{tag}_{mode}_picks{step}"]
+                psi = torch.zeros(R, Sk, device="cuda")
+                rsum = torch.zeros(R, device="cuda")
+                if mode == "prebeam":
+                    cand = g[f"{tag}_{mode}_cand{step}"]
+                    part = torch.zeros(R, S, dtype=torch.int32, device="cuda")
+                    part[:n_hyp] = torch.from_numpy(cand).int().cuda()
+                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S,
+                                                        L.ptr(last_tok), L.ptr(part), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t),
+                                                        L.ptr(psi), L.ptr(rsum), L.stream()), "prebeam")
+                    psi_c, rsum_c, sp = psi.cpu().numpy(), rsum.cpu().numpy(), s_prev.cpu().numpy()
+                    for h in range(n_hyp):
+                        for s_, c in enumerate(cand[h]):
+                            want = ref[h, c]
+                            got = (LOGZERO if c == 0 else (rsum_c[h] if c == V - 1 else psi_c[h, s_])) - sp[h]
+                            assert abs(got - want) < 1e-3 or (want < -1e9 and got < -1e9), (tag, mode, step, h, c, got, want)
+                        assert abs((rsum_c[h] - sp[h]) - ref[h, V - 1]) < 1e-3
+                    new_psi = []
+                    for h, t in picks:
+                        col = int(np.nonzero(cand[h] == t)[0][-1])
+                        new_psi.append((int(h) * S + col, float(psi_c[h, col])))
+                    rprev = i32([p[0] for p in new_psi] + [0] * (R - len(new_psi)))
+                    s_prev = torch.tensor([p[1] for p in new_psi] + [0.0] * (R - len(new_psi)), device="cuda")
+                else:
+                    scores = torch.zeros(R, V, device="cuda")
+                    L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, 1, 1,
+                                                     L.ptr(last_tok), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(s_prev),
+                                                     L.ptr(scores), L.stream()), "full")
+                    got = scores[:n_hyp].cpu().numpy()
+                    live = ref > -1e9
+                    assert np.abs(got[live] - ref[live]).max() < 1e-3, (tag, mode, step)
+                    assert (got[~live] < -1e9).all()
+                    # survivor chains are recomputed by the pre-beam kernel on the picked tokens (S = 1 candidate per new hyp)
+                    part = i32([[int(t)] for _, t in picks])
+                    rows_last = i32([last[int(h)] for h, _ in picks])
+                    rp = i32([int(rprev[int(h)].item()) for h, _ in picks])
+                    n_new = i32([len(picks)])
+                    psi2 = torch.zeros(R, 1, device="cuda")
+                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_new), beam, R, 1,
+                                                        L.ptr(rows_last), L.ptr(part), L.ptr(rp), L.ptr(r_buf), T, L.ptr(step_t),
+                                                        L.ptr(psi2), L.ptr(rsum), L.stream()), "prebeam(recompute)")
+                    sp_old = s_prev.cpu().numpy()
+                    for j, (h, t) in enumerate(picks):
+                        assert abs((psi2[j, 0].item() - sp_old[h]) - ref[h, t]) < 1e-3
+                    rprev = i32(list(range(len(picks))) + [0] * (R - len(picks)))
+                    s_prev = torch.cat([psi2[:len(picks), 0], torch.zeros(R - len(picks), device="cuda")])
+                n_hyp = len(picks)
