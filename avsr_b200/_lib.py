@@ -64,7 +64,12 @@ def load() -> C.CDLL:
     return _lib
 
 
+launch_count = 0      # kernels enqueued through check() since the caller last reset it (bench.py's gpu_launches)
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = load().avsr_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

@@ -69,6 +69,8 @@ class BatchedBeamSearch:
         self.w_dec = float(np.float32(1.0 - ctc_weight))
         self.w_ctc = float(np.float32(ctc_weight))
         self.use_graph = use_graph
+        self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
+        self.last_session = None
         self._sessions = {}
         L.load()
 
@@ -227,6 +229,7 @@ class BatchedBeamSearch:
             raise RuntimeError(f"bad decode input: x {tuple(x_packed.shape)}, lengths {lengths}")
         B, tmax, F = len(lengths), max(lengths), x_packed.shape[0]
         s = self._session(B, tmax, F)
+        self.last_session = s
         self.prepare(s, x_packed, lengths)
         n_steps = tmax if max_steps is None else min(tmax, max_steps)
         self._step(s)                                   # position 0 eagerly (also warms every kernel up)
@@ -236,14 +239,18 @@ class BatchedBeamSearch:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 # capture runs no kernels; state is untouched
+                n0 = L.launch_count
                 with torch.cuda.graph(g):
                     self._step(s)
+                s["launches_per_step"] = L.launch_count - n0
+                L.launch_count = n0
                 s["graph"] = g
             while done_steps < n_steps:
                 n = min(self.POLL_EVERY, n_steps - done_steps)
                 for _ in range(n):
                     if self.use_graph:
                         s["graph"].replay()
+                        self.graph_launches += s["launches_per_step"]
                     else:
                         self._step(s)
                 done_steps += n

@@ -37,7 +37,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5;
     const int off = work_off[blockIdx.x], T = work_T[blockIdx.x], q0 = work_q0[blockIdx.x];
     const int h = blockIdx.y;
-    const int nkb = (T + KB - 1) / KB;
+    // TMA needs a 16-byte aligned global address for the innermost coordinate (tokens, in V^T): start the key range at
+    // the previous multiple of 8 tokens and mask the `kshift` leading keys, which belong to the previous utterance.
+    const int kshift = off & 7;
+    const int koff = off - kshift;
+    const int nk = T + kshift;
+    const int nkb = (nk + KB - 1) / KB;
 
     if (tid == 0) {
         tc::mbar_init(bar_qk, 1);
@@ -61,10 +66,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
     if (tid == 0) {
         tc::mbar_arrive_expect_tx(bar_qk, (1 + nkb) * TILE16K);
         tc::tma_load_2d(sQ, &tmQK, bar_qk, h * 64, off + q0);
-        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(sK + kb * TILE16K, &tmQK, bar_qk, 1024 + h * 64, off + kb * KB);
+        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(sK + kb * TILE16K, &tmQK, bar_qk, 1024 + h * 64, koff + kb * KB);
         tc::mbar_arrive_expect_tx(&bar_v[0], TILE16K);
-        tc::tma_load_2d(sV, &tmV, &bar_v[0], off, h * 64);
-        tc::tma_load_2d(sV + 8192, &tmV, &bar_v[0], off + 64, h * 64);
+        tc::tma_load_2d(sV, &tmV, &bar_v[0], koff, h * 64);
+        tc::tma_load_2d(sV + 8192, &tmV, &bar_v[0], koff + 64, h * 64);
     }
     tc::mbar_wait(bar_qk, 0);
 
@@ -87,7 +92,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
         tc::mbar_wait(bar_s, ph_s);
         ph_s ^= 1;
         tc::tc_fence_after();
-        const int nvalid = min(KB, T - kb * KB);
+        const int lo = kshift - kb * KB, hi = nk - kb * KB;       // valid keys of this block: lo <= column < hi
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
@@ -95,7 +100,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < nvalid) m = fmaxf(m, __uint_as_float(r[j]));
+                if (c * 32 + j >= lo && c * 32 + j < hi) m = fmaxf(m, __uint_as_float(r[j]));
         }
         tc::tc_fence_before();
         __syncthreads();
@@ -119,13 +124,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
         if (tid == 0 && kb + 1 < nkb) {     // prefetch V^T of the next block
             uint8_t* dst = sV + ((kb + 1) & 1) * TILE16K;
             tc::mbar_arrive_expect_tx(&bar_v[(kb + 1) & 1], TILE16K);
-            tc::tma_load_2d(dst, &tmV, &bar_v[(kb + 1) & 1], off + (kb + 1) * KB, h * 64);
-            tc::tma_load_2d(dst + 8192, &tmV, &bar_v[(kb + 1) & 1], off + (kb + 1) * KB + 64, h * 64);
+            tc::tma_load_2d(dst, &tmV, &bar_v[(kb + 1) & 1], koff + (kb + 1) * KB, h * 64);
+            tc::tma_load_2d(dst + 8192, &tmV, &bar_v[(kb + 1) & 1], koff + (kb + 1) * KB + 64, h * 64);
         }
         tc::mbar_wait(bar_s, ph_s);
         ph_s ^= 1;
         tc::tc_fence_after();
-        const int nvalid = min(KB, T - kb * KB);
+        const int lo = kshift - kb * KB, hi = nk - kb * KB;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
@@ -138,8 +143,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = g * 8 + e * 2;
-                    float p0 = (c * 32 + j < nvalid) ? exp2f(__uint_as_float(r[j]) * L2E - mL) : 0.f;
-                    float p1 = (c * 32 + j + 1 < nvalid) ? exp2f(__uint_as_float(r[j + 1]) * L2E - mL) : 0.f;
+                    float p0 = (c * 32 + j >= lo && c * 32 + j < hi) ? exp2f(__uint_as_float(r[j]) * L2E - mL) : 0.f;
+                    float p1 = (c * 32 + j + 1 >= lo && c * 32 + j + 1 < hi) ? exp2f(__uint_as_float(r[j + 1]) * L2E - mL) : 0.f;
                     __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
                     // the row sum uses the bf16-rounded probabilities that the tensor core will actually multiply
                     sum += __bfloat162float(b.x) + __bfloat162float(b.y);
@@ -206,7 +211,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
 extern "C" int avsr_attention_varlen(const void* qk, const void* vt, long long ld_vt, void* out, long long F, const int* work_off,
                                      const int* work_T, const int* work_q0, int n_work, int max_T, cudaStream_t stream) {
     AVSR_REQUIRE(qk && vt && out && work_off && work_T && work_q0 && n_work > 0 && F > 0, "avsr_attention_varlen: bad arguments");
-    AVSR_REQUIRE(max_T <= MAX_KB * KB, "avsr_attention_varlen: utterance of %d frames exceeds the supported %d", max_T, MAX_KB * KB);
+    AVSR_REQUIRE(max_T + 7 <= MAX_KB * KB, "avsr_attention_varlen: utterance of %d frames exceeds the supported %d", max_T, MAX_KB * KB - 7);
     static bool configured = false;
     if (!configured) {
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));

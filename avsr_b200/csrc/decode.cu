@@ -85,7 +85,8 @@ dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* __res
         vbase = vc + (long long)utt_off[utt] * kv_ld + head * DH;
         kstride = kv_ld;
     }
-    const unsigned char* arow = anc + (long long)row * lmax;
+    // anc is double-buffered on step parity: [2][R][lmax]; the half written at the end of step-1 is (step & 1)
+    const unsigned char* arow = anc + ((long long)(step & 1) * R + row) * lmax;
     const int rbase = utt * beam;
 
     float mx = -INFINITY;

@@ -1,0 +1,345 @@
+"""Headline benchmark of the avsr_cocktail hot path: audio-seconds decoded per second (RTFx).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the whole hot path over one batch: AV-HuBERT-large encoder forward + joint CTC/attention beam
+search (beam 3) over 32 synthetic 15 s utterances (BASELINE.json configs[1]); each rank owns its own batch (utterances
+are independent: no data-path collective, weak scaling).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+T_FRAMES = 375          # 15 s at 25 fps
+BATCH = 32
+BEAM = 3
+FPS = 25.0
+METRIC = "audio-sec decoded/sec (RTFx)"
+UNIT = "audio-s/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_sample(sd, dec_steps_hi=20, dec_steps_lo=4, T=T_FRAMES):
+    """Times the oracle port of the reference's CPU path on ONE utterance of the workload: the full encoder plus two
+    truncated beam searches (dec_steps_lo / dec_steps_hi decode positions, reference compute pattern: no KV cache), and
+    extrapolates the decode linearly to the T positions a random-init model always runs."""
+    from avsr_b200 import synth
+    from oracle import avsr_oracle as O
+    video, audio = synth.make_inputs(1234, T)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        x = O.encoder_forward(sd, audio, video)[0]
+        t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.beam_search(sd, x, BEAM, kv_cache=False, max_steps=dec_steps_lo)
+        t_lo = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.beam_search(sd, x, BEAM, kv_cache=False, max_steps=dec_steps_hi)
+        t_hi = time.perf_counter() - t0
+    per_step = (t_hi - t_lo) / (dec_steps_hi - dec_steps_lo)
+    t_dec = t_lo + per_step * (T - dec_steps_lo)
+    t_utt = t_enc + t_dec
+    return dict(t_sample=t_enc + t_lo + t_hi, t_utt=t_utt, t_enc=t_enc, t_dec=t_dec, per_step=per_step,
+                rtfx=(T / FPS) / t_utt,
+                sample=f"1 of {BATCH} utterances (T={T}, beam {BEAM}): full encoder + beam search truncated at {dec_steps_lo} and "
+                       f"{dec_steps_hi} positions in the reference compute pattern (no KV cache), decode extrapolated linearly to {T} positions")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from avsr_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(0)
+    n = args.steps + args.warmup
+    hi = 20 if n <= 6 else (12 if n <= 12 else 8)
+    res = []
+    for i in range(n):
+        r = cpu_reference_sample(sd, dec_steps_hi=hi)
+        if i >= args.warmup:
+            res.append(r)
+    t_utt = float(np.mean([r["t_utt"] for r in res]))
+    value = (T_FRAMES / FPS) / t_utt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([r["t_sample"] for r in res])) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": res[0]["sample"],
+                         "extrapolated_s_per_utterance": t_utt, "encoder_s": float(np.mean([r["t_enc"] for r in res])),
+                         "decode_s_per_position": float(np.mean([r["per_step"] for r in res]))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _config(n_gpus):
+    return {"workload": f"configs[1]: {BATCH} synthetic 15 s utterances per GPU (T={T_FRAMES} frames 88x88 gray + 104-dim stacked fbank), "
+                        f"AV-HuBERT-large encoder (bf16 tensor-core GEMMs, fp32 residual stream) + joint CTC/attention beam search "
+                        f"(beam {BEAM}, ctc_weight 0.1, fp32), random-init weights: every utterance decodes all {T_FRAMES} positions",
+            "utterances_per_gpu": BATCH, "frames": T_FRAMES, "beam": BEAM, "parallelism": f"utterance-sharded x{n_gpus}",
+            "l2_policy": "inputs (372 MB video / step) larger than the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------- B200 arm
+def _kernel_rooflines(model, peaks):
+    """Isolated CUDA-event timings of the three kernels the north star names, at the workload's shapes."""
+    from avsr_b200 import _lib as L
+    lib = L.load()
+    dev = model.device
+    out = {}
+
+    def timeit(fn, n=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e-3
+
+    # (1) decode-step skinny fp32 GEMM (dominant kernel of the step): FFN w_1 [3072,1024], R = 96 rows, cycling over the 6
+    #     layers' weights so that they stream from HBM as in the real step (373 MB of decoder weights > L2)
+    R, N, K = BATCH * BEAM, 3072, 1024
+    a = torch.randn(R, K, device=dev)
+    ns = lib.avsr_sgemm_skinny_splits(R, N, K)
+    part = torch.empty(ns * R * N, device=dev)
+    ws = [l["w1"] for l in model.decoder_weights.layers] + [l["wqkv"] for l in model.decoder_weights.layers]
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    state = {"i": 0}
+
+    def skinny():
+        w = ws[state["i"] % len(ws)]
+        state["i"] += 1
+        L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(w), L.ll(K), R, N, K, L.ptr(part), ns, L.stream()), "skinny")
+    t = timeit(skinny, n=48)
+    byts = 4.0 * (N * K + R * K + ns * R * N)
+    out["decoder_skinny_gemm_fp32"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                       "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
+                                       "shape": f"[{R},{K}]x[{N},{K}]^T split-K {ns}", "gflops_fp32": 2.0 * R * N * K / t / 1e9}
+    # (2) encoder FFN GEMM on tcgen05: [12000,1024]x[4096,1024]^T, bias + GELU, bf16 out
+    M = BATCH * T_FRAMES
+    lay = model.encoder.w.layers[0]
+    x = torch.randn(M, 1024, device=dev).bfloat16()
+    y = torch.empty(M, 4096, device=dev, dtype=torch.bfloat16)
+    ep = L.make_epilogue(bias=lay["b1"], act=L.ACT_GELU, out_bf16=y, ld_bf16=4096)
+    t = timeit(lambda: L.gemm_bf16(x, lay["w1"], M, 4096, 1024, ep), n=20)
+    fl = 2.0 * M * 4096 * 1024
+    out["encoder_ffn1_gemm_bf16_tcgen05"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": peaks["tf"], "unit": "TFLOP/s",
+                                             "frac": fl / t / 1e12 / peaks["tf"], "traffic": None, "us_per_launch": t * 1e6,
+                                             "shape": f"[{M},1024]x[4096,1024]^T"}
+    # (3) full-vocabulary CTC prefix scoring (cfg 5 / SURVEY 8d): B=32 utterances x 3 hyps, algorithmic bytes
+    #     4*T*V + 4*n_h*V + 16*T*n_h per utterance-step
+    V, T, nh = model.odim, T_FRAMES, BEAM
+    logp = torch.log_softmax(torch.randn(BATCH * T, V, device=dev), -1)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+    utt_off, utt_T = i32([b * T for b in range(BATCH)]), i32([T] * BATCH)
+    n_run, last = i32([nh] * BATCH), i32([7] * (BATCH * nh))
+    r_buf = torch.full((2, BATCH * nh, T, 2), -1e10, device=dev)
+    r_buf[..., 1] = -5.0
+    rprev, step_t = i32(list(range(BATCH * nh))), i32([2])
+    s_prev, scores = torch.zeros(BATCH * nh, device=dev), torch.empty(BATCH * nh, V, device=dev)
+
+    def ctc_full():
+        flush.zero_()
+        L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), nh, BATCH, 1,
+                                         L.ptr(last), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(s_prev), L.ptr(scores),
+                                         L.stream()), "ctc_full")
+    t_both = timeit(ctc_full, n=10)
+    t_flush = timeit(lambda: flush.zero_(), n=10)
+    t = max(t_both - t_flush, 1e-9)
+    byts = BATCH * (4.0 * T * V + 4.0 * nh * V + 16.0 * T * nh)
+    out["ctc_prefix_full_vocab"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                    "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
+                                    "shape": f"{BATCH} utt x {nh} hyps x T={T} x V={V} (L2 flushed between launches)"}
+    return out
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from avsr_b200 import _lib as L
+    from avsr_b200 import synth
+    from avsr_b200.model import AVSRCocktailB200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU for the B200 arm (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = _peaks()
+    sd = synth.make_state_dict(0)
+    model = AVSRCocktailB200(sd, device=dev, beam_size=BEAM)
+    # rank r decodes utterances with seeds 1234 + 32 r ... (cfg 2 recipe)
+    vids, auds = [], []
+    for i in range(BATCH):
+        v, a = synth.make_inputs(1234 + rank * BATCH + i, T_FRAMES)
+        vids.append(v); auds.append(a)
+    video_h = torch.cat(vids, 0).pin_memory()
+    audio_h = torch.cat(auds, 0).pin_memory()
+    video_d, audio_d = video_h.to(dev), audio_h.to(dev)
+    audio_s = BATCH * T_FRAMES / FPS
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        sync_all()
+        return ms, res
+
+    step_dev = lambda: model.infer_batch(video_d, audio_d)
+
+    def step_e2e():
+        v = video_h.to(dev, non_blocking=True)
+        a = audio_h.to(dev, non_blocking=True)
+        nb = model.infer_batch(v, a)
+        return [h[0].yseq.tolist() for h in nb]          # host-side 1-best token ids (what evaluation.py consumes)
+
+    for _ in range(args.warmup):
+        res = step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.launch_count = 0
+    ms, res = timed(step_dev, args.steps)
+    launches = L.launch_count + model.beam_search.graph_launches
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e, toks = timed(step_e2e, max(1, min(args.steps, 3)))
+    n_e2e = max(1, min(args.steps, 3))
+    # gather hypotheses (token ids) like a sharded evaluation would; traffic is a few KB
+    n_tok = sum(len(h[0].yseq) for h in res)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [h[0].yseq.tolist() for h in res])
+        n_tok = sum(len(y) for g in gathered for y in g)
+    value = world * audio_s * args.steps / (ms * 1e-3)
+    e2e = world * audio_s * n_e2e / (ms_e2e * 1e-3)
+    if rank == 0:
+        roof = _kernel_rooflines(model, peaks)
+        cpu = cpu_reference_sample(sd) if world == 1 and not args.no_cpu_baseline else None
+        s = model.beam_search.last_session
+        d2h = sum(s[k].numel() * s[k].element_size() for k in ("hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j",
+                                                                "end_len", "end_score", "end_dec", "end_ctc")) + 8 * ((T_FRAMES // 16) + 2)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 encoder GEMMs / f32 decode", "data": "synthetic", "config": _config(world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(video_h.numel() * 4 + audio_h.numel() * 4),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": dict(roof["decoder_skinny_gemm_fp32"], kernel="sgemm_tn_kernel<96,64,16,6,4> (decoder step projections)",
+                             peak_source=peaks["src"]),
+            "rooflines": roof,
+            "decoded_tokens": int(n_tok),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu["rtfx"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu["sample"],
+                                    "extrapolated_s_per_utterance": cpu["t_utt"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
