@@ -49,7 +49,13 @@ class BatchedBeamSearch:
     POLL_EVERY = 16
 
     def __init__(self, weights: DecoderWeights, beam_size: int = 3, ctc_weight: float = 0.1, pre_beam_ratio: float = 1.5,
-                 token_list: Optional[Sequence[str]] = None, device="cuda:0", use_graph: bool = True):
+                 token_list: Optional[Sequence[str]] = None, device="cuda:0", use_graph: bool = True,
+                 precision: str = "bf16x3"):
+        """precision: numerics of the decoder / CTC-head projections.  "bf16x3" = three-term bf16 split of both operands on
+        the tcgen05 tensor cores (fp32-level accuracy, default); "fp32" = plain fp32 FMA on the CUDA cores."""
+        if precision not in ("bf16x3", "fp32"):
+            raise RuntimeError(f"unknown precision {precision!r}")
+        self.precision = precision
         self.w = weights
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -111,8 +117,16 @@ class BatchedBeamSearch:
         s["vc"] = torch.empty(nl, lmax, R, 1024, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
-        ns = max(lib.avsr_sgemm_skinny_splits(R, n, k) for n, k in ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024)))
-        s["part"] = torch.empty(ns * R * max(3072, V), dtype=torch.float32, device=dev)
+        shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
+        if self.precision == "bf16x3":
+            s["a6"] = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device=dev)
+            s["att6"] = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device=dev)
+            s["ffn6"] = torch.zeros(R, 6 * 3072, dtype=torch.bfloat16, device=dev)
+            s["x6"] = torch.empty(F, 6 * 1024, dtype=torch.bfloat16, device=dev)
+            n_part = max(self.tc_plan(R, n, 6 * k)[1] * R * n for n, k in shapes)
+        else:
+            n_part = max(lib.avsr_sgemm_skinny_splits(R, n, k) * R * n for n, k in shapes)
+        s["part"] = torch.empty(n_part, dtype=torch.float32, device=dev)
         # per-utterance precomputed tensors
         s["logp"] = torch.empty(F, V, dtype=torch.float32, device=dev)
         s["ckv"] = torch.empty(F, nl * 2 * 1024, dtype=torch.float32, device=dev)
@@ -130,20 +144,47 @@ class BatchedBeamSearch:
         return s
 
     # ------------------------------------------------------------------------------------------ one decode step
-    def _skinny(self, s, a, w, N, K):
+    @staticmethod
+    def tc_plan(R: int, N: int, K6: int):
+        """(bn, splits) of the split-K tensor-core GEMM for a skinny [R, K6] x [N, K6]^T product: enough work items to put
+        every SM on the weight stream, at least two 64-wide k-blocks per item."""
+        bn = 64 if N <= 1024 else 128
+        tiles = -(-R // 128) * -(-N // bn)
+        num_kb = K6 // 64
+        splits = max(1, min(num_kb // 2, -(-148 // tiles)))
+        while splits > 1 and (splits - 1) * -(-num_kb // splits) >= num_kb:
+            splits -= 1
+        return bn, splits
+
+    def _proj(self, s, key_a, lay, name, N, K):
+        """partial sums of act[R,K] @ W[N,K]^T into s['part']; returns the number of K splits."""
         lib = L.load()
         R = s["R"]
-        ns = lib.avsr_sgemm_skinny_splits(R, N, K)
-        L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(a.stride(0)), L.ptr(w), L.ll(K), R, N, K, L.ptr(s["part"]), ns, L.stream()),
-                "avsr_sgemm_skinny")
+        if self.precision == "bf16x3":
+            bn, ns = self.tc_plan(R, N, 6 * K)
+            a6 = s[key_a + "6"]
+            L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(lay[name + "6"]), L.ll(6 * K), R, N, 6 * K,
+                                                 L.ptr(s["part"]), ns, bn, L.stream()), "avsr_gemm_bf16_tc_splitk")
+        else:
+            a = s[key_a]
+            ns = lib.avsr_sgemm_skinny_splits(R, N, K)
+            L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(lay[name]), L.ll(K), R, N, K, L.ptr(s["part"]), ns, L.stream()),
+                    "avsr_sgemm_skinny")
         return ns
 
-    def _epi(self, s, ns, N, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, ln_out=None):
+    def _epi(self, s, ns, N, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, key_out=None):
+        """bias / act / residual / LayerNorm over the reduced partial sums; the result that feeds the next projection is
+        written as fp32 (s[key_out]) on the CUDA-core path or in bf16x3 layout (s[key_out + '6']) on the tensor-core path."""
         lib = L.load()
         g, b = (ln if ln is not None else (None, None))
+        tc = self.precision == "bf16x3"
+        ln_out = s[key_out] if (key_out is not None and ln is not None and not tc) else None
+        if key_out is not None and ln is None and not tc:
+            out = s[key_out]
+        split = s[key_out + "6"] if (key_out is not None and tc) else None
         L.check(lib.avsr_splitk_epilogue(L.ptr(s["part"]), ns, s["R"], N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
                                          L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(ln_out), L.ll(1024),
-                                         L.ptr(s["row_active"]), L.stream()), "avsr_splitk_epilogue")
+                                         L.ptr(s["row_active"]), L.ptr(split), L.stream()), "avsr_splitk_epilogue")
 
     def _step(self, s):
         """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
@@ -151,39 +192,42 @@ class BatchedBeamSearch:
         w = self.w
         R, beam, S, V, lmax = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab, s["lmax"]
         st = L.stream
+        tc = self.precision == "bf16x3"
         l0 = w.layers[0]
         L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
-                                      L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), L.ptr(s["a"]), st()),
-                "avsr_dec_embed_ln")
+                                      L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]),
+                                      None if tc else L.ptr(s["a"]), L.ptr(s["a6"]) if tc else None, st()), "avsr_dec_embed_ln")
         nl = w.n_layers
         kvld = nl * 2 * 1024
+        att_f32 = None if tc else L.ptr(s["att"])
+        att_split = L.ptr(s["att6"]) if tc else None
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93)
-            ns = self._skinny(s, s["a"], lay["wqkv"], 3072, 1024)
+            ns = self._proj(s, "a", lay, "wqkv", 3072, 1024)
             self._epi(s, ns, 3072, lay["bqkv"], out=s["qkv"])
             L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
                                            lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
-                                           L.ptr(s["att"]), lmax, L.ll(0), st()), "avsr_dec_attn_step(self)")
-            ns = self._skinny(s, s["att"], lay["wo"], 1024, 1024)
-            self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), ln_out=s["a"])
+                                           att_f32, lmax, L.ll(0), att_split, st()), "avsr_dec_attn_step(self)")
+            ns = self._proj(s, "att", lay, "wo", 1024, 1024)
+            self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
-            ns = self._skinny(s, s["a"], lay["wq2"], 1024, 1024)
+            ns = self._proj(s, "a", lay, "wq2", 1024, 1024)
             self._epi(s, ns, 1024, lay["bq2"], out=s["q2"])
             ck = s["ckv"][:, li * 2048:]
             cv = s["ckv"][:, li * 2048 + 1024:]
             L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
-                                           L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), L.ptr(s["att"]),
-                                           s["tmax"], L.ll(kvld), st()), "avsr_dec_attn_step(src)")
-            ns = self._skinny(s, s["att"], lay["wo2"], 1024, 1024)
-            self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), ln_out=s["a"])
+                                           L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
+                                           s["tmax"], L.ll(kvld), att_split, st()), "avsr_dec_attn_step(src)")
+            ns = self._proj(s, "att", lay, "wo2", 1024, 1024)
+            self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
-            ns = self._skinny(s, s["a"], lay["w1"], 3072, 1024)
-            self._epi(s, ns, 3072, lay["b1"], act=L.ACT_RELU, out=s["ffn"])
-            ns = self._skinny(s, s["ffn"], lay["w2"], 1024, 3072)
+            ns = self._proj(s, "a", lay, "w1", 3072, 1024)
+            self._epi(s, ns, 3072, lay["b1"], act=L.ACT_RELU, key_out="ffn")
+            ns = self._proj(s, "ffn", lay, "w2", 1024, 3072)
             nxt = (w.layers[li + 1]["n1_g"], w.layers[li + 1]["n1_b"]) if li + 1 < nl else (w.after_g, w.after_b)
-            self._epi(s, ns, 1024, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, ln_out=s["a"])
+            self._epi(s, ns, 1024, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
         # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
-        ns = self._skinny(s, s["a"], w.out_w, V, 1024)
+        ns = self._proj(s, "a", {"out": w.out_w, "out6": w.out_w6}, "out", V, 1024)
         L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
                                              L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
         # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
@@ -203,11 +247,17 @@ class BatchedBeamSearch:
         """CTC posteriors (scorers/ctc.py:87-99) and the once-per-utterance cross-attention K/V projection."""
         w, V = self.w, self.n_vocab
         F = x_packed.shape[0]
-        L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
         lib = L.load()
-        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(V), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
         n = w.ckv_w.shape[0]
-        L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+        if self.precision == "bf16x3":
+            # fp32-accurate projections on the tensor cores: K' = 6 * 1024 (see weights.split3_weight)
+            L.check(lib.avsr_split3(L.ptr(x_packed), L.ll(1024), L.ptr(s["x6"]), L.ll(F), 1024, L.stream()), "avsr_split3")
+            L.gemm_bf16(s["x6"], w.ctc_w6, F, V, 6144, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
+            L.gemm_bf16(s["x6"], w.ckv_w6, F, n, 6144, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+        else:
+            L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
+            L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(V), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
         B, beam = s["B"], self.beam_size
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
         s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))

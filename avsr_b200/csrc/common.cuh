@@ -75,6 +75,19 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
+// fp32 -> three bf16 terms (x = a1 + a2 + a3 to ~2^-24 relative) laid out for the "bf16x3" tensor-core GEMM that keeps
+// fp32-level accuracy on the decode side: the row [a1 | a1 | a2 | a1 | a2 | a3] (6 blocks of K) is multiplied with the
+// weight row [w1 | w2 | w1 | w3 | w2 | w1], i.e. the six largest cross terms of (a1+a2+a3)(w1+w2+w3).
+__device__ __forceinline__ void avsr_split3_store(__nv_bfloat16* row_base, int K, int c, float v) {
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a1);
+    const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+    row_base[c] = a1; row_base[K + c] = a1; row_base[3 * K + c] = a1;
+    row_base[2 * K + c] = a2; row_base[4 * K + c] = a2;
+    row_base[5 * K + c] = a3;
+}
+
 __device__ __forceinline__ float avsr_apply_act(float v, int act, float slope) {
     if (act == AVSR_ACT_GELU) return gelu_erf(v);
     if (act == AVSR_ACT_RELU) return fmaxf(v, 0.f);

@@ -50,20 +50,45 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
     if (step == 0) {
         for (int u = 0; u < start; ++u) cum += lp[(long long)u * V + blank];
     }
-    for (int t = start; t < T; ++t) {
-        if (step == 0) { pn = LOGZERO; pb = cum; }
-        else { const float2 v = rp[t - 1]; pn = v.x; pb = v.y; }
-        const float x = lp[(long long)t * V + c];
-        const float xb = lp[(long long)t * V + blank];
-        const float phi = same ? pb : lse2(pn, pb);
-        const float term = phi + x;
-        if (term > M) { Ssum = Ssum * expf(M - term) + 1.f; M = term; }
-        else Ssum += expf(term - M);
-        const float nrn = lse2(rn, phi) + x;
-        const float nrb = lse2(rn, rb) + xb;
-        rn = nrn; rb = nrb;
-        ro[t] = make_float2(rn, rb);
-        if (step == 0) cum += xb;
+    // The chain is serial in t, but its inputs are not: fetch them CH steps ahead (double-buffered registers) so that the
+    // ~1 us global-load latency overlaps the logaddexp arithmetic instead of being paid once per time step.
+    constexpr int CH = 8;
+    float xa[CH], xba[CH], xn[CH], xbn[CH];
+    float2 pa[CH], pnx[CH];
+    auto fetch = [&](int t0, float (&xs)[CH], float (&xbs)[CH], float2 (&ps)[CH]) {
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int t = t0 + u;
+            if (t < T) {
+                xs[u] = __ldg(lp + (long long)t * V + c);
+                xbs[u] = __ldg(lp + (long long)t * V + blank);
+                if (step > 0) ps[u] = rp[t - 1];
+            }
+        }
+    };
+    fetch(start, xa, xba, pa);
+    for (int t0 = start; t0 < T; t0 += CH) {
+        fetch(t0 + CH, xn, xbn, pnx);
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int t = t0 + u;
+            if (t < T) {
+                if (step == 0) { pn = LOGZERO; pb = cum; }
+                else { pn = pa[u].x; pb = pa[u].y; }
+                const float x = xa[u], xb = xba[u];
+                const float phi = same ? pb : lse2(pn, pb);
+                const float term = phi + x;
+                if (term > M) { Ssum = Ssum * expf(M - term) + 1.f; M = term; }
+                else Ssum += expf(term - M);
+                const float nrn = lse2(rn, phi) + x;
+                const float nrb = lse2(rn, rb) + xb;
+                rn = nrn; rb = nrb;
+                ro[t] = make_float2(rn, rb);
+                if (step == 0) cum += xb;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) { xa[u] = xn[u]; xba[u] = xbn[u]; pa[u] = pnx[u]; }
     }
     psi[gid] = M + logf(Ssum);
     if (s == 0) {

@@ -185,6 +185,16 @@ cast_bf16_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __r
     out[r * ldo + c] = __float2bfloat16_rn(in[r * ldi + c]);
 }
 
+// fp32 [rows, K] -> bf16 [rows, 6K] (bf16x3 activation layout, see avsr_split3_store)
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out, long long rows, int K) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= rows * K) return;
+    const long long r = i / K;
+    const int c = (int)(i % K);
+    avsr_split3_store(out + r * 6 * K, K, c, in[r * ldi + c]);
+}
+
 }  // namespace
 
 #define GRID1D(total) ((int)(((total) + 255) / 256 > 148 * 64 ? 148 * 64 : ((total) + 255) / 256))
@@ -256,6 +266,13 @@ extern "C" int avsr_posconv_im2col(const void* x, void* out, const int* frame_t,
 extern "C" int avsr_cast_bf16(const float* in, long long ldi, void* out, long long ldo, long long rows, int cols, cudaStream_t stream) {
     AVSR_REQUIRE(in && out && rows > 0 && cols > 0, "avsr_cast_bf16: bad arguments");
     cast_bf16_kernel<<<cdiv(rows * cols, 256), 256, 0, stream>>>(in, ldi, (__nv_bfloat16*)out, ldo, rows, cols);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && rows > 0 && K > 0, "avsr_split3: bad arguments");
+    split3_kernel<<<cdiv(rows * K, 256), 256, 0, stream>>>(in, ldi, (__nv_bfloat16*)out, rows, K);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

@@ -122,10 +122,15 @@ __device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, 
     }
 }
 
+constexpr int NUM_EPI_WARPS = 8;                    // two per TMEM lane quadrant, each taking half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+
+// splits > 1: split-K. Work item = (z, m-tile, n-tile); item z covers k-blocks [z*kb_per_split, (z+1)*kb_per_split) and
+// stores its raw fp32 partial sums at ep.out_f32 + z*M*ld_f32 (the caller reduces them in a fixed order).
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               const AvsrEpilogue ep) {
+               const AvsrEpilogue ep_in, int splits, int kb_per_split) {
     using C = Cfg<BN>;
     constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -139,8 +144,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
     const int tiles_m = (M + BM - 1) / BM;
-    const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = (K + BK - 1) / BK;
+    const int tiles_mn = tiles_m * tiles_n;
+    const int num_tiles = tiles_mn * splits;
+    const int num_kb_total = (K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -149,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(&tfull[a], 1);
-            tc::mbar_init(&tempty[a], 4);
+            tc::mbar_init(&tempty[a], NUM_EPI_WARPS);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA);
@@ -169,8 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
+                const int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
+                const int kb0 = z * kb_per_split, kb1 = min(num_kb_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -188,10 +196,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_mn;
+                const int kb0 = z * kb_per_split, kb1 = min(num_kb_total, kb0 + kb_per_split);
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
                     const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
@@ -199,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t bdesc = tc::umma_desc_sw128(sa + A_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
                     tc::umma_commit(&empty[stage]);     // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -209,16 +219,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
+        const int half = (warp - 2) >> 2;               // which half of the tile's columns
+        constexpr int CHUNKS = BN / 32 / 2 > 0 ? BN / 32 / 2 : 1;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
+            const int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
+            AvsrEpilogue ep = ep_in;
+            if (splits > 1) ep.out_f32 = ep_in.out_f32 + (long long)z * M * ep_in.ld_f32;
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
             const int row = m0 + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int cc = 0; cc < CHUNKS; ++cc) {
+                const int c = half * CHUNKS + cc;
+                if (BN == 32 && half == 1) break;
                 uint32_t r[32];
                 tc::tmem_ld_32x32(taddr + c * 32, r);
                 tc::tmem_ld_wait();
@@ -241,16 +258,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 int g_sm_count = 0;
 
 template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, int splits, cudaStream_t stream) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const int tiles = cdiv(M, BM) * cdiv(N, BN);
+    const int num_kb = cdiv(K, BK);
+    const int kbps = cdiv(num_kb, splits);
+    const int tiles = cdiv(M, BM) * cdiv(N, BN) * splits;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-    gemm_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, splits, kbps);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }
@@ -298,10 +317,8 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 }  // namespace tc
 
-// C[M,N] = epilogue(A[M,K] * B[N,K]^T); A, B bf16 row-major with leading dimensions lda/ldb (elements, multiples of 8).
-// bn_hint: 0 = choose the N tile automatically, else 64 / 128 / 256.
-extern "C" int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                                 const AvsrEpilogue* ep, int bn_hint, cudaStream_t stream) {
+static int gemm_entry(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue* ep,
+                      int bn_hint, int splits, cudaStream_t stream) {
     AVSR_REQUIRE(A && B && ep, "avsr_gemm_bf16_tc: null operand");
     AVSR_REQUIRE(M > 0 && N > 0 && K > 0, "avsr_gemm_bf16_tc: bad shape %dx%dx%d", M, N, K);
     AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_gemm_bf16_tc: no output buffer");
@@ -314,7 +331,7 @@ extern "C" int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, lo
     if (bn == 0) {
         if (N <= 64) bn = 64;
         else if (N <= 128) bn = 128;
-        else bn = (cdiv(M, BM) * cdiv(N, 256) >= 2 * g_sm_count) ? 256 : 128;
+        else bn = (cdiv(M, BM) * cdiv(N, 256) * splits >= 2 * g_sm_count) ? 256 : 128;
     }
     AVSR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "avsr_gemm_bf16_tc: bad bn_hint %d", bn_hint);
     CUtensorMap ta, tb;
@@ -322,7 +339,27 @@ extern "C" int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, lo
     if (rc != AVSR_OK) return rc;
     rc = tc::make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)bn, BK);
     if (rc != AVSR_OK) return rc;
-    if (bn == 64) return launch<64>(ta, tb, M, N, K, *ep, stream);
-    if (bn == 128) return launch<128>(ta, tb, M, N, K, *ep, stream);
-    return launch<256>(ta, tb, M, N, K, *ep, stream);
+    if (bn == 64) return launch<64>(ta, tb, M, N, K, *ep, splits, stream);
+    if (bn == 128) return launch<128>(ta, tb, M, N, K, *ep, splits, stream);
+    return launch<256>(ta, tb, M, N, K, *ep, splits, stream);
+}
+
+// C[M,N] = epilogue(A[M,K] * B[N,K]^T); A, B bf16 row-major with leading dimensions lda/ldb (elements, multiples of 8).
+// bn_hint: 0 = choose the N tile automatically, else 64 / 128 / 256.
+extern "C" int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                                 const AvsrEpilogue* ep, int bn_hint, cudaStream_t stream) {
+    return gemm_entry(A, lda, B, ldb, M, N, K, ep, bn_hint, 1, stream);
+}
+
+// Split-K form for skinny operands (decode step): part[z][M][N] (fp32) = A[:, Kz] * B[:, Kz]^T for z < splits.
+extern "C" int avsr_gemm_bf16_tc_splitk(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, float* part,
+                                        int splits, int bn_hint, cudaStream_t stream) {
+    AVSR_REQUIRE(part && splits >= 1 && splits <= cdiv(K, BK), "avsr_gemm_bf16_tc_splitk: bad splits %d", splits);
+    AvsrEpilogue ep = {};
+    ep.out_f32 = part;
+    ep.ld_f32 = N;
+    // every split must own at least one k-block, otherwise its partial would stay unwritten
+    const int num_kb = cdiv(K, BK), kbps = cdiv(num_kb, splits);
+    AVSR_REQUIRE((splits - 1) * kbps < num_kb, "avsr_gemm_bf16_tc_splitk: %d splits leave an empty split for K=%d", splits, K);
+    return gemm_entry(A, lda, B, ldb, M, N, K, &ep, bn_hint, splits, stream);
 }

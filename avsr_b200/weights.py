@@ -114,10 +114,22 @@ class EncoderWeights:
                 raise RuntimeError(f"unsupported checkpoint: {k} is {tuple(sd[k].shape) if k in sd else 'missing'}, expected {shp}")
 
 
-class DecoderWeights:
-    """fp32 operands of the 6-layer transformer decoder + CTC head."""
+def split3_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] -> bf16 [N,6K] = [w1|w2|w1|w3|w2|w1] with w = w1+w2+w3 (three bf16 terms, ~24 mantissa bits).
+    Paired with activations laid out [a1|a1|a2|a1|a2|a3] (csrc/common.cuh avsr_split3_store) one bf16 tensor-core GEMM
+    over 6K accumulates the six largest cross terms of (a1+a2+a3)(w1+w2+w3): fp32-level accuracy at tensor-core speed."""
+    w = w.float()
+    w1 = w.bfloat16()
+    r = w - w1.float()
+    w2 = r.bfloat16()
+    w3 = (r - w2.float()).bfloat16()
+    return torch.cat([w1, w2, w1, w3, w2, w1], dim=1).contiguous()
 
-    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device):
+
+class DecoderWeights:
+    """Operands of the 6-layer transformer decoder + CTC head: fp32 (CUDA-core path) and bf16x3 (tensor-core path)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device, keep_fp32: bool = True):
         sd = _strip(sd)
         f32 = lambda t: t.to(device=device, dtype=torch.float32).contiguous()
         d = "decoder."
@@ -163,3 +175,10 @@ class DecoderWeights:
             raise RuntimeError("CTC head and decoder vocabulary sizes differ")
         self.sos = self.eos = self.V - 1          # e2e_asr_avhubert.py:96-98
         self.blank = 0
+        # bf16x3 operands for the tensor-core decode path
+        for lay in self.layers:
+            for k in ("wqkv", "wo", "wq2", "wo2", "w1", "w2"):
+                lay[k + "6"] = split3_weight(lay[k])
+        self.out_w6 = split3_weight(self.out_w)
+        self.ctc_w6 = split3_weight(self.ctc_w)
+        self.ckv_w6 = split3_weight(self.ckv_w)

@@ -167,23 +167,39 @@ def _kernel_rooflines(model, peaks):
 
     # (1) decode-step skinny fp32 GEMM (dominant kernel of the step): FFN w_1 [3072,1024], R = 96 rows, cycling over the 6
     #     layers' weights so that they stream from HBM as in the real step (373 MB of decoder weights > L2)
+    #     Algorithmic bytes per launch = fp32 weight matrix + activations + output = 4*(N*K + R*K + R*N);
+    #     the bf16x3 operand layout actually streams 12 B per weight, which is what `frac` is charged for.
     R, N, K = BATCH * BEAM, 3072, 1024
-    a = torch.randn(R, K, device=dev)
-    ns = lib.avsr_sgemm_skinny_splits(R, N, K)
-    part = torch.empty(ns * R * N, device=dev)
-    ws = [l["w1"] for l in model.decoder_weights.layers] + [l["wqkv"] for l in model.decoder_weights.layers]
     flush = torch.empty(64 * 1024 * 1024, device=dev)
     state = {"i": 0}
+    byts = 4.0 * (N * K + R * K + R * N)
+    if model.beam_search.precision == "bf16x3":
+        bn, ns = model.beam_search.tc_plan(R, N, 6 * K)
+        a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
+        part = torch.empty(ns * R * N, device=dev)
+        ws = [l["w16"] for l in model.decoder_weights.layers] + [l["wqkv6"] for l in model.decoder_weights.layers]
 
-    def skinny():
-        w = ws[state["i"] % len(ws)]
-        state["i"] += 1
-        L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(w), L.ll(K), R, N, K, L.ptr(part), ns, L.stream()), "skinny")
+        def skinny():
+            w = ws[state["i"] % len(ws)]
+            state["i"] += 1
+            L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(w), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn,
+                                                 L.stream()), "tc splitk")
+        kname = f"gemm_tc_kernel<{bn}> split-K {ns}, bf16x3 operands (decoder step projections)"
+    else:
+        a = torch.randn(R, K, device=dev)
+        ns = lib.avsr_sgemm_skinny_splits(R, N, K)
+        part = torch.empty(ns * R * N, device=dev)
+        ws = [l["w1"] for l in model.decoder_weights.layers] + [l["wqkv"] for l in model.decoder_weights.layers]
+
+        def skinny():
+            w = ws[state["i"] % len(ws)]
+            state["i"] += 1
+            L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(w), L.ll(K), R, N, K, L.ptr(part), ns, L.stream()), "skinny")
+        kname = f"sgemm_tn_kernel<96,64,16,6,4> split-K {ns} (decoder step projections)"
     t = timeit(skinny, n=48)
-    byts = 4.0 * (N * K + R * K + ns * R * N)
-    out["decoder_skinny_gemm_fp32"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                       "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
-                                       "shape": f"[{R},{K}]x[{N},{K}]^T split-K {ns}", "gflops_fp32": 2.0 * R * N * K / t / 1e9}
+    out["decoder_step_projection"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                      "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
+                                      "shape": f"[{R},{K}]x[{N},{K}]^T", "kernel": kname, "gflops_fp32_equiv": 2.0 * R * N * K / t / 1e9}
     # (2) encoder FFN GEMM on tcgen05: [12000,1024]x[4096,1024]^T, bias + GELU, bf16 out
     M = BATCH * T_FRAMES
     lay = model.encoder.w.layers[0]
@@ -272,6 +288,14 @@ def run_b200(args):
         sync_all()
         return ms, res
 
+    if args.profile_decode_steps:
+        # profiling aid (ncu launch lists): truncated decode, eager launches, no timing claims
+        model.beam_search.use_graph = False
+        model.infer_batch(video_d, audio_d, max_steps=args.profile_decode_steps)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "decode_steps": args.profile_decode_steps}), flush=True)
+        return
     step_dev = lambda: model.infer_batch(video_d, audio_d)
 
     def step_e2e():
@@ -313,8 +337,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(video_h.numel() * 4 + audio_h.numel() * 4),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": dict(roof["decoder_skinny_gemm_fp32"], kernel="sgemm_tn_kernel<96,64,16,6,4> (decoder step projections)",
-                             peak_source=peaks["src"]),
+            "roofline": dict(roof["decoder_step_projection"], peak_source=peaks["src"]),
             "rooflines": roof,
             "decoded_tokens": int(n_tok),
         }
@@ -334,6 +357,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-decode-steps", type=int, default=0,
+                    help="profiling aid: run ONE pass with the decode truncated to this many positions and exit (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,13 @@ int avsr_abi_version(void);
  * Wav2Vec2Attention/FeedForward/PositionalConvEmbedding (modeling_wav2vec2.py:326-573). */
 int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue* ep,
                       int bn_hint, avsr_stream_t stream);
+/* Split-K form for skinny operands: part[z][M][N] fp32 raw partial sums (reduced by avsr_splitk_epilogue). With the
+ * "bf16x3" operand layout (avsr_split3 / *_split outputs: [a1|a1|a2|a1|a2|a3] x [w1|w2|w1|w3|w2|w1]) this gives
+ * fp32-accurate decoder projections on the tensor cores (src/nets/backend/transformer/decoder_layer.py:58-121). */
+int avsr_gemm_bf16_tc_splitk(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, float* part,
+                             int splits, int bn_hint, avsr_stream_t stream);
+/* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
+int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */
 int avsr_attention_varlen(const void* qk, const void* vt, long long ld_vt, void* out, long long F, const int* work_off,
                           const int* work_T, const int* work_q0, int n_work, int max_T, avsr_stream_t stream);
@@ -121,14 +128,14 @@ int avsr_sgemm_skinny(const float* A, long long lda, const float* W, long long l
                       avsr_stream_t stream);
 int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
                          long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
-                         float* ln_out, long long ld_ln, const int* row_active, avsr_stream_t stream);
+                         float* ln_out, long long ld_ln, const int* row_active, void* split_out, avsr_stream_t stream);
 int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_stream_t stream);
 /* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
-                      const float* gamma, const float* beta, float eps, float* x, float* a, avsr_stream_t stream);
+                      const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
 int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
                        const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step, float* out,
-                       int max_keys, long long kv_ld, avsr_stream_t stream);
+                       int max_keys, long long kv_ld, void* out_split, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
                              int* part_ids, int S, avsr_stream_t stream);
 /* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes. */

@@ -93,12 +93,40 @@ def test_sgemm_skinny_and_epilogue(L, R, N, K):
         act[R // 2] = 0
         out, ln = torch.zeros(R, N, device="cuda"), torch.zeros(R, N, device="cuda")
         L.check(lib.avsr_splitk_epilogue(L.ptr(part), ns, R, N, L.ptr(bias), 0, L.ptr(res), L.ll(N), L.ptr(out), L.ll(N), L.ptr(g),
-                                         L.ptr(b), C.c_float(1e-12), L.ptr(ln), L.ll(N), L.ptr(act), L.stream()), "epilogue")
+                                         L.ptr(b), C.c_float(1e-12), L.ptr(ln), L.ll(N), L.ptr(act), None, L.stream()), "epilogue")
         want = ref + bias + res
         keep = act.bool()
         assert (out[keep] - want[keep]).abs().max().item() < 1e-4
         assert (ln[keep] - F.layer_norm(want, (N,), g, b, 1e-12)[keep]).abs().max().item() < 1e-4
         assert out[~keep].abs().max().item() == 0.0
+        # bf16x3 output of the same LayerNorm: the three terms must add back to the fp32 value (to ~2^-24 relative)
+        sp = torch.zeros(R, 6 * N, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.avsr_splitk_epilogue(L.ptr(part), ns, R, N, L.ptr(bias), 0, L.ptr(res), L.ll(N), None, L.ll(N), L.ptr(g),
+                                         L.ptr(b), C.c_float(1e-12), None, L.ll(N), L.ptr(act), L.ptr(sp), L.stream()), "epilogue split")
+        blocks = sp.float().view(R, 6, N)
+        assert torch.equal(blocks[:, 0], blocks[:, 1]) and torch.equal(blocks[:, 0], blocks[:, 3]) and torch.equal(blocks[:, 2], blocks[:, 4])
+        back = blocks[:, 0].double() + blocks[:, 2].double() + blocks[:, 5].double()
+        assert (back[keep] - ln[keep].double()).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("R,N,K", [(96, 1024, 1024), (96, 3072, 1024), (160, 1024, 3072), (96, 5049, 1024), (3, 1024, 1024)])
+def test_bf16x3_tensor_core_gemm_is_fp32_accurate(L, R, N, K):
+    """Decode-side projections on the tensor cores: activations / weights split into three bf16 terms, split-K partials."""
+    from avsr_b200.weights import split3_weight
+    from avsr_b200.beam_search import BatchedBeamSearch
+    lib = L.load()
+    a, w = _rand(R, K, seed=1), _rand(N, K, seed=2, scale=0.03)
+    a6 = torch.zeros(R, 6 * K, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_split3(L.ptr(a), L.ll(K), L.ptr(a6), L.ll(R), K, L.stream()), "split3")
+    w6 = split3_weight(w)
+    bn, ns = BatchedBeamSearch.tc_plan(R, N, 6 * K)
+    part = torch.full((ns, R, N), float("nan"), device="cuda")
+    L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(w6), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn, L.stream()), "tc splitk")
+    ref = a.double() @ w.double().t()
+    got = part.double().sum(0)
+    err = (got - ref).abs().max().item()
+    fp32_err = ((a @ w.t()).double() - ref).abs().max().item()
+    assert err < 2e-5 * (K ** 0.5) and err < 4 * fp32_err + 1e-6, (err, fp32_err)
 
 
 def test_layernorm(L):

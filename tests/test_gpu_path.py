@@ -56,11 +56,12 @@ def _check_nbest(nbest, golden, T, beam):
 
 @pytest.mark.parametrize("T", [12, 30])
 @pytest.mark.parametrize("beam", [3, 5])
-@pytest.mark.parametrize("graph", [False, True])
-def test_beam_search_vs_reference_golden(state_dict, gpu_model, golden, T, beam, graph):
-    """Decode from the reference's own fp32 encoder output: token-identical n-best at beam 3 and 5."""
+@pytest.mark.parametrize("graph,precision", [(False, "fp32"), (True, "fp32"), (False, "bf16x3"), (True, "bf16x3")])
+def test_beam_search_vs_reference_golden(state_dict, gpu_model, golden, T, beam, graph, precision):
+    """Decode from the reference's own fp32 encoder output: token-identical n-best at beam 3 and 5, on both numerics paths
+    (fp32 CUDA-core FMA and the three-term bf16 split on the tensor cores)."""
     from avsr_b200.beam_search import BatchedBeamSearch
-    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam, use_graph=graph)
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam, use_graph=graph, precision=precision)
     x = torch.from_numpy(golden[f"enc_T{T}"]).cuda()
     nbest = bs(x)
     _check_nbest(nbest, golden, T, beam)
