@@ -113,8 +113,9 @@ class BatchedBeamSearch:
         s["qkv"], s["ffn"] = f32(R, 3072), f32(R, 3072)
         s["dec_logp"] = f32(R, V)
         s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
-        s["kc"] = torch.empty(nl, lmax, R, 1024, dtype=torch.float32, device=dev)
-        s["vc"] = torch.empty(nl, lmax, R, 1024, dtype=torch.float32, device=dev)
+        # self-attention caches, head-major: [layer][head][pos][row][64]
+        s["kc"] = torch.empty(nl, 16, lmax, R, 64, dtype=torch.float32, device=dev)
+        s["vc"] = torch.empty(nl, 16, lmax, R, 64, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
         shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
@@ -130,6 +131,8 @@ class BatchedBeamSearch:
         # per-utterance precomputed tensors
         s["logp"] = torch.empty(F, V, dtype=torch.float32, device=dev)
         s["ckv"] = torch.empty(F, nl * 2 * 1024, dtype=torch.float32, device=dev)
+        # cross-attention K/V, head-major: [layer][k|v][head][frame][64] (one contiguous span per (utterance, head))
+        s["ckv_t"] = torch.empty(nl, 2, 16, F, 64, dtype=torch.float32, device=dev)
         st = L.BeamState()
         st.B, st.beam, st.S, st.V, st.lmax, st.tmax = B, beam, S, V, lmax, tmax
         st.blank, st.eos, st.cap = self.w.blank, self.eos, cap
@@ -151,7 +154,7 @@ class BatchedBeamSearch:
         bn = 64 if N <= 1024 else 128
         tiles = -(-R // 128) * -(-N // bn)
         num_kb = K6 // 64
-        splits = max(1, min(num_kb // 2, -(-148 // tiles)))
+        splits = max(1, min(num_kb // 2, 148 // tiles))        # tiles * splits <= 148: one work item per SM, one wave
         while splits > 1 and (splits - 1) * -(-num_kb // splits) >= num_kb:
             splits -= 1
         return bn, splits
@@ -207,17 +210,16 @@ class BatchedBeamSearch:
             self._epi(s, ns, 3072, lay["bqkv"], out=s["qkv"])
             L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
                                            lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
-                                           att_f32, lmax, L.ll(0), att_split, st()), "avsr_dec_attn_step(self)")
+                                           att_f32, lmax, L.ll(64), L.ll(lmax * R * 64), att_split, st()), "avsr_dec_attn_step(self)")
             ns = self._proj(s, "att", lay, "wo", 1024, 1024)
             self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
             ns = self._proj(s, "a", lay, "wq2", 1024, 1024)
             self._epi(s, ns, 1024, lay["bq2"], out=s["q2"])
-            ck = s["ckv"][:, li * 2048:]
-            cv = s["ckv"][:, li * 2048 + 1024:]
+            ck, cv = s["ckv_t"][li, 0], s["ckv_t"][li, 1]
             L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
                                            L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
-                                           s["tmax"], L.ll(kvld), att_split, st()), "avsr_dec_attn_step(src)")
+                                           s["tmax"], L.ll(64), L.ll(s["F"] * 64), att_split, st()), "avsr_dec_attn_step(src)")
             ns = self._proj(s, "att", lay, "wo2", 1024, 1024)
             self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
@@ -258,6 +260,7 @@ class BatchedBeamSearch:
             L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
             L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(V), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
+        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), n, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
         s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))

@@ -88,6 +88,26 @@ __device__ __forceinline__ void avsr_split3_store(__nv_bfloat16* row_base, int K
     row_base[5 * K + c] = a3;
 }
 
+// Four consecutive columns at once (c % 4 == 0, K % 4 == 0): six 8-byte stores instead of 24 two-byte ones.
+__device__ __forceinline__ void avsr_split3_store4(__nv_bfloat16* row_base, int K, int c, float4 v) {
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    __align__(8) __nv_bfloat16 t1[4], t2[4], t3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t1[i] = __float2bfloat16_rn(in[i]);
+        const float r1 = in[i] - __bfloat162float(t1[i]);
+        t2[i] = __float2bfloat16_rn(r1);
+        t3[i] = __float2bfloat16_rn(r1 - __bfloat162float(t2[i]));
+    }
+    const uint2 u1 = *reinterpret_cast<const uint2*>(t1), u2 = *reinterpret_cast<const uint2*>(t2), u3 = *reinterpret_cast<const uint2*>(t3);
+    *reinterpret_cast<uint2*>(row_base + c) = u1;
+    *reinterpret_cast<uint2*>(row_base + K + c) = u1;
+    *reinterpret_cast<uint2*>(row_base + 3 * K + c) = u1;
+    *reinterpret_cast<uint2*>(row_base + 2 * K + c) = u2;
+    *reinterpret_cast<uint2*>(row_base + 4 * K + c) = u2;
+    *reinterpret_cast<uint2*>(row_base + 5 * K + c) = u3;
+}
+
 __device__ __forceinline__ float avsr_apply_act(float v, int act, float slope) {
     if (act == AVSR_ACT_GELU) return gelu_erf(v);
     if (act == AVSR_ACT_RELU) return fmaxf(v, 0.f);

@@ -38,149 +38,176 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
     const float4 y = make_float4(d0 * rstd * gg.x + bb.x, d1 * rstd * gg.y + bb.y, d2 * rstd * gg.z + bb.z, d3 * rstd * gg.w + bb.w);
     if (a) *reinterpret_cast<float4*>(a + (long long)row * D + c) = y;
     if (a_split) {
-        __nv_bfloat16* sr = a_split + (long long)row * 6 * D;
-        avsr_split3_store(sr, D, c, y.x); avsr_split3_store(sr, D, c + 1, y.y);
-        avsr_split3_store(sr, D, c + 2, y.z); avsr_split3_store(sr, D, c + 3, y.w);
+        avsr_split3_store4(a_split + (long long)row * 6 * D, D, c, y);
     }
 }
 
-// Single-query attention: one CTA (4 warps) per (row, head); the keys are split across the warps and the partial
-// (max, sum, weighted V) results are merged through shared memory.  MODE 0: self-attention over the cached positions
-// 0..step-1 plus the current token (whose k, v are read from qkv and appended to the cache).  MODE 1: cross-attention
-// over the T frames of the row's utterance.
+// Single-query attention with the K / V rows staged through shared memory in 128-key tiles (coalesced 256-byte row loads).
+// MODE 1 (cross-attention): one CTA per (utterance, head); the utterance's T frames of K and V are read from HBM ONCE and
+//   shared by all its live hyps (<= MAXH), which is what bounds this kernel: 2 * T * 256 B per (utterance, head).
+// MODE 0 (self-attention): one CTA per (row, head); keys are the row's own history, gathered through the ancestry table,
+//   plus the current token whose k, v come from qkv (and are appended to the cache here).
+// Pass 1 computes all scores (thread = key), a block-wide softmax follows, pass 2 accumulates V (warp = 32 keys of the
+// tile, lane = 2 output dims) and the four warps' partial sums are merged through shared memory.
+constexpr int MAXH = 8;
+constexpr int KT = 128;                  // keys per staged tile
+constexpr int KSTR = DH + 1;             // padded row stride (floats) of the staged K tile: conflict-free row-per-thread reads
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
 dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* __restrict__ kc, float* __restrict__ vc,
                      const unsigned char* __restrict__ anc, int lmax, const int* __restrict__ n_run, const int* __restrict__ utt_off,
                      const int* __restrict__ utt_T, int beam, int R, const int* __restrict__ step_p, float* __restrict__ out,
-                     int smax, long long kv_ld, __nv_bfloat16* __restrict__ out_split) {
-    extern __shared__ float sc_all[];          // [smax] scores / probabilities of all keys
-    __shared__ float s_m[4], s_s[4];
-    __shared__ float s_o[4][DH];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x;
+                     int smax, long long kv_ld, long long head_stride, __nv_bfloat16* __restrict__ out_split) {
+    extern __shared__ float smem[];
+    float* tile = smem;                              // [KT][KSTR] (K pass) / [KT][DH] (V pass)
+    float* qs = tile + KT * KSTR;                    // [nh][DH]
+    float* sc = qs + MAXH * DH;                      // [nh][smax]
+    __shared__ float s_red[4][MAXH];
+    __shared__ float s_o[4][MAXH][DH];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int head = blockIdx.y;
-    const int utt = row / beam;
-    if ((row % beam) >= n_run[utt]) return;
     const int step = *step_p;
-
-    float q[DH];
-    const float* qp = q_in + (long long)row * ldq + head * DH;
-#pragma unroll
-    for (int i = 0; i < DH; i += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(qp + i);
-        q[i] = t.x; q[i + 1] = t.y; q[i + 2] = t.z; q[i + 3] = t.w;
-    }
-    int n;                       // number of keys
-    const float* kbase;
-    const float* vbase;
-    long long kstride;
-    if (MODE == 0) {
-        n = step + 1;
-        if (warp == 0) {         // append this position's k, v to the cache (slot = this row)
-            const float* kp = qp + D;
-            const float* vp = qp + 2 * D;
-            float* kd = kc + ((long long)step * R + row) * D + head * DH;
-            float* vd = vc + ((long long)step * R + row) * D + head * DH;
-            kd[lane] = kp[lane]; kd[lane + 32] = kp[lane + 32];
-            vd[lane] = vp[lane]; vd[lane + 32] = vp[lane + 32];
-        }
-        kbase = kc + head * DH;
-        vbase = vc + head * DH;
-        kstride = (long long)R * D;
-    } else {
+    int nh, row0, utt, n;
+    if (MODE == 1) {
+        utt = blockIdx.x;
+        nh = n_run[utt];
+        row0 = utt * beam;
         n = utt_T[utt];
-        kbase = kc + (long long)utt_off[utt] * kv_ld + head * DH;
-        vbase = vc + (long long)utt_off[utt] * kv_ld + head * DH;
-        kstride = kv_ld;
+    } else {
+        row0 = blockIdx.x;
+        utt = row0 / beam;
+        nh = ((row0 % beam) < n_run[utt]) ? 1 : 0;
+        n = step + 1;
     }
-    // anc is double-buffered on step parity: [2][R][lmax]; the half written at the end of step-1 is (step & 1)
-    const unsigned char* arow = anc + ((long long)(step & 1) * R + row) * lmax;
+    if (nh == 0) return;
+    // ancestry row staged in shared memory first, so that a key row's address does not hang on a dependent global load
+    unsigned char* arow = reinterpret_cast<unsigned char*>(sc + (size_t)(MODE == 1 ? MAXH : 1) * smax);
+    if (MODE == 0) {
+        const unsigned char* ag = anc + ((long long)(step & 1) * R + row0) * lmax;
+        for (int i = tid; i < step; i += 128) arow[i] = ag[i];
+    }
     const int rbase = utt * beam;
-    const int per = (n + 3) >> 2;
-    const int p0 = warp * per, p1 = min(n, p0 + per);
+    const float* qrow0 = q_in + (long long)row0 * ldq + head * DH;
 
-    float mx = -INFINITY;
-    for (int p = p0 + lane; p < p1; p += 32) {
-        const float* kp;
-        if (MODE == 0) {
-            kp = (p == step) ? (qp + D) : (kbase + (long long)p * kstride + (long long)(rbase + arow[p]) * D);
-        } else {
-            kp = kbase + (long long)p * kstride;
-        }
-        float4 kk[DH / 4];
+    for (int i = tid; i < nh * DH; i += 128) qs[i] = q_in[(long long)(row0 + i / DH) * ldq + head * DH + (i % DH)];
+    if (MODE == 0 && warp == 0) {                    // append this position's k, v to the cache (slot = this row)
+        float* kd = kc + head * head_stride + ((long long)step * R + row0) * kv_ld;
+        float* vd = vc + head * head_stride + ((long long)step * R + row0) * kv_ld;
+        kd[lane] = qrow0[D + lane]; kd[lane + 32] = qrow0[D + lane + 32];
+        vd[lane] = qrow0[2 * D + lane]; vd[lane + 32] = qrow0[2 * D + lane + 32];
+    }
+    auto src_ptr = [&](const float* base, int p, int which) -> const float* {
+        if (MODE == 1) return base + head * head_stride + ((long long)utt_off[utt] + p) * kv_ld;
+        if (p == step) return qrow0 + (which + 1) * D;
+        return base + head * head_stride + ((long long)p * R + rbase + arow[p]) * kv_ld;
+    };
+
+    // ---------------- pass 1: scores
+    for (int t0 = 0; t0 < n; t0 += KT) {
+        __syncthreads();
+        {                                            // 16 consecutive threads fetch one key row (256 B); all 16 row loads
+            const float* src[16];                    // of a thread are in flight before the first one is consumed
+            float4 v[16];
 #pragma unroll
-        for (int i = 0; i < DH / 4; ++i) kk[i] = *reinterpret_cast<const float4*>(kp + 4 * i);
-        float s = 0.f;
+            for (int j = 0; j < 16; ++j) {
+                const int p = t0 + (tid >> 4) + 8 * j;
+                src[j] = (p < n) ? src_ptr(kc, p, 0) + 4 * (tid & 15) : nullptr;
+            }
 #pragma unroll
-        for (int i = 0; i < DH / 4; ++i) {
-            s = fmaf(q[4 * i], kk[i].x, s); s = fmaf(q[4 * i + 1], kk[i].y, s);
-            s = fmaf(q[4 * i + 2], kk[i].z, s); s = fmaf(q[4 * i + 3], kk[i].w, s);
+            for (int j = 0; j < 16; ++j) v[j] = src[j] ? *reinterpret_cast<const float4*>(src[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float* d = tile + ((tid >> 4) + 8 * j) * KSTR + 4 * (tid & 15);
+                d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+            }
         }
-        s *= 0.125f;
-        sc_all[p] = s;
-        mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int p = p0 + lane; p < p1; p += 32) {
-        const float e = expf(sc_all[p] - mx);
-        sc_all[p] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    int p = p0;
-    for (; p + 1 < p1; p += 2) {
-        const float* va;
-        const float* vb;
-        if (MODE == 0) {
-            va = (p == step) ? (qp + 2 * D) : (vbase + (long long)p * kstride + (long long)(rbase + arow[p]) * D);
-            vb = (p + 1 == step) ? (qp + 2 * D) : (vbase + (long long)(p + 1) * kstride + (long long)(rbase + arow[p + 1]) * D);
-        } else {
-            va = vbase + (long long)p * kstride;
-            vb = va + kstride;
+        __syncthreads();
+        const int p = t0 + tid;
+        if (p < n) {
+            float kk[DH];
+#pragma unroll
+            for (int i = 0; i < DH; ++i) kk[i] = tile[tid * KSTR + i];
+            for (int h = 0; h < nh; ++h) {
+                float s = 0.f;
+#pragma unroll
+                for (int i = 0; i < DH; ++i) s = fmaf(qs[h * DH + i], kk[i], s);
+                sc[h * smax + p] = s * 0.125f;
+            }
         }
-        const float2 ta = *reinterpret_cast<const float2*>(va + lane * 2);
-        const float2 tb = *reinterpret_cast<const float2*>(vb + lane * 2);
-        const float wa = sc_all[p], wb = sc_all[p + 1];
-        o0 = fmaf(wa, ta.x, o0); o1 = fmaf(wa, ta.y, o1);
-        o2 = fmaf(wb, tb.x, o2); o3 = fmaf(wb, tb.y, o3);
     }
-    if (p < p1) {
-        const float* va;
-        if (MODE == 0) va = (p == step) ? (qp + 2 * D) : (vbase + (long long)p * kstride + (long long)(rbase + arow[p]) * D);
-        else va = vbase + (long long)p * kstride;
-        const float2 ta = *reinterpret_cast<const float2*>(va + lane * 2);
-        const float wa = sc_all[p];
-        o0 = fmaf(wa, ta.x, o0); o1 = fmaf(wa, ta.y, o1);
-    }
-    o0 += o2; o1 += o3;
-    if (lane == 0) { s_m[warp] = mx; s_s[warp] = sum; }
-    s_o[warp][lane * 2] = o0;
-    s_o[warp][lane * 2 + 1] = o1;
     __syncthreads();
-    if (warp == 0) {
-        const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-        float tot = 0.f, a0 = 0.f, a1 = 0.f;
+    // ---------------- softmax statistics per hyp (block-wide)
+    float inv[MAXH];
+    for (int h = 0; h < nh; ++h) {
+        float mx = -INFINITY;
+        for (int p = tid; p < n; p += 128) mx = fmaxf(mx, sc[h * smax + p]);
+        mx = warp_max(mx);
+        if (lane == 0) s_red[warp][h] = mx;
+    }
+    __syncthreads();
+    for (int h = 0; h < nh; ++h) {
+        const float mx = fmaxf(fmaxf(s_red[0][h], s_red[1][h]), fmaxf(s_red[2][h], s_red[3][h]));
+        float sum = 0.f;
+        for (int p = tid; p < n; p += 128) {
+            const float e = expf(sc[h * smax + p] - mx);
+            sc[h * smax + p] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        __syncthreads();                             // all reads of s_red[.][h] (max) are done before it is reused
+        if (lane == 0) s_red[warp][h] = sum;
+        __syncthreads();
+        inv[h] = 1.f / (s_red[0][h] + s_red[1][h] + s_red[2][h] + s_red[3][h]);
+        __syncthreads();
+    }
+    // ---------------- pass 2: weighted sum of V
+    float acc[MAXH][2];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const float f = (s_m[w] == -INFINITY) ? 0.f : expf(s_m[w] - M);     // a warp with no keys contributes nothing
-            tot += s_s[w] * f;
-            a0 += s_o[w][lane * 2] * f;
-            a1 += s_o[w][lane * 2 + 1] * f;
+    for (int h = 0; h < MAXH; ++h) acc[h][0] = acc[h][1] = 0.f;
+    for (int t0 = 0; t0 < n; t0 += KT) {
+        __syncthreads();
+        {
+            const float* src[16];
+            float4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int p = t0 + (tid >> 4) + 8 * j;
+                src[j] = (p < n) ? src_ptr(vc, p, 1) + 4 * (tid & 15) : nullptr;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = src[j] ? *reinterpret_cast<const float4*>(src[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(tile + ((tid >> 4) + 8 * j) * DH + 4 * (tid & 15)) = v[j];
         }
-        const float inv = 1.f / tot;
-        if (out) *reinterpret_cast<float2*>(out + (long long)row * D + head * DH + lane * 2) = make_float2(a0 * inv, a1 * inv);
-        if (out_split) {
-            __nv_bfloat16* sr = out_split + (long long)row * 6 * D;
-            avsr_split3_store(sr, D, head * DH + lane * 2, a0 * inv);
-            avsr_split3_store(sr, D, head * DH + lane * 2 + 1, a1 * inv);
+        __syncthreads();
+        const int kend = min(32, n - t0 - warp * 32);
+        for (int k = 0; k < kend; ++k) {
+            const int key = warp * 32 + k;
+            const float2 v = *reinterpret_cast<const float2*>(tile + key * DH + lane * 2);
+#pragma unroll
+            for (int h = 0; h < MAXH; ++h) {
+                if (h < nh) {
+                    const float w = sc[h * smax + t0 + key];
+                    acc[h][0] = fmaf(w, v.x, acc[h][0]);
+                    acc[h][1] = fmaf(w, v.y, acc[h][1]);
+                }
+            }
         }
+    }
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+        if (h < nh) { s_o[warp][h][lane * 2] = acc[h][0]; s_o[warp][h][lane * 2 + 1] = acc[h][1]; }
+    }
+    __syncthreads();
+    for (int i = tid; i < nh * DH; i += 128) {
+        const int h = i / DH, d = i % DH;
+        const float v = (s_o[0][h][d] + s_o[1][h][d] + s_o[2][h][d] + s_o[3][h][d]) * inv[h];
+        const long long row = row0 + h;
+        if (out) out[row * D + head * DH + d] = v;
+        if (out_split) avsr_split3_store(out_split + row * 6 * D, D, head * DH + d, v);
     }
 }
-
 
 // logits = sum_z part[z][row] + bias ; logp = log_softmax(logits) -> dec_logp[row] ; part_ids[row] = top-S token ids.
 __global__ void __launch_bounds__(256)
@@ -270,21 +297,32 @@ extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* l
     return AVSR_OK;
 }
 
-// mode 0: self-attention step. q_in = qkv [R, 3072] (q | k | v of the current position), kc/vc = this layer's caches
-// [lmax][R][1024]; anc [R][lmax].  mode 1: cross-attention. q_in = q [R, 1024], kc/vc = this layer's cross K/V [F][1024].
+// mode 0: self-attention step. q_in = qkv [R, 3072] (q | k | v of the current position), kc/vc = this layer's caches,
+// element (pos, row, head, d) at head*head_stride + (pos*R + row)*kv_ld + d; anc [2][R][lmax].
+// mode 1: cross-attention. q_in = q [R, 1024], kc/vc = this layer's cross K / V, element (frame, head, d) at
+// head*head_stride + frame*kv_ld + d.  out (fp32 [R,1024]) and/or out_split (bf16x3 [R, 6*1024]).
 extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
                                   const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step,
-                                  float* out, int max_keys, long long kv_ld, void* out_split, cudaStream_t stream) {
+                                  float* out, int max_keys, long long kv_ld, long long head_stride, void* out_split, cudaStream_t stream) {
     AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && max_keys > 0, "avsr_dec_attn_step: bad arguments");
     AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
+    AVSR_REQUIRE(beam <= MAXH && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max %d)", beam, MAXH);
     const int smax = (max_keys + 3) & ~3;
-    const size_t smem = (size_t)smax * sizeof(float);
-    AVSR_REQUIRE(smem <= 48 * 1024, "avsr_dec_attn_step: %d keys exceed the shared-memory strip", max_keys);
-    dim3 grid(R, HEADS);
+    const int nh = mode == 1 ? beam : 1;
+    const size_t smem = ((size_t)KT * KSTR + MAXH * DH + (size_t)nh * smax) * sizeof(float) + (mode == 0 ? (size_t)smax : 0);
+    AVSR_REQUIRE(smem <= 160 * 1024, "avsr_dec_attn_step: %d keys x %d hyps exceed shared memory", max_keys, nh);
+    static size_t configured[2] = {0, 0};
+    if (smem > 48 * 1024 && smem > configured[mode]) {
+        if (mode == 0) AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        else AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured[mode] = 160 * 1024;
+    }
     if (mode == 0)
-        dec_attn_step_kernel<0><<<grid, 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, smax, kv_ld, (__nv_bfloat16*)out_split);
+        dec_attn_step_kernel<0><<<dim3(R, HEADS), 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out,
+                                                                      smax, kv_ld, head_stride, (__nv_bfloat16*)out_split);
     else
-        dec_attn_step_kernel<1><<<grid, 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, smax, kv_ld, (__nv_bfloat16*)out_split);
+        dec_attn_step_kernel<1><<<dim3(R / beam, HEADS), 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step,
+                                                                             out, smax, kv_ld, head_stride, (__nv_bfloat16*)out_split);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

@@ -195,6 +195,18 @@ split3_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __rest
     avsr_split3_store(out + r * 6 * K, K, c, in[r * ldi + c]);
 }
 
+// [F, ncol] -> [ncol/64][F][64]: float4 per thread
+__global__ void __launch_bounds__(256)
+kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int ncol) {
+    const long long total = F * (ncol / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / (ncol / 4);
+        const int c = (int)(i % (ncol / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(in + f * ncol + c);
+        *reinterpret_cast<float4*>(out + ((long long)(c / 64) * F + f) * 64 + (c % 64)) = v;
+    }
+}
+
 }  // namespace
 
 #define GRID1D(total) ((int)(((total) + 255) / 256 > 148 * 64 ? 148 * 64 : ((total) + 255) / 256))
@@ -273,6 +285,14 @@ extern "C" int avsr_cast_bf16(const float* in, long long ldi, void* out, long lo
 extern "C" int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, cudaStream_t stream) {
     AVSR_REQUIRE(in && out && rows > 0 && K > 0, "avsr_split3: bad arguments");
     split3_kernel<<<cdiv(rows * K, 256), 256, 0, stream>>>(in, ldi, (__nv_bfloat16*)out, rows, K);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && F > 0 && ncol > 0 && (ncol & 63) == 0, "avsr_kv_head_major: bad arguments");
+    const long long total = F * (ncol / 4);
+    kv_head_major_kernel<<<GRID1D(total), 256, 0, stream>>>(in, out, F, ncol);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

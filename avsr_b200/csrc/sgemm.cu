@@ -185,12 +185,28 @@ splitk_epilogue_kernel(const float* __restrict__ part, int nsplit, int M, int N,
             }
             if (out) *reinterpret_cast<float4*>(out + (long long)row * ldo + c) = v;
             if (ln_g) { *reinterpret_cast<float4*>(rowbuf + c) = v; lsum += (v.x + v.y) + (v.z + v.w); }
-            else if (split_out) {
-                __nv_bfloat16* sr = split_out + (long long)row * 6 * N;
-                avsr_split3_store(sr, N, c, v.x); avsr_split3_store(sr, N, c + 1, v.y);
-                avsr_split3_store(sr, N, c + 2, v.z); avsr_split3_store(sr, N, c + 3, v.w);
-            }
+            else if (split_out) avsr_split3_store4(split_out + (long long)row * 6 * N, N, c, v);
         }
+        if (ln_g == nullptr) return;
+        // LayerNorm of the finished row (values of this thread's columns are still in rowbuf; same thread re-reads them)
+        const float mean = block_sum(lsum, red) / (float)N;
+        float lvar = 0.f;
+        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+            const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
+            const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+            lvar += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+        const float rstd = rsqrtf(block_sum(lvar, red) / (float)N + ln_eps);
+        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+            const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
+            const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c);
+            const float4 b4 = *reinterpret_cast<const float4*>(ln_b + c);
+            const float4 y = make_float4((t.x - mean) * rstd * g4.x + b4.x, (t.y - mean) * rstd * g4.y + b4.y,
+                                         (t.z - mean) * rstd * g4.z + b4.z, (t.w - mean) * rstd * g4.w + b4.w);
+            if (ln_out) *reinterpret_cast<float4*>(ln_out + (long long)row * ld_ln + c) = y;
+            if (split_out) avsr_split3_store4(split_out + (long long)row * 6 * N, N, c, y);
+        }
+        return;
     } else {
         for (int c = threadIdx.x; c < N; c += blockDim.x) {
             float v = 0.f;

@@ -135,7 +135,9 @@ int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, co
                       const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
 int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
                        const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step, float* out,
-                       int max_keys, long long kv_ld, void* out_split, avsr_stream_t stream);
+                       int max_keys, long long kv_ld, long long head_stride, void* out_split, avsr_stream_t stream);
+/* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span). */
+int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
                              int* part_ids, int S, avsr_stream_t stream);
 /* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes. */

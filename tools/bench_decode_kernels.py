@@ -1,0 +1,104 @@
+"""Dev aid: CUDA-event timings of the individual decode-step kernels at a chosen position (default: mid-utterance)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avsr_b200 import _lib as L
+from avsr_b200.beam_search import BatchedBeamSearch
+from avsr_b200.weights import split3_weight
+
+lib = L.load()
+dev = "cuda"
+B, beam, T, V = 32, 3, 375, 5049
+step = int(sys.argv[1]) if len(sys.argv) > 1 else 187
+R, S, lmax, nl = B * beam, 4, T + 1, 6
+i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+
+
+def timeit(fn, n=24):
+    """n launches captured in one CUDA graph (as in the real decode loop: no host launch overhead), replayed 5 times."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (5 * n) * 1e3
+
+
+n_run, utt_off, utt_T = i32([beam] * B), i32([b * T for b in range(B)]), i32([T] * B)
+step_t = i32([step])
+qkv = torch.randn(R, 3072, device=dev)
+q2 = torch.randn(R, 1024, device=dev)
+kc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+vc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+anc = torch.randint(0, beam, (2, R, lmax), dtype=torch.uint8, device=dev)
+if len(sys.argv) > 2 and sys.argv[2] == 'shared':
+    anc.zero_()          # all hyps of an utterance descend from slot 0 (converged beam): physical rows are shared
+ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
+att = torch.empty(R, 1024, device=dev)
+att6 = torch.empty(R, 6144, device=dev, dtype=torch.bfloat16)
+li = {"i": 0}
+
+
+def self_attn():
+    l = li["i"] % nl; li["i"] += 1
+    L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run), L.ptr(utt_off),
+                                   L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), L.stream()), "self")
+
+
+def cross_attn():
+    l = li["i"] % nl; li["i"] += 1
+    L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
+                                   L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(64), L.ll(B * T * 64),
+                                   L.ptr(att6), L.stream()), "cross")
+
+
+print(f"step={step}  R={R}")
+print(f"self-attn  : {timeit(self_attn):8.1f} us")
+print(f"cross-attn : {timeit(cross_attn):8.1f} us   (K/V bytes per launch {B*T*2048*4/1e6:.0f} MB -> {B*T*2048*4/1e3/timeit(cross_attn):.0f} GB/s)")
+
+# split-K tensor-core projections (weights cycled so they stream from HBM)
+for (N, K) in ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024)):
+    ws = [split3_weight(torch.randn(N, K, device=dev) * 0.02) for _ in range(8)]
+    a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
+    bn, ns = BatchedBeamSearch.tc_plan(R, N, 6 * K)
+    part = torch.empty(ns, R, N, device=dev)
+    def g():
+        w = ws[li["i"] % 8]; li["i"] += 1
+        L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(w), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn, L.stream()), "g")
+    t = timeit(g)
+    print(f"proj N={N} K={K} bn={bn} splits={ns}: {t:8.1f} us   ({N*K*12/1e3/t:.0f} GB/s of bf16x3 weights)")
+    bias, res, gam, bet = (torch.randn(N, device=dev) for _ in range(2)) if False else (torch.randn(N, device=dev), torch.randn(R, 1024, device=dev), torch.randn(N, device=dev), torch.randn(N, device=dev))
+    act = torch.ones(R, dtype=torch.int32, device=dev)
+    if N == 1024:
+        x = torch.randn(R, N, device=dev)
+        a6o = torch.empty(R, 6 * N, device=dev, dtype=torch.bfloat16)
+        def e():
+            L.check(lib.avsr_splitk_epilogue(L.ptr(part), ns, R, N, L.ptr(bias), 0, L.ptr(x), L.ll(N), L.ptr(x), L.ll(N), L.ptr(gam), L.ptr(bet),
+                                             C.c_float(1e-12), None, L.ll(N), L.ptr(act), L.ptr(a6o), L.stream()), "e")
+        print(f"   epilogue(res+LN+split) ns={ns}: {timeit(e):8.1f} us")
+    del ws
+
+# CTC prefix (pre-beam) and fusion
+logp = torch.log_softmax(torch.randn(B * T, V, device=dev), -1)
+last, part_ids = i32([7] * R), torch.randint(1, V - 1, (R, S), dtype=torch.int32, device=dev)
+r_buf = torch.full((2, R * S, T, 2), -30.0, device=dev)
+rprev = i32([r * S for r in range(R)])
+psi, rsum = torch.empty(R, S, device=dev), torch.empty(R, device=dev)
+def ctc():
+    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S, L.ptr(last), L.ptr(part_ids),
+                                        L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(psi), L.ptr(rsum), L.stream()), "ctc")
+print(f"ctc prebeam: {timeit(ctc):8.1f} us")
