@@ -118,6 +118,11 @@ class BatchedBeamSearch:
         s["vc"] = torch.empty(nl, 16, lmax, R, 64, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
+        # scratch of the key-chunked step attention (csrc/decode.cu): partial (sum e*v, max, sum) per chunk + merge tickets
+        nch = lib.avsr_dec_attn_chunks(lmax)
+        s["att_po"] = torch.empty(B, 16, nch, beam, 64, dtype=torch.float32, device=dev)
+        s["att_pms"] = torch.empty(B, 16, nch, beam, 2, dtype=torch.float32, device=dev)
+        s["att_tickets"] = i32(B, 16)
         shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
         if self.precision == "bf16x3":
             s["a6"] = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device=dev)
@@ -204,13 +209,14 @@ class BatchedBeamSearch:
         kvld = nl * 2 * 1024
         att_f32 = None if tc else L.ptr(s["att"])
         att_split = L.ptr(s["att6"]) if tc else None
+        scratch = (L.ptr(s["att_po"]), L.ptr(s["att_pms"]), L.ptr(s["att_tickets"]))
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93)
             ns = self._proj(s, "a", lay, "wqkv", 3072, 1024)
             self._epi(s, ns, 3072, lay["bqkv"], out=s["qkv"])
             L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
                                            lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
-                                           att_f32, lmax, L.ll(64), L.ll(lmax * R * 64), att_split, st()), "avsr_dec_attn_step(self)")
+                                           att_f32, lmax, L.ll(64), L.ll(lmax * R * 64), att_split, *scratch, st()), "avsr_dec_attn_step(self)")
             ns = self._proj(s, "att", lay, "wo", 1024, 1024)
             self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
@@ -219,7 +225,7 @@ class BatchedBeamSearch:
             ck, cv = s["ckv_t"][li, 0], s["ckv_t"][li, 1]
             L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
                                            L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
-                                           s["tmax"], L.ll(64), L.ll(s["F"] * 64), att_split, st()), "avsr_dec_attn_step(src)")
+                                           s["tmax"], L.ll(64), L.ll(s["F"] * 64), att_split, *scratch, st()), "avsr_dec_attn_step(src)")
             ns = self._proj(s, "att", lay, "wo2", 1024, 1024)
             self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)

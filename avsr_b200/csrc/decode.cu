@@ -42,170 +42,220 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
     }
 }
 
-// Single-query attention with the K / V rows staged through shared memory in 128-key tiles (coalesced 256-byte row loads).
-// MODE 1 (cross-attention): one CTA per (utterance, head); the utterance's T frames of K and V are read from HBM ONCE and
-//   shared by all its live hyps (<= MAXH), which is what bounds this kernel: 2 * T * 256 B per (utterance, head).
-// MODE 0 (self-attention): one CTA per (row, head); keys are the row's own history, gathered through the ancestry table,
-//   plus the current token whose k, v come from qkv (and are appended to the cache here).
-// Pass 1 computes all scores (thread = key), a block-wide softmax follows, pass 2 accumulates V (warp = 32 keys of the
-// tile, lane = 2 output dims) and the four warps' partial sums are merged through shared memory.
+// Single-query attention of one decode position, split over key chunks (flash-decoding form).
+// One CTA (128 threads) per (utterance, head, chunk of CK keys); all live hyps (<= MAXH) of the utterance are served by
+// the same CTA so that a K / V row shared by several hyps is read from HBM once:
+//   MODE 1 (cross-attention): keys = the utterance's T frames, identical for every hyp (2 * T * 256 B per (utt, head)).
+//   MODE 0 (self-attention):  keys = each hyp's own history, gathered through the ancestry table (hyps of a beam mostly
+//                             share their ancestors), plus the current token whose k, v come from qkv and are appended
+//                             to the cache here.
+// Pass 1: thread = key, the 256-byte K row goes straight to registers (16 float4 loads in flight per thread).
+// Local softmax statistics (max, sum) per hyp.  Pass 2: half-warp = key, lane = 4 output dims, 8 keys in flight per lane.
+// With more than one chunk the partial (max, sum, sum e*v) are written to scratch and the LAST CTA of the (utt, head)
+// group (atomic ticket) merges them in chunk order, so the result does not depend on which CTA arrives last.
+// (A variant that staged the rows with 256-byte bulk async copies into shared memory measured slower: 49 vs 41 us for the
+// cross-attention of 32 x 375 frames; the kernel is bound by its chain of dependent round trips, not by load issue.)
 constexpr int MAXH = 8;
-constexpr int KT = 128;                  // keys per staged tile
-constexpr int KSTR = DH + 1;             // padded row stride (floats) of the staged K tile: conflict-free row-per-thread reads
+constexpr int CK = 128;                  // keys per chunk
 
 template <int MODE>
 __global__ void __launch_bounds__(128)
-dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* __restrict__ kc, float* __restrict__ vc,
-                     const unsigned char* __restrict__ anc, int lmax, const int* __restrict__ n_run, const int* __restrict__ utt_off,
-                     const int* __restrict__ utt_T, int beam, int R, const int* __restrict__ step_p, float* __restrict__ out,
-                     int smax, long long kv_ld, long long head_stride, __nv_bfloat16* __restrict__ out_split) {
-    extern __shared__ float smem[];
-    float* tile = smem;                              // [KT][KSTR] (K pass) / [KT][DH] (V pass)
-    float* qs = tile + KT * KSTR;                    // [nh][DH]
-    float* sc = qs + MAXH * DH;                      // [nh][smax]
+dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* kc, float* vc, const unsigned char* __restrict__ anc,
+                     int lmax, const int* __restrict__ n_run, const int* __restrict__ utt_off, const int* __restrict__ utt_T,
+                     int beam, int R, const int* __restrict__ step_p, float* __restrict__ out, long long kv_ld,
+                     long long head_stride, __nv_bfloat16* __restrict__ out_split, float* __restrict__ part_o,
+                     float* __restrict__ part_ms, int* __restrict__ tickets) {
+    __shared__ __align__(16) float qs[MAXH][DH];
+    __shared__ float sc[MAXH][CK];
+    __shared__ unsigned char aslot[MAXH][CK];
+    __shared__ __align__(16) float s_o[4][MAXH][DH];
     __shared__ float s_red[4][MAXH];
-    __shared__ float s_o[4][MAXH][DH];
+    __shared__ float s_m[MAXH], s_s[MAXH];
+    __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int head = blockIdx.y;
+    const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z, nch = gridDim.z;
+    // the three scalars are independent: issue their loads together instead of one round trip each
+    const int nh = n_run[utt];
     const int step = *step_p;
-    int nh, row0, utt, n;
-    if (MODE == 1) {
-        utt = blockIdx.x;
-        nh = n_run[utt];
-        row0 = utt * beam;
-        n = utt_T[utt];
-    } else {
-        row0 = blockIdx.x;
-        utt = row0 / beam;
-        nh = ((row0 % beam) < n_run[utt]) ? 1 : 0;
-        n = step + 1;
-    }
+    const int T_utt = (MODE == 1) ? utt_T[utt] : 0;
+    const long long uoff = (MODE == 1) ? (long long)utt_off[utt] : 0;
     if (nh == 0) return;
-    // ancestry row staged in shared memory first, so that a key row's address does not hang on a dependent global load
-    unsigned char* arow = reinterpret_cast<unsigned char*>(sc + (size_t)(MODE == 1 ? MAXH : 1) * smax);
-    if (MODE == 0) {
-        const unsigned char* ag = anc + ((long long)(step & 1) * R + row0) * lmax;
-        for (int i = tid; i < step; i += 128) arow[i] = ag[i];
-    }
-    const int rbase = utt * beam;
-    const float* qrow0 = q_in + (long long)row0 * ldq + head * DH;
+    const int n = (MODE == 1) ? T_utt : step + 1;
+    const int nact = (n + CK - 1) / CK;
+    if (chunk >= nact) return;
+    const int row0 = utt * beam;
+    const int p0 = chunk * CK;
+    const int p = p0 + tid;
+    const bool valid = p < n;
+    const float* kbase = kc + head * head_stride;
+    const float* vbase = vc + head * head_stride;
 
-    for (int i = tid; i < nh * DH; i += 128) qs[i] = q_in[(long long)(row0 + i / DH) * ldq + head * DH + (i % DH)];
-    if (MODE == 0 && warp == 0) {                    // append this position's k, v to the cache (slot = this row)
-        float* kd = kc + head * head_stride + ((long long)step * R + row0) * kv_ld;
-        float* vd = vc + head * head_stride + ((long long)step * R + row0) * kv_ld;
-        kd[lane] = qrow0[D + lane]; kd[lane + 32] = qrow0[D + lane + 32];
-        vd[lane] = qrow0[2 * D + lane]; vd[lane + 32] = qrow0[2 * D + lane + 32];
+    for (int i = tid; i < nh * DH; i += 128) qs[i / DH][i % DH] = q_in[(long long)(row0 + i / DH) * ldq + head * DH + (i % DH)];
+    if (MODE == 0) {
+        if (step >= p0 && step < p0 + CK) {          // this chunk owns the current position: append k, v (slot = the row itself)
+            for (int i = tid; i < nh * DH; i += 128) {
+                const int h = i / DH, d = i % DH;
+                const float* qr = q_in + (long long)(row0 + h) * ldq + head * DH + d;
+                const long long o = head * head_stride + ((long long)step * R + row0 + h) * kv_ld + d;
+                kc[o] = qr[D];
+                vc[o] = qr[2 * D];
+            }
+        }
+        for (int h = 0; h < nh; ++h) {
+            unsigned char s = 0;
+            if (p < step) s = anc[((long long)(step & 1) * R + row0 + h) * lmax + p];
+            else if (p == step) s = (unsigned char)h;
+            aslot[h][tid] = s;
+        }
     }
-    auto src_ptr = [&](const float* base, int p, int which) -> const float* {
-        if (MODE == 1) return base + head * head_stride + ((long long)utt_off[utt] + p) * kv_ld;
-        if (p == step) return qrow0 + (which + 1) * D;
-        return base + head * head_stride + ((long long)p * R + rbase + arow[p]) * kv_ld;
+    __syncthreads();                                 // qs / aslot ready, appended k / v visible to the whole CTA
+
+    auto row_ptr = [&](const float* base, int pos, int slot) -> const float* {
+        if (MODE == 1) return base + (uoff + pos) * kv_ld;
+        return base + ((long long)pos * R + row0 + slot) * kv_ld;
     };
 
-    // ---------------- pass 1: scores
-    for (int t0 = 0; t0 < n; t0 += KT) {
-        __syncthreads();
-        {                                            // 16 consecutive threads fetch one key row (256 B); all 16 row loads
-            const float* src[16];                    // of a thread are in flight before the first one is consumed
-            float4 v[16];
+    // ---------------- pass 1: scores of this chunk's keys for every hyp
+    {
+        float kk[DH];
+        int cur = -1;
+        for (int h = 0; h < nh; ++h) {
+            const int slot = (MODE == 1) ? 0 : (int)aslot[h][tid];
+            if (valid && slot != cur) {
+                const float4* src = reinterpret_cast<const float4*>(row_ptr(kbase, p, slot));
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int p = t0 + (tid >> 4) + 8 * j;
-                src[j] = (p < n) ? src_ptr(kc, p, 0) + 4 * (tid & 15) : nullptr;
+                for (int j = 0; j < DH / 4; ++j) {
+                    const float4 v = src[j];
+                    kk[4 * j] = v.x; kk[4 * j + 1] = v.y; kk[4 * j + 2] = v.z; kk[4 * j + 3] = v.w;
+                }
+                cur = slot;
             }
+            float s = 0.f;
+            if (valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = src[j] ? *reinterpret_cast<const float4*>(src[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float* d = tile + ((tid >> 4) + 8 * j) * KSTR + 4 * (tid & 15);
-                d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+                for (int i = 0; i < DH; ++i) s = fmaf(qs[h][i], kk[i], s);
             }
-        }
-        __syncthreads();
-        const int p = t0 + tid;
-        if (p < n) {
-            float kk[DH];
-#pragma unroll
-            for (int i = 0; i < DH; ++i) kk[i] = tile[tid * KSTR + i];
-            for (int h = 0; h < nh; ++h) {
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < DH; ++i) s = fmaf(qs[h * DH + i], kk[i], s);
-                sc[h * smax + p] = s * 0.125f;
-            }
+            sc[h][tid] = valid ? s * 0.125f : -INFINITY;
         }
     }
-    __syncthreads();
-    // ---------------- softmax statistics per hyp (block-wide)
-    float inv[MAXH];
+    // ---------------- local softmax statistics per hyp
     for (int h = 0; h < nh; ++h) {
-        float mx = -INFINITY;
-        for (int p = tid; p < n; p += 128) mx = fmaxf(mx, sc[h * smax + p]);
-        mx = warp_max(mx);
+        const float mx = warp_max(sc[h][tid]);
         if (lane == 0) s_red[warp][h] = mx;
     }
     __syncthreads();
-    for (int h = 0; h < nh; ++h) {
-        const float mx = fmaxf(fmaxf(s_red[0][h], s_red[1][h]), fmaxf(s_red[2][h], s_red[3][h]));
-        float sum = 0.f;
-        for (int p = tid; p < n; p += 128) {
-            const float e = expf(sc[h * smax + p] - mx);
-            sc[h * smax + p] = e;
-            sum += e;
+    float e_own[MAXH];
+#pragma unroll
+    for (int h = 0; h < MAXH; ++h) {
+        e_own[h] = 0.f;
+        if (h < nh) {
+            const float mx = fmaxf(fmaxf(s_red[0][h], s_red[1][h]), fmaxf(s_red[2][h], s_red[3][h]));
+            e_own[h] = valid ? expf(sc[h][tid] - mx) : 0.f;
+            if (tid == 0) s_m[h] = mx;
         }
-        sum = warp_sum(sum);
-        __syncthreads();                             // all reads of s_red[.][h] (max) are done before it is reused
-        if (lane == 0) s_red[warp][h] = sum;
-        __syncthreads();
-        inv[h] = 1.f / (s_red[0][h] + s_red[1][h] + s_red[2][h] + s_red[3][h]);
-        __syncthreads();
     }
-    // ---------------- pass 2: weighted sum of V
-    float acc[MAXH][2];
+    __syncthreads();                                 // every read of s_red (max) done before it is reused for the sums
 #pragma unroll
-    for (int h = 0; h < MAXH; ++h) acc[h][0] = acc[h][1] = 0.f;
-    for (int t0 = 0; t0 < n; t0 += KT) {
-        __syncthreads();
-        {
-            const float* src[16];
-            float4 v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int p = t0 + (tid >> 4) + 8 * j;
-                src[j] = (p < n) ? src_ptr(vc, p, 1) + 4 * (tid & 15) : nullptr;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = src[j] ? *reinterpret_cast<const float4*>(src[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(tile + ((tid >> 4) + 8 * j) * DH + 4 * (tid & 15)) = v[j];
+    for (int h = 0; h < MAXH; ++h) {
+        if (h < nh) {
+            sc[h][tid] = e_own[h];
+            const float sm = warp_sum(e_own[h]);
+            if (lane == 0) s_red[warp][h] = sm;
         }
-        __syncthreads();
-        const int kend = min(32, n - t0 - warp * 32);
-        for (int k = 0; k < kend; ++k) {
-            const int key = warp * 32 + k;
-            const float2 v = *reinterpret_cast<const float2*>(tile + key * DH + lane * 2);
+    }
+    __syncthreads();
+    if (tid < nh) s_s[tid] = s_red[0][tid] + s_red[1][tid] + s_red[2][tid] + s_red[3][tid];
+
+    // ---------------- pass 2: sum_p e[p] * V[p] ; half-warp = key, lane = 4 dims
+    float acc[MAXH][4];
 #pragma unroll
-            for (int h = 0; h < MAXH; ++h) {
-                if (h < nh) {
-                    const float w = sc[h * smax + t0 + key];
-                    acc[h][0] = fmaf(w, v.x, acc[h][0]);
-                    acc[h][1] = fmaf(w, v.y, acc[h][1]);
+    for (int h = 0; h < MAXH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+    const int half = lane >> 4, l4 = (lane & 15) * 4;
+#pragma unroll
+    for (int i0 = 0; i0 < 16; i0 += 8) {
+        float4 v0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kl = warp * 32 + half + 2 * (i0 + i);
+            const int pos = p0 + kl;
+            v0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pos < n) v0[i] = *reinterpret_cast<const float4*>(row_ptr(vbase, pos, (MODE == 1) ? 0 : (int)aslot[0][kl]) + l4);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kl = warp * 32 + half + 2 * (i0 + i);
+            const int pos = p0 + kl;
+            if (pos < n) {
+                const int slot0 = (MODE == 1) ? 0 : (int)aslot[0][kl];
+#pragma unroll
+                for (int h = 0; h < MAXH; ++h) {
+                    if (h < nh) {
+                        float4 v = v0[i];
+                        if (MODE == 0 && h > 0) {
+                            const int slot = (int)aslot[h][kl];
+                            if (slot != slot0) v = *reinterpret_cast<const float4*>(row_ptr(vbase, pos, slot) + l4);
+                        }
+                        const float w = sc[h][kl];
+                        acc[h][0] = fmaf(w, v.x, acc[h][0]); acc[h][1] = fmaf(w, v.y, acc[h][1]);
+                        acc[h][2] = fmaf(w, v.z, acc[h][2]); acc[h][3] = fmaf(w, v.w, acc[h][3]);
+                    }
                 }
             }
         }
     }
 #pragma unroll
     for (int h = 0; h < MAXH; ++h) {
-        if (h < nh) { s_o[warp][h][lane * 2] = acc[h][0]; s_o[warp][h][lane * 2 + 1] = acc[h][1]; }
+        if (h < nh) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[h][j] += __shfl_xor_sync(0xffffffffu, acc[h][j], 16);
+            if (half == 0) *reinterpret_cast<float4*>(&s_o[warp][h][l4]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+        }
     }
     __syncthreads();
-    for (int i = tid; i < nh * DH; i += 128) {
-        const int h = i / DH, d = i % DH;
-        const float v = (s_o[0][h][d] + s_o[1][h][d] + s_o[2][h][d] + s_o[3][h][d]) * inv[h];
+
+    auto store_out = [&](int h, int d, float v) {
         const long long row = row0 + h;
         if (out) out[row * D + head * DH + d] = v;
         if (out_split) avsr_split3_store(out_split + row * 6 * D, D, head * DH + d, v);
+    };
+    if (nact == 1) {
+        for (int i = tid; i < nh * DH; i += 128) {
+            const int h = i / DH, d = i % DH;
+            store_out(h, d, (s_o[0][h][d] + s_o[1][h][d] + s_o[2][h][d] + s_o[3][h][d]) / s_s[h]);
+        }
+        return;
+    }
+    // ---------------- several chunks: publish the partial, the last CTA of the group merges all of them
+    const long long grp = (long long)utt * gridDim.y + head;
+    float* po = part_o + ((grp * nch + chunk) * beam) * DH;
+    float* pms = part_ms + ((grp * nch + chunk) * beam) * 2;
+    for (int i = tid; i < nh * DH; i += 128) {
+        const int h = i / DH, d = i % DH;
+        po[i] = s_o[0][h][d] + s_o[1][h][d] + s_o[2][h][d] + s_o[3][h][d];
+    }
+    if (tid < nh) { pms[2 * tid] = s_m[tid]; pms[2 * tid + 1] = s_s[tid]; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(&tickets[grp], 1);
+        s_last = (t == nact - 1) ? 1 : 0;
+        if (s_last) tickets[grp] = 0;                // re-armed for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = tid; i < nh * DH; i += 128) {
+        const int h = i / DH, d = i % DH;
+        float M = -INFINITY;
+        for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(part_ms + ((grp * nch + c) * beam + h) * 2));
+        float S = 0.f, o = 0.f;
+        for (int c = 0; c < nact; ++c) {
+            const float* q = part_ms + ((grp * nch + c) * beam + h) * 2;
+            const float f = expf(__ldcg(q) - M);
+            S = fmaf(__ldcg(q + 1), f, S);
+            o = fmaf(__ldcg(part_o + ((grp * nch + c) * beam) * DH + i), f, o);
+        }
+        store_out(h, d, o / S);
     }
 }
 
@@ -301,28 +351,28 @@ extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* l
 // element (pos, row, head, d) at head*head_stride + (pos*R + row)*kv_ld + d; anc [2][R][lmax].
 // mode 1: cross-attention. q_in = q [R, 1024], kc/vc = this layer's cross K / V, element (frame, head, d) at
 // head*head_stride + frame*kv_ld + d.  out (fp32 [R,1024]) and/or out_split (bf16x3 [R, 6*1024]).
+// Scratch for the split over key chunks (nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64],
+// part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once by the caller (the kernel re-arms them).
+extern "C" int avsr_dec_attn_chunks(int max_keys) { return (max_keys + CK - 1) / CK; }
+
 extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
                                   const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step,
-                                  float* out, int max_keys, long long kv_ld, long long head_stride, void* out_split, cudaStream_t stream) {
+                                  float* out, int max_keys, long long kv_ld, long long head_stride, void* out_split, float* part_o,
+                                  float* part_ms, int* tickets, cudaStream_t stream) {
     AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && max_keys > 0, "avsr_dec_attn_step: bad arguments");
     AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
     AVSR_REQUIRE(beam <= MAXH && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max %d)", beam, MAXH);
-    const int smax = (max_keys + 3) & ~3;
-    const int nh = mode == 1 ? beam : 1;
-    const size_t smem = ((size_t)KT * KSTR + MAXH * DH + (size_t)nh * smax) * sizeof(float) + (mode == 0 ? (size_t)smax : 0);
-    AVSR_REQUIRE(smem <= 160 * 1024, "avsr_dec_attn_step: %d keys x %d hyps exceed shared memory", max_keys, nh);
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[mode]) {
-        if (mode == 0) AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        else AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured[mode] = 160 * 1024;
-    }
+    AVSR_REQUIRE((kv_ld & 3) == 0 && (head_stride & 3) == 0, "avsr_dec_attn_step: K/V rows must be 16-byte aligned");
+    const int nch = (max_keys + CK - 1) / CK;
+    AVSR_REQUIRE(nch == 1 || (part_o && part_ms && tickets), "avsr_dec_attn_step: %d keys need the chunk scratch buffers", max_keys);
+    AVSR_REQUIRE(nch <= 65535, "avsr_dec_attn_step: too many keys");
+    const dim3 grid(R / beam, HEADS, nch);
     if (mode == 0)
-        dec_attn_step_kernel<0><<<dim3(R, HEADS), 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out,
-                                                                      smax, kv_ld, head_stride, (__nv_bfloat16*)out_split);
+        dec_attn_step_kernel<0><<<grid, 128, 0, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, kv_ld,
+                                                          head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets);
     else
-        dec_attn_step_kernel<1><<<dim3(R / beam, HEADS), 128, smem, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step,
-                                                                             out, smax, kv_ld, head_stride, (__nv_bfloat16*)out_split);
+        dec_attn_step_kernel<1><<<grid, 128, 0, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, kv_ld,
+                                                          head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

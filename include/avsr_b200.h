@@ -133,9 +133,16 @@ int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_st
 /* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
                       const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
+/* One decode position of MultiHeadedAttention (transformer/attention.py:38-106) with cached K/V, split over chunks of
+ * keys: mode 0 = self-attention over the hypothesis' own history (found through the ancestry table `anc`, the current
+ * k/v are appended to kc/vc), mode 1 = source attention over the utterance's precomputed K/V.  Scratch (caller-owned,
+ * nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64] fp32, part_ms [R/beam][16][nch][beam][2] fp32,
+ * tickets [R/beam][16] int32 zeroed once. */
+int avsr_dec_attn_chunks(int max_keys);
 int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
                        const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step, float* out,
-                       int max_keys, long long kv_ld, long long head_stride, void* out_split, avsr_stream_t stream);
+                       int max_keys, long long kv_ld, long long head_stride, void* out_split, float* part_o, float* part_ms,
+                       int* tickets, avsr_stream_t stream);
 /* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span). */
 int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,

@@ -26,6 +26,15 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_cfg0():
+    """BASELINE.json configs[0]: one 15 s utterance (T=375), reference encoder output + reference n-best at beam 3 / 5
+    (oracle/gen_golden_cfg0.py)."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cfg0_T375.npz"))
+    return {k: g[k] for k in g.files}
+
+
+@pytest.fixture(scope="session")
 def golden_ctc():
     import numpy as np
     g = np.load(os.path.join(ROOT, "tests", "golden", "ctc_prefix.npz"))

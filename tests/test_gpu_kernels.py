@@ -243,3 +243,92 @@ def test_log_softmax_and_logits_topk(L):
         assert (logp[r] - want[r]).abs().max().item() < 1e-5
         assert ids[r].tolist() == torch.topk(want[r], S)[1].tolist()
     assert ids[5].tolist() == [-1] * S                       # dead row untouched
+
+
+@pytest.mark.parametrize("beam,step", [(3, 0), (3, 5), (3, 127), (3, 128), (5, 300), (3, 375), (8, 140)])
+def test_dec_attn_step_self(L, beam, step):
+    """Self-attention of one decode position over a random cache and a random ancestry table (decoder_layer.py:82-93,
+    attention.py:38-106 restated in torch fp32): chunked kernel incl. the multi-chunk merge and the k/v append."""
+    lib = L.load()
+    B, lmax = 4, 376
+    R = B * beam
+    g = torch.Generator().manual_seed(100 + step)
+    kc = torch.randn(16, lmax, R, 64, generator=g).cuda()
+    vc = torch.randn(16, lmax, R, 64, generator=g).cuda()
+    qkv = torch.randn(R, 3072, generator=g).cuda()
+    n_run = torch.tensor([beam, max(1, beam - 1), 0, 1][:B], dtype=torch.int32, device="cuda")
+    anc = torch.randint(0, beam, (2, R, lmax), generator=g, dtype=torch.uint8)
+    shared = max(0, step - 6)                           # old positions: all hyps of an utterance share one ancestor slot
+    anc[:, :, :shared] = anc[:, ::beam, :shared].repeat_interleave(beam, 1)
+    anc = anc.cuda()
+    step_t = torch.tensor([step], dtype=torch.int32, device="cuda")
+    nch = lib.avsr_dec_attn_chunks(lmax)
+    po = torch.empty(B, 16, nch, beam, 64, device="cuda")
+    pms = torch.empty(B, 16, nch, beam, 2, device="cuda")
+    tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
+    out = torch.full((R, 1024), 7.0, device="cuda")
+    out6 = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device="cuda")
+    kc0, vc0 = kc.clone(), vc.clone()
+    for _ in range(2):                                   # twice: the merge tickets must re-arm themselves
+        L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc), L.ptr(vc), L.ptr(anc), lmax, L.ptr(n_run), None, None, beam, R,
+                                       L.ptr(step_t), L.ptr(out), lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(out6), L.ptr(po), L.ptr(pms),
+                                       L.ptr(tick), L.stream()), "dec_attn_step(self)")
+    torch.cuda.synchronize()
+    assert tick.abs().sum().item() == 0
+    a = anc[step & 1].cpu().long()
+    for b in range(B):
+        for h in range(beam):
+            row = b * beam + h
+            if h >= int(n_run[b]):
+                assert (out[row] == 7.0).all()           # dead rows untouched
+                assert (kc[:, step, row] == kc0[:, step, row]).all()
+                continue
+            rows = torch.tensor([b * beam + int(a[row, p]) for p in range(step)] + [row], dtype=torch.long)
+            q = qkv[row, :1024].view(16, 64)
+            kcur, vcur = qkv[row, 1024:2048].view(16, 64), qkv[row, 2048:].view(16, 64)
+            assert torch.equal(kc[:, step, row], kcur) and torch.equal(vc[:, step, row], vcur)
+            K = torch.cat([kc0[:, torch.arange(step), rows[:-1]], kcur[:, None]], 1)          # [16, step+1, 64]
+            Vv = torch.cat([vc0[:, torch.arange(step), rows[:-1]], vcur[:, None]], 1)
+            att = torch.softmax(torch.einsum("hd,hpd->hp", q, K) / 8.0, -1)
+            want = torch.einsum("hp,hpd->hd", att, Vv).reshape(1024)
+            assert (out[row] - want).abs().max().item() < 2e-5, (b, h)
+            o6 = out6[row].float().view(6, 1024)
+            assert (o6[0] + o6[2] + o6[5] - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("beam,lengths", [(3, [375, 12, 130, 257]), (5, [128, 129, 1, 375])])
+def test_dec_attn_step_cross(L, beam, lengths):
+    """Source attention of one decode position: every live hyp of an utterance attends over that utterance's frames."""
+    lib = L.load()
+    B, tmax, Fr = len(lengths), max(lengths), sum(lengths)
+    R = B * beam
+    g = torch.Generator().manual_seed(7)
+    kc = torch.randn(16, Fr, 64, generator=g).cuda()
+    vc = torch.randn(16, Fr, 64, generator=g).cuda()
+    q = torch.randn(R, 1024, generator=g).cuda()
+    n_run = torch.tensor([beam, 1, 0, beam - 1][:B], dtype=torch.int32, device="cuda")
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
+    utt_off = torch.from_numpy(offs).cuda()
+    utt_T = torch.tensor(lengths, dtype=torch.int32, device="cuda")
+    step_t = torch.tensor([3], dtype=torch.int32, device="cuda")
+    nch = lib.avsr_dec_attn_chunks(tmax)
+    po = torch.empty(B, 16, nch, beam, 64, device="cuda")
+    pms = torch.empty(B, 16, nch, beam, 2, device="cuda")
+    tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
+    out = torch.full((R, 1024), 7.0, device="cuda")
+    for _ in range(2):
+        L.check(lib.avsr_dec_attn_step(1, L.ptr(q), L.ll(1024), L.ptr(kc), L.ptr(vc), None, tmax + 1, L.ptr(n_run), L.ptr(utt_off),
+                                       L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), tmax, L.ll(64), L.ll(Fr * 64), None, L.ptr(po),
+                                       L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(src)")
+    torch.cuda.synchronize()
+    assert tick.abs().sum().item() == 0
+    for b in range(B):
+        K, Vv = kc[:, offs[b]:offs[b] + lengths[b]], vc[:, offs[b]:offs[b] + lengths[b]]
+        for h in range(beam):
+            row = b * beam + h
+            if h >= int(n_run[b]):
+                assert (out[row] == 7.0).all()
+                continue
+            att = torch.softmax(torch.einsum("hd,hpd->hp", q[row].view(16, 64), K) / 8.0, -1)
+            want = torch.einsum("hp,hpd->hd", att, Vv).reshape(1024)
+            assert (out[row] - want).abs().max().item() < 2e-5, (b, h)

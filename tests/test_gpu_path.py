@@ -71,6 +71,25 @@ def test_beam_search_vs_reference_golden(state_dict, gpu_model, golden, T, beam,
     assert isinstance(d["yseq"], list) and isinstance(d["score"], float) and set(d["scores"]) == {"decoder", "ctc"}
 
 
+@pytest.mark.parametrize("beam", [3, 5])
+def test_beam_search_vs_reference_cfg0_T375(gpu_model, golden_cfg0, beam):
+    """BASELINE.json configs[0] at full size: T=375 frames, decode from the reference's encoder output, n-best
+    token-identical to the reference's BatchBeamSearch at beam 3 and 5 (377-token hypotheses)."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    g = golden_cfg0
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam)
+    nbest = bs(torch.from_numpy(g["enc"]).cuda())
+    score = g[f"nbest_b{beam}_score"]
+    n = int((score > -1e8).sum())
+    assert len(nbest) >= n >= beam
+    for k in range(n):
+        assert nbest[k].yseq.tolist() == g[f"nbest_b{beam}_yseq"][k].tolist(), (beam, k)
+        ln = len(g[f"nbest_b{beam}_yseq"][k])
+        assert abs(float(nbest[k].score) - score[k]) <= 1e-3 * ln
+        assert abs(float(nbest[k].scores["decoder"]) - g[f"nbest_b{beam}_dec"][k]) <= 1e-3 * ln
+        assert abs(float(nbest[k].scores["ctc"]) - g[f"nbest_b{beam}_ctc"][k]) <= 1e-2 * ln
+
+
 def test_batched_decode_equals_single_runs(gpu_model, golden):
     """Mixed-length batch: every utterance must evolve exactly as its own B=1 run."""
     from avsr_b200.beam_search import BatchedBeamSearch

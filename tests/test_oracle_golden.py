@@ -66,6 +66,19 @@ def test_beam_search_matches_reference_T30(state_dict, golden):
         _check_nbest(O.beam_search(state_dict, x, beam, kv_cache=True), golden, 30, beam)
 
 
+def test_beam_search_matches_reference_cfg0_T375(state_dict, golden_cfg0):
+    """configs[0] at full size (T=375, beam 3): the oracle reproduces the reference n-best token for token."""
+    g = golden_cfg0
+    assert np.array_equal(g["fingerprint"], np.array(__import__("avsr_b200.synth", fromlist=["x"]).fingerprint(state_dict)))
+    hyps = O.beam_search(state_dict, torch.from_numpy(g["enc"]), 3, kv_cache=True)
+    score = g["nbest_b3_score"]
+    n = int((score > -1e8).sum())
+    assert n == 3
+    for k in range(n):
+        assert hyps[k].yseq == g["nbest_b3_yseq"][k].tolist(), k
+        assert abs(hyps[k].score - score[k]) < 1e-3 * len(hyps[k].yseq)
+
+
 def test_ctc_prefix_matches_reference(golden_ctc):
     """Replays the golden CTCPrefixScoreTH call sequences (pre-beam + full-vocabulary, repeated-token, blank-in-pre-beam
     and eos cases) through the oracle."""

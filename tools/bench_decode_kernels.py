@@ -50,20 +50,24 @@ if len(sys.argv) > 2 and sys.argv[2] == 'shared':
 ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
 att = torch.empty(R, 1024, device=dev)
 att6 = torch.empty(R, 6144, device=dev, dtype=torch.bfloat16)
+nch = lib.avsr_dec_attn_chunks(lmax)
+po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch, beam, 2, device=dev)
+tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
+scr = (L.ptr(po), L.ptr(pms), L.ptr(tick))
 li = {"i": 0}
 
 
 def self_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run), L.ptr(utt_off),
-                                   L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), L.stream()), "self")
+                                   L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), *scr, L.stream()), "self")
 
 
 def cross_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
                                    L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(64), L.ll(B * T * 64),
-                                   L.ptr(att6), L.stream()), "cross")
+                                   L.ptr(att6), *scr, L.stream()), "cross")
 
 
 print(f"step={step}  R={R}")
