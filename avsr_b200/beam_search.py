@@ -134,7 +134,8 @@ class BatchedBeamSearch:
             n_part = max(lib.avsr_sgemm_skinny_splits(R, n, k) * R * n for n, k in shapes)
         s["part"] = torch.empty(n_part, dtype=torch.float32, device=dev)
         # per-utterance precomputed tensors
-        s["logp"] = torch.empty(F, V, dtype=torch.float32, device=dev)
+        s["ldp"] = (V + 31) // 32 * 32              # posterior row pitch: 128-byte aligned rows (V = 5049 -> 5056)
+        s["logp"] = torch.zeros(F, s["ldp"], dtype=torch.float32, device=dev)
         s["ckv"] = torch.empty(F, nl * 2 * 1024, dtype=torch.float32, device=dev)
         # cross-attention K/V, head-major: [layer][k|v][head][frame][64] (one contiguous span per (utterance, head))
         s["ckv_t"] = torch.empty(nl, 2, 16, F, 64, dtype=torch.float32, device=dev)
@@ -239,7 +240,7 @@ class BatchedBeamSearch:
         L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
                                              L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
         # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
-        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
+        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, s["ldp"], w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
                                             beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
                                             L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
                 "avsr_ctc_prefix_prebeam")
@@ -260,12 +261,12 @@ class BatchedBeamSearch:
         if self.precision == "bf16x3":
             # fp32-accurate projections on the tensor cores: K' = 6 * 1024 (see weights.split3_weight)
             L.check(lib.avsr_split3(L.ptr(x_packed), L.ll(1024), L.ptr(s["x6"]), L.ll(F), 1024, L.stream()), "avsr_split3")
-            L.gemm_bf16(s["x6"], w.ctc_w6, F, V, 6144, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
+            L.gemm_bf16(s["x6"], w.ctc_w6, F, V, 6144, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
             L.gemm_bf16(s["x6"], w.ckv_w6, F, n, 6144, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         else:
-            L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=V))
+            L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
             L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
-        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(V), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
+        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
         L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), n, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)

@@ -21,7 +21,7 @@ __device__ __forceinline__ float lse2(float a, float b) {
 // r_buf [2][R*S][tmax][2] ping-pongs on step parity; rprev_idx[row] is the chain (in the "current" half) that the
 // surviving hypothesis inherited.  Outputs psi[row][s] (log prefix probability) and rsum_last[row] = r_sum[T-1].
 __global__ void __launch_bounds__(128)
-ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, const int* __restrict__ utt_off,
+ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int blank, const int* __restrict__ utt_off,
                           const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
                           const int* __restrict__ last_tok, const int* __restrict__ part_ids, const int* __restrict__ rprev_idx,
                           float* __restrict__ r_buf, int tmax, const int* __restrict__ step_p, float* __restrict__ psi,
@@ -33,7 +33,7 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
     if ((row % beam) >= n_run[utt]) return;
     const int step = *step_p;
     const int T = utt_T[utt];
-    const float* lp = logp + (long long)utt_off[utt] * V;
+    const float* lp = logp + (long long)utt_off[utt] * ldp;
     const int c = part_ids[row * S + s];
     const bool same = (c == last_tok[row]);
     const int cur = step & 1;
@@ -48,7 +48,7 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
     float cum = 0.f;                                           // step 0: running sum of blank log-probs
     float pn = LOGZERO, pb = LOGZERO;                          // previous-label chains at t-1
     if (step == 0) {
-        for (int u = 0; u < start; ++u) cum += lp[(long long)u * V + blank];
+        for (int u = 0; u < start; ++u) cum += lp[(long long)u * ldp + blank];
     }
     // The chain is serial in t, but its inputs are not: fetch them CH steps ahead (double-buffered registers) so that the
     // ~1 us global-load latency overlaps the logaddexp arithmetic instead of being paid once per time step.
@@ -60,8 +60,8 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
         for (int u = 0; u < CH; ++u) {
             const int t = t0 + u;
             if (t < T) {
-                xs[u] = __ldg(lp + (long long)t * V + c);
-                xbs[u] = __ldg(lp + (long long)t * V + blank);
+                xs[u] = __ldg(lp + (long long)t * ldp + c);
+                xbs[u] = __ldg(lp + (long long)t * ldp + blank);
                 if (step > 0) ps[u] = rp[t - 1];
             }
         }
@@ -96,7 +96,7 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
         if (step == 0) {
             // cum currently holds sum_{u<T} x[u,blank] only when the loop ran to T; recompute for clarity
             float cs = 0.f;
-            for (int u = 0; u < T; ++u) cs += lp[(long long)u * V + blank];
+            for (int u = 0; u < T; ++u) cs += lp[(long long)u * ldp + blank];
             en = LOGZERO; eb = cs;
         } else {
             const float2 v = rp[T - 1];
@@ -107,78 +107,252 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int blank, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Full-vocabulary mode (scoring_ids=None, ctc_prefix_score.py:115-119): one thread per token column scores every live
-// hypothesis of its utterance, so each log-posterior row is read from HBM once (coalesced) and shared by all hyps.
-// The previous-label chains and r_sum are staged in shared memory per CTA.  Writes only scores[row][V]
-// (= log_psi - s_prev); survivor chains are recomputed by the pre-beam kernel on the chosen tokens.
+// Full-vocabulary mode (scoring_ids=None, ctc_prefix_score.py:115-119).  For every live hyp h and token c
+//     log_psi[h][c] = logsumexp( r[start-1,0][c], { log_phi[h][t-1](c) + x[t][c] : t = start .. T-1 } )
+// where log_phi[h][t] = r_sum[h][t] of the parent prefix, except for c == last token of h where it is the blank-ending
+// forward variable.  None of this depends on the NEW forward variables r[t][c] (they are only state for the next step
+// and are recomputed for the survivors by the pre-beam kernel), so the sum over t is a skinny matrix product
+//     Psi[h][c] = exp(M_h) * sum_t E[h][t-1] * P[t][c],   E[h][t] = exp(r_sum[h][t] - M_h),  P = exp(x),
+// with ONE exp per log-posterior shared by all hyps (the log-domain recursion needs ~5 MUFU ops per (t, hyp, token) and
+// is SFU-bound at ~11 % of HBM peak).  The log-posteriors are read from HBM exactly once, coalesced; E lives in shared
+// memory.  Cells the linear form cannot represent (c == last token, or a sum that underflows fp32) are re-evaluated
+// exactly in the log domain by a warp each, so every cell matches the reference to fp32 rounding.
+//
+// Work decomposition (HBM-bound streaming): the log-posteriors of an utterance are one dense [T][ldp] block whose rows are
+// 16-byte aligned (ldp % 4 == 0; the producer pads V = 5049 to 5056).  CTA = (utterance, group of FV_CG columns, time
+// split); a thread owns four consecutive columns, reads them with one 16-byte load per row and keeps 2 x FV_UT rows in
+// flight (a form with 4-byte loads of 5 strided columns had too few bytes in flight per SM and stalled at 45 % of HBM
+// peak; before that, ~27 instructions per posterior made it issue-bound at 37 %).  The sums for up to FV_NHP hyps live in
+// registers.  With more than one time split the partial sums are published and the last CTA of a (utterance, column
+// group) to finish (ticket) adds them in split order, takes the logarithm and writes the scores.
 constexpr int FV_MAXH = 8;
-__global__ void __launch_bounds__(128)
-ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int blank, int eos, const int* __restrict__ utt_off,
+constexpr int FV_THREADS = 256;
+constexpr int FV_CG = FV_THREADS * 4;     // columns per group
+constexpr int FV_UT = 8;                  // rows per batch (two batches in flight)
+constexpr int FV_NHP = 5;                 // hyps accumulated per pass over the block (beam <= 5: the block is read once)
+constexpr int FV_ES = 8;                  // row stride of the E table in shared memory (floats): one or two 16-byte reads per row
+constexpr int FV_NSPECIAL = 1024;
+constexpr float FV_TINY = 1e-30f;
+
+// rows t .. t+FV_UT-1 of this thread's four columns; rows past the end are clamped (their weight is skipped by the consumer)
+__device__ __forceinline__ void fv_load(const float* __restrict__ lpc, int ldp, int t, int t_last, float4 (&x)[FV_UT]) {
+#pragma unroll
+    for (int u = 0; u < FV_UT; ++u) x[u] = __ldg(reinterpret_cast<const float4*>(lpc + (long long)min(t + u, t_last) * ldp));
+}
+
+template <int NH>
+__device__ __forceinline__ void fv_consume(const float* __restrict__ s_E, int t, int t_hi, const float4 (&x)[FV_UT], float (&acc)[4][FV_NHP]) {
+#pragma unroll
+    for (int u = 0; u < FV_UT; ++u) {
+        if (t + u < t_hi) {                          // uniform across the CTA
+            float ev[8];
+            const float4 e0 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES);
+            ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w;
+            if (NH > 4) {
+                const float4 e1 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES + 4);
+                ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
+            }
+            // ex2.approx(x * log2 e): relative error ~2^-21, far below the rounding of the fp32 sum itself
+            const float pr[4] = {__expf(x[u].x), __expf(x[u].y), __expf(x[u].z), __expf(x[u].w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int h = 0; h < NH; ++h) acc[k][h] = fmaf(ev[h], pr[k], acc[k][h]);
+        }
+    }
+}
+
+// acc[k][h] += sum_{t in [t_lo, t_hi)} E[h][t-1] * exp(x[t][c0 + k]); the next batch is requested before the current one is
+// consumed (two register buffers, loop unrolled by two so that no values are moved).
+template <int NH>
+__device__ __forceinline__ void fv_stream(const float* __restrict__ lpc, int ldp, int t_lo, int t_hi, const float* __restrict__ s_E,
+                                          float4 (&xa)[FV_UT], float (&acc)[4][FV_NHP]) {
+    const int t_last = t_hi - 1;
+    float4 xb[FV_UT];
+    for (int t = t_lo; t < t_hi; t += 2 * FV_UT) {
+        fv_load(lpc, ldp, t + FV_UT, t_last, xb);
+        fv_consume<NH>(s_E, t, t_hi, xa, acc);
+        fv_load(lpc, ldp, t + 2 * FV_UT, t_last, xa);
+        fv_consume<NH>(s_E, t + FV_UT, t_hi, xb, acc);
+    }
+}
+
+// exact log-domain value of one cell (the reference's formula): logsumexp over t of phi[t-1] + x[t][c], plus r[start-1,0]
+__device__ __forceinline__ float fv_exact_warp(const float* __restrict__ lp, int ldp, int c, int start, int T, const float* phi, int nh,
+                                               int h, float x0, int lane) {
+    float mx = x0;
+    for (int t = start + lane; t < T; t += 32) mx = fmaxf(mx, phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int t = start + lane; t < T; t += 32) sum += expf(phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c] - mx);
+    sum = warp_sum(sum);
+    return mx + logf(sum + expf(x0 - mx));
+}
+
+__global__ void __launch_bounds__(FV_THREADS, 2)
+ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank, int eos, const int* __restrict__ utt_off,
                        const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
                        const int* __restrict__ last_tok, const int* __restrict__ rprev_idx, const float* __restrict__ r_buf,
-                       int tmax, const int* __restrict__ step_p, const float* __restrict__ s_prev, float* __restrict__ scores) {
-    extern __shared__ float sm[];                   // [T][nh] phi_same (= rb_prev), [T][nh] r_sum
+                       int tmax, const int* __restrict__ step_p, const float* __restrict__ s_prev, float* __restrict__ scores,
+                       int ncg, int tsplit, float* __restrict__ part, int* __restrict__ tickets) {
+    extern __shared__ __align__(16) float sm[];     // s_E [T][FV_ES], s_rs [T][nh] (r_sum), s_pb [T][nh] (blank-ending)
+    __shared__ float s_M[FV_MAXH];
+    __shared__ float s_red[FV_THREADS / 32][FV_MAXH];
+    __shared__ int s_nspecial, s_last;
+    __shared__ int s_special[FV_NSPECIAL];
     const int utt = blockIdx.y;
+    const int cg = blockIdx.x % ncg, z = blockIdx.x / ncg;
     const int nh = n_run[utt];
-    if (nh == 0) return;
     const int step = *step_p;
     const int T = utt_T[utt];
-    const float* lp = logp + (long long)utt_off[utt] * V;
-    float* s_pb = sm;
-    float* s_rs = sm + (size_t)T * nh;
+    const long long uoff = utt_off[utt];
+    if (nh == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* lp = logp + uoff * ldp;
+    float* s_E = sm;
+    float* s_rs = sm + (size_t)T * FV_ES;
+    float* s_pb = s_rs + (size_t)T * nh;
     const int cur = step & 1;
-    for (int i = threadIdx.x; i < T * nh; i += blockDim.x) {
-        const int t = i / nh, h = i % nh;
-        float pn, pb;
-        if (step == 0) {
-            pn = LOGZERO;
-            float cs = 0.f;                         // cumulative blank log-prob (first call only; O(T^2/2) adds per CTA)
-            for (int u = 0; u <= t; ++u) cs += lp[(long long)u * V + blank];
-            pb = cs;
-        } else {
-            const float2 v = (reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + rprev_idx[utt * beam + h]) * tmax)[t];
-            pn = v.x; pb = v.y;
+    const int start = step > 1 ? step : 1;
+    const int per = (T - start + tsplit - 1) / tsplit;
+    const int t_lo = start + z * per, t_hi = min(T, t_lo + per);
+    if (tid == 0) s_nspecial = 0;
+    // this thread's columns c0 .. c0+3 (columns >= V lie in the row padding or are clamped; they are dropped at the end)
+    const int c0 = cg * FV_CG + 4 * tid;
+    const float* lpc = lp + min(c0, ldp - 4);
+    // ---- first batch of log-posteriors: requested now, consumed after the preamble below (its latency is hidden)
+    float4 xa[FV_UT];
+    if (t_lo < t_hi) fv_load(lpc, ldp, t_lo, t_hi - 1, xa);
+    // ---- parent forward variables -> r_sum, blank-ending part, per-hyp maximum over the time range that is used
+    if (step == 0) {
+        if (tid == 0) {                             // r_prev[:,1] = cumsum(x[:, blank]) (ctc_prefix_score.py:58-63), r_prev[:,0] = logzero
+            float cs = 0.f;
+            for (int t = 0; t < T; ++t) {
+                cs += lp[(long long)t * ldp + blank];
+                for (int h = 0; h < nh; ++h) { s_pb[t * nh + h] = cs; s_rs[t * nh + h] = lse2(LOGZERO, cs); }
+            }
         }
-        s_pb[i] = pb;
-        s_rs[i] = lse2(pn, pb);
+    } else {
+        for (int i = tid; i < T * nh; i += FV_THREADS) {
+            const int t = i / nh, h = i % nh;
+            const float2 v = (reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + rprev_idx[utt * beam + h]) * tmax)[t];
+            s_pb[i] = v.y;
+            s_rs[i] = lse2(v.x, v.y);
+        }
     }
     __syncthreads();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= V) return;
-    const int start = step > 1 ? step : 1;
-    float rn[FV_MAXH], rb[FV_MAXH], M[FV_MAXH], Ss[FV_MAXH];
-    int lastt[FV_MAXH];
-#pragma unroll
-    for (int h = 0; h < FV_MAXH; ++h) {
-        rn[h] = (step == 0) ? lp[c] : LOGZERO;
-        rb[h] = LOGZERO;
-        M[h] = rn[h];
-        Ss[h] = 1.f;
-        lastt[h] = h < nh ? last_tok[utt * beam + h] : -1;
+    for (int h = 0; h < nh; ++h) {
+        float mx = -INFINITY;
+        for (int t = start - 1 + tid; t <= T - 2; t += FV_THREADS) mx = fmaxf(mx, s_rs[t * nh + h]);
+        mx = warp_max(mx);
+        if (lane == 0) s_red[warp][h] = mx;
     }
-    for (int t = start; t < T; ++t) {
-        const float x = lp[(long long)t * V + c];
-        const float xb = lp[(long long)t * V + blank];
+    __syncthreads();
+    if (tid < nh) {
+        float mx = -INFINITY;
+        for (int w = 0; w < FV_THREADS / 32; ++w) mx = fmaxf(mx, s_red[w][tid]);
+        s_M[tid] = (mx == -INFINITY) ? 0.f : mx;    // T == 1: no recursion term at all
+    }
+    __syncthreads();
+
+    // ---- finalisation of one cell from its linear-domain sum `a` (all time splits added)
+    auto finish = [&](int h, int c, float a) {
+        const int row = utt * beam + h;
+        const float x0 = (step == 0) ? lp[c] : LOGZERO;          // r[start-1, 0]: x[0][c] for the empty prefix, else logzero
+        a += expf(x0 - s_M[h]);
+        if (c == last_tok[row] || !(a > FV_TINY) || !(a < 1e30f)) {
+            const int slot = atomicAdd(&s_nspecial, 1);          // exact log-domain evaluation by a warp below
+            if (slot < FV_NSPECIAL) { s_special[slot] = c * FV_MAXH + h; return; }
+            const float* phi = (c == last_tok[row]) ? s_pb : s_rs;   // list full (pathological input): this thread does it alone
+            float mx = x0;
+            for (int t = start; t < T; ++t) mx = fmaxf(mx, phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c]);
+            float sum = expf(x0 - mx);
+            for (int t = start; t < T; ++t) sum += expf(phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c] - mx);
+            float lpsi = mx + logf(sum);
+            if (c == eos) lpsi = s_rs[(T - 1) * nh + h];
+            if (c == blank) lpsi = LOGZERO;
+            scores[(long long)row * V + c] = lpsi - s_prev[row];
+            return;
+        }
+        float lpsi = s_M[h] + logf(a);
+        if (c == eos) lpsi = s_rs[(T - 1) * nh + h];
+        if (c == blank) lpsi = LOGZERO;
+        scores[(long long)row * V + c] = lpsi - s_prev[row];
+    };
+
+    // ---- main pass(es): stream this CTA's rows, FV_NHP hyps at a time
+    for (int h0 = 0; h0 < nh; h0 += FV_NHP) {
+        const int ng = min(FV_NHP, nh - h0);
+        float acc[4][FV_NHP];
 #pragma unroll
-        for (int h = 0; h < FV_MAXH; ++h) {
-            if (h < nh) {
-                const float phi = (c == lastt[h]) ? s_pb[(t - 1) * nh + h] : s_rs[(t - 1) * nh + h];
-                const float term = phi + x;
-                if (term > M[h]) { Ss[h] = Ss[h] * expf(M[h] - term) + 1.f; M[h] = term; }
-                else Ss[h] += expf(term - M[h]);
-                const float nrn = lse2(rn[h], phi) + x;
-                rb[h] = lse2(rn[h], rb[h]) + xb;
-                rn[h] = nrn;
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int h = 0; h < FV_NHP; ++h) acc[k][h] = 0.f;
+        if (h0 > 0) __syncthreads();                 // the previous pass is done with the table
+        for (int i = tid; i < T * FV_ES; i += FV_THREADS) {          // E table of this pass: hyp h0 + j in column j
+            const int t = i / FV_ES, j = i % FV_ES;
+            s_E[i] = j < ng ? expf(s_rs[t * nh + h0 + j] - s_M[h0 + j]) : 0.f;
+        }
+        __syncthreads();
+        if (h0 > 0 && t_lo < t_hi) fv_load(lpc, ldp, t_lo, t_hi - 1, xa);
+        if (c0 < V) {
+            switch (ng) {
+                case 1: fv_stream<1>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+                case 2: fv_stream<2>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+                case 3: fv_stream<3>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+                case 4: fv_stream<4>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+                default: fv_stream<5>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k;
+            if (c < V) {
+#pragma unroll
+                for (int h = 0; h < FV_NHP; ++h) {
+                    if (h < ng) {
+                        if (tsplit == 1) finish(h0 + h, c, acc[k][h]);
+                        else part[(((long long)utt * tsplit + z) * beam + h0 + h) * V + c] = acc[k][h];
+                    }
+                }
             }
         }
     }
+    if (tsplit > 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int tk = atomicAdd(&tickets[utt * ncg + cg], 1);
+            s_last = (tk == tsplit - 1) ? 1 : 0;
+            if (s_last) tickets[utt * ncg + cg] = 0;             // re-armed for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int h = 0; h < nh; ++h) {
 #pragma unroll
-    for (int h = 0; h < FV_MAXH; ++h) {
-        if (h < nh) {
-            float lpsi = M[h] + logf(Ss[h]);
-            if (c == eos) lpsi = s_rs[(T - 1) * nh + h];
-            if (c == blank) lpsi = LOGZERO;
-            scores[(long long)(utt * beam + h) * V + c] = lpsi - s_prev[utt * beam + h];
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                if (c < V) {
+                    float a = 0.f;
+                    for (int zz = 0; zz < tsplit; ++zz) a += __ldcg(part + (((long long)utt * tsplit + zz) * beam + h) * V + c);
+                    finish(h, c, a);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- exact path: one warp per special cell
+    const int nsp = min(s_nspecial, FV_NSPECIAL);
+    for (int i = warp; i < nsp; i += FV_THREADS / 32) {
+        const int cx = s_special[i] / FV_MAXH, h = s_special[i] % FV_MAXH;
+        const int row = utt * beam + h;
+        const float x0 = (step == 0) ? lp[cx] : LOGZERO;
+        float lpsi = fv_exact_warp(lp, ldp, cx, start, T, (cx == last_tok[row]) ? s_pb : s_rs, nh, h, x0, lane);
+        if (lane == 0) {
+            if (cx == eos) lpsi = s_rs[(T - 1) * nh + h];
+            if (cx == blank) lpsi = LOGZERO;
+            scores[(long long)row * V + cx] = lpsi - s_prev[row];
         }
     }
 }
@@ -355,29 +529,55 @@ __global__ void beam_step_advance_kernel(int* step, const int* n_run, int B, int
 
 }  // namespace
 
-extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int blank, const int* utt_off, const int* utt_T, const int* n_run,
+extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run,
                                        int beam, int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx,
                                        float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, cudaStream_t stream) {
     AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && part_ids && rprev_idx && r_buf && step && psi && rsum_last,
                  "avsr_ctc_prefix_prebeam: null argument");
-    AVSR_REQUIRE(R > 0 && S > 0 && beam > 0 && tmax > 0, "avsr_ctc_prefix_prebeam: bad sizes");
-    ctc_prefix_prebeam_kernel<<<cdiv((long long)R * S, 128), 128, 0, stream>>>(logp, V, blank, utt_off, utt_T, n_run, beam, R, S, last_tok,
+    AVSR_REQUIRE(R > 0 && S > 0 && beam > 0 && tmax > 0 && ldp >= V, "avsr_ctc_prefix_prebeam: bad sizes");
+    ctc_prefix_prebeam_kernel<<<cdiv((long long)R * S, 128), 128, 0, stream>>>(logp, V, ldp, blank, utt_off, utt_T, n_run, beam, R, S, last_tok,
                                                                              part_ids, rprev_idx, r_buf, tmax, step, psi, rsum_last);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }
 
-extern "C" int avsr_ctc_prefix_full(const float* logp, int V, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
+// Work split of the full-vocabulary kernel: *ncg column groups x *tsplit time splits per utterance, sized so that one wave of
+// CTAs (two per SM) covers the batch.  Scratch the caller provides: part [B][tsplit][beam][V] fp32 (unused if tsplit == 1),
+// tickets [B][ncg] int32 zeroed once.
+extern "C" int avsr_ctc_prefix_full_plan(int B, int V, int* ncg, int* tsplit) {
+    AVSR_REQUIRE(B > 0 && V > 0 && ncg && tsplit, "avsr_ctc_prefix_full_plan: bad arguments");
+    int sms = 0, dev = 0;
+    AVSR_CHECK_CUDA(cudaGetDevice(&dev));
+    AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *ncg = cdiv(V, FV_CG);
+    int ts = (2 * sms) / (B * *ncg);                 // two CTAs per SM, all resident at once
+    *tsplit = ts < 1 ? 1 : (ts > 16 ? 16 : ts);
+    return AVSR_OK;
+}
+
+extern "C" int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
                                     int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
-                                    const int* step, const float* s_prev, float* scores, cudaStream_t stream) {
+                                    const int* step, const float* s_prev, float* scores, float* part, int* tickets, cudaStream_t stream) {
     AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && rprev_idx && r_buf && step && s_prev && scores,
                  "avsr_ctc_prefix_full: null argument");
-    AVSR_REQUIRE(beam <= FV_MAXH, "avsr_ctc_prefix_full: beam %d exceeds %d", beam, FV_MAXH);
-    const size_t smem = (size_t)2 * tmax * beam * sizeof(float);
-    AVSR_REQUIRE(smem <= 48 * 1024, "avsr_ctc_prefix_full: T*beam too large for shared memory");
-    dim3 grid(cdiv(V, 128), B);
-    ctc_prefix_full_kernel<<<grid, 128, smem, stream>>>(logp, V, blank, eos, utt_off, utt_T, n_run, beam, B * beam, S, last_tok, rprev_idx,
-                                                       r_buf, tmax, step, s_prev, scores);
+    AVSR_REQUIRE(beam >= 1 && beam <= FV_MAXH, "avsr_ctc_prefix_full: beam %d exceeds %d", beam, FV_MAXH);
+    AVSR_REQUIRE(B > 0 && B <= 65535 && V > 0 && tmax > 0, "avsr_ctc_prefix_full: bad sizes");
+    AVSR_REQUIRE(ldp >= V && (ldp & 3) == 0 && (reinterpret_cast<uintptr_t>(logp) & 15) == 0,
+                 "avsr_ctc_prefix_full: posterior rows must be 16-byte aligned (pitch %d floats, base %p)", ldp, (const void*)logp);
+    int ncg = 0, tsplit = 0;
+    int rc = avsr_ctc_prefix_full_plan(B, V, &ncg, &tsplit);
+    if (rc != AVSR_OK) return rc;
+    AVSR_REQUIRE(tsplit == 1 || (part && tickets), "avsr_ctc_prefix_full: %d time splits need the scratch buffers", tsplit);
+    const size_t smem = ((size_t)tmax * FV_ES + (size_t)2 * tmax * beam) * sizeof(float);
+    AVSR_REQUIRE(smem <= 160 * 1024, "avsr_ctc_prefix_full: T*beam too large for shared memory");
+    static size_t configured = 0;
+    if (smem > 32 * 1024 && smem > configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = 160 * 1024;
+    }
+    dim3 grid(ncg * tsplit, B);
+    ctc_prefix_full_kernel<<<grid, FV_THREADS, smem, stream>>>(logp, V, ldp, blank, eos, utt_off, utt_T, n_run, beam, B * beam, S, last_tok,
+                                                               rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, tsplit, part, tickets);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

@@ -25,12 +25,18 @@ template <int BN>
 struct Cfg {
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (188 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int COLPAR_BYTES = 2 * 2 * BN * 4;        // per accumulator buffer: bias[BN] + prelu[BN] staged for the epilogue
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLPAR_BYTES;
 };
 
-__device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, int col0, int M, int N, const uint32_t (&r)[32]) {
+// One 32-column chunk of one accumulator row.  `cb` / `cp` point at this chunk's per-column bias / PReLU slopes staged in
+// shared memory by the epilogue warps BEFORE they wait for the accumulator (a global load here would expose a full memory
+// latency per chunk: with two epilogue warps per scheduler nothing hides it).  `rbias` is the per-row bias (bias_mode 2),
+// `res` the residual values of this chunk already in registers (has_res), both fetched ahead of use as well.
+__device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, int col0, int M, int N, const uint32_t (&r)[32],
+                                               const float* cb, const float* cp, float rbias, const float (&res)[32], bool has_res) {
     if (row >= M) return;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
@@ -39,48 +45,42 @@ __device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, 
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (ep.bias != nullptr) {
         if (ep.bias_mode == 2) {
-            const float b = ep.bias[row];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += b;
+            for (int j = 0; j < 32; ++j) v[j] += rbias;
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += __ldg(ep.bias + col0 + j);
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(cb + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
         }
     }
     if (ep.act != AVSR_ACT_NONE && !ep.act_after_residual) {
+        if (ep.act == AVSR_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float s = (ep.act == AVSR_ACT_PRELU && j < ncols) ? __ldg(ep.prelu + col0 + j) : 0.f;
-            v[j] = avsr_apply_act(v[j], ep.act, s);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        } else if (ep.act == AVSR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * cp[j];
         }
     }
-    if (ep.residual != nullptr) {
-        if (ep.res_dtype == 0) {
-            const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col0;
-            if (ncols == 32 && (ep.ldr & 3) == 0) {
+    if (has_res) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(rp + j);
-                    v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < ncols) v[j] += rp[j];
-            }
-        } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += __bfloat162float(rp[j]);
-        }
+        for (int j = 0; j < 32; ++j) v[j] += res[j];
     }
     if (ep.act != AVSR_ACT_NONE && ep.act_after_residual) {
+        if (ep.act == AVSR_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float s = (ep.act == AVSR_ACT_PRELU && j < ncols) ? __ldg(ep.prelu + col0 + j) : 0.f;
-            v[j] = avsr_apply_act(v[j], ep.act, s);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        } else if (ep.act == AVSR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * cp[j];
         }
     }
     if (ep.row_mask != nullptr && ep.row_mask[row] == 0) {
@@ -122,6 +122,46 @@ __device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, 
     }
 }
 
+// residual values of one 32-column chunk of one row -> registers (zero where out of range)
+__device__ __forceinline__ void load_residual(const AvsrEpilogue& ep, int row, int col0, int M, int N, float (&res)[32]) {
+    const int ncols = min(32, N - col0);
+    if (row >= M || ncols <= 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) res[j] = 0.f;
+        return;
+    }
+    if (ep.res_dtype == 0) {
+        const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col0;
+        if (ncols == 32 && (ep.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rp + j);
+                res[j] = t.x; res[j + 1] = t.y; res[j + 2] = t.z; res[j + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) res[j] = (j < ncols) ? rp[j] : 0.f;
+        }
+    } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + col0;
+        if (ncols == 32 && (ep.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(rp + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(h[q]);
+                    res[j + 2 * q] = f.x; res[j + 2 * q + 1] = f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) res[j] = (j < ncols) ? __bfloat162float(rp[j]) : 0.f;
+        }
+    }
+}
+
 constexpr int NUM_EPI_WARPS = 8;                    // two per TMEM lane quadrant, each taking half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
@@ -140,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* colpar = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256);       // [2 acc][bias BN | prelu BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
@@ -220,7 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
         const int half = (warp - 2) >> 2;               // which half of the tile's columns
+        const int etid = threadIdx.x - 64;              // 0 .. 32 * NUM_EPI_WARPS - 1
         constexpr int CHUNKS = BN / 32 / 2 > 0 ? BN / 32 / 2 : 1;
+        const bool col_bias = ep_in.bias != nullptr && ep_in.bias_mode != 2;
+        const bool has_prelu = ep_in.act == AVSR_ACT_PRELU && ep_in.prelu != nullptr;
+        const bool has_res = ep_in.residual != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -228,18 +273,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
             AvsrEpilogue ep = ep_in;
             if (splits > 1) ep.out_f32 = ep_in.out_f32 + (long long)z * M * ep_in.ld_f32;
+            const int row = m0 + quad * 32 + lane;
+            // ---- everything the epilogue needs from global memory is requested BEFORE waiting for the accumulator
+            float* cpar = colpar + acc * 2 * BN;
+            if (col_bias || has_prelu) {
+                for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) {
+                    const int col = n0 + i;
+                    if (col_bias) cpar[i] = col < N ? __ldg(ep_in.bias + col) : 0.f;
+                    if (has_prelu) cpar[BN + i] = col < N ? __ldg(ep_in.prelu + col) : 0.f;
+                }
+            }
+            const float rbias = (ep_in.bias != nullptr && ep_in.bias_mode == 2 && row < M) ? __ldg(ep_in.bias + row) : 0.f;
+            float res[32];
+            const int c_first = half * CHUNKS;
+            if (has_res && !(BN == 32 && half == 1)) load_residual(ep, row, n0 + c_first * 32, M, N, res);
+            if (col_bias || has_prelu) asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
             tc::mbar_wait(&tfull[acc], acc_phase);
             tc::tc_fence_after();
-            const int row = m0 + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
             for (int cc = 0; cc < CHUNKS; ++cc) {
-                const int c = half * CHUNKS + cc;
+                const int c = c_first + cc;
                 if (BN == 32 && half == 1) break;
                 uint32_t r[32];
                 tc::tmem_ld_32x32(taddr + c * 32, r);
+                float res_next[32];
+                const bool more = has_res && cc + 1 < CHUNKS;
+                if (more) load_residual(ep, row, n0 + (c + 1) * 32, M, N, res_next);      // in flight while this chunk is processed
                 tc::tmem_ld_wait();
-                epilogue_chunk(ep, row, n0 + c * 32, M, N, r);
+                epilogue_chunk(ep, row, n0 + c * 32, M, N, r, cpar + c * 32, cpar + BN + c * 32, rbias, res, has_res);
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) res[j] = res_next[j];
+                }
             }
             tc::tc_fence_before();
             __syncwarp();

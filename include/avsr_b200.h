@@ -147,13 +147,19 @@ int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, fl
 int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
                              int* part_ids, int S, avsr_stream_t stream);
-/* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes. */
-int avsr_ctc_prefix_prebeam(const float* logp, int V, int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam,
+/* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes.  logp = CTC
+ * log-posteriors [sum(T), V] with row pitch ldp floats (the full-vocabulary kernel needs ldp % 4 == 0 and a 16-byte
+ * aligned base: its rows are read with 16-byte loads). */
+int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam,
                             int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx, float* r_buf, int tmax,
                             const int* step, float* psi, float* rsum_last, avsr_stream_t stream);
-int avsr_ctc_prefix_full(const float* logp, int V, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
+/* Full-vocabulary mode.  avsr_ctc_prefix_full_plan gives the work split (*ncg column groups x *tsplit time splits per
+ * utterance); caller-owned scratch: part [B][tsplit][beam][V] fp32 (may be NULL when tsplit == 1), tickets [B][ncg] int32
+ * zeroed once. */
+int avsr_ctc_prefix_full_plan(int B, int V, int* ncg, int* tsplit);
+int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
                          int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
-                         const int* step, const float* s_prev, float* scores, avsr_stream_t stream);
+                         const int* step, const float* s_prev, float* scores, float* part, int* tickets, avsr_stream_t stream);
 /* BatchBeamSearch.search fusion + batch_beam top-k + post_process + end_detect
  * (src/nets/batch_beam_search.py:86-110,222-349; src/nets/e2e_asr_common.py:18-48). */
 int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,

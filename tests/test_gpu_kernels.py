@@ -332,3 +332,74 @@ def test_dec_attn_step_cross(L, beam, lengths):
             att = torch.softmax(torch.einsum("hd,hpd->hp", q[row].view(16, 64), K) / 8.0, -1)
             want = torch.einsum("hp,hpd->hd", att, Vv).reshape(1024)
             assert (out[row] - want).abs().max().item() < 2e-5, (b, h)
+
+
+@pytest.mark.parametrize("B,beam,V,step", [(1, 3, 5049, 2), (5, 5, 5049, 7), (80, 3, 700, 3), (3, 8, 2600, 1), (2, 3, 5049, 0)])
+def test_ctc_prefix_full_vs_torch(L, B, beam, V, step):
+    """Full-vocabulary CTC prefix scores (ctc_prefix_score.py:68-187 with scoring_ids=None) against the log-domain formula in
+    torch, for every split plan: B=1 (16 time splits), B=5 (14), B=80 (no split: scores straight from registers), beam 8 (two
+    passes over the block), step 0 (empty prefix)."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(B * 100 + beam)
+    lengths = [int(v) for v in torch.randint(20, 60, (B,), generator=g)]
+    tmax, Fr = max(lengths), sum(lengths)
+    ldp = (V + 3) // 4 * 4                                              # 16-byte aligned rows, padding filled with garbage
+    logp_p = torch.full((Fr, ldp), float("nan"))
+    logp_p[:, :V] = torch.log_softmax(torch.randn(Fr, V, generator=g) * 3.0, -1)
+    logp_p = logp_p.cuda()
+    logp = logp_p[:, :V]
+    offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
+    R = B * beam
+    n_run_l = [1 if step == 0 else 1 + (b % beam) for b in range(B)]
+    if B > 2:
+        n_run_l[1] = 0
+    blank, eos = 0, V - 1
+    r_buf = torch.full((2, R, tmax, 2), -1e10)
+    r_buf[step & 1] = -torch.rand(R, tmax, 2, generator=g) * 40.0 - torch.arange(tmax).view(1, tmax, 1) * 3.0
+    r_buf[step & 1, :, : max(0, step - 1)] = -1e10                      # a prefix of length L needs at least L frames
+    r_buf = r_buf.cuda()
+    last = torch.randint(1, V - 1, (R,), generator=g, dtype=torch.int32)
+    if step == 0:
+        last[:] = eos
+    s_prev = (-torch.rand(R, generator=g) * 50).cuda() if step else torch.zeros(R).cuda()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")
+    rprev = i32(list(range(R)))
+    scores = torch.full((R, V), 123.0, device="cuda")
+    ncg, ts = C.c_int(0), C.c_int(0)
+    L.check(lib.avsr_ctc_prefix_full_plan(B, V, C.byref(ncg), C.byref(ts)), "plan")
+    part = torch.empty(B, ts.value, beam, V, device="cuda")
+    tick = torch.zeros(B, ncg.value, dtype=torch.int32, device="cuda")
+    d_off, d_T, d_run, d_last, d_step = i32(offs), i32(lengths), i32(n_run_l), last.cuda(), i32([step])   # keep the buffers alive
+    L.check(lib.avsr_ctc_prefix_full(L.ptr(logp_p), V, ldp, blank, eos, L.ptr(d_off), L.ptr(d_T), L.ptr(d_run), beam, B, 1,
+                                     L.ptr(d_last), L.ptr(rprev), L.ptr(r_buf), tmax, L.ptr(d_step), L.ptr(s_prev),
+                                     L.ptr(scores), L.ptr(part), L.ptr(tick), L.stream()), "ctc_full")
+    torch.cuda.synchronize()
+    assert int(tick.abs().sum().item()) == 0
+    start = max(step, 1)
+    for b in range(B):
+        T = lengths[b]
+        x = logp[offs[b]:offs[b] + T].double().cpu()
+        for h in range(beam):
+            row = b * beam + h
+            if h >= n_run_l[b]:
+                assert (scores[row] == 123.0).all()
+                continue
+            if step == 0:
+                pn = torch.full((T,), -1e10, dtype=torch.float64)
+                pb = torch.cumsum(x[:, blank], 0)
+            else:
+                pn, pb = r_buf[step & 1, row, :T, 0].double().cpu(), r_buf[step & 1, row, :T, 1].double().cpu()
+            rs = torch.logaddexp(pn, pb)
+            phi = rs.unsqueeze(1).repeat(1, V)
+            phi[:, int(last[row])] = pb
+            terms = phi[start - 1:T - 1] + x[start:T]
+            x0 = x[0] if step == 0 else torch.full((V,), -1e10, dtype=torch.float64)
+            want = torch.logsumexp(torch.cat([terms, x0.unsqueeze(0)], 0), 0)
+            want[eos] = rs[T - 1]
+            want[blank] = -1e10
+            want = want - float(s_prev[row])
+            got = scores[row].double().cpu()
+            live = want > -1e9
+            err = (got[live] - want[live]).abs().max().item()
+            assert err < 2e-4, (b, h, err)
+            assert (got[~live] < -1e9).all()

@@ -150,7 +150,10 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
     for tag in ("small", "vocab"):
         T, V, n_h, S = [int(v) for v in g[f"{tag}_shape"]]
         gen = torch.Generator().manual_seed(77)
-        logp = torch.log_softmax(torch.randn(1, T, V, generator=gen) * 2.0, dim=-1)[0].cuda().contiguous()
+        ldp = (V + 3) // 4 * 4
+        logp = torch.zeros(T, ldp)
+        logp[:, :V] = torch.log_softmax(torch.randn(1, T, V, generator=gen) * 2.0, dim=-1)[0]
+        logp = logp.cuda()
         beam, R = n_h, n_h
         i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")
         utt_off, utt_T = i32([0]), i32([T])
@@ -171,7 +174,7 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
                     cand = g[f"{tag}_{mode}_cand{step}"]
                     part = torch.zeros(R, S, dtype=torch.int32, device="cuda")
                     part[:n_hyp] = torch.from_numpy(cand).int().cuda()
-                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S,
+                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, ldp, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S,
                                                         L.ptr(last_tok), L.ptr(part), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t),
                                                         L.ptr(psi), L.ptr(rsum), L.stream()), "prebeam")
                     psi_c, rsum_c, sp = psi.cpu().numpy(), rsum.cpu().numpy(), s_prev.cpu().numpy()
@@ -189,9 +192,16 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
                     s_prev = torch.tensor([p[1] for p in new_psi] + [0.0] * (R - len(new_psi)), device="cuda")
                 else:
                     scores = torch.zeros(R, V, device="cuda")
-                    L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, 1, 1,
-                                                     L.ptr(last_tok), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(s_prev),
-                                                     L.ptr(scores), L.stream()), "full")
+                    ncg, ts = C.c_int(0), C.c_int(0)
+                    L.check(lib.avsr_ctc_prefix_full_plan(1, V, C.byref(ncg), C.byref(ts)), "plan")
+                    assert ts.value == 16 and ncg.value == -(-V // 1024)           # one utterance: the time axis is split 16 ways
+                    fpart = torch.empty(1, ts.value, beam, V, device="cuda")
+                    ftick = torch.zeros(1, ncg.value, dtype=torch.int32, device="cuda")
+                    for _ in range(2):                                             # twice: the tickets must re-arm themselves
+                        L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, 1, 1,
+                                                         L.ptr(last_tok), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(s_prev),
+                                                         L.ptr(scores), L.ptr(fpart), L.ptr(ftick), L.stream()), "full")
+                    assert int(ftick.abs().sum().item()) == 0
                     got = scores[:n_hyp].cpu().numpy()
                     live = ref > -1e9
                     assert np.abs(got[live] - ref[live]).max() < 1e-3, (tag, mode, step)
@@ -202,7 +212,7 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
                     rp = i32([int(rprev[int(h)].item()) for h, _ in picks])
                     n_new = i32([len(picks)])
                     psi2 = torch.zeros(R, 1, device="cuda")
-                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_new), beam, R, 1,
+                    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, ldp, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_new), beam, R, 1,
                                                         L.ptr(rows_last), L.ptr(part), L.ptr(rp), L.ptr(r_buf), T, L.ptr(step_t),
                                                         L.ptr(psi2), L.ptr(rsum), L.stream()), "prebeam(recompute)")
                     sp_old = s_prev.cpu().numpy()

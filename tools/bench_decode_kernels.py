@@ -103,6 +103,6 @@ r_buf = torch.full((2, R * S, T, 2), -30.0, device=dev)
 rprev = i32([r * S for r in range(R)])
 psi, rsum = torch.empty(R, S, device=dev), torch.empty(R, device=dev)
 def ctc():
-    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S, L.ptr(last), L.ptr(part_ids),
+    L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S, L.ptr(last), L.ptr(part_ids),
                                         L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(psi), L.ptr(rsum), L.stream()), "ctc")
 print(f"ctc prebeam: {timeit(ctc):8.1f} us")

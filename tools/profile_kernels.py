@@ -1,0 +1,90 @@
+"""Dev aid for ncu: a few launches of the kernels the roofline names, at the bench workload's shapes (no timing claims).
+
+    python tools/profile_kernels.py [ctc] [attn] [gemm] [skinny]
+"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avsr_b200 import _lib as L
+from avsr_b200.beam_search import BatchedBeamSearch
+from avsr_b200.weights import split3_weight
+
+lib = L.load()
+dev = "cuda"
+which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "skinny"}
+B, beam, T, V = 32, 3, 375, 5049
+R = B * beam
+i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+flush = torch.empty(64 * 1024 * 1024, device=dev)
+n_run, utt_off, utt_T = i32([beam] * B), i32([b * T for b in range(B)]), i32([T] * B)
+step_t = i32([187])
+
+if "ctc" in which:
+    ldp = (V + 31) // 32 * 32
+    logp = torch.zeros(B * T, ldp, device=dev)
+    logp[:, :V] = torch.log_softmax(torch.randn(B * T, V, device=dev), -1)
+    last = i32([7] * R)
+    r_buf = torch.full((2, R, T, 2), -1e10, device=dev)
+    r_buf[..., 1] = -5.0
+    rprev, st2 = i32(list(range(R))), i32([2])
+    s_prev, scores = torch.zeros(R, device=dev), torch.empty(R, V, device=dev)
+    ncg, ts = C.c_int(0), C.c_int(0)
+    L.check(lib.avsr_ctc_prefix_full_plan(B, V, C.byref(ncg), C.byref(ts)), "plan")
+    fpart = torch.empty(B, ts.value, beam, V, device=dev)
+    ftick = torch.zeros(B, ncg.value, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        flush.zero_()
+        L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, B, 1, L.ptr(last),
+                                         L.ptr(rprev), L.ptr(r_buf), T, L.ptr(st2), L.ptr(s_prev), L.ptr(scores), L.ptr(fpart),
+                                         L.ptr(ftick), L.stream()), "ctc_full")
+    torch.cuda.synchronize()
+
+if "attn" in which:
+    lmax, nl = T + 1, 2
+    qkv, q2 = torch.randn(R, 3072, device=dev), torch.randn(R, 1024, device=dev)
+    kc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+    vc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+    anc = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
+    ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
+    att6 = torch.empty(R, 6144, device=dev, dtype=torch.bfloat16)
+    nch = lib.avsr_dec_attn_chunks(lmax)
+    po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch, beam, 2, device=dev)
+    tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
+    scr = (L.ptr(po), L.ptr(pms), L.ptr(tick))
+    for it in range(3):
+        l = it % nl
+        flush.zero_()
+        L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run), L.ptr(utt_off),
+                                       L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), *scr,
+                                       L.stream()), "self")
+        L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax, L.ptr(n_run), L.ptr(utt_off),
+                                       L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(64), L.ll(B * T * 64), L.ptr(att6), *scr,
+                                       L.stream()), "cross")
+    torch.cuda.synchronize()
+
+if "gemm" in which:
+    M, N, K = B * T, 4096, 1024
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.02).bfloat16()
+    bias = torch.randn(N, device=dev)
+    o16 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ep = L.make_epilogue(bias=bias, act=L.ACT_GELU, out_bf16=o16, ld_bf16=N)
+    for _ in range(3):
+        L.gemm_bf16(a, w, M, N, K, ep)
+    torch.cuda.synchronize()
+
+if "skinny" in which:
+    N, K = 3072, 1024
+    ws = [split3_weight(torch.randn(N, K, device=dev) * 0.02) for _ in range(3)]
+    a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
+    bn, ns = BatchedBeamSearch.tc_plan(R, N, 6 * K)
+    part = torch.empty(ns, R, N, device=dev)
+    for i in range(3):
+        flush.zero_()
+        L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(ws[i]), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn, L.stream()), "g")
+    torch.cuda.synchronize()
+print("ok")
