@@ -75,6 +75,7 @@ class BatchedBeamSearch:
         self.w_dec = float(np.float32(1.0 - ctc_weight))
         self.w_ctc = float(np.float32(ctc_weight))
         self.use_graph = use_graph
+        self.fuse_epilogue = False
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
         self.last_session = None
         self._sessions = {}
@@ -125,11 +126,17 @@ class BatchedBeamSearch:
         s["att_tickets"] = i32(B, 16)
         shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
         if self.precision == "bf16x3":
-            s["a6"] = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device=dev)
-            s["att6"] = torch.zeros(R, 6 * 1024, dtype=torch.bfloat16, device=dev)
-            s["ffn6"] = torch.zeros(R, 6 * 3072, dtype=torch.bfloat16, device=dev)
+            # activations of the step in compact bf16x3 form [a1|a2|a3] (operands of csrc/gemm_x3.cu)
+            s["a3"] = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device=dev)
+            s["att3"] = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device=dev)
+            s["ffn3"] = torch.zeros(R, 3 * 3072, dtype=torch.bfloat16, device=dev)
             s["x6"] = torch.empty(F, 6 * 1024, dtype=torch.bfloat16, device=dev)
-            n_part = max(self.tc_plan(R, n, 6 * k)[1] * R * n for n, k in shapes)
+            n_part = max(lib.avsr_gemm_x3_splits(R, n, k) * R * n for n, k in shapes)
+            s["gbar"] = torch.zeros(2, dtype=torch.int32, device=dev)          # grid-barrier state of the fused projections
+            # the fused form needs one CTA per work item, all resident: tiles x splits <= SMs (true up to R = 128 rows)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            s["fused_ok"] = {(n, k): (-(-n // 128)) * (-(-R // 128)) * lib.avsr_gemm_x3_splits(R, n, k) <= sms and R <= 128
+                             for n, k in shapes}
         else:
             n_part = max(lib.avsr_sgemm_skinny_splits(R, n, k) * R * n for n, k in shapes)
         s["part"] = torch.empty(n_part, dtype=torch.float32, device=dev)
@@ -153,27 +160,14 @@ class BatchedBeamSearch:
         return s
 
     # ------------------------------------------------------------------------------------------ one decode step
-    @staticmethod
-    def tc_plan(R: int, N: int, K6: int):
-        """(bn, splits) of the split-K tensor-core GEMM for a skinny [R, K6] x [N, K6]^T product: enough work items to put
-        every SM on the weight stream, at least two 64-wide k-blocks per item."""
-        bn = 64 if N <= 1024 else 128
-        tiles = -(-R // 128) * -(-N // bn)
-        num_kb = K6 // 64
-        splits = max(1, min(num_kb // 2, 148 // tiles))        # tiles * splits <= 148: one work item per SM, one wave
-        while splits > 1 and (splits - 1) * -(-num_kb // splits) >= num_kb:
-            splits -= 1
-        return bn, splits
-
     def _proj(self, s, key_a, lay, name, N, K):
         """partial sums of act[R,K] @ W[N,K]^T into s['part']; returns the number of K splits."""
         lib = L.load()
         R = s["R"]
         if self.precision == "bf16x3":
-            bn, ns = self.tc_plan(R, N, 6 * K)
-            a6 = s[key_a + "6"]
-            L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(lay[name + "6"]), L.ll(6 * K), R, N, 6 * K,
-                                                 L.ptr(s["part"]), ns, bn, L.stream()), "avsr_gemm_bf16_tc_splitk")
+            ns = lib.avsr_gemm_x3_splits(R, N, K)
+            L.check(lib.avsr_gemm_x3_splitk(L.ptr(s[key_a + "3"]), L.ll(3 * K), L.ptr(lay[name + "3"]), L.ll(3 * K), R, N, K,
+                                            L.ptr(s["part"]), L.stream()), "avsr_gemm_x3_splitk")
         else:
             a = s[key_a]
             ns = lib.avsr_sgemm_skinny_splits(R, N, K)
@@ -181,17 +175,29 @@ class BatchedBeamSearch:
                     "avsr_sgemm_skinny")
         return ns
 
-    def _epi(self, s, ns, N, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, key_out=None):
-        """bias / act / residual / LayerNorm over the reduced partial sums; the result that feeds the next projection is
-        written as fp32 (s[key_out]) on the CUDA-core path or in bf16x3 layout (s[key_out + '6']) on the tensor-core path."""
+    def _linear(self, s, key_a, lay, name, N, K, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, key_out=None):
+        """One nn.Linear of the step plus its glue: act[R,K] @ W[N,K]^T + bias ; act ; + residual -> out ; LayerNorm -> the
+        operand of the next projection (fp32 s[key_out] on the CUDA-core path, compact bf16x3 s[key_out + '3'] on the
+        tensor-core path).  Split-K projection + row-wise epilogue kernel.  ``fuse_epilogue=True`` runs both in ONE launch
+        (projection, grid barrier, epilogue; avsr_gemm_x3_fused); it measured SLOWER on B200 (1.41 vs 1.19 ms per position):
+        two projection CTAs cannot share an SM (197 KB of shared memory each), so back-to-back fused projections lose the
+        weight prefetch that a programmatic dependent launch gets behind a small epilogue kernel."""
         lib = L.load()
+        R = s["R"]
         g, b = (ln if ln is not None else (None, None))
         tc = self.precision == "bf16x3"
         ln_out = s[key_out] if (key_out is not None and ln is not None and not tc) else None
         if key_out is not None and ln is None and not tc:
             out = s[key_out]
-        split = s[key_out + "6"] if (key_out is not None and tc) else None
-        L.check(lib.avsr_splitk_epilogue(L.ptr(s["part"]), ns, s["R"], N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
+        split = s[key_out + "3"] if (key_out is not None and tc) else None
+        if tc and self.fuse_epilogue and s["fused_ok"][(N, K)]:
+            L.check(lib.avsr_gemm_x3_fused(L.ptr(s[key_a + "3"]), L.ll(3 * K), L.ptr(lay[name + "3"]), L.ll(3 * K), R, N, K, L.ptr(s["part"]),
+                                           L.ptr(bias), act, L.ptr(residual), L.ll(1024), L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b),
+                                           C.c_float(1e-12), L.ptr(ln_out), L.ll(1024), L.ptr(s["row_active"]), L.ptr(split),
+                                           L.ptr(s["gbar"]), L.stream()), "avsr_gemm_x3_fused")
+            return
+        ns = self._proj(s, key_a, lay, name, N, K)
+        L.check(lib.avsr_splitk_epilogue(L.ptr(s["part"]), ns, R, N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
                                          L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(ln_out), L.ll(1024),
                                          L.ptr(s["row_active"]), L.ptr(split), L.stream()), "avsr_splitk_epilogue")
 
@@ -205,38 +211,32 @@ class BatchedBeamSearch:
         l0 = w.layers[0]
         L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
                                       L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]),
-                                      None if tc else L.ptr(s["a"]), L.ptr(s["a6"]) if tc else None, st()), "avsr_dec_embed_ln")
+                                      None if tc else L.ptr(s["a"]), L.ptr(s["a3"]) if tc else None, st()), "avsr_dec_embed_ln")
         nl = w.n_layers
         kvld = nl * 2 * 1024
         att_f32 = None if tc else L.ptr(s["att"])
-        att_split = L.ptr(s["att6"]) if tc else None
+        att_split = L.ptr(s["att3"]) if tc else None
         scratch = (L.ptr(s["att_po"]), L.ptr(s["att_pms"]), L.ptr(s["att_tickets"]))
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93)
-            ns = self._proj(s, "a", lay, "wqkv", 3072, 1024)
-            self._epi(s, ns, 3072, lay["bqkv"], out=s["qkv"])
+            self._linear(s, "a", lay, "wqkv", 3072, 1024, lay["bqkv"], out=s["qkv"])
             L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
                                            lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
                                            att_f32, lmax, L.ll(64), L.ll(lmax * R * 64), att_split, *scratch, st()), "avsr_dec_attn_step(self)")
-            ns = self._proj(s, "att", lay, "wo", 1024, 1024)
-            self._epi(s, ns, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
+            self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
-            ns = self._proj(s, "a", lay, "wq2", 1024, 1024)
-            self._epi(s, ns, 1024, lay["bq2"], out=s["q2"])
+            self._linear(s, "a", lay, "wq2", 1024, 1024, lay["bq2"], out=s["q2"])
             ck, cv = s["ckv_t"][li, 0], s["ckv_t"][li, 1]
             L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
                                            L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
                                            s["tmax"], L.ll(64), L.ll(s["F"] * 64), att_split, *scratch, st()), "avsr_dec_attn_step(src)")
-            ns = self._proj(s, "att", lay, "wo2", 1024, 1024)
-            self._epi(s, ns, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
+            self._linear(s, "att", lay, "wo2", 1024, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
-            ns = self._proj(s, "a", lay, "w1", 3072, 1024)
-            self._epi(s, ns, 3072, lay["b1"], act=L.ACT_RELU, key_out="ffn")
-            ns = self._proj(s, "ffn", lay, "w2", 1024, 3072)
+            self._linear(s, "a", lay, "w1", 3072, 1024, lay["b1"], act=L.ACT_RELU, key_out="ffn")
             nxt = (w.layers[li + 1]["n1_g"], w.layers[li + 1]["n1_b"]) if li + 1 < nl else (w.after_g, w.after_b)
-            self._epi(s, ns, 1024, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
+            self._linear(s, "ffn", lay, "w2", 1024, 3072, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
         # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
-        ns = self._proj(s, "a", {"out": w.out_w, "out6": w.out_w6}, "out", V, 1024)
+        ns = self._proj(s, "a", {"out": w.out_w, "out3": getattr(w, "out_w3", None)}, "out", V, 1024)
         L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
                                              L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
         # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
@@ -295,23 +295,28 @@ class BatchedBeamSearch:
         self._step(s)                                   # position 0 eagerly (also warms every kernel up)
         done_steps = 1
         if n_steps > 1:
+            chunk = self.POLL_EVERY
             if self.use_graph and s["graph"] is None:
                 torch.cuda.synchronize()
+                # ONE graph holds POLL_EVERY positions (every kernel reads the position and liveness from device memory), so
+                # the kernels of consecutive positions chain through programmatic dependent launch inside the graph and
+                # the host only replays + polls.  Capture runs no kernels; state is untouched.
                 g = torch.cuda.CUDAGraph()
-                # capture runs no kernels; state is untouched
                 n0 = L.launch_count
                 with torch.cuda.graph(g):
-                    self._step(s)
-                s["launches_per_step"] = L.launch_count - n0
+                    for _ in range(chunk):
+                        self._step(s)
+                s["launches_per_graph"] = L.launch_count - n0
                 L.launch_count = n0
                 s["graph"] = g
             while done_steps < n_steps:
-                n = min(self.POLL_EVERY, n_steps - done_steps)
-                for _ in range(n):
-                    if self.use_graph:
-                        s["graph"].replay()
-                        self.graph_launches += s["launches_per_step"]
-                    else:
+                n = min(chunk, n_steps - done_steps)
+                if self.use_graph and (n == chunk or max_steps is None):
+                    # a replay past the last position only runs no-op kernels (every utterance has n_run == 0 by then)
+                    s["graph"].replay()
+                    self.graph_launches += s["launches_per_graph"]
+                else:
+                    for _ in range(n):
                         self._step(s)
                 done_steps += n
                 if int(s["any_running"].item()) == 0:

@@ -40,6 +40,30 @@ void avsr_set_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL): the kernels of one decode position form a chain in which every kernel is
+// launched while its predecessor is still running; it may do work that does not depend on the predecessor (barrier /
+// TMEM set-up, weight prefetch) and must call pdl_wait() before it touches anything an earlier kernel of the chain wrote
+// or still reads.  Data written before the chain started (weights, cross-attention K/V, posteriors) needs no wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t avsr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -125,6 +149,30 @@ __device__ __forceinline__ void avsr_split3_store4(__nv_bfloat16* row_base, int 
     *reinterpret_cast<uint2*>(row_base + 2 * K + c) = u2;
     *reinterpret_cast<uint2*>(row_base + 4 * K + c) = u2;
     *reinterpret_cast<uint2*>(row_base + 5 * K + c) = u3;
+}
+
+// Compact form for the decoder step's own GEMM (csrc/gemm_x3.cu): row = [a1 | a2 | a3] (3 blocks of K); the six cross
+// terms are formed by six MMAs per k step instead of by repeating the terms along K.
+__device__ __forceinline__ void avsr_split3c_store(__nv_bfloat16* row_base, int K, int c, float v) {
+    const __nv_bfloat16 a1 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(a1);
+    const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+    row_base[c] = a1; row_base[K + c] = a2; row_base[2 * K + c] = a3;
+}
+__device__ __forceinline__ void avsr_split3c_store4(__nv_bfloat16* row_base, int K, int c, float4 v) {
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    __align__(8) __nv_bfloat16 t1[4], t2[4], t3[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t1[i] = __float2bfloat16_rn(in[i]);
+        const float r1 = in[i] - __bfloat162float(t1[i]);
+        t2[i] = __float2bfloat16_rn(r1);
+        t3[i] = __float2bfloat16_rn(r1 - __bfloat162float(t2[i]));
+    }
+    *reinterpret_cast<uint2*>(row_base + c) = *reinterpret_cast<const uint2*>(t1);
+    *reinterpret_cast<uint2*>(row_base + K + c) = *reinterpret_cast<const uint2*>(t2);
+    *reinterpret_cast<uint2*>(row_base + 2 * K + c) = *reinterpret_cast<const uint2*>(t3);
 }
 
 __device__ __forceinline__ float avsr_apply_act(float v, int act, float slope) {

@@ -27,6 +27,8 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int bl
                           float* __restrict__ r_buf, int tmax, const int* __restrict__ step_p, float* __restrict__ psi,
                           float* __restrict__ rsum_last) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (gid >= R * S) return;
     const int row = gid / S, s = gid % S;
     const int utt = row / beam;
@@ -385,6 +387,8 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     __shared__ int s_parent[MAXB];
     __shared__ int s_newcnt;
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int nrun = st.n_run[b];
     if (nrun == 0) return;
     const int beam = st.beam, V = st.V, S = st.S;
@@ -521,6 +525,8 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
 }
 
 __global__ void beam_step_advance_kernel(int* step, const int* n_run, int B, int* any_running) {
+    pdl_trigger();
+    pdl_wait();
     int live = 0;
     for (int b = 0; b < B; ++b) live += n_run[b] > 0;
     *any_running = live;
@@ -535,9 +541,8 @@ extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int bl
     AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && part_ids && rprev_idx && r_buf && step && psi && rsum_last,
                  "avsr_ctc_prefix_prebeam: null argument");
     AVSR_REQUIRE(R > 0 && S > 0 && beam > 0 && tmax > 0 && ldp >= V, "avsr_ctc_prefix_prebeam: bad sizes");
-    ctc_prefix_prebeam_kernel<<<cdiv((long long)R * S, 128), 128, 0, stream>>>(logp, V, ldp, blank, utt_off, utt_T, n_run, beam, R, S, last_tok,
-                                                                             part_ids, rprev_idx, r_buf, tmax, step, psi, rsum_last);
-    AVSR_LAUNCH_CHECK();
+    AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_prebeam_kernel, dim3(cdiv((long long)R * S, 128)), dim3(128), 0, stream, logp, V, ldp, blank, utt_off,
+                                    utt_T, n_run, beam, R, S, last_tok, part_ids, rprev_idx, r_buf, tmax, step, psi, rsum_last));
     return AVSR_OK;
 }
 
@@ -587,14 +592,13 @@ extern "C" int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float*
     AVSR_REQUIRE(st && dec_logp && part_ids && psi && rsum_last, "avsr_beam_fuse_topk_advance: null argument");
     AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0, "avsr_beam_fuse_topk_advance: beam %d unsupported (max %d)", st->beam, MAXB);
     AVSR_REQUIRE(st->beam <= 255, "avsr_beam_fuse_topk_advance: ancestry slots are 8-bit");
-    beam_fuse_topk_advance_kernel<<<st->B, 256, 0, stream>>>(*st, dec_logp, part_ids, psi, rsum_last, w_dec, w_ctc);
-    AVSR_LAUNCH_CHECK();
+    AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, part_ids, psi, rsum_last,
+                                    w_dec, w_ctc));
     return AVSR_OK;
 }
 
 extern "C" int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, cudaStream_t stream) {
     AVSR_REQUIRE(step && n_run && any_running && B > 0, "avsr_beam_step_advance: bad arguments");
-    beam_step_advance_kernel<<<1, 1, 0, stream>>>(step, n_run, B, any_running);
-    AVSR_LAUNCH_CHECK();
+    AVSR_CHECK_CUDA(avsr_launch_pdl(beam_step_advance_kernel, dim3(1), dim3(1), 0, stream, step, n_run, B, any_running));
     return AVSR_OK;
 }

@@ -22,6 +22,8 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
                     __nv_bfloat16* __restrict__ a_split) {
     __shared__ float red[32];
     const int row = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if ((row % beam) >= n_run[row / beam]) return;
     const int step = *step_p;
     const int c = threadIdx.x * 4;
@@ -38,7 +40,7 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
     const float4 y = make_float4(d0 * rstd * gg.x + bb.x, d1 * rstd * gg.y + bb.y, d2 * rstd * gg.z + bb.z, d3 * rstd * gg.w + bb.w);
     if (a) *reinterpret_cast<float4*>(a + (long long)row * D + c) = y;
     if (a_split) {
-        avsr_split3_store4(a_split + (long long)row * 6 * D, D, c, y);
+        avsr_split3c_store4(a_split + (long long)row * 3 * D, D, c, y);
     }
 }
 
@@ -74,21 +76,33 @@ dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* kc, f
     __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z, nch = gridDim.z;
-    // the three scalars are independent: issue their loads together instead of one round trip each
-    const int nh = n_run[utt];
-    const int step = *step_p;
+    const int row0 = utt * beam;
+    const int p0 = chunk * CK;
+    const int p = p0 + tid;
+    const float* kbase = kc + head * head_stride;
+    const float* vbase = vc + head * head_stride;
+    pdl_trigger();
+    // Cross-attention K / V, utt_T and utt_off were written before this chain of kernels started: the thread's K row is
+    // requested BEFORE waiting for the predecessor kernel (which produces q), so its HBM latency overlaps that kernel.
     const int T_utt = (MODE == 1) ? utt_T[utt] : 0;
     const long long uoff = (MODE == 1) ? (long long)utt_off[utt] : 0;
+    float kk[DH];
+    if (MODE == 1 && p < T_utt) {
+        const float4* src = reinterpret_cast<const float4*>(kbase + (uoff + p) * kv_ld);
+#pragma unroll
+        for (int j = 0; j < DH / 4; ++j) {
+            const float4 v = __ldg(src + j);
+            kk[4 * j] = v.x; kk[4 * j + 1] = v.y; kk[4 * j + 2] = v.z; kk[4 * j + 3] = v.w;
+        }
+    }
+    pdl_wait();
+    const int nh = n_run[utt];
+    const int step = *step_p;
     if (nh == 0) return;
     const int n = (MODE == 1) ? T_utt : step + 1;
     const int nact = (n + CK - 1) / CK;
     if (chunk >= nact) return;
-    const int row0 = utt * beam;
-    const int p0 = chunk * CK;
-    const int p = p0 + tid;
     const bool valid = p < n;
-    const float* kbase = kc + head * head_stride;
-    const float* vbase = vc + head * head_stride;
 
     for (int i = tid; i < nh * DH; i += 128) qs[i / DH][i % DH] = q_in[(long long)(row0 + i / DH) * ldq + head * DH + (i % DH)];
     if (MODE == 0) {
@@ -117,8 +131,7 @@ dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* kc, f
 
     // ---------------- pass 1: scores of this chunk's keys for every hyp
     {
-        float kk[DH];
-        int cur = -1;
+        int cur = (MODE == 1) ? 0 : -1;
         for (int h = 0; h < nh; ++h) {
             const int slot = (MODE == 1) ? 0 : (int)aslot[h][tid];
             if (valid && slot != cur) {
@@ -216,7 +229,7 @@ dec_attn_step_kernel(const float* __restrict__ q_in, long long ldq, float* kc, f
     auto store_out = [&](int h, int d, float v) {
         const long long row = row0 + h;
         if (out) out[row * D + head * DH + d] = v;
-        if (out_split) avsr_split3_store(out_split + row * 6 * D, D, head * DH + d, v);
+        if (out_split) avsr_split3c_store(out_split + row * 3 * D, D, head * DH + d, v);
     };
     if (nact == 1) {
         for (int i = tid; i < nh * DH; i += 128) {
@@ -267,6 +280,8 @@ dec_logits_lsm_topk_kernel(const float* __restrict__ part, int nsplit, int R, in
     __shared__ float red[32];
     __shared__ int redi[32];
     const int row = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if ((row % beam) >= n_run[row / beam]) return;
     float mx = -INFINITY;
     for (int c = threadIdx.x; c < V; c += blockDim.x) {
@@ -342,8 +357,8 @@ extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* l
                                  void* a_split, cudaStream_t stream) {
     AVSR_REQUIRE(emb && pe && last_tok && n_run && step && gamma && beta && x && (a || a_split) && R > 0 && beam > 0,
                  "avsr_dec_embed_ln: bad arguments");
-    dec_embed_ln_kernel<<<R, 256, 0, stream>>>(emb, pe, last_tok, n_run, beam, step, gamma, beta, eps, x, a, (__nv_bfloat16*)a_split);
-    AVSR_LAUNCH_CHECK();
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_embed_ln_kernel, dim3(R), dim3(256), 0, stream, emb, pe, last_tok, n_run, beam, step, gamma, beta, eps, x,
+                                    a, (__nv_bfloat16*)a_split));
     return AVSR_OK;
 }
 
@@ -368,12 +383,11 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, fl
     AVSR_REQUIRE(nch <= 65535, "avsr_dec_attn_step: too many keys");
     const dim3 grid(R / beam, HEADS, nch);
     if (mode == 0)
-        dec_attn_step_kernel<0><<<grid, 128, 0, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, kv_ld,
-                                                          head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets);
+        AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_step_kernel<0>, grid, dim3(128), 0, stream, q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T,
+                                        beam, R, step, out, kv_ld, head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets));
     else
-        dec_attn_step_kernel<1><<<grid, 128, 0, stream>>>(q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, kv_ld,
-                                                          head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets);
-    AVSR_LAUNCH_CHECK();
+        AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_step_kernel<1>, grid, dim3(128), 0, stream, q_in, ldq, kc, vc, anc, lmax, n_run, utt_off, utt_T,
+                                        beam, R, step, out, kv_ld, head_stride, (__nv_bfloat16*)out_split, part_o, part_ms, tickets));
     return AVSR_OK;
 }
 
@@ -381,8 +395,8 @@ extern "C" int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, in
                                         float* logp, int* part_ids, int S, cudaStream_t stream) {
     AVSR_REQUIRE(part && bias && n_run && logp && part_ids && R > 0 && V > 0 && S > 0 && S <= V, "avsr_dec_logits_lsm_topk: bad arguments");
     AVSR_REQUIRE((size_t)V * 4 <= 48 * 1024, "avsr_dec_logits_lsm_topk: vocabulary %d too large for the shared-memory row", V);
-    dec_logits_lsm_topk_kernel<<<R, 256, (size_t)V * 4, stream>>>(part, nsplit, R, V, bias, n_run, beam, logp, part_ids, S);
-    AVSR_LAUNCH_CHECK();
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_logits_lsm_topk_kernel, dim3(R), dim3(256), (size_t)V * 4, stream, part, nsplit, R, V, bias, n_run, beam,
+                                    logp, part_ids, S));
     return AVSR_OK;
 }
 

@@ -10,6 +10,7 @@
 // skinny per-step operands (M = utterances x beam <= ~192 rows), whose deterministic partial sums are combined by
 // avsr_splitk_epilogue (fixed summation order -> run-to-run identical tokens).
 #include "common.cuh"
+#include "splitk_epilogue.cuh"
 
 namespace {
 
@@ -140,100 +141,14 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
     }
 }
 
-// One CTA per output row: v = sum_z part[z][row][:] + bias ; act ; + residual -> out (fp32);
-// optionally a LayerNorm of the finished row -> ln_out (fp32), which is the input of the next projection.
+// One CTA per output row (see splitk_epilogue.cuh).
 __global__ void __launch_bounds__(256)
-splitk_epilogue_kernel(const float* __restrict__ part, int nsplit, int M, int N, const float* __restrict__ bias, int act,
-                       const float* residual, long long ldr, float* out, long long ldo,   /* may alias (in-place) */
-                       const float* __restrict__ ln_g, const float* __restrict__ ln_b, float ln_eps, float* __restrict__ ln_out,
-                       long long ld_ln, const int* __restrict__ row_active, __nv_bfloat16* __restrict__ split_out) {
+splitk_epilogue_kernel(const SplitKEpi e) {
     extern __shared__ float rowbuf[];
     __shared__ float red[32];
-    const int row = blockIdx.x;
-    if (row_active != nullptr && row_active[row] == 0) return;
-    float lsum = 0.f;
-    const long long zstride = (long long)M * N;
-    if ((N & 3) == 0 && (ldr & 3) == 0 && (ldo & 3) == 0) {
-        // vector path: 4 columns per thread, the nsplit partial loads of a column group are issued 4 at a time
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
-            const float* p = part + (long long)row * N + c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            int z = 0;
-            for (; z + 4 <= nsplit; z += 4) {
-                const float4 a0 = *reinterpret_cast<const float4*>(p + (z + 0) * zstride);
-                const float4 a1 = *reinterpret_cast<const float4*>(p + (z + 1) * zstride);
-                const float4 a2 = *reinterpret_cast<const float4*>(p + (z + 2) * zstride);
-                const float4 a3 = *reinterpret_cast<const float4*>(p + (z + 3) * zstride);
-                v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
-                v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
-                v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
-                v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
-            }
-            for (; z < nsplit; ++z) {
-                const float4 a0 = *reinterpret_cast<const float4*>(p + z * zstride);
-                v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
-            }
-            if (bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + c);
-                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            }
-            if (act == AVSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            else if (act == AVSR_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-            if (residual) {
-                const float4 r4 = *reinterpret_cast<const float4*>(residual + (long long)row * ldr + c);
-                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-            }
-            if (out) *reinterpret_cast<float4*>(out + (long long)row * ldo + c) = v;
-            if (ln_g) { *reinterpret_cast<float4*>(rowbuf + c) = v; lsum += (v.x + v.y) + (v.z + v.w); }
-            else if (split_out) avsr_split3_store4(split_out + (long long)row * 6 * N, N, c, v);
-        }
-        if (ln_g == nullptr) return;
-        // LayerNorm of the finished row (values of this thread's columns are still in rowbuf; same thread re-reads them)
-        const float mean = block_sum(lsum, red) / (float)N;
-        float lvar = 0.f;
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
-            const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
-            const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
-            lvar += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        }
-        const float rstd = rsqrtf(block_sum(lvar, red) / (float)N + ln_eps);
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
-            const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
-            const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c);
-            const float4 b4 = *reinterpret_cast<const float4*>(ln_b + c);
-            const float4 y = make_float4((t.x - mean) * rstd * g4.x + b4.x, (t.y - mean) * rstd * g4.y + b4.y,
-                                         (t.z - mean) * rstd * g4.z + b4.z, (t.w - mean) * rstd * g4.w + b4.w);
-            if (ln_out) *reinterpret_cast<float4*>(ln_out + (long long)row * ld_ln + c) = y;
-            if (split_out) avsr_split3_store4(split_out + (long long)row * 6 * N, N, c, y);
-        }
-        return;
-    } else {
-        for (int c = threadIdx.x; c < N; c += blockDim.x) {
-            float v = 0.f;
-            for (int z = 0; z < nsplit; ++z) v += part[z * zstride + (long long)row * N + c];
-            if (bias) v += bias[c];
-            if (act == AVSR_ACT_RELU) v = fmaxf(v, 0.f);
-            else if (act == AVSR_ACT_GELU) v = gelu_erf(v);
-            if (residual) v += residual[(long long)row * ldr + c];
-            if (out) out[(long long)row * ldo + c] = v;
-            if (ln_g) { rowbuf[c] = v; lsum += v; }
-            else if (split_out) avsr_split3_store(split_out + (long long)row * 6 * N, N, c, v);
-        }
-    }
-    if (ln_g == nullptr) return;
-    const float mean = block_sum(lsum, red) / (float)N;
-    float lvar = 0.f;
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        const float d = rowbuf[c] - mean;
-        lvar += d * d;
-    }
-    const float var = block_sum(lvar, red) / (float)N;
-    const float rstd = rsqrtf(var + ln_eps);
-    for (int c = threadIdx.x; c < N; c += blockDim.x) {
-        const float y = (rowbuf[c] - mean) * rstd * ln_g[c] + ln_b[c];
-        if (ln_out) ln_out[(long long)row * ld_ln + c] = y;
-        if (split_out) avsr_split3_store(split_out + (long long)row * 6 * N, N, c, y);
-    }
+    pdl_trigger();
+    pdl_wait();
+    avsr_splitk_epilogue_row(e, blockIdx.x, rowbuf, red);
 }
 
 int g_sms = 0;
@@ -293,8 +208,7 @@ extern "C" int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N,
     AVSR_REQUIRE(!ln_out || ln_g, "avsr_splitk_epilogue: ln_out needs gamma/beta");
     AVSR_REQUIRE(!ln_g || (ln_b && N * 4 <= 48 * 1024), "avsr_splitk_epilogue: LayerNorm needs gamma/beta and N <= 12288");
     const size_t smem = ln_g ? (size_t)N * 4 : 0;
-    splitk_epilogue_kernel<<<M, 256, smem, stream>>>(part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps,
-                                                     ln_out, ld_ln, row_active, (__nv_bfloat16*)split_out);
-    AVSR_LAUNCH_CHECK();
+    SplitKEpi e = {part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps, ln_out, ld_ln, row_active, (__nv_bfloat16*)split_out};
+    AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel, dim3(M), dim3(256), smem, stream, e));
     return AVSR_OK;
 }

@@ -126,6 +126,17 @@ def split3_weight(w: torch.Tensor) -> torch.Tensor:
     return torch.cat([w1, w2, w1, w3, w2, w1], dim=1).contiguous()
 
 
+def split3_weight_compact(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [N,K] -> bf16 [N,3K] = [w1|w2|w3] (w = w1+w2+w3): operand of the decoder step's own GEMM (csrc/gemm_x3.cu), which
+    forms the six cross terms with six MMAs per k step, so a weight is streamed from HBM as 6 bytes instead of 12."""
+    w = w.float()
+    w1 = w.bfloat16()
+    r = w - w1.float()
+    w2 = r.bfloat16()
+    w3 = (r - w2.float()).bfloat16()
+    return torch.cat([w1, w2, w3], dim=1).contiguous()
+
+
 class DecoderWeights:
     """Operands of the 6-layer transformer decoder + CTC head: fp32 (CUDA-core path) and bf16x3 (tensor-core path)."""
 
@@ -178,7 +189,7 @@ class DecoderWeights:
         # bf16x3 operands for the tensor-core decode path
         for lay in self.layers:
             for k in ("wqkv", "wo", "wq2", "wo2", "w1", "w2"):
-                lay[k + "6"] = split3_weight(lay[k])
-        self.out_w6 = split3_weight(self.out_w)
-        self.ctc_w6 = split3_weight(self.ctc_w)
+                lay[k + "3"] = split3_weight_compact(lay[k])            # per-position projections (gemm_x3)
+        self.out_w3 = split3_weight_compact(self.out_w)
+        self.ctc_w6 = split3_weight(self.ctc_w)                         # once-per-utterance projections (generic GEMM, K' = 6K)
         self.ckv_w6 = split3_weight(self.ckv_w)

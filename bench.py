@@ -168,22 +168,21 @@ def _kernel_rooflines(model, peaks):
     # (1) decode-step skinny fp32 GEMM (dominant kernel of the step): FFN w_1 [3072,1024], R = 96 rows, cycling over the 6
     #     layers' weights so that they stream from HBM as in the real step (373 MB of decoder weights > L2)
     #     Algorithmic bytes per launch = fp32 weight matrix + activations + output = 4*(N*K + R*K + R*N);
-    #     the bf16x3 operand layout actually streams 12 B per weight, which is what `frac` is charged for.
+    #     the compact bf16x3 operands actually stream 6 B per weight, which is what `frac` is charged for.
     R, N, K = BATCH * BEAM, 3072, 1024
     state = {"i": 0}
     byts = 4.0 * (N * K + R * K + R * N)
     if model.beam_search.precision == "bf16x3":
-        bn, ns = model.beam_search.tc_plan(R, N, 6 * K)
-        a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
+        ns = lib.avsr_gemm_x3_splits(R, N, K)
+        a3 = torch.randn(R, 3 * K, device=dev).bfloat16()
         part = torch.empty(ns * R * N, device=dev)
-        ws = [l["w16"] for l in model.decoder_weights.layers] + [l["wqkv6"] for l in model.decoder_weights.layers]
+        ws = [l["w13"] for l in model.decoder_weights.layers] + [l["wqkv3"] for l in model.decoder_weights.layers]
 
         def skinny():
             w = ws[state["i"] % len(ws)]
             state["i"] += 1
-            L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(w), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn,
-                                                 L.stream()), "tc splitk")
-        kname = f"gemm_tc_kernel<{bn}> split-K {ns}, bf16x3 operands (decoder step projections)"
+            L.check(lib.avsr_gemm_x3_splitk(L.ptr(a3), L.ll(3 * K), L.ptr(w), L.ll(3 * K), R, N, K, L.ptr(part), L.stream()), "gemm_x3")
+        kname = f"gemm_x3_kernel split-K {ns}, compact bf16x3 operands, 6 MMAs per k step (decoder step projections)"
     else:
         a = torch.randn(R, K, device=dev)
         ns = lib.avsr_sgemm_skinny_splits(R, N, K)

@@ -96,6 +96,20 @@ int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb
  * fp32-accurate decoder projections on the tensor cores (src/nets/backend/transformer/decoder_layer.py:58-121). */
 int avsr_gemm_bf16_tc_splitk(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, float* part,
                              int splits, int bn_hint, avsr_stream_t stream);
+/* Decoder-step projections, compact bf16x3 form: part[z][R][N] (fp32, z < avsr_gemm_x3_splits) = A3 * W3^T restricted to
+ * the z-th K range, A3 = [a1|a2|a3] ([R, 3K] bf16), W3 = [w1|w2|w3] ([N, 3K] bf16), six MMAs per k step (fp32-level
+ * accuracy, 6 bytes per weight streamed).  Launched with programmatic dependent launch: the weight tiles are requested
+ * while the kernel producing A3 is still running.  K % 64 == 0. */
+int avsr_gemm_x3_splits(int R, int N, int K);
+int avsr_gemm_x3_splitk(const void* A3, long long lda, const void* W3, long long ldw, int R, int N, int K, float* part,
+                        avsr_stream_t stream);
+/* The same projection followed IN THE SAME LAUNCH (grid-wide barrier) by its row-wise epilogue, arguments as
+ * avsr_splitk_epilogue; gbar = two zero-initialised uint32 (barrier state, reusable by every launch on the stream).
+ * Needs tiles * splits <= number of SMs (one CTA per work item, all resident). */
+int avsr_gemm_x3_fused(const void* A3, long long lda, const void* W3, long long ldw, int R, int N, int K, float* part,
+                       const float* bias, int act, const float* residual, long long ldr, float* out, long long ldo,
+                       const float* ln_g, const float* ln_b, float ln_eps, float* ln_out, long long ld_ln,
+                       const int* row_active, void* split_out, unsigned* gbar, avsr_stream_t stream);
 /* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
 int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */

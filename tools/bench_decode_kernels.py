@@ -8,7 +8,7 @@ import torch
 
 from avsr_b200 import _lib as L
 from avsr_b200.beam_search import BatchedBeamSearch
-from avsr_b200.weights import split3_weight
+from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
@@ -49,7 +49,7 @@ if len(sys.argv) > 2 and sys.argv[2] == 'shared':
     anc.zero_()          # all hyps of an utterance descend from slot 0 (converged beam): physical rows are shared
 ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
 att = torch.empty(R, 1024, device=dev)
-att6 = torch.empty(R, 6144, device=dev, dtype=torch.bfloat16)
+att6 = torch.empty(R, 3072, device=dev, dtype=torch.bfloat16)
 nch = lib.avsr_dec_attn_chunks(lmax)
 po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch, beam, 2, device=dev)
 tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
@@ -76,20 +76,20 @@ print(f"cross-attn : {timeit(cross_attn):8.1f} us   (K/V bytes per launch {B*T*2
 
 # split-K tensor-core projections (weights cycled so they stream from HBM)
 for (N, K) in ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024)):
-    ws = [split3_weight(torch.randn(N, K, device=dev) * 0.02) for _ in range(8)]
-    a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
-    bn, ns = BatchedBeamSearch.tc_plan(R, N, 6 * K)
+    ws = [split3_weight_compact(torch.randn(N, K, device=dev) * 0.02) for _ in range(8)]
+    a3 = torch.randn(R, 3 * K, device=dev).bfloat16()
+    ns = lib.avsr_gemm_x3_splits(R, N, K)
     part = torch.empty(ns, R, N, device=dev)
     def g():
         w = ws[li["i"] % 8]; li["i"] += 1
-        L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(w), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn, L.stream()), "g")
+        L.check(lib.avsr_gemm_x3_splitk(L.ptr(a3), L.ll(3 * K), L.ptr(w), L.ll(3 * K), R, N, K, L.ptr(part), L.stream()), "g")
     t = timeit(g)
-    print(f"proj N={N} K={K} bn={bn} splits={ns}: {t:8.1f} us   ({N*K*12/1e3/t:.0f} GB/s of bf16x3 weights)")
+    print(f"proj N={N} K={K} splits={ns}: {t:8.1f} us   ({N*K*6/1e3/t:.0f} GB/s of bf16x3 weights)")
     bias, res, gam, bet = (torch.randn(N, device=dev) for _ in range(2)) if False else (torch.randn(N, device=dev), torch.randn(R, 1024, device=dev), torch.randn(N, device=dev), torch.randn(N, device=dev))
     act = torch.ones(R, dtype=torch.int32, device=dev)
     if N == 1024:
         x = torch.randn(R, N, device=dev)
-        a6o = torch.empty(R, 6 * N, device=dev, dtype=torch.bfloat16)
+        a6o = torch.empty(R, 3 * N, device=dev, dtype=torch.bfloat16)
         def e():
             L.check(lib.avsr_splitk_epilogue(L.ptr(part), ns, R, N, L.ptr(bias), 0, L.ptr(x), L.ll(N), L.ptr(x), L.ll(N), L.ptr(gam), L.ptr(bet),
                                              C.c_float(1e-12), None, L.ll(N), L.ptr(act), L.ptr(a6o), L.stream()), "e")

@@ -10,8 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from avsr_b200 import _lib as L
-from avsr_b200.beam_search import BatchedBeamSearch
-from avsr_b200.weights import split3_weight
+from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
@@ -50,7 +49,7 @@ if "attn" in which:
     vc = torch.randn(nl, 16, lmax, R, 64, device=dev)
     anc = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
     ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
-    att6 = torch.empty(R, 6144, device=dev, dtype=torch.bfloat16)
+    att6 = torch.empty(R, 3072, device=dev, dtype=torch.bfloat16)
     nch = lib.avsr_dec_attn_chunks(lmax)
     po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch, beam, 2, device=dev)
     tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
@@ -79,12 +78,12 @@ if "gemm" in which:
 
 if "skinny" in which:
     N, K = 3072, 1024
-    ws = [split3_weight(torch.randn(N, K, device=dev) * 0.02) for _ in range(3)]
-    a6 = torch.randn(R, 6 * K, device=dev).bfloat16()
-    bn, ns = BatchedBeamSearch.tc_plan(R, N, 6 * K)
+    ws = [split3_weight_compact(torch.randn(N, K, device=dev) * 0.02) for _ in range(3)]
+    a3 = torch.randn(R, 3 * K, device=dev).bfloat16()
+    ns = lib.avsr_gemm_x3_splits(R, N, K)
     part = torch.empty(ns, R, N, device=dev)
     for i in range(3):
         flush.zero_()
-        L.check(lib.avsr_gemm_bf16_tc_splitk(L.ptr(a6), L.ll(6 * K), L.ptr(ws[i]), L.ll(6 * K), R, N, 6 * K, L.ptr(part), ns, bn, L.stream()), "g")
+        L.check(lib.avsr_gemm_x3_splitk(L.ptr(a3), L.ll(3 * K), L.ptr(ws[i]), L.ll(3 * K), R, N, K, L.ptr(part), L.stream()), "g")
     torch.cuda.synchronize()
 print("ok")
