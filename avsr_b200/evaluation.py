@@ -1,0 +1,98 @@
+"""Sharded, batched evaluation driver for the B200 path.
+
+What the reference does (/root/reference/script/evaluation.py:387-404, ``eval_lrs2``): loop over the samples, one
+``AVSRCocktailModel.inference(videos, audios)`` each, normalise hypothesis and label, ``jiwer.wer`` over the two lists, print
+``WER: ...`` (``:553``).  Here the same result comes from: shard the utterances over the ranks (``sharding.shard_utterances``),
+decode each rank's share in length-bucketed batches through ``AVSRCocktailB200.infer_batch`` (every utterance evolves as its
+own B=1 run), ``all_gather`` the 1-best token ids, ``all_reduce`` [edits, reference words].  No collective on the hot path.
+
+The model only needs ``infer_batch(videos[B,1,T,88,88], audios[B,104,T], lengths) -> n-best per utterance`` and ``eos``;
+the CPU tests drive this module with a stand-in model under ``gloo``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import sharding as S
+
+
+@dataclass
+class EvalResult:
+    wer: float
+    edits: int
+    ref_words: int
+    hyp_tokens: Dict[int, List[int]] = field(default_factory=dict)      # utterance id -> 1-best token ids (no sos / eos)
+    hyp_text: Dict[int, str] = field(default_factory=dict)
+    audio_seconds: float = 0.0
+    n_batches: int = 0
+
+
+def strip_sos_eos(yseq: Sequence[int], eos: int) -> List[int]:
+    """``nbest[0]["yseq"][1:]`` with the trailing ``<eos>`` dropped: what script/evaluation.py:105-107 turns into text
+    (it strips the literal "<eos>" from the string instead)."""
+    toks = [int(t) for t in yseq[1:]]
+    while toks and toks[-1] == eos:
+        toks.pop()
+    return toks
+
+
+def pad_batch(samples: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
+    """samples: (video [1,T,88,88] or [T,88,88], audio [104,T]) per utterance -> videos [B,1,Tmax,88,88], audios
+    [B,104,Tmax] zero-padded, and the frame counts (the kernels never read the padding)."""
+    lengths = [int(a.shape[-1]) for _, a in samples]
+    tmax = max(lengths)
+    B = len(samples)
+    videos = torch.zeros(B, 1, tmax, 88, 88, dtype=torch.float32)
+    audios = torch.zeros(B, 104, tmax, dtype=torch.float32)
+    for b, (v, a) in enumerate(samples):
+        v = v.reshape(-1, 88, 88)
+        if v.shape[0] != lengths[b] or a.shape[0] != 104:
+            raise RuntimeError(f"utterance {b}: video {tuple(v.shape)} and audio {tuple(a.shape)} disagree")
+        videos[b, 0, :lengths[b]] = v
+        audios[b, :, :lengths[b]] = a
+    return videos, audios, lengths
+
+
+def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
+                     references: Optional[Sequence[str]] = None, ids_to_text: Optional[Callable[[Sequence[int]], str]] = None,
+                     normalize: Optional[Callable[[str], str]] = None, max_utts: int = 32, max_frames: int = 12288,
+                     device="cpu", fps: float = 25.0, group=None) -> EvalResult:
+    """Decode utterances 0..N-1 (``lengths[i]`` frames each, inputs from ``load_sample(i)``) on all ranks of the default
+    process group and return the corpus result on every rank.
+
+    references / ids_to_text / normalize: label strings, the tokenizer's ``post_process`` and ``norm_string``; when any is
+    missing the WER is computed on token ids written as decimal words (references then are token-id strings too).
+    ``device``: where the gather / reduce tensors live ("cuda" under nccl, "cpu" under gloo)."""
+    rank, world = S._world(group)
+    mine = S.shard_utterances(lengths, world)[rank]
+    batches = S.bucket_batches(mine, lengths, max_utts=max_utts, max_frames=max_frames)
+    eos = int(model.eos)
+    ids, toks = [], []
+    for batch in batches:
+        samples = [load_sample(i) for i in batch]
+        videos, audios, lens = pad_batch(samples)
+        if lens != [int(lengths[i]) for i in batch]:
+            raise RuntimeError("load_sample returned utterances whose lengths differ from `lengths`")
+        nbest = model.infer_batch(videos, audios, lens)
+        for i, hyps in zip(batch, nbest):
+            ids.append(i)
+            toks.append(strip_sos_eos(hyps[0].yseq.tolist() if hasattr(hyps[0].yseq, "tolist") else hyps[0].yseq, eos))
+    all_toks = S.gather_hypotheses(ids, toks, device=device, group=group)
+    if sorted(all_toks) != list(range(len(lengths))):
+        raise RuntimeError("sharding lost or duplicated utterances")
+    to_text = ids_to_text if ids_to_text is not None else (lambda t: " ".join(str(int(x)) for x in t))
+    norm = normalize if normalize is not None else (lambda s: s)
+    text = {i: norm(to_text(all_toks[i]).replace("<eos>", "").replace("<unk>", "")) for i in all_toks}
+    edits = nref = 0
+    if references is not None:
+        # each rank scores its own utterances; the sums meet in one all_reduce
+        for i in mine:
+            e, n = S.corpus_wer([norm(references[i].replace("<unk>", ""))], [text[i]])
+            edits += e
+            nref += n
+    wer, e, n = S.reduce_wer(edits, nref, device=device, group=group)
+    return EvalResult(wer=wer, edits=e, ref_words=n, hyp_tokens=all_toks, hyp_text=text,
+                      audio_seconds=sum(int(t) for t in lengths) / fps, n_batches=len(batches))

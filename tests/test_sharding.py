@@ -1,0 +1,163 @@
+"""Host logic of the multi-GPU path on CPU: sharding plan, batching, gather / WER reduce under gloo with world_size 2.
+
+Reference behaviour being reproduced: the sequential loop + corpus-level jiwer WER of script/evaluation.py:387-404.
+"""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from avsr_b200 import evaluation as E
+from avsr_b200 import sharding as S
+
+
+def _lev_ref(a, b):
+    """Textbook O(nm) Levenshtein in pure Python."""
+    d = list(range(len(b) + 1))
+    for i in range(1, len(a) + 1):
+        prev, d[0] = d[0], i
+        for j in range(1, len(b) + 1):
+            cur = min(prev + (a[i - 1] != b[j - 1]), d[j] + 1, d[j - 1] + 1)
+            prev, d[j] = d[j], cur
+    return d[len(b)]
+
+
+def test_word_edit_distance_matches_textbook():
+    rng = random.Random(0)
+    vocab = ["a", "b", "c", "dd", "e"]
+    assert S.word_edit_distance([], []) == 0
+    assert S.word_edit_distance(["a"], []) == 1
+    assert S.word_edit_distance([], ["a", "b"]) == 2
+    assert S.word_edit_distance("the cat sat".split(), "the cat sat".split()) == 0
+    assert S.word_edit_distance("the cat sat on the mat".split(), "cat sat on a mat please".split()) == 3
+    for _ in range(200):
+        a = [rng.choice(vocab) for _ in range(rng.randint(0, 12))]
+        b = [rng.choice(vocab) for _ in range(rng.randint(0, 12))]
+        assert S.word_edit_distance(a, b) == _lev_ref(a, b), (a, b)
+
+
+def test_corpus_wer_is_sum_of_edits_over_sum_of_words():
+    refs = ["a b c d", "e f", "g"]
+    hyps = ["a x c", "e f", ""]
+    e, n = S.corpus_wer(refs, hyps)
+    assert (e, n) == (2 + 0 + 1, 7)
+
+
+def test_shard_plan_is_a_balanced_partition():
+    # cfg 3 length law
+    rng = np.random.default_rng(2024)
+    lengths = np.clip(np.round(25 * rng.lognormal(np.log(1.3), 0.6, 1243)), 12, 155).astype(int).tolist()
+    for world in (1, 2, 4, 8):
+        shards = S.shard_utterances(lengths, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(len(lengths)))
+        loads = [sum(S.utterance_cost(lengths[i]) for i in s) for s in shards]
+        assert max(loads) / (sum(loads) / world) < 1.01          # greedy longest-first: < 1 % imbalance on 1243 utterances
+        assert S.shard_utterances(lengths, world) == shards     # deterministic: every rank derives the same plan
+    with pytest.raises(ValueError):
+        S.shard_utterances(lengths, 0)
+
+
+def test_bucket_batches_respect_limits_and_keep_lengths_close():
+    lengths = [375] * 5 + [50, 60, 70, 300, 12, 13, 155]
+    idx = list(range(len(lengths)))
+    batches = S.bucket_batches(idx, lengths, max_utts=4, max_frames=1000)
+    assert sorted(i for b in batches for i in b) == idx
+    for b in batches:
+        assert len(b) <= 4
+        assert sum(lengths[i] for i in b) <= 1000 or len(b) == 1
+    firsts = [lengths[b[0]] for b in batches]
+    assert firsts == sorted(firsts, reverse=True)
+    assert S.bucket_batches([], lengths) == []
+    # a single utterance longer than max_frames still gets its own batch
+    assert S.bucket_batches([0], [5000], max_frames=100) == [[0]]
+
+
+class _Hyp:
+    def __init__(self, yseq):
+        self.yseq = torch.tensor(yseq, dtype=torch.int64)
+
+
+class _StandInModel:
+    """Deterministic stand-in for AVSRCocktailB200.infer_batch: the 'hypothesis' of an utterance is a function of its own
+    input only, so any sharding / batching must give the same corpus result."""
+    eos = 5048
+
+    def infer_batch(self, videos, audios, lengths):
+        out = []
+        for b, t in enumerate(lengths):
+            assert float(videos[b, 0, t:].abs().sum()) == 0.0 and float(audios[b, :, t:].abs().sum()) == 0.0
+            key = int(round(float(audios[b, :, :t].sum()) * 7 + float(videos[b, 0, :t].sum())))
+            n = 1 + (key % 5)
+            toks = [1 + ((key * (k + 3)) % 40) for k in range(n)]
+            out.append([_Hyp([self.eos] + toks + [self.eos])])
+        return out
+
+
+def _sample(i, lengths):
+    g = torch.Generator().manual_seed(100 + i)
+    t = lengths[i]
+    return torch.randint(0, 3, (1, t, 88, 88), generator=g).float(), torch.randint(0, 5, (104, t), generator=g).float()
+
+
+def _refs(lengths):
+    return [" ".join(str((i * 7 + k) % 40) for k in range(1 + i % 4)) for i in range(len(lengths))]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, lengths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = E.evaluate_sharded(_StandInModel(), lengths, lambda i: _sample(i, lengths), references=_refs(lengths),
+                                 max_utts=3, max_frames=64)
+        # uneven contribution: rank 1 sends nothing, rank 0 sends two ragged rows
+        g = S.gather_hypotheses([5, 9] if rank == 0 else [], [[1, 2, 3], []] if rank == 0 else [])
+        q.put((rank, res.wer, res.edits, res.ref_words, res.hyp_tokens, g))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_world2_equals_single_process():
+    lengths = [12, 30, 7, 22, 15, 9, 31, 5, 18]
+    single = E.evaluate_sharded(_StandInModel(), lengths, lambda i: _sample(i, lengths), references=_refs(lengths))
+    assert single.ref_words == sum(len(r.split()) for r in _refs(lengths))
+    assert sorted(single.hyp_tokens) == list(range(len(lengths)))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, wer, edits, nref, toks, g in got:
+        assert (edits, nref) == (single.edits, single.ref_words)
+        assert wer == pytest.approx(single.wer)
+        assert toks == single.hyp_tokens
+        assert g == {5: [1, 2, 3], 9: []}
+
+
+def test_strip_and_pad():
+    assert E.strip_sos_eos([5048, 3, 4, 5048], 5048) == [3, 4]
+    assert E.strip_sos_eos([5048], 5048) == []
+    v, a, lens = E.pad_batch([(torch.ones(1, 3, 88, 88), torch.ones(104, 3)), (torch.ones(5, 88, 88), torch.ones(104, 5))])
+    assert v.shape == (2, 1, 5, 88, 88) and a.shape == (2, 104, 5) and lens == [3, 5]
+    assert float(v[0, 0, 3:].sum()) == 0.0
+    with pytest.raises(RuntimeError):
+        E.pad_batch([(torch.ones(4, 88, 88), torch.ones(104, 3))])
