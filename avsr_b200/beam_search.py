@@ -110,13 +110,14 @@ class BatchedBeamSearch:
         s["end_score"], s["end_dec"], s["end_ctc"] = f32(B, cap), f32(B, cap), f32(B, cap)
         s["best_len"], s["best_all"] = f32(B, tmax + 4), f32(B)
         # activations of one decoder step
-        s["x"], s["a"], s["att"], s["q2"] = f32(R, 1024), f32(R, 1024), f32(R, 1024), f32(R, 1024)
-        s["qkv"], s["ffn"] = f32(R, 3072), f32(R, 3072)
+        s["x"], s["a"], s["att"] = f32(R, 1024), f32(R, 1024), f32(R, 1024)
+        s["ffn"] = f32(R, 3072)
         s["dec_logp"] = f32(R, V)
         s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
-        # self-attention caches, head-major: [layer][head][pos][row][64]
-        s["kc"] = torch.empty(nl, 16, lmax, R, 64, dtype=torch.float32, device=dev)
-        s["vc"] = torch.empty(nl, 16, lmax, R, 64, dtype=torch.float32, device=dev)
+        # self-attention caches, one contiguous span per (utterance, head): keys transposed in 16-byte groups
+        # [layer][utt][head][16][pos*beam+slot][4], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
+        s["kc"] = torch.empty(nl, B, 16, 16, lmax * beam, 4, dtype=torch.float32, device=dev)
+        s["vc"] = torch.empty(nl, B, 16, lmax * beam, 64, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
         # scratch of the key-chunked step attention (csrc/decode.cu): partial (sum e*v, max, sum) per chunk + merge tickets
@@ -218,18 +219,18 @@ class BatchedBeamSearch:
         att_split = L.ptr(s["att3"]) if tc else None
         scratch = (L.ptr(s["att_po"]), L.ptr(s["att_pms"]), L.ptr(s["att_tickets"]))
         for li, lay in enumerate(w.layers):
-            # self-attention (decoder_layer.py:82-93)
-            self._linear(s, "a", lay, "wqkv", 3072, 1024, lay["bqkv"], out=s["qkv"])
-            L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]),
-                                           lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
-                                           att_f32, lmax, L.ll(64), L.ll(lmax * R * 64), att_split, *scratch, st()), "avsr_dec_attn_step(self)")
+            # self-attention (decoder_layer.py:82-93); the attention kernel sums the split-K partials of q | k | v itself
+            ns = self._proj(s, "a", lay, "wqkv", 3072, 1024)
+            L.check(lib.avsr_dec_attn_step(0, L.ptr(s["part"]), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]),
+                                           L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R,
+                                           L.ptr(s["step"]), att_f32, lmax, L.ll(0), att_split, *scratch, st()), "avsr_dec_attn_step(self)")
             self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
-            self._linear(s, "a", lay, "wq2", 1024, 1024, lay["bq2"], out=s["q2"])
+            ns = self._proj(s, "a", lay, "wq2", 1024, 1024)
             ck, cv = s["ckv_t"][li, 0], s["ckv_t"][li, 1]
-            L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), L.ptr(ck), L.ptr(cv), None, lmax, L.ptr(s["n_run"]),
-                                           L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
-                                           s["tmax"], L.ll(64), L.ll(s["F"] * 64), att_split, *scratch, st()), "avsr_dec_attn_step(src)")
+            L.check(lib.avsr_dec_attn_step(1, L.ptr(s["part"]), L.ll(1024), ns, L.ptr(lay["bq2"]), L.ptr(ck), L.ptr(cv), None, lmax,
+                                           L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
+                                           s["tmax"], L.ll(s["F"]), att_split, *scratch, st()), "avsr_dec_attn_step(src)")
             self._linear(s, "att", lay, "wo2", 1024, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
             self._linear(s, "a", lay, "w1", 3072, 1024, lay["b1"], act=L.ACT_RELU, key_out="ffn")
@@ -267,7 +268,7 @@ class BatchedBeamSearch:
             L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
             L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
-        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), n, L.stream()), "avsr_kv_head_major")
+        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), n, 1, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
         s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))

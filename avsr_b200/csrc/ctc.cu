@@ -16,96 +16,125 @@ __device__ __forceinline__ float lse2(float a, float b) {
     return m + logf(1.f + expf(n - m));
 }
 
+// logaddexp of the serial forward chain: ex2.approx / lg2.approx instead of the IEEE-exact sequences.  The operands are log
+// probabilities of magnitude 1e0..1e3 whose own fp32 spacing (1e-7..6e-5) is far above the ~2e-7 absolute error of the
+// approximations, and the chain is the critical path of the kernel (T dependent steps).
+__device__ __forceinline__ float lse2_chain(float a, float b) {
+    const float m = fmaxf(a, b), n = fminf(a, b);
+    return m + __logf(1.f + __expf(n - m));
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// Pre-beam mode: one thread per (row, candidate) owns one forward chain over time.
+// Pre-beam mode: one CTA per hypothesis row, two phases.
+//   Phase A (all 128 threads, parallel over time): gather the candidates' log-posterior columns x[t][c_s] and the blank
+//   column into shared memory, turn the parent's forward variables into log_phi (r_sum) and the blank-ending part.
+//   Phase B: warp 0 runs the S serial forward chains (one lane each; per step only the two logaddexp of
+//   ctc_prefix_score.py:156-161 are on the dependency chain, everything else was precomputed), while warps 1-3 reduce
+//   log_psi = logsumexp_t(log_phi[t-1] + x[t]) in parallel (max, then sum of exponentials, as torch.logsumexp does).
 // r_buf [2][R*S][tmax][2] ping-pongs on step parity; rprev_idx[row] is the chain (in the "current" half) that the
 // surviving hypothesis inherited.  Outputs psi[row][s] (log prefix probability) and rsum_last[row] = r_sum[T-1].
-__global__ void __launch_bounds__(128)
+constexpr int PB_THREADS = 128;
+constexpr int PB_MAXS = 12;
+
+__global__ void __launch_bounds__(PB_THREADS)
 ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int blank, const int* __restrict__ utt_off,
                           const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
                           const int* __restrict__ last_tok, const int* __restrict__ part_ids, const int* __restrict__ rprev_idx,
-                          float* __restrict__ r_buf, int tmax, const int* __restrict__ step_p, float* __restrict__ psi,
+                          float* __restrict__ r_buf, int tmax, int pitch, const int* __restrict__ step_p, float* __restrict__ psi,
                           float* __restrict__ rsum_last) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ float pb_sm[];                 // xs [S][pitch], xb [pitch], phi [pitch], pbk [pitch]
+    __shared__ float s_rmax[3][PB_MAXS], s_rsum[3][PB_MAXS];
+    const int row = blockIdx.x, utt = row / beam;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* xs = pb_sm;
+    float* xb = pb_sm + (size_t)S * pitch;
+    float* phi = xb + pitch;
+    float* pbk = phi + pitch;
     pdl_trigger();
-    pdl_wait();
-    if (gid >= R * S) return;
-    const int row = gid / S, s = gid % S;
-    const int utt = row / beam;
-    if ((row % beam) >= n_run[utt]) return;
-    const int step = *step_p;
+    // the posteriors were written before the chain of step kernels started: the blank column is fetched before the wait
     const int T = utt_T[utt];
     const float* lp = logp + (long long)utt_off[utt] * ldp;
-    const int c = part_ids[row * S + s];
-    const bool same = (c == last_tok[row]);
+    for (int t = tid; t < T; t += PB_THREADS) xb[t] = __ldg(lp + (long long)t * ldp + blank);
+    pdl_wait();
+    if ((row % beam) >= n_run[utt]) return;
+    const int step = *step_p;
     const int cur = step & 1;
-    const float2* rp = reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + (step > 0 ? rprev_idx[row] : 0)) * tmax;
-    float2* ro = reinterpret_cast<float2*>(r_buf) + ((long long)(cur ^ 1) * R * S + gid) * tmax;
-
     const int start = step > 1 ? step : 1;
-    float rn = (step == 0) ? lp[c] : LOGZERO;
-    float rb = LOGZERO;
-    ro[start - 1] = make_float2(rn, rb);
-    float M = rn, Ssum = 1.f;                                  // running logsumexp of {rn[start-1]} U {phi[t-1] + x[t]}
-    float cum = 0.f;                                           // step 0: running sum of blank log-probs
-    float pn = LOGZERO, pb = LOGZERO;                          // previous-label chains at t-1
-    if (step == 0) {
-        for (int u = 0; u < start; ++u) cum += lp[(long long)u * ldp + blank];
-    }
-    // The chain is serial in t, but its inputs are not: fetch them CH steps ahead (double-buffered registers) so that the
-    // ~1 us global-load latency overlaps the logaddexp arithmetic instead of being paid once per time step.
-    constexpr int CH = 8;
-    float xa[CH], xba[CH], xn[CH], xbn[CH];
-    float2 pa[CH], pnx[CH];
-    auto fetch = [&](int t0, float (&xs)[CH], float (&xbs)[CH], float2 (&ps)[CH]) {
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int t = t0 + u;
-            if (t < T) {
-                xs[u] = __ldg(lp + (long long)t * ldp + c);
-                xbs[u] = __ldg(lp + (long long)t * ldp + blank);
-                if (step > 0) ps[u] = rp[t - 1];
-            }
+    const int last = last_tok[row];
+    const float2* rp = reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + (step > 0 ? rprev_idx[row] : 0)) * tmax;
+
+    // ---- phase A
+    for (int t = tid; t < T; t += PB_THREADS) {
+        for (int s = 0; s < S; ++s) xs[s * pitch + t] = __ldg(lp + (long long)t * ldp + part_ids[row * S + s]);
+        if (step > 0) {
+            const float2 p = rp[t];
+            phi[t] = lse2(p.x, p.y);
+            pbk[t] = p.y;
         }
-    };
-    fetch(start, xa, xba, pa);
-    for (int t0 = start; t0 < T; t0 += CH) {
-        fetch(t0 + CH, xn, xbn, pnx);
-#pragma unroll
-        for (int u = 0; u < CH; ++u) {
-            const int t = t0 + u;
-            if (t < T) {
-                if (step == 0) { pn = LOGZERO; pb = cum; }
-                else { pn = pa[u].x; pb = pa[u].y; }
-                const float x = xa[u], xb = xba[u];
-                const float phi = same ? pb : lse2(pn, pb);
-                const float term = phi + x;
-                if (term > M) { Ssum = Ssum * expf(M - term) + 1.f; M = term; }
-                else Ssum += expf(term - M);
-                const float nrn = lse2(rn, phi) + x;
-                const float nrb = lse2(rn, rb) + xb;
-                rn = nrn; rb = nrb;
+    }
+    __syncthreads();
+    if (step == 0 && tid == 0) {
+        // empty prefix: r_prev[:,0] = logzero, r_prev[:,1] = cumsum(x[:, blank]) (ctc_prefix_score.py:58-63)
+        float cum = 0.f;
+        for (int t = 0; t < T; ++t) {
+            cum += xb[t];
+            pbk[t] = cum;
+            phi[t] = lse2(LOGZERO, cum);
+        }
+    }
+    if (step == 0) __syncthreads();
+
+    // ---- phase B
+    if (warp == 0) {
+        if (lane < S) {
+            const int s = lane;
+            const int c = part_ids[row * S + s];
+            const float* ph = (c == last) ? pbk : phi;
+            const float* x = xs + s * pitch;
+            float2* ro = reinterpret_cast<float2*>(r_buf) + ((long long)(cur ^ 1) * R * S + (long long)row * S + s) * tmax;
+            float rn = (step == 0) ? x[0] : LOGZERO;
+            float rb = LOGZERO;
+            ro[start - 1] = make_float2(rn, rb);
+#pragma unroll 4
+            for (int t = start; t < T; ++t) {
+                const float nrn = lse2_chain(rn, ph[t - 1]) + x[t];
+                const float nrb = lse2_chain(rn, rb) + xb[t];
+                rn = nrn;
+                rb = nrb;
                 ro[t] = make_float2(rn, rb);
-                if (step == 0) cum += xb;
             }
         }
-#pragma unroll
-        for (int u = 0; u < CH; ++u) { xa[u] = xn[u]; xba[u] = xbn[u]; pa[u] = pnx[u]; }
+        return;
     }
-    psi[gid] = M + logf(Ssum);
-    if (s == 0) {
-        float en, eb;
-        if (step == 0) {
-            // cum currently holds sum_{u<T} x[u,blank] only when the loop ran to T; recompute for clarity
-            float cs = 0.f;
-            for (int u = 0; u < T; ++u) cs += lp[(long long)u * ldp + blank];
-            en = LOGZERO; eb = cs;
-        } else {
-            const float2 v = rp[T - 1];
-            en = v.x; eb = v.y;
-        }
-        rsum_last[row] = lse2(en, eb);
+    const int tt = tid - 32, w3 = warp - 1;
+    for (int s = 0; s < S; ++s) {
+        const float* ph = (part_ids[row * S + s] == last) ? pbk : phi;
+        const float* x = xs + s * pitch;
+        float mx = -INFINITY;
+        for (int t = start + tt; t < T; t += PB_THREADS - 32) mx = fmaxf(mx, ph[t - 1] + x[t]);
+        mx = warp_max(mx);
+        if (lane == 0) s_rmax[w3][s] = mx;
     }
+    asm volatile("bar.sync 1, 96;" ::: "memory");
+    for (int s = 0; s < S; ++s) {
+        const float* ph = (part_ids[row * S + s] == last) ? pbk : phi;
+        const float* x = xs + s * pitch;
+        const float r0 = (step == 0) ? x[0] : LOGZERO;                       // r[start-1, 0]
+        const float M = fmaxf(fmaxf(s_rmax[0][s], s_rmax[1][s]), fmaxf(s_rmax[2][s], r0));
+        float sum = 0.f;
+        for (int t = start + tt; t < T; t += PB_THREADS - 32) sum += expf(ph[t - 1] + x[t] - M);
+        sum = warp_sum(sum);
+        if (lane == 0) s_rsum[w3][s] = sum;
+    }
+    asm volatile("bar.sync 1, 96;" ::: "memory");
+    if (tt < S) {
+        const int s = tt;
+        const float r0 = (step == 0) ? xs[s * pitch] : LOGZERO;
+        const float M = fmaxf(fmaxf(s_rmax[0][s], s_rmax[1][s]), fmaxf(s_rmax[2][s], r0));
+        const float sum = ((s_rsum[0][s] + s_rsum[1][s]) + s_rsum[2][s]) + expf(r0 - M);
+        psi[row * S + s] = M + logf(sum);
+    }
+    if (tt == 32) rsum_last[row] = phi[T - 1];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -540,9 +569,17 @@ extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int bl
                                        float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, cudaStream_t stream) {
     AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && part_ids && rprev_idx && r_buf && step && psi && rsum_last,
                  "avsr_ctc_prefix_prebeam: null argument");
-    AVSR_REQUIRE(R > 0 && S > 0 && beam > 0 && tmax > 0 && ldp >= V, "avsr_ctc_prefix_prebeam: bad sizes");
-    AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_prebeam_kernel, dim3(cdiv((long long)R * S, 128)), dim3(128), 0, stream, logp, V, ldp, blank, utt_off,
-                                    utt_T, n_run, beam, R, S, last_tok, part_ids, rprev_idx, r_buf, tmax, step, psi, rsum_last));
+    AVSR_REQUIRE(R > 0 && S > 0 && S <= PB_MAXS && beam > 0 && tmax > 0 && ldp >= V, "avsr_ctc_prefix_prebeam: bad sizes (S <= %d)", PB_MAXS);
+    const int pitch = tmax | 1;                       // odd pitch: the S chains read their columns without bank conflicts
+    const size_t smem = (size_t)(S + 3) * pitch * sizeof(float);
+    AVSR_REQUIRE(smem <= 200 * 1024, "avsr_ctc_prefix_prebeam: %d frames x %d candidates do not fit shared memory", tmax, S);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_prebeam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_prebeam_kernel, dim3(R), dim3(PB_THREADS), smem, stream, logp, V, ldp, blank, utt_off,
+                                    utt_T, n_run, beam, R, S, last_tok, part_ids, rprev_idx, r_buf, tmax, pitch, step, psi, rsum_last));
     return AVSR_OK;
 }
 

@@ -1,0 +1,414 @@
+// Single-query attention of one decode position (MultiHeadedAttention.forward for a query of length 1,
+// src/nets/backend/transformer/attention.py:38-106, called from DecoderLayer.forward, decoder_layer.py:82-107), KV-cache
+// form: the reference re-projects K and V of every cached token / source frame at every step (decoder.py:153-183).
+//
+// HBM-streaming design:
+//   * CTA (128 threads) = (utterance, head, chunk of 128 keys).  All live hyps of the utterance are served by the same CTA,
+//     so a K / V row shared by several hyps is read from HBM once.
+//   * K is stored TRANSPOSED in 16-byte groups, K^T[j][row][4] (j = dim / 4): thread = key, its sixteen 16-byte loads are
+//     coalesced across the warp and put the whole 64-float key in registers; the dot products with the (few) queries are
+//     plain FMAs against broadcast shared-memory reads: no shuffles, no redundant work.  V stays row-major [row][64]: a
+//     half-warp reads one row (lane = 4 output dims).  The K tile AND the first half of the V tile (96 KB per CTA) are
+//     requested before anything is computed; the second half of V is requested as soon as the key registers are free, so
+//     a tile costs ONE exposed memory round trip.
+//   * mode 1 (source attention): rows = the utterance's frames.  The loads are issued BEFORE griddepcontrol.wait (the cross
+//     K/V were written before the chain of step kernels started), i.e. while the query projection is still running.
+//   * mode 0 (self-attention): a hyp finds its history through the ancestry table anc[row][pos] = slot; the CTA builds the
+//     list of DISTINCT (pos, slot) rows its live hyps reference, each with the bit mask of the hyps that use it (beams
+//     mostly share their ancestors), and streams exactly those rows, 128 at a time.  k / v of the current position are
+//     appended by the CTA that owns the chunk containing it.
+//   * softmax statistics per tile (exact max, then exponentials), running (max, sum, sum e*v) across the tiles of a CTA,
+//     partial results of the chunks merged in chunk order by the last CTA of the (utterance, head) group (atomic ticket):
+//     the result never depends on scheduling.
+//   * The query (and the current k, v) can be taken straight from the split-K partial sums of the projection that produced
+//     them (sum over splits in split order + bias), which saves one epilogue launch per attention.
+#include "common.cuh"
+
+namespace {
+
+constexpr int D = 1024;
+constexpr int HEADS = 16;
+constexpr int DH = 64;
+constexpr int CK = 128;                  // positions (self) / frames (cross) per chunk = keys per tile = threads per CTA
+constexpr int NHW = 8;                   // half-warps per CTA
+constexpr int VR = CK / NHW;             // V rows per half-warp and tile (16), loaded in two halves
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int MODE, int NH>
+__global__ void __launch_bounds__(CK, (NH <= 4) ? 4 : 2)
+dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit, const float* __restrict__ q_bias, float* kc, float* vc,
+                       const unsigned char* __restrict__ anc, int lmax, const int* __restrict__ n_run, const int* __restrict__ utt_off,
+                       const int* __restrict__ utt_T, int beam, int R, const int* __restrict__ step_p, float* __restrict__ out,
+                       long long n_frames, __nv_bfloat16* __restrict__ out_split, float* __restrict__ part_o,
+                       float* __restrict__ part_ms, int* __restrict__ tickets, int nch) {
+    extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target)
+    __shared__ __align__(16) float qs[NH][DH];
+    __shared__ __align__(16) float qpart[NH][DH];                  // second half of the split-K sums of q
+    __shared__ unsigned rlist[(MODE == 0) ? CK * NH : 1];          // (row index << 8) | hyp mask, row = pos * beam + slot
+    __shared__ float sc[NH][CK];
+    __shared__ __align__(16) float s_o[NHW][NH][DH];
+    __shared__ float s_redm[4][NH], s_reds[4][NH];
+    __shared__ float s_run[2][NH];                                 // running max / sum over the tiles of this CTA
+    __shared__ int s_wcnt[4];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hw = tid >> 4, l16 = tid & 15;
+    const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z;
+    const int row0 = utt * beam;
+    const int p0 = chunk * CK;
+    pdl_trigger();
+
+    // K^T base (float4 index [j][row]) and V base ([row][64]) of this (utterance, head); nr = rows per j plane
+    const float* kbase;
+    const float* vbase;
+    long long nr;
+    int T_utt = 0;
+    if (MODE == 1) {
+        T_utt = utt_T[utt];
+        nr = n_frames;
+        kbase = kc + (long long)head * n_frames * DH + (long long)utt_off[utt] * 4;
+        vbase = vc + (long long)head * n_frames * DH + (long long)utt_off[utt] * DH;
+    } else {
+        nr = (long long)lmax * beam;
+        kbase = kc + (long long)(utt * HEADS + head) * nr * DH;
+        vbase = vc + (long long)(utt * HEADS + head) * nr * DH;
+    }
+
+    float4 kreg[DH / 4];
+    auto load_k = [&](long long r, bool ok) {
+#pragma unroll
+        for (int j = 0; j < DH / 4; ++j) {
+            kreg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const float4* p = reinterpret_cast<const float4*>(kbase) + (long long)j * nr + r;
+                kreg[j] = (MODE == 1) ? __ldg(p) : *p;             // mode 0: plain loads (this CTA may just have written the row)
+            }
+        }
+    };
+    // V row with tile-local key index jl = hw + 8 * i goes to vtile[jl]; every thread later reads back exactly the 16 bytes
+    // it copied (lane = 4 output dims), so its own cp.async.wait_all is all the synchronisation the tile needs.
+    auto copy_v = [&](int i, long long r, bool ok) {
+        if (ok) cp_async16(vtile + (hw + NHW * i) * DH + 4 * l16, vbase + r * DH + 4 * l16);
+    };
+    if (MODE == 1) {
+        // whole tile requested before the wait; rows past the end of the utterance are skipped
+        load_k(p0 + tid, p0 + tid < T_utt);
+#pragma unroll
+        for (int i = 0; i < VR; ++i) copy_v(i, p0 + hw + NHW * i, p0 + hw + NHW * i < T_utt);
+    }
+    pdl_wait();
+    const int nh = n_run[utt];
+    const int step = *step_p;
+    if (nh == 0) { cp_async_wait_all(); return; }
+    const int n = (MODE == 1) ? T_utt : step + 1;
+    const int nact = (n + CK - 1) / CK;
+    if (chunk >= nact) { cp_async_wait_all(); return; }
+
+    // ---- query: 16-byte groups, all split-K terms of a group requested at once (two threads share a group when there are
+    //      few hyps); the current k / v of the chunk that owns this position go straight to the cache
+    const long long zstride = (long long)R * ldq;
+    auto gather4 = [&](int row, int col, int z0, int z1) -> float4 {       // sum over splits [z0, z1) in split order
+        const float* p = q_in + (long long)row * ldq + col;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int z = z0;
+        for (; z + 8 <= z1; z += 8) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(reinterpret_cast<const float4*>(p + (z + u) * zstride));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { v.x += t[u].x; v.y += t[u].y; v.z += t[u].z; v.w += t[u].w; }
+        }
+        for (; z < z1; ++z) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(p + z * zstride));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        return v;
+    };
+    const int G = nh * (DH / 4);                     // 16-byte groups of the query block
+    const bool two = nsplit > 1 && 2 * G <= CK;      // two threads per group: splits [0, zh) and [zh, nsplit)
+    const int zh = two ? (nsplit + 1) / 2 : nsplit;
+    if (nsplit <= 0) {
+        for (int g = tid; g < G; g += CK) {
+            const int h = g / (DH / 4), j = g % (DH / 4);
+            *reinterpret_cast<float4*>(&qs[h][4 * j]) = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + head * DH + 4 * j);
+        }
+    } else {
+        for (int g = tid; g < (two ? 2 * G : G); g += CK) {
+            const int sub = g / G, gg = g % G;
+            const int h = gg / (DH / 4), j = gg % (DH / 4);
+            const float4 v = gather4(row0 + h, head * DH + 4 * j, sub == 0 ? 0 : zh, sub == 0 ? zh : nsplit);
+            *reinterpret_cast<float4*>(sub == 0 ? &qs[h][4 * j] : &qpart[h][4 * j]) = v;
+        }
+    }
+    if (MODE == 0 && step >= p0 && step < p0 + CK) {
+        for (int g = tid; g < 2 * G; g += CK) {
+            const int kv = g / G, gg = g % G;
+            const int h = gg / (DH / 4), j = gg % (DH / 4);
+            const int col = (1 + kv) * D + head * DH + 4 * j;
+            float4 v;
+            if (nsplit <= 0) v = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + col);
+            else {
+                v = gather4(row0 + h, col, 0, nsplit);
+                const float4 b4 = *reinterpret_cast<const float4*>(q_bias + col);
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            }
+            const long long rr = (long long)step * beam + h;
+            const long long cb = (long long)(utt * HEADS + head) * nr * DH;
+            if (kv == 0) *reinterpret_cast<float4*>(kc + cb + ((long long)j * nr + rr) * 4) = v;
+            else *reinterpret_cast<float4*>(vc + cb + rr * DH + 4 * j) = v;
+        }
+    }
+    // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
+    int nrows = (MODE == 1) ? min(CK, T_utt - p0) : 0;
+    if (MODE == 0) {
+        const int p = p0 + tid;
+        unsigned msk[NH];
+#pragma unroll
+        for (int s = 0; s < NH; ++s) msk[s] = 0u;
+        if (p < n) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                if (h < nh) {
+                    const int slot = (p < step) ? (int)anc[((long long)(step & 1) * R + row0 + h) * lmax + p] : h;
+#pragma unroll
+                    for (int s = 0; s < NH; ++s) msk[s] |= (slot == s) ? (1u << h) : 0u;
+                }
+            }
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < NH; ++s) cnt += msk[s] != 0u;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        __syncthreads();                             // also: the appended k / v are visible to the whole CTA
+        int base = incl - cnt;
+        for (int w = 0; w < warp; ++w) base += s_wcnt[w];
+        nrows = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+#pragma unroll
+        for (int s = 0; s < NH; ++s)
+            if (msk[s] != 0u) rlist[base++] = ((unsigned)(p * beam + s) << 8) | msk[s];
+    }
+    if (tid < NH) { s_run[0][tid] = -INFINITY; s_run[1][tid] = 0.f; }
+    __syncthreads();                                 // qs / qpart, rlist, s_run ready
+    if (nsplit > 0) {                                // finish the query: (first half + second half) + bias
+        for (int g = tid; g < G; g += CK) {
+            const int h = g / (DH / 4), j = g % (DH / 4);
+            float4 v = *reinterpret_cast<const float4*>(&qs[h][4 * j]);
+            if (two) {
+                const float4 w = *reinterpret_cast<const float4*>(&qpart[h][4 * j]);
+                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+            const float4 b4 = *reinterpret_cast<const float4*>(q_bias + head * DH + 4 * j);
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            *reinterpret_cast<float4*>(&qs[h][4 * j]) = v;
+        }
+    }
+    float acc[NH][4];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+
+    const int ntiles = (nrows + CK - 1) / CK;        // mode 1: always 1
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int t0 = tile * CK;
+        unsigned my = 0xffu;                         // hyp mask of this thread's key
+        const bool kvalid = t0 + tid < nrows;
+        if (MODE == 0) {
+            my = kvalid ? rlist[t0 + tid] : 0u;
+            load_k((long long)(my >> 8), kvalid);
+#pragma unroll
+            for (int i = 0; i < VR; ++i) {
+                const int j = t0 + hw + NHW * i;
+                copy_v(i, j < nrows ? (long long)(rlist[j] >> 8) : 0, j < nrows);
+            }
+        }
+        if (tile == 0) __syncthreads();              // finished query visible (the loads above are already in flight)
+        // ---- scores of this thread's key against every live hyp
+        float s[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) s[h] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DH / 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                if (h < nh) {
+                    const float4 q = *reinterpret_cast<const float4*>(&qs[h][4 * j]);
+                    s[h] = fmaf(q.x, kreg[j].x, s[h]); s[h] = fmaf(q.y, kreg[j].y, s[h]);
+                    s[h] = fmaf(q.z, kreg[j].z, s[h]); s[h] = fmaf(q.w, kreg[j].w, s[h]);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            if (h < nh) {
+                s[h] = (kvalid && ((my >> h) & 1u)) ? s[h] * 0.125f : -INFINITY;
+                const float mx = warp_max(s[h]);
+                if (lane == 0) s_redm[warp][h] = mx;
+            }
+        }
+        __syncthreads();                             // (1) tile maxima visible
+        float scale[NH], mnew[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            scale[h] = 1.f;
+            mnew[h] = -INFINITY;
+            if (h < nh) {
+                const float mt = fmaxf(fmaxf(s_redm[0][h], s_redm[1][h]), fmaxf(s_redm[2][h], s_redm[3][h]));
+                const float mo = s_run[0][h];
+                const float mn = fmaxf(mo, mt);      // -inf only while no key of hyp h has been seen yet
+                float e = 0.f;
+                if (mn > -INFINITY) {
+                    e = expf(s[h] - mn);             // masked / invalid keys: exp(-inf) = 0
+                    scale[h] = expf(mo - mn);        // mo = -inf -> 0 (nothing accumulated yet)
+                }
+                mnew[h] = mn;
+                sc[h][tid] = e;
+                const float sm = warp_sum(e);
+                if (lane == 0) s_reds[warp][h] = sm;
+            }
+        }
+        cp_async_wait_all();                         // this thread's V pieces have landed
+        __syncthreads();                             // (2) exponentials and warp sums visible; everyone has read s_run
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            if (h < nh && tid == h) {
+                s_run[1][h] = s_run[1][h] * scale[h] + ((s_reds[0][h] + s_reds[1][h]) + (s_reds[2][h] + s_reds[3][h]));
+                s_run[0][h] = mnew[h];
+            }
+        }
+        // ---- acc = acc * scale + sum_keys e * V : half-warp = key row, lane = 4 output dims
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            if (h < nh) {
+                acc[h][0] *= scale[h]; acc[h][1] *= scale[h]; acc[h][2] *= scale[h]; acc[h][3] *= scale[h];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VR; ++i) {
+            const int jl = hw + NHW * i;
+            if (t0 + jl < nrows) {                   // uniform per half-warp; rows that were not copied hold stale data
+                const float4 v = *reinterpret_cast<const float4*>(vtile + jl * DH + 4 * l16);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    if (h < nh) {
+                        const float w = sc[h][jl];
+                        acc[h][0] = fmaf(w, v.x, acc[h][0]); acc[h][1] = fmaf(w, v.y, acc[h][1]);
+                        acc[h][2] = fmaf(w, v.z, acc[h][2]); acc[h][3] = fmaf(w, v.w, acc[h][3]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- merge the eight half-warp accumulators (fixed order); they all refer to the same running max
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+        if (h < nh) *reinterpret_cast<float4*>(&s_o[hw][h][4 * l16]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    __syncthreads();
+
+    auto store_out = [&](int h, int d, float v) {
+        const long long row = row0 + h;
+        if (out) out[row * D + head * DH + d] = v;
+        if (out_split) avsr_split3c_store(out_split + row * 3 * D, D, head * DH + d, v);
+    };
+    const long long grp = (long long)utt * HEADS + head;
+    float* po = part_o + ((grp * nch + chunk) * beam) * DH;
+    float* pms = part_ms + ((grp * nch + chunk) * beam) * 2;
+    for (int i = tid; i < nh * DH; i += CK) {
+        const int h = i / DH, d = i % DH;
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < NHW; ++w) o += s_o[w][h][d];
+        if (nact == 1) store_out(h, d, o / s_run[1][h]);
+        else {
+            po[i] = o;
+            if (d == 0) { pms[2 * h] = s_run[0][h]; pms[2 * h + 1] = s_run[1][h]; }
+        }
+    }
+    if (nact == 1) return;
+    // ---- several chunks: the last CTA of the group to arrive merges all partials in chunk order
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(&tickets[grp], 1);
+        s_last = (t == nact - 1) ? 1 : 0;
+        if (s_last) tickets[grp] = 0;                // re-armed for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = tid; i < nh * DH; i += CK) {
+        const int h = i / DH, d = i % DH;
+        float M = -INFINITY;
+        for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(part_ms + ((grp * nch + c) * beam + h) * 2));
+        float S = 0.f, o = 0.f;
+        for (int c = 0; c < nact; ++c) {
+            const float* q = part_ms + ((grp * nch + c) * beam + h) * 2;
+            const float f = expf(__ldcg(q) - M);
+            S = fmaf(__ldcg(q + 1), f, S);
+            o = fmaf(__ldcg(part_o + ((grp * nch + c) * beam) * DH + i), f, o);
+        }
+        store_out(h, d, o / S);
+    }
+}
+
+}  // namespace
+
+// Chunks of scratch per (utterance, head) the caller must provide for up to max_keys positions / frames.
+extern "C" int avsr_dec_attn_chunks(int max_keys) { return (max_keys + CK - 1) / CK; }
+
+// mode 0: self-attention step.  Query / current k / current v = columns [0,1024) / [1024,2048) / [2048,3072) of q_in
+//   ([R, ldq] fp32).  kc / vc = this layer's caches; with row = pos*beam + slot and nr = lmax*beam, key element
+//   (utt, head, row, d) is at ((utt*16 + head)*16 + d/4)*nr*4 + row*4 + d%4 (transposed in 16-byte groups) and value
+//   element at ((utt*16 + head)*nr + row)*64 + d.  anc [2][R][lmax] (uint8 slot per position, double-buffered on step
+//   parity).  The current k / v are written to the cache at (pos = *step, slot = the hyp's own slot).
+// mode 1: source attention.  Query = columns [0,1024) of q_in; kc / vc = this layer's cross K / V over the n_frames packed
+//   frames of all utterances (utt_off / utt_T index them): key element (head, frame, d) at (head*16 + d/4)*n_frames*4 +
+//   frame*4 + d%4, value element at (head*n_frames + frame)*64 + d (the layout avsr_kv_head_major writes).
+// nsplit > 0: q_in holds the split-K partial sums part[z][R][ldq] of the projection (z < nsplit); they are summed in split
+//   order and q_bias[ldq] is added.  nsplit == 0: q_in is the finished projection.
+// out (fp32 [R,1024]) and / or out_split (compact bf16x3 [R, 3*1024]).  Scratch (nch = avsr_dec_attn_chunks(max_keys)):
+// part_o [R/beam][16][nch][beam][64], part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once by the
+// caller (the kernel re-arms them).
+extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
+                                  const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
+                                  int R, const int* step, float* out, int max_keys, long long n_frames, void* out_split,
+                                  float* part_o, float* part_ms, int* tickets, cudaStream_t stream) {
+    AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && max_keys > 0, "avsr_dec_attn_step: bad arguments");
+    AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T && n_frames > 0), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
+    AVSR_REQUIRE(beam <= 8 && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max 8)", beam);
+    AVSR_REQUIRE(nsplit >= 0 && (nsplit == 0 || q_bias), "avsr_dec_attn_step: partial-sum input needs the bias");
+    AVSR_REQUIRE((ldq & 3) == 0 && ((uintptr_t)q_in & 15) == 0 && ((uintptr_t)q_bias & 15) == 0 && ((uintptr_t)kc & 15) == 0 &&
+                     ((uintptr_t)vc & 15) == 0,
+                 "avsr_dec_attn_step: q_in / q_bias / kc / vc must be 16-byte aligned and ldq a multiple of 4");
+    AVSR_REQUIRE(mode == 1 || (long long)lmax * beam < (1 << 24), "avsr_dec_attn_step: cache too long");
+    const int nch = (max_keys + CK - 1) / CK;
+    AVSR_REQUIRE(nch == 1 || (part_o && part_ms && tickets), "avsr_dec_attn_step: %d keys need the chunk scratch buffers", max_keys);
+    AVSR_REQUIRE(nch <= 65535, "avsr_dec_attn_step: too many keys");
+    const dim3 grid(R / beam, HEADS, nch);
+    static bool configured = false;
+    if (!configured) {                                // static + dynamic shared memory of the 8-hyp variants exceeds 48 KB
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
+        configured = true;
+    }
+#define AVSR_ATTN_LAUNCH(MODE, NH)                                                                                                   \
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<MODE, NH>, grid, dim3(CK), (size_t)CK * DH * sizeof(float), stream, q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, \
+                                    n_run, utt_off, utt_T, beam, R, step, out, n_frames, (__nv_bfloat16*)out_split, part_o, part_ms,    \
+                                    tickets, nch))
+    if (mode == 0) {
+        if (beam <= 4) AVSR_ATTN_LAUNCH(0, 4); else AVSR_ATTN_LAUNCH(0, 8);
+    } else {
+        if (beam <= 4) AVSR_ATTN_LAUNCH(1, 4); else AVSR_ATTN_LAUNCH(1, 8);
+    }
+#undef AVSR_ATTN_LAUNCH
+    return AVSR_OK;
+}

@@ -195,15 +195,21 @@ split3_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __rest
     avsr_split3_store(out + r * 6 * K, K, c, in[r * ldi + c]);
 }
 
-// [F, ncol] -> [ncol/64][F][64]: float4 per thread
+// [F, ncol] -> [ncol/64][F][64]: float4 per thread.  kt_period > 0: 64-column blocks whose index b has (b / 16) % kt_period == 0
+// (the K halves of [k | v] pairs of 16 heads) are written transposed in 16-byte groups, [b][16][F][4], the layout the decode
+// step's attention reads keys in (csrc/dec_attn.cu).
 __global__ void __launch_bounds__(256)
-kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int ncol) {
+kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int ncol, int kt_period) {
     const long long total = F * (ncol / 4);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long f = i / (ncol / 4);
         const int c = (int)(i % (ncol / 4)) * 4;
         const float4 v = *reinterpret_cast<const float4*>(in + f * ncol + c);
-        *reinterpret_cast<float4*>(out + ((long long)(c / 64) * F + f) * 64 + (c % 64)) = v;
+        const int b = c / 64;
+        if (kt_period > 0 && ((b / 16) % kt_period) == 0)
+            *reinterpret_cast<float4*>(out + (long long)b * F * 64 + ((long long)((c % 64) >> 2) * F + f) * 4) = v;
+        else
+            *reinterpret_cast<float4*>(out + ((long long)b * F + f) * 64 + (c % 64)) = v;
     }
 }
 
@@ -289,10 +295,11 @@ extern "C" int avsr_split3(const float* in, long long ldi, void* out, long long 
     return AVSR_OK;
 }
 
-extern "C" int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, cudaStream_t stream) {
+extern "C" int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, int k_transposed, cudaStream_t stream) {
     AVSR_REQUIRE(in && out && F > 0 && ncol > 0 && (ncol & 63) == 0, "avsr_kv_head_major: bad arguments");
+    AVSR_REQUIRE(!k_transposed || (ncol % 2048) == 0, "avsr_kv_head_major: k_transposed needs [k(1024) | v(1024)] column pairs");
     const long long total = F * (ncol / 4);
-    kv_head_major_kernel<<<GRID1D(total), 256, 0, stream>>>(in, out, F, ncol);
+    kv_head_major_kernel<<<GRID1D(total), 256, 0, stream>>>(in, out, F, ncol, k_transposed ? 2 : 0);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

@@ -147,18 +147,27 @@ int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_st
 /* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
                       const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
-/* One decode position of MultiHeadedAttention (transformer/attention.py:38-106) with cached K/V, split over chunks of
- * keys: mode 0 = self-attention over the hypothesis' own history (found through the ancestry table `anc`, the current
- * k/v are appended to kc/vc), mode 1 = source attention over the utterance's precomputed K/V.  Scratch (caller-owned,
- * nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64] fp32, part_ms [R/beam][16][nch][beam][2] fp32,
- * tickets [R/beam][16] int32 zeroed once. */
+/* One decode position of MultiHeadedAttention (transformer/attention.py:38-106, called from decoder_layer.py:82-107) with
+ * cached K/V, streamed once (csrc/dec_attn.cu).  Keys are stored transposed in 16-byte groups, values row-major.
+ * mode 0 = self-attention over the hypothesis' own history: query / current k / current v = columns [0,1024) / [1024,2048) /
+ *   [2048,3072) of q_in; kc / vc = this layer's caches: with row = pos*beam + slot and nr = lmax*beam, key element
+ *   (utt, head, row, d) at ((utt*16 + head)*16 + d/4)*nr*4 + row*4 + d%4, value element at ((utt*16 + head)*nr + row)*64 + d;
+ *   anc [2][R][lmax] = slot that holds position pos of a row's history (double-buffered on step parity); the current k / v
+ *   are appended at (pos = *step, slot = own slot).
+ * mode 1 = source attention over the utterance's precomputed K/V (n_frames packed frames of all utterances): key element
+ *   (head, frame, d) at (head*16 + d/4)*n_frames*4 + frame*4 + d%4, value element at (head*n_frames + frame)*64 + d.
+ * nsplit > 0: q_in = split-K partial sums part[z][R][ldq] of the projection, summed here in split order + q_bias.
+ * Scratch (caller-owned, nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64] fp32,
+ * part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once. */
 int avsr_dec_attn_chunks(int max_keys);
-int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, float* kc, float* vc, const unsigned char* anc, int lmax,
-                       const int* n_run, const int* utt_off, const int* utt_T, int beam, int R, const int* step, float* out,
-                       int max_keys, long long kv_ld, long long head_stride, void* out_split, float* part_o, float* part_ms,
-                       int* tickets, avsr_stream_t stream);
-/* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span). */
-int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, avsr_stream_t stream);
+int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
+                       const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
+                       const int* step, float* out, int max_keys, long long n_frames, void* out_split, float* part_o,
+                       float* part_ms, int* tickets, avsr_stream_t stream);
+/* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span).  k_transposed:
+ * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][16][F][4] (transposed in 16-byte groups), the
+ * key layout avsr_dec_attn_step mode 1 reads. */
+int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, int k_transposed, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
                              int* part_ids, int S, avsr_stream_t stream);
 /* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes.  logp = CTC

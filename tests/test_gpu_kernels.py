@@ -272,17 +272,36 @@ def test_log_softmax_and_logits_topk(L):
     assert ids[5].tolist() == [-1] * S                       # dead row untouched
 
 
-@pytest.mark.parametrize("beam,step", [(3, 0), (3, 5), (3, 127), (3, 128), (5, 300), (3, 375), (8, 140)])
-def test_dec_attn_step_self(L, beam, step):
+def _as_partials(x, nsplit, seed):
+    """[R, N] -> (part [nsplit, R, N], bias [N]) with sum_z part[z] + bias == x up to fp32 rounding (the attention kernels can
+    take their query straight from the split-K partial sums of the projection)."""
+    if nsplit == 0:
+        return x, None
+    g = torch.Generator().manual_seed(seed)
+    bias = torch.randn(x.shape[1], generator=g).cuda()
+    part = torch.randn(nsplit, *x.shape, generator=g).cuda()
+    part[nsplit - 1] = x - bias - part[:nsplit - 1].sum(0)
+    return part.contiguous(), bias
+
+
+@pytest.mark.parametrize("beam,step,nsplit", [(3, 0, 0), (3, 5, 6), (3, 127, 0), (3, 128, 3), (5, 300, 0), (3, 375, 6), (8, 140, 2),
+                                              (4, 260, 0)])
+def test_dec_attn_step_self(L, beam, step, nsplit):
     """Self-attention of one decode position over a random cache and a random ancestry table (decoder_layer.py:82-93,
-    attention.py:38-106 restated in torch fp32): chunked kernel incl. the multi-chunk merge and the k/v append."""
+    attention.py:38-106 restated in torch fp32): streaming kernel incl. the distinct-row list, the multi-chunk merge, the
+    k/v append and the query taken from split-K partial sums."""
     lib = L.load()
     B, lmax = 4, 376
     R = B * beam
     g = torch.Generator().manual_seed(100 + step)
-    kc = torch.randn(16, lmax, R, 64, generator=g).cuda()
-    vc = torch.randn(16, lmax, R, 64, generator=g).cuda()
+    kc_log = torch.randn(B, 16, lmax, beam, 64, generator=g).cuda()    # logical [utt][head][pos][slot][64]
+    vc = torch.randn(B, 16, lmax, beam, 64, generator=g).cuda()
+    # physical key cache: transposed in 16-byte groups, [utt][head][16][pos*beam+slot][4]
+    to_phys = lambda k: k.reshape(B, 16, lmax * beam, 16, 4).permute(0, 1, 3, 2, 4).contiguous()
+    to_log = lambda k: k.permute(0, 1, 3, 2, 4).reshape(B, 16, lmax, beam, 64)
+    kc = to_phys(kc_log)
     qkv = torch.randn(R, 3072, generator=g).cuda()
+    q_in, q_bias = _as_partials(qkv, nsplit, 5)
     n_run = torch.tensor([beam, max(1, beam - 1), 0, 1][:B], dtype=torch.int32, device="cuda")
     anc = torch.randint(0, beam, (2, R, lmax), generator=g, dtype=torch.uint8)
     shared = max(0, step - 6)                           # old positions: all hyps of an utterance share one ancestor slot
@@ -295,36 +314,42 @@ def test_dec_attn_step_self(L, beam, step):
     tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
     out = torch.full((R, 1024), 7.0, device="cuda")
     out6 = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device="cuda")
-    kc0, vc0 = kc.clone(), vc.clone()
+    kc0, vc0 = kc_log.clone(), vc.clone()
     for _ in range(2):                                   # twice: the merge tickets must re-arm themselves
-        L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc), L.ptr(vc), L.ptr(anc), lmax, L.ptr(n_run), None, None, beam, R,
-                                       L.ptr(step_t), L.ptr(out), lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(out6), L.ptr(po), L.ptr(pms),
-                                       L.ptr(tick), L.stream()), "dec_attn_step(self)")
+        L.check(lib.avsr_dec_attn_step(0, L.ptr(q_in), L.ll(3072), nsplit, L.ptr(q_bias), L.ptr(kc), L.ptr(vc), L.ptr(anc), lmax,
+                                       L.ptr(n_run), None, None, beam, R, L.ptr(step_t), L.ptr(out), lmax, L.ll(0), L.ptr(out6),
+                                       L.ptr(po), L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(self)")
     torch.cuda.synchronize()
     assert tick.abs().sum().item() == 0
+    kc = to_log(kc)
     a = anc[step & 1].cpu().long()
+    tol = 2e-5 if nsplit == 0 else 1e-4                  # the partial-sum form adds the rounding of the split sums
     for b in range(B):
         for h in range(beam):
             row = b * beam + h
             if h >= int(n_run[b]):
                 assert (out[row] == 7.0).all()           # dead rows untouched
-                assert (kc[:, step, row] == kc0[:, step, row]).all()
+                assert (kc[b, :, step, h] == kc0[b, :, step, h]).all()
                 continue
-            rows = torch.tensor([b * beam + int(a[row, p]) for p in range(step)] + [row], dtype=torch.long)
+            slots = torch.tensor([int(a[row, p]) for p in range(step)], dtype=torch.long)
             q = qkv[row, :1024].view(16, 64)
             kcur, vcur = qkv[row, 1024:2048].view(16, 64), qkv[row, 2048:].view(16, 64)
-            assert torch.equal(kc[:, step, row], kcur) and torch.equal(vc[:, step, row], vcur)
-            K = torch.cat([kc0[:, torch.arange(step), rows[:-1]], kcur[:, None]], 1)          # [16, step+1, 64]
-            Vv = torch.cat([vc0[:, torch.arange(step), rows[:-1]], vcur[:, None]], 1)
+            assert (kc[b, :, step, h] - kcur).abs().max().item() < tol and (vc[b, :, step, h] - vcur).abs().max().item() < tol
+            K = torch.cat([kc0[b][:, torch.arange(step), slots], kc[b, :, step, h][:, None]], 1)          # [16, step+1, 64]
+            Vv = torch.cat([vc0[b][:, torch.arange(step), slots], vc[b, :, step, h][:, None]], 1)
             att = torch.softmax(torch.einsum("hd,hpd->hp", q, K) / 8.0, -1)
             want = torch.einsum("hp,hpd->hd", att, Vv).reshape(1024)
-            assert (out[row] - want).abs().max().item() < 2e-5, (b, h)
+            assert (out[row] - want).abs().max().item() < tol, (b, h)
             o3 = out6[row].float().view(3, 1024)
-            assert (o3[0] + o3[1] + o3[2] - want).abs().max().item() < 2e-5
+            assert (o3[0] + o3[1] + o3[2] - want).abs().max().item() < tol
+    # positions other than the current one are never written
+    keep = torch.ones(lmax, dtype=torch.bool)
+    keep[step] = False
+    assert torch.equal(kc[:, :, keep], kc0[:, :, keep]) and torch.equal(vc[:, :, keep], vc0[:, :, keep])
 
 
-@pytest.mark.parametrize("beam,lengths", [(3, [375, 12, 130, 257]), (5, [128, 129, 1, 375])])
-def test_dec_attn_step_cross(L, beam, lengths):
+@pytest.mark.parametrize("beam,lengths,nsplit", [(3, [375, 12, 130, 257], 0), (5, [128, 129, 1, 375], 16), (3, [400, 384, 385, 900], 4)])
+def test_dec_attn_step_cross(L, beam, lengths, nsplit):
     """Source attention of one decode position: every live hyp of an utterance attends over that utterance's frames."""
     lib = L.load()
     B, tmax, Fr = len(lengths), max(lengths), sum(lengths)
@@ -332,7 +357,9 @@ def test_dec_attn_step_cross(L, beam, lengths):
     g = torch.Generator().manual_seed(7)
     kc = torch.randn(16, Fr, 64, generator=g).cuda()
     vc = torch.randn(16, Fr, 64, generator=g).cuda()
+    kc_phys = kc.reshape(16, Fr, 16, 4).permute(0, 2, 1, 3).contiguous()       # keys transposed in 16-byte groups: [head][16][F][4]
     q = torch.randn(R, 1024, generator=g).cuda()
+    q_in, q_bias = _as_partials(q, nsplit, 6)
     n_run = torch.tensor([beam, 1, 0, beam - 1][:B], dtype=torch.int32, device="cuda")
     offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
     utt_off = torch.from_numpy(offs).cuda()
@@ -344,11 +371,12 @@ def test_dec_attn_step_cross(L, beam, lengths):
     tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
     out = torch.full((R, 1024), 7.0, device="cuda")
     for _ in range(2):
-        L.check(lib.avsr_dec_attn_step(1, L.ptr(q), L.ll(1024), L.ptr(kc), L.ptr(vc), None, tmax + 1, L.ptr(n_run), L.ptr(utt_off),
-                                       L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), tmax, L.ll(64), L.ll(Fr * 64), None, L.ptr(po),
-                                       L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(src)")
+        L.check(lib.avsr_dec_attn_step(1, L.ptr(q_in), L.ll(1024), nsplit, L.ptr(q_bias), L.ptr(kc_phys), L.ptr(vc), None, tmax + 1, L.ptr(n_run),
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), tmax, L.ll(Fr), None,
+                                       L.ptr(po), L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(src)")
     torch.cuda.synchronize()
     assert tick.abs().sum().item() == 0
+    tol = 2e-5 if nsplit == 0 else 1e-4
     for b in range(B):
         K, Vv = kc[:, offs[b]:offs[b] + lengths[b]], vc[:, offs[b]:offs[b] + lengths[b]]
         for h in range(beam):
@@ -358,7 +386,7 @@ def test_dec_attn_step_cross(L, beam, lengths):
                 continue
             att = torch.softmax(torch.einsum("hd,hpd->hp", q[row].view(16, 64), K) / 8.0, -1)
             want = torch.einsum("hp,hpd->hd", att, Vv).reshape(1024)
-            assert (out[row] - want).abs().max().item() < 2e-5, (b, h)
+            assert (out[row] - want).abs().max().item() < tol, (b, h)
 
 
 @pytest.mark.parametrize("B,beam,V,step", [(1, 3, 5049, 2), (5, 5, 5049, 7), (80, 3, 700, 3), (3, 8, 2600, 1), (2, 3, 5049, 0)])

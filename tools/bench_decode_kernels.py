@@ -42,8 +42,8 @@ n_run, utt_off, utt_T = i32([beam] * B), i32([b * T for b in range(B)]), i32([T]
 step_t = i32([step])
 qkv = torch.randn(R, 3072, device=dev)
 q2 = torch.randn(R, 1024, device=dev)
-kc = torch.randn(nl, 16, lmax, R, 64, device=dev)
-vc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+kc = torch.randn(nl, B, 16, 16, lmax * beam, 4, device=dev)        # keys transposed in 16-byte groups
+vc = torch.randn(nl, B, 16, lmax * beam, 64, device=dev)
 anc = torch.randint(0, beam, (2, R, lmax), dtype=torch.uint8, device=dev)
 if len(sys.argv) > 2 and sys.argv[2] == 'shared':
     anc.zero_()          # all hyps of an utterance descend from slot 0 (converged beam): physical rows are shared
@@ -55,18 +55,22 @@ po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch,
 tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
 scr = (L.ptr(po), L.ptr(pms), L.ptr(tick))
 li = {"i": 0}
+# the attention kernels take q (and the current k, v) from the split-K partial sums of their projection, as in the real step
+NSQ, NSC = lib.avsr_gemm_x3_splits(R, 3072, 1024), lib.avsr_gemm_x3_splits(R, 1024, 1024)
+qkv_p, qkv_b = torch.randn(NSQ, R, 3072, device=dev), torch.randn(3072, device=dev)
+q2_p, q2_b = torch.randn(NSC, R, 1024, device=dev), torch.randn(1024, device=dev)
 
 
 def self_attn():
     l = li["i"] % nl; li["i"] += 1
-    L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run), L.ptr(utt_off),
-                                   L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), *scr, L.stream()), "self")
+    L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv_p), L.ll(3072), NSQ, L.ptr(qkv_b), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run),
+                                   L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(0), L.ptr(att6), *scr, L.stream()), "self")
 
 
 def cross_attn():
     l = li["i"] % nl; li["i"] += 1
-    L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
-                                   L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(64), L.ll(B * T * 64),
+    L.check(lib.avsr_dec_attn_step(1, L.ptr(q2_p), L.ll(1024), NSC, L.ptr(q2_b), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
+                                   L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(B * T),
                                    L.ptr(att6), *scr, L.stream()), "cross")
 
 

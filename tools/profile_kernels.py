@@ -45,8 +45,8 @@ if "ctc" in which:
 if "attn" in which:
     lmax, nl = T + 1, 2
     qkv, q2 = torch.randn(R, 3072, device=dev), torch.randn(R, 1024, device=dev)
-    kc = torch.randn(nl, 16, lmax, R, 64, device=dev)
-    vc = torch.randn(nl, 16, lmax, R, 64, device=dev)
+    kc = torch.randn(nl, B, 16, 16, lmax * beam, 4, device=dev)
+    vc = torch.randn(nl, B, 16, lmax * beam, 64, device=dev)
     anc = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
     ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
     att6 = torch.empty(R, 3072, device=dev, dtype=torch.bfloat16)
@@ -57,11 +57,11 @@ if "attn" in which:
     for it in range(3):
         l = it % nl
         flush.zero_()
-        L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run), L.ptr(utt_off),
-                                       L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(64), L.ll(lmax * R * 64), L.ptr(att6), *scr,
+        L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), 0, None, L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run),
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(0), L.ptr(att6), *scr,
                                        L.stream()), "self")
-        L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax, L.ptr(n_run), L.ptr(utt_off),
-                                       L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(64), L.ll(B * T * 64), L.ptr(att6), *scr,
+        L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), 0, None, L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax, L.ptr(n_run),
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(B * T), L.ptr(att6), *scr,
                                        L.stream()), "cross")
     torch.cuda.synchronize()
 
