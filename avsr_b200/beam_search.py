@@ -114,9 +114,9 @@ class BatchedBeamSearch:
         s["ffn"] = f32(R, 3072)
         s["dec_logp"] = f32(R, V)
         s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
-        # self-attention caches, one contiguous span per (utterance, head): keys transposed in 16-byte groups
-        # [layer][utt][head][16][pos*beam+slot][4], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
-        s["kc"] = torch.empty(nl, B, 16, 16, lmax * beam, 4, dtype=torch.float32, device=dev)
+        # self-attention caches, one contiguous span per (utterance, head): keys transposed in 32-byte groups
+        # [layer][utt][head][8][pos*beam+slot][8], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
+        s["kc"] = torch.empty(nl, B, 16, 8, lmax * beam, 8, dtype=torch.float32, device=dev)
         s["vc"] = torch.empty(nl, B, 16, lmax * beam, 64, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()

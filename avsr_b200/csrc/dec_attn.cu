@@ -5,12 +5,12 @@
 // HBM-streaming design:
 //   * CTA (128 threads) = (utterance, head, chunk of 128 keys).  All live hyps of the utterance are served by the same CTA,
 //     so a K / V row shared by several hyps is read from HBM once.
-//   * K is stored TRANSPOSED in 16-byte groups, K^T[j][row][4] (j = dim / 4): thread = key, its sixteen 16-byte loads are
-//     coalesced across the warp and put the whole 64-float key in registers; the dot products with the (few) queries are
-//     plain FMAs against broadcast shared-memory reads: no shuffles, no redundant work.  V stays row-major [row][64]: a
-//     half-warp reads one row (lane = 4 output dims).  The K tile AND the first half of the V tile (96 KB per CTA) are
-//     requested before anything is computed; the second half of V is requested as soon as the key registers are free, so
-//     a tile costs ONE exposed memory round trip.
+//   * K is stored TRANSPOSED in 32-byte groups, K^T[j][row][8] (j = dim / 8): thread = key, its loads are coalesced across
+//     the warp (whole 32-byte sectors per row, also when only every beam-th row of the self-attention cache is live) and put
+//     the 64-float key in registers; the dot products with the (few) queries are plain FMAs against broadcast
+//     shared-memory reads: no shuffles, no redundant work.  V stays row-major [row][64] and goes to shared memory with
+//     cp.async (no registers held): a half-warp owns 16 consecutive keys, lane = 4 output dims, and reads back exactly the
+//     bytes it copied.  K tile and V tile (64 KB per CTA) are requested before anything is computed.
 //   * mode 1 (source attention): rows = the utterance's frames.  The loads are issued BEFORE griddepcontrol.wait (the cross
 //     K/V were written before the chain of step kernels started), i.e. while the query projection is still running.
 //   * mode 0 (self-attention): a hyp finds its history through the ancestry table anc[row][pos] = slot; the CTA builds the
@@ -21,7 +21,8 @@
 //     partial results of the chunks merged in chunk order by the last CTA of the (utterance, head) group (atomic ticket):
 //     the result never depends on scheduling.
 //   * The query (and the current k, v) can be taken straight from the split-K partial sums of the projection that produced
-//     them (sum over splits in split order + bias), which saves one epilogue launch per attention.
+//     them (sum over splits in a fixed order + bias), which saves one epilogue launch per attention.
+//   * The body is instantiated for the exact number of live hyps: no per-hyp guards in the inner loops.
 #include "common.cuh"
 
 namespace {
@@ -31,83 +32,63 @@ constexpr int HEADS = 16;
 constexpr int DH = 64;
 constexpr int CK = 128;                  // positions (self) / frames (cross) per chunk = keys per tile = threads per CTA
 constexpr int NHW = 8;                   // half-warps per CTA
-constexpr int VR = CK / NHW;             // V rows per half-warp and tile (16), loaded in two halves
+constexpr int VR = CK / NHW;             // V rows per half-warp and tile (16 consecutive keys)
+constexpr int KG = 8;                    // floats per key group (32 bytes = one sector)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int MODE, int NH>
-__global__ void __launch_bounds__(CK, (NH <= 4) ? 4 : 2)
-dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit, const float* __restrict__ q_bias, float* kc, float* vc,
-                       const unsigned char* __restrict__ anc, int lmax, const int* __restrict__ n_run, const int* __restrict__ utt_off,
-                       const int* __restrict__ utt_T, int beam, int R, const int* __restrict__ step_p, float* __restrict__ out,
-                       long long n_frames, __nv_bfloat16* __restrict__ out_split, float* __restrict__ part_o,
-                       float* __restrict__ part_ms, int* __restrict__ tickets, int nch) {
-    extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target)
-    __shared__ __align__(16) float qs[NH][DH];
-    __shared__ __align__(16) float qpart[NH][DH];                  // second half of the split-K sums of q
-    __shared__ unsigned rlist[(MODE == 0) ? CK * NH : 1];          // (row index << 8) | hyp mask, row = pos * beam + slot
-    __shared__ float sc[NH][CK];
-    __shared__ __align__(16) float s_o[NHW][NH][DH];
-    __shared__ float s_redm[4][NH], s_reds[4][NH];
-    __shared__ float s_run[2][NH];                                 // running max / sum over the tiles of this CTA
-    __shared__ int s_wcnt[4];
-    __shared__ int s_last;
+struct AttnArgs {
+    const float* q_in; long long ldq; int nsplit; const float* q_bias;
+    float* kc; float* vc; const unsigned char* anc; int lmax;
+    const int* n_run; const int* utt_off; const int* utt_T; int beam; int R; const int* step_p;
+    float* out; long long n_frames; __nv_bfloat16* out_split; float* part_o; float* part_ms; int* tickets; int nch;
+};
+
+template <int NH>
+struct AttnSmem {
+    float qs[NH][DH];                    // finished queries
+    float qpart[NH][DH];                 // second half of the split-K sums
+    float sc[NH][CK];                    // exponentials of the current tile
+    float s_o[NHW][NH][DH];
+    float s_redm[4][NH], s_reds[4][NH];
+    float s_run[2][NH];                  // running max / sum over the tiles of this CTA
+    int s_wcnt[4];
+    int s_last;
+};
+
+// K of one key: 16 x 16-byte loads, two per 32-byte group.  MODE 0 uses plain loads (this CTA may just have written the row).
+template <int MODE>
+__device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbase, long long nr, long long r, bool ok) {
+#pragma unroll
+    for (int j = 0; j < DH / KG; ++j) {
+        kreg[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        kreg[2 * j + 1] = kreg[2 * j];
+        if (ok) {
+            const float4* p = reinterpret_cast<const float4*>(kbase + ((long long)j * nr + r) * KG);
+            kreg[2 * j] = (MODE == 1) ? __ldg(p) : p[0];
+            kreg[2 * j + 1] = (MODE == 1) ? __ldg(p + 1) : p[1];
+        }
+    }
+}
+
+// Everything after griddepcontrol.wait, for exactly NHT live hyps (NH = hyp slots of the beam).
+template <int MODE, int NH, int NHT>
+__device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, unsigned* rlist, float* vtile, float4 (&kreg)[DH / 4],
+                                          const float* kbase, const float* vbase, long long nr, int T_utt, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z;
+    const int beam = a.beam, R = a.R, nsplit = a.nsplit;
     const int row0 = utt * beam;
     const int p0 = chunk * CK;
-    pdl_trigger();
-
-    // K^T base (float4 index [j][row]) and V base ([row][64]) of this (utterance, head); nr = rows per j plane
-    const float* kbase;
-    const float* vbase;
-    long long nr;
-    int T_utt = 0;
-    if (MODE == 1) {
-        T_utt = utt_T[utt];
-        nr = n_frames;
-        kbase = kc + (long long)head * n_frames * DH + (long long)utt_off[utt] * 4;
-        vbase = vc + (long long)head * n_frames * DH + (long long)utt_off[utt] * DH;
-    } else {
-        nr = (long long)lmax * beam;
-        kbase = kc + (long long)(utt * HEADS + head) * nr * DH;
-        vbase = vc + (long long)(utt * HEADS + head) * nr * DH;
-    }
-
-    float4 kreg[DH / 4];
-    auto load_k = [&](long long r, bool ok) {
-#pragma unroll
-        for (int j = 0; j < DH / 4; ++j) {
-            kreg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-                const float4* p = reinterpret_cast<const float4*>(kbase) + (long long)j * nr + r;
-                kreg[j] = (MODE == 1) ? __ldg(p) : *p;             // mode 0: plain loads (this CTA may just have written the row)
-            }
-        }
-    };
-    // V row with tile-local key index jl = hw + 8 * i goes to vtile[jl]; every thread later reads back exactly the 16 bytes
-    // it copied (lane = 4 output dims), so its own cp.async.wait_all is all the synchronisation the tile needs.
-    auto copy_v = [&](int i, long long r, bool ok) {
-        if (ok) cp_async16(vtile + (hw + NHW * i) * DH + 4 * l16, vbase + r * DH + 4 * l16);
-    };
-    if (MODE == 1) {
-        // whole tile requested before the wait; rows past the end of the utterance are skipped
-        load_k(p0 + tid, p0 + tid < T_utt);
-#pragma unroll
-        for (int i = 0; i < VR; ++i) copy_v(i, p0 + hw + NHW * i, p0 + hw + NHW * i < T_utt);
-    }
-    pdl_wait();
-    const int nh = n_run[utt];
-    const int step = *step_p;
-    if (nh == 0) { cp_async_wait_all(); return; }
     const int n = (MODE == 1) ? T_utt : step + 1;
     const int nact = (n + CK - 1) / CK;
-    if (chunk >= nact) { cp_async_wait_all(); return; }
+    const float* q_in = a.q_in;
+    const long long ldq = a.ldq;
+    const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(vtile) + (uint32_t)((hw * VR) * DH + 4 * l16) * 4u;   // this thread's V slots
 
     // ---- query: 16-byte groups, all split-K terms of a group requested at once (two threads share a group when there are
     //      few hyps); the current k / v of the chunk that owns this position go straight to the cache
@@ -129,20 +110,20 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
         }
         return v;
     };
-    const int G = nh * (DH / 4);                     // 16-byte groups of the query block
+    constexpr int G = NHT * (DH / 4);                // 16-byte groups of the query block
     const bool two = nsplit > 1 && 2 * G <= CK;      // two threads per group: splits [0, zh) and [zh, nsplit)
     const int zh = two ? (nsplit + 1) / 2 : nsplit;
     if (nsplit <= 0) {
         for (int g = tid; g < G; g += CK) {
             const int h = g / (DH / 4), j = g % (DH / 4);
-            *reinterpret_cast<float4*>(&qs[h][4 * j]) = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + head * DH + 4 * j);
+            *reinterpret_cast<float4*>(&sm.qs[h][4 * j]) = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + head * DH + 4 * j);
         }
     } else {
         for (int g = tid; g < (two ? 2 * G : G); g += CK) {
             const int sub = g / G, gg = g % G;
             const int h = gg / (DH / 4), j = gg % (DH / 4);
             const float4 v = gather4(row0 + h, head * DH + 4 * j, sub == 0 ? 0 : zh, sub == 0 ? zh : nsplit);
-            *reinterpret_cast<float4*>(sub == 0 ? &qs[h][4 * j] : &qpart[h][4 * j]) = v;
+            *reinterpret_cast<float4*>(sub == 0 ? &sm.qs[h][4 * j] : &sm.qpart[h][4 * j]) = v;
         }
     }
     if (MODE == 0 && step >= p0 && step < p0 + CK) {
@@ -154,13 +135,13 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
             if (nsplit <= 0) v = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + col);
             else {
                 v = gather4(row0 + h, col, 0, nsplit);
-                const float4 b4 = *reinterpret_cast<const float4*>(q_bias + col);
+                const float4 b4 = *reinterpret_cast<const float4*>(a.q_bias + col);
                 v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
             }
             const long long rr = (long long)step * beam + h;
             const long long cb = (long long)(utt * HEADS + head) * nr * DH;
-            if (kv == 0) *reinterpret_cast<float4*>(kc + cb + ((long long)j * nr + rr) * 4) = v;
-            else *reinterpret_cast<float4*>(vc + cb + rr * DH + 4 * j) = v;
+            if (kv == 0) *reinterpret_cast<float4*>(a.kc + cb + ((long long)(j >> 1) * nr + rr) * KG + (j & 1) * 4) = v;
+            else *reinterpret_cast<float4*>(a.vc + cb + rr * DH + 4 * j) = v;
         }
     }
     // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
@@ -172,12 +153,10 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
         for (int s = 0; s < NH; ++s) msk[s] = 0u;
         if (p < n) {
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                if (h < nh) {
-                    const int slot = (p < step) ? (int)anc[((long long)(step & 1) * R + row0 + h) * lmax + p] : h;
+            for (int h = 0; h < NHT; ++h) {
+                const int slot = (p < step) ? (int)a.anc[((long long)(step & 1) * R + row0 + h) * a.lmax + p] : h;
 #pragma unroll
-                    for (int s = 0; s < NH; ++s) msk[s] |= (slot == s) ? (1u << h) : 0u;
-                }
+                for (int s = 0; s < NH; ++s) msk[s] |= (slot == s) ? (1u << h) : 0u;
             }
         }
         int cnt = 0;
@@ -189,120 +168,118 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) s_wcnt[warp] = incl;
+        if (lane == 31) sm.s_wcnt[warp] = incl;
         __syncthreads();                             // also: the appended k / v are visible to the whole CTA
         int base = incl - cnt;
-        for (int w = 0; w < warp; ++w) base += s_wcnt[w];
-        nrows = s_wcnt[0] + s_wcnt[1] + s_wcnt[2] + s_wcnt[3];
+        for (int w = 0; w < warp; ++w) base += sm.s_wcnt[w];
+        nrows = sm.s_wcnt[0] + sm.s_wcnt[1] + sm.s_wcnt[2] + sm.s_wcnt[3];
 #pragma unroll
         for (int s = 0; s < NH; ++s)
             if (msk[s] != 0u) rlist[base++] = ((unsigned)(p * beam + s) << 8) | msk[s];
     }
-    if (tid < NH) { s_run[0][tid] = -INFINITY; s_run[1][tid] = 0.f; }
+    if (tid < NHT) { sm.s_run[0][tid] = -INFINITY; sm.s_run[1][tid] = 0.f; }
     __syncthreads();                                 // qs / qpart, rlist, s_run ready
     if (nsplit > 0) {                                // finish the query: (first half + second half) + bias
         for (int g = tid; g < G; g += CK) {
             const int h = g / (DH / 4), j = g % (DH / 4);
-            float4 v = *reinterpret_cast<const float4*>(&qs[h][4 * j]);
+            float4 v = *reinterpret_cast<const float4*>(&sm.qs[h][4 * j]);
             if (two) {
-                const float4 w = *reinterpret_cast<const float4*>(&qpart[h][4 * j]);
+                const float4 w = *reinterpret_cast<const float4*>(&sm.qpart[h][4 * j]);
                 v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
             }
-            const float4 b4 = *reinterpret_cast<const float4*>(q_bias + head * DH + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(a.q_bias + head * DH + 4 * j);
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            *reinterpret_cast<float4*>(&qs[h][4 * j]) = v;
+            *reinterpret_cast<float4*>(&sm.qs[h][4 * j]) = v;
         }
     }
-    float acc[NH][4];
+    float acc[NHT][4];
 #pragma unroll
-    for (int h = 0; h < NH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+    for (int h = 0; h < NHT; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
 
     const int ntiles = (nrows + CK - 1) / CK;        // mode 1: always 1
     for (int tile = 0; tile < ntiles; ++tile) {
         const int t0 = tile * CK;
         unsigned my = 0xffu;                         // hyp mask of this thread's key
         const bool kvalid = t0 + tid < nrows;
+        const int nv = min(VR, nrows - t0 - hw * VR);                // valid V rows of this half-warp in this tile (may be <= 0)
         if (MODE == 0) {
             my = kvalid ? rlist[t0 + tid] : 0u;
-            load_k((long long)(my >> 8), kvalid);
+            load_k<0>(kreg, kbase, nr, (long long)(my >> 8), kvalid);
 #pragma unroll
-            for (int i = 0; i < VR; ++i) {
-                const int j = t0 + hw + NHW * i;
-                copy_v(i, j < nrows ? (long long)(rlist[j] >> 8) : 0, j < nrows);
-            }
+            for (int i = 0; i < VR; ++i)
+                if (i < nv) cp_async16(vt_s + i * DH * 4, vbase + (long long)(rlist[t0 + hw * VR + i] >> 8) * DH + 4 * l16);
         }
         if (tile == 0) __syncthreads();              // finished query visible (the loads above are already in flight)
         // ---- scores of this thread's key against every live hyp
-        float s[NH];
+        float s[NHT];
 #pragma unroll
-        for (int h = 0; h < NH; ++h) s[h] = 0.f;
+        for (int h = 0; h < NHT; ++h) s[h] = 0.f;
 #pragma unroll
         for (int j = 0; j < DH / 4; ++j) {
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                if (h < nh) {
-                    const float4 q = *reinterpret_cast<const float4*>(&qs[h][4 * j]);
-                    s[h] = fmaf(q.x, kreg[j].x, s[h]); s[h] = fmaf(q.y, kreg[j].y, s[h]);
-                    s[h] = fmaf(q.z, kreg[j].z, s[h]); s[h] = fmaf(q.w, kreg[j].w, s[h]);
-                }
+            for (int h = 0; h < NHT; ++h) {
+                const float4 q = *reinterpret_cast<const float4*>(&sm.qs[h][4 * j]);
+                s[h] = fmaf(q.x, kreg[j].x, s[h]); s[h] = fmaf(q.y, kreg[j].y, s[h]);
+                s[h] = fmaf(q.z, kreg[j].z, s[h]); s[h] = fmaf(q.w, kreg[j].w, s[h]);
             }
         }
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            if (h < nh) {
-                s[h] = (kvalid && ((my >> h) & 1u)) ? s[h] * 0.125f : -INFINITY;
-                const float mx = warp_max(s[h]);
-                if (lane == 0) s_redm[warp][h] = mx;
-            }
+        for (int h = 0; h < NHT; ++h) {
+            s[h] = (kvalid && ((my >> h) & 1u)) ? s[h] * 0.125f : -INFINITY;
+            const float mx = warp_max(s[h]);
+            if (lane == 0) sm.s_redm[warp][h] = mx;
         }
         __syncthreads();                             // (1) tile maxima visible
-        float scale[NH], mnew[NH];
+        float scale[NHT], mnew[NHT];
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
+        for (int h = 0; h < NHT; ++h) {
+            const float mt = fmaxf(fmaxf(sm.s_redm[0][h], sm.s_redm[1][h]), fmaxf(sm.s_redm[2][h], sm.s_redm[3][h]));
+            const float mo = sm.s_run[0][h];
+            const float mn = fmaxf(mo, mt);          // -inf only while no key of hyp h has been seen yet
+            float e = 0.f;
             scale[h] = 1.f;
-            mnew[h] = -INFINITY;
-            if (h < nh) {
-                const float mt = fmaxf(fmaxf(s_redm[0][h], s_redm[1][h]), fmaxf(s_redm[2][h], s_redm[3][h]));
-                const float mo = s_run[0][h];
-                const float mn = fmaxf(mo, mt);      // -inf only while no key of hyp h has been seen yet
-                float e = 0.f;
-                if (mn > -INFINITY) {
-                    e = expf(s[h] - mn);             // masked / invalid keys: exp(-inf) = 0
-                    scale[h] = expf(mo - mn);        // mo = -inf -> 0 (nothing accumulated yet)
-                }
-                mnew[h] = mn;
-                sc[h][tid] = e;
-                const float sm = warp_sum(e);
-                if (lane == 0) s_reds[warp][h] = sm;
+            if (mn > -INFINITY) {
+                e = expf(s[h] - mn);                 // masked / invalid keys: exp(-inf) = 0
+                scale[h] = expf(mo - mn);            // mo = -inf -> 0 (nothing accumulated yet)
             }
+            mnew[h] = mn;
+            sm.sc[h][tid] = e;
+            const float sum = warp_sum(e);
+            if (lane == 0) sm.s_reds[warp][h] = sum;
         }
         cp_async_wait_all();                         // this thread's V pieces have landed
         __syncthreads();                             // (2) exponentials and warp sums visible; everyone has read s_run
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            if (h < nh && tid == h) {
-                s_run[1][h] = s_run[1][h] * scale[h] + ((s_reds[0][h] + s_reds[1][h]) + (s_reds[2][h] + s_reds[3][h]));
-                s_run[0][h] = mnew[h];
+        for (int h = 0; h < NHT; ++h) {
+            if (tid == h) {
+                sm.s_run[1][h] = sm.s_run[1][h] * scale[h] + ((sm.s_reds[0][h] + sm.s_reds[1][h]) + (sm.s_reds[2][h] + sm.s_reds[3][h]));
+                sm.s_run[0][h] = mnew[h];
             }
         }
-        // ---- acc = acc * scale + sum_keys e * V : half-warp = key row, lane = 4 output dims
+        // ---- acc = acc * scale + sum_keys e * V : half-warp = 16 consecutive keys, lane = 4 output dims
+        if (tile > 0) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            if (h < nh) {
-                acc[h][0] *= scale[h]; acc[h][1] *= scale[h]; acc[h][2] *= scale[h]; acc[h][3] *= scale[h];
-            }
+            for (int h = 0; h < NHT; ++h) { acc[h][0] *= scale[h]; acc[h][1] *= scale[h]; acc[h][2] *= scale[h]; acc[h][3] *= scale[h]; }
         }
+        const float* vrow = vtile + (hw * VR) * DH + 4 * l16;
 #pragma unroll
-        for (int i = 0; i < VR; ++i) {
-            const int jl = hw + NHW * i;
-            if (t0 + jl < nrows) {                   // uniform per half-warp; rows that were not copied hold stale data
-                const float4 v = *reinterpret_cast<const float4*>(vtile + jl * DH + 4 * l16);
+        for (int i4 = 0; i4 < VR / 4; ++i4) {
+            if (4 * i4 < nv) {                       // uniform per half-warp; rows that were not copied hold stale data
+                float w[NHT][4];
 #pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    if (h < nh) {
-                        const float w = sc[h][jl];
-                        acc[h][0] = fmaf(w, v.x, acc[h][0]); acc[h][1] = fmaf(w, v.y, acc[h][1]);
-                        acc[h][2] = fmaf(w, v.z, acc[h][2]); acc[h][3] = fmaf(w, v.w, acc[h][3]);
+                for (int h = 0; h < NHT; ++h) {
+                    const float4 t = *reinterpret_cast<const float4*>(&sm.sc[h][hw * VR + 4 * i4]);
+                    w[h][0] = t.x; w[h][1] = t.y; w[h][2] = t.z; w[h][3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (4 * i4 + u < nv) {
+                        const float4 v = *reinterpret_cast<const float4*>(vrow + (4 * i4 + u) * DH);
+#pragma unroll
+                        for (int h = 0; h < NHT; ++h) {
+                            acc[h][0] = fmaf(w[h][u], v.x, acc[h][0]); acc[h][1] = fmaf(w[h][u], v.y, acc[h][1]);
+                            acc[h][2] = fmaf(w[h][u], v.z, acc[h][2]); acc[h][3] = fmaf(w[h][u], v.w, acc[h][3]);
+                        }
                     }
                 }
             }
@@ -310,27 +287,27 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
     }
     // ---- merge the eight half-warp accumulators (fixed order); they all refer to the same running max
 #pragma unroll
-    for (int h = 0; h < NH; ++h)
-        if (h < nh) *reinterpret_cast<float4*>(&s_o[hw][h][4 * l16]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+    for (int h = 0; h < NHT; ++h) *reinterpret_cast<float4*>(&sm.s_o[hw][h][4 * l16]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
     __syncthreads();
 
     auto store_out = [&](int h, int d, float v) {
         const long long row = row0 + h;
-        if (out) out[row * D + head * DH + d] = v;
-        if (out_split) avsr_split3c_store(out_split + row * 3 * D, D, head * DH + d, v);
+        if (a.out) a.out[row * D + head * DH + d] = v;
+        if (a.out_split) avsr_split3c_store(a.out_split + row * 3 * D, D, head * DH + d, v);
     };
     const long long grp = (long long)utt * HEADS + head;
-    float* po = part_o + ((grp * nch + chunk) * beam) * DH;
-    float* pms = part_ms + ((grp * nch + chunk) * beam) * 2;
-    for (int i = tid; i < nh * DH; i += CK) {
+    const int nch = a.nch;
+    float* po = a.part_o + ((grp * nch + chunk) * beam) * DH;
+    float* pms = a.part_ms + ((grp * nch + chunk) * beam) * 2;
+    for (int i = tid; i < NHT * DH; i += CK) {
         const int h = i / DH, d = i % DH;
         float o = 0.f;
 #pragma unroll
-        for (int w = 0; w < NHW; ++w) o += s_o[w][h][d];
-        if (nact == 1) store_out(h, d, o / s_run[1][h]);
+        for (int w = 0; w < NHW; ++w) o += sm.s_o[w][h][d];
+        if (nact == 1) store_out(h, d, o / sm.s_run[1][h]);
         else {
             po[i] = o;
-            if (d == 0) { pms[2 * h] = s_run[0][h]; pms[2 * h + 1] = s_run[1][h]; }
+            if (d == 0) { pms[2 * h] = sm.s_run[0][h]; pms[2 * h + 1] = sm.s_run[1][h]; }
         }
     }
     if (nact == 1) return;
@@ -338,26 +315,91 @@ dec_attn_stream_kernel(const float* __restrict__ q_in, long long ldq, int nsplit
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const int t = atomicAdd(&tickets[grp], 1);
-        s_last = (t == nact - 1) ? 1 : 0;
-        if (s_last) tickets[grp] = 0;                // re-armed for the next launch
+        const int t = atomicAdd(&a.tickets[grp], 1);
+        sm.s_last = (t == nact - 1) ? 1 : 0;
+        if (sm.s_last) a.tickets[grp] = 0;           // re-armed for the next launch
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!sm.s_last) return;
     __threadfence();
-    for (int i = tid; i < nh * DH; i += CK) {
+    for (int i = tid; i < NHT * DH; i += CK) {
         const int h = i / DH, d = i % DH;
         float M = -INFINITY;
-        for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(part_ms + ((grp * nch + c) * beam + h) * 2));
+        for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(a.part_ms + ((grp * nch + c) * beam + h) * 2));
         float S = 0.f, o = 0.f;
         for (int c = 0; c < nact; ++c) {
-            const float* q = part_ms + ((grp * nch + c) * beam + h) * 2;
+            const float* q = a.part_ms + ((grp * nch + c) * beam + h) * 2;
             const float f = expf(__ldcg(q) - M);
             S = fmaf(__ldcg(q + 1), f, S);
-            o = fmaf(__ldcg(part_o + ((grp * nch + c) * beam) * DH + i), f, o);
+            o = fmaf(__ldcg(a.part_o + ((grp * nch + c) * beam) * DH + i), f, o);
         }
         store_out(h, d, o / S);
     }
+}
+
+template <int MODE, int NH>
+__global__ void __launch_bounds__(CK, (NH <= 4) ? 4 : 2)
+dec_attn_stream_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target)
+    __shared__ __align__(16) AttnSmem<NH> sm;
+    __shared__ unsigned rlist[(MODE == 0) ? CK * NH : 1];          // (row index << 8) | hyp mask, row = pos * beam + slot
+    const int tid = threadIdx.x;
+    const int hw = tid >> 4, l16 = tid & 15;
+    const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z;
+    const int p0 = chunk * CK;
+    pdl_trigger();
+
+    // K^T base (groups [j][row][8]) and V base ([row][64]) of this (utterance, head); nr = rows per j plane
+    const float* kbase;
+    const float* vbase;
+    long long nr;
+    int T_utt = 0;
+    float4 kreg[DH / 4];
+    if (MODE == 1) {
+        T_utt = a.utt_T[utt];
+        nr = a.n_frames;
+        const long long uoff = a.utt_off[utt];
+        kbase = a.kc + (long long)head * nr * DH + uoff * KG;
+        vbase = a.vc + (long long)head * nr * DH + uoff * DH;
+        // whole tile requested before the wait; rows past the end of the utterance are skipped
+        load_k<1>(kreg, kbase, nr, p0 + tid, p0 + tid < T_utt);
+        const int nv = T_utt - p0 - hw * VR;
+        const float* vsrc = vbase + (long long)(p0 + hw * VR) * DH + 4 * l16;
+        const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(vtile) + (uint32_t)((hw * VR) * DH + 4 * l16) * 4u;
+#pragma unroll
+        for (int i = 0; i < VR; ++i)
+            if (i < nv) cp_async16(vt_s + i * DH * 4, vsrc + i * DH);
+    } else {
+        nr = (long long)a.lmax * a.beam;
+        kbase = a.kc + (long long)(utt * HEADS + head) * nr * DH;
+        vbase = a.vc + (long long)(utt * HEADS + head) * nr * DH;
+    }
+    pdl_wait();
+    const int nh = a.n_run[utt];
+    const int step = *a.step_p;
+    const int n = (MODE == 1) ? T_utt : step + 1;
+    if (nh == 0 || p0 >= n) { cp_async_wait_all(); return; }
+#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step)
+    if (NH <= 4) {
+        switch (nh) {
+            case 1: AVSR_BODY(1); break;
+            case 2: AVSR_BODY(2); break;
+            case 3: AVSR_BODY(3); break;
+            default: AVSR_BODY(4); break;
+        }
+    } else {
+        switch (nh) {
+            case 1: AVSR_BODY(1); break;
+            case 2: AVSR_BODY(2); break;
+            case 3: AVSR_BODY(3); break;
+            case 4: AVSR_BODY(4); break;
+            case 5: AVSR_BODY(5); break;
+            case 6: AVSR_BODY(6); break;
+            case 7: AVSR_BODY(7); break;
+            default: AVSR_BODY(8); break;
+        }
+    }
+#undef AVSR_BODY
 }
 
 }  // namespace
@@ -367,13 +409,13 @@ extern "C" int avsr_dec_attn_chunks(int max_keys) { return (max_keys + CK - 1) /
 
 // mode 0: self-attention step.  Query / current k / current v = columns [0,1024) / [1024,2048) / [2048,3072) of q_in
 //   ([R, ldq] fp32).  kc / vc = this layer's caches; with row = pos*beam + slot and nr = lmax*beam, key element
-//   (utt, head, row, d) is at ((utt*16 + head)*16 + d/4)*nr*4 + row*4 + d%4 (transposed in 16-byte groups) and value
+//   (utt, head, row, d) is at ((utt*16 + head)*8 + d/8)*nr*8 + row*8 + d%8 (transposed in 32-byte groups) and value
 //   element at ((utt*16 + head)*nr + row)*64 + d.  anc [2][R][lmax] (uint8 slot per position, double-buffered on step
 //   parity).  The current k / v are written to the cache at (pos = *step, slot = the hyp's own slot).
 // mode 1: source attention.  Query = columns [0,1024) of q_in; kc / vc = this layer's cross K / V over the n_frames packed
-//   frames of all utterances (utt_off / utt_T index them): key element (head, frame, d) at (head*16 + d/4)*n_frames*4 +
-//   frame*4 + d%4, value element at (head*n_frames + frame)*64 + d (the layout avsr_kv_head_major writes).
-// nsplit > 0: q_in holds the split-K partial sums part[z][R][ldq] of the projection (z < nsplit); they are summed in split
+//   frames of all utterances (utt_off / utt_T index them): key element (head, frame, d) at (head*8 + d/8)*n_frames*8 +
+//   frame*8 + d%8, value element at (head*n_frames + frame)*64 + d (the layout avsr_kv_head_major writes).
+// nsplit > 0: q_in holds the split-K partial sums part[z][R][ldq] of the projection (z < nsplit); they are summed in a fixed
 //   order and q_bias[ldq] is added.  nsplit == 0: q_in is the finished projection.
 // out (fp32 [R,1024]) and / or out_split (compact bf16x3 [R, 3*1024]).  Scratch (nch = avsr_dec_attn_chunks(max_keys)):
 // part_o [R/beam][16][nch][beam][64], part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once by the
@@ -386,29 +428,29 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
     AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T && n_frames > 0), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
     AVSR_REQUIRE(beam <= 8 && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max 8)", beam);
     AVSR_REQUIRE(nsplit >= 0 && (nsplit == 0 || q_bias), "avsr_dec_attn_step: partial-sum input needs the bias");
-    AVSR_REQUIRE((ldq & 3) == 0 && ((uintptr_t)q_in & 15) == 0 && ((uintptr_t)q_bias & 15) == 0 && ((uintptr_t)kc & 15) == 0 &&
+    AVSR_REQUIRE((ldq & 3) == 0 && ((uintptr_t)q_in & 15) == 0 && ((uintptr_t)q_bias & 15) == 0 && ((uintptr_t)kc & 31) == 0 &&
                      ((uintptr_t)vc & 15) == 0,
-                 "avsr_dec_attn_step: q_in / q_bias / kc / vc must be 16-byte aligned and ldq a multiple of 4");
+                 "avsr_dec_attn_step: q_in / q_bias / vc must be 16-byte aligned, kc 32-byte aligned and ldq a multiple of 4");
     AVSR_REQUIRE(mode == 1 || (long long)lmax * beam < (1 << 24), "avsr_dec_attn_step: cache too long");
     const int nch = (max_keys + CK - 1) / CK;
     AVSR_REQUIRE(nch == 1 || (part_o && part_ms && tickets), "avsr_dec_attn_step: %d keys need the chunk scratch buffers", max_keys);
     AVSR_REQUIRE(nch <= 65535, "avsr_dec_attn_step: too many keys");
     const dim3 grid(R / beam, HEADS, nch);
     static bool configured = false;
-    if (!configured) {                                // static + dynamic shared memory of the 8-hyp variants exceeds 48 KB
+    if (!configured) {                                // static + dynamic shared memory of the 8-slot variants exceeds 48 KB
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
         configured = true;
     }
-#define AVSR_ATTN_LAUNCH(MODE, NH)                                                                                                   \
-    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<MODE, NH>, grid, dim3(CK), (size_t)CK * DH * sizeof(float), stream, q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, \
-                                    n_run, utt_off, utt_T, beam, R, step, out, n_frames, (__nv_bfloat16*)out_split, part_o, part_ms,    \
-                                    tickets, nch))
+    const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, n_frames,
+                        (__nv_bfloat16*)out_split, part_o, part_ms, tickets, nch};
+    const size_t smem = (size_t)CK * DH * sizeof(float);
     if (mode == 0) {
-        if (beam <= 4) AVSR_ATTN_LAUNCH(0, 4); else AVSR_ATTN_LAUNCH(0, 8);
+        if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 4>, grid, dim3(CK), smem, stream, a));
+        else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 8>, grid, dim3(CK), smem, stream, a));
     } else {
-        if (beam <= 4) AVSR_ATTN_LAUNCH(1, 4); else AVSR_ATTN_LAUNCH(1, 8);
+        if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 4>, grid, dim3(CK), smem, stream, a));
+        else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 8>, grid, dim3(CK), smem, stream, a));
     }
-#undef AVSR_ATTN_LAUNCH
     return AVSR_OK;
 }

@@ -196,7 +196,7 @@ split3_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __rest
 }
 
 // [F, ncol] -> [ncol/64][F][64]: float4 per thread.  kt_period > 0: 64-column blocks whose index b has (b / 16) % kt_period == 0
-// (the K halves of [k | v] pairs of 16 heads) are written transposed in 16-byte groups, [b][16][F][4], the layout the decode
+// (the K halves of [k | v] pairs of 16 heads) are written transposed in 32-byte groups, [b][8][F][8], the layout the decode
 // step's attention reads keys in (csrc/dec_attn.cu).
 __global__ void __launch_bounds__(256)
 kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int ncol, int kt_period) {
@@ -207,7 +207,7 @@ kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long
         const float4 v = *reinterpret_cast<const float4*>(in + f * ncol + c);
         const int b = c / 64;
         if (kt_period > 0 && ((b / 16) % kt_period) == 0)
-            *reinterpret_cast<float4*>(out + (long long)b * F * 64 + ((long long)((c % 64) >> 2) * F + f) * 4) = v;
+            *reinterpret_cast<float4*>(out + (long long)b * F * 64 + ((long long)((c % 64) >> 3) * F + f) * 8 + (c & 4)) = v;
         else
             *reinterpret_cast<float4*>(out + ((long long)b * F + f) * 64 + (c % 64)) = v;
     }

@@ -148,14 +148,14 @@ int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_st
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
                       const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
 /* One decode position of MultiHeadedAttention (transformer/attention.py:38-106, called from decoder_layer.py:82-107) with
- * cached K/V, streamed once (csrc/dec_attn.cu).  Keys are stored transposed in 16-byte groups, values row-major.
+ * cached K/V, streamed once (csrc/dec_attn.cu).  Keys are stored transposed in 32-byte groups, values row-major.
  * mode 0 = self-attention over the hypothesis' own history: query / current k / current v = columns [0,1024) / [1024,2048) /
  *   [2048,3072) of q_in; kc / vc = this layer's caches: with row = pos*beam + slot and nr = lmax*beam, key element
- *   (utt, head, row, d) at ((utt*16 + head)*16 + d/4)*nr*4 + row*4 + d%4, value element at ((utt*16 + head)*nr + row)*64 + d;
+ *   (utt, head, row, d) at ((utt*16 + head)*8 + d/8)*nr*8 + row*8 + d%8, value element at ((utt*16 + head)*nr + row)*64 + d;
  *   anc [2][R][lmax] = slot that holds position pos of a row's history (double-buffered on step parity); the current k / v
  *   are appended at (pos = *step, slot = own slot).
  * mode 1 = source attention over the utterance's precomputed K/V (n_frames packed frames of all utterances): key element
- *   (head, frame, d) at (head*16 + d/4)*n_frames*4 + frame*4 + d%4, value element at (head*n_frames + frame)*64 + d.
+ *   (head, frame, d) at (head*8 + d/8)*n_frames*8 + frame*8 + d%8, value element at (head*n_frames + frame)*64 + d.
  * nsplit > 0: q_in = split-K partial sums part[z][R][ldq] of the projection, summed here in split order + q_bias.
  * Scratch (caller-owned, nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64] fp32,
  * part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once. */
@@ -165,7 +165,7 @@ int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, c
                        const int* step, float* out, int max_keys, long long n_frames, void* out_split, float* part_o,
                        float* part_ms, int* tickets, avsr_stream_t stream);
 /* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span).  k_transposed:
- * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][16][F][4] (transposed in 16-byte groups), the
+ * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][8][F][8] (transposed in 32-byte groups), the
  * key layout avsr_dec_attn_step mode 1 reads. */
 int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, int k_transposed, avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,

@@ -296,8 +296,8 @@ def test_dec_attn_step_self(L, beam, step, nsplit):
     g = torch.Generator().manual_seed(100 + step)
     kc_log = torch.randn(B, 16, lmax, beam, 64, generator=g).cuda()    # logical [utt][head][pos][slot][64]
     vc = torch.randn(B, 16, lmax, beam, 64, generator=g).cuda()
-    # physical key cache: transposed in 16-byte groups, [utt][head][16][pos*beam+slot][4]
-    to_phys = lambda k: k.reshape(B, 16, lmax * beam, 16, 4).permute(0, 1, 3, 2, 4).contiguous()
+    # physical key cache: transposed in 32-byte groups, [utt][head][8][pos*beam+slot][8]
+    to_phys = lambda k: k.reshape(B, 16, lmax * beam, 8, 8).permute(0, 1, 3, 2, 4).contiguous()
     to_log = lambda k: k.permute(0, 1, 3, 2, 4).reshape(B, 16, lmax, beam, 64)
     kc = to_phys(kc_log)
     qkv = torch.randn(R, 3072, generator=g).cuda()
@@ -357,7 +357,7 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
     g = torch.Generator().manual_seed(7)
     kc = torch.randn(16, Fr, 64, generator=g).cuda()
     vc = torch.randn(16, Fr, 64, generator=g).cuda()
-    kc_phys = kc.reshape(16, Fr, 16, 4).permute(0, 2, 1, 3).contiguous()       # keys transposed in 16-byte groups: [head][16][F][4]
+    kc_phys = kc.reshape(16, Fr, 8, 8).permute(0, 2, 1, 3).contiguous()        # keys transposed in 32-byte groups: [head][8][F][8]
     q = torch.randn(R, 1024, generator=g).cuda()
     q_in, q_bias = _as_partials(q, nsplit, 6)
     n_run = torch.tensor([beam, 1, 0, beam - 1][:B], dtype=torch.int32, device="cuda")

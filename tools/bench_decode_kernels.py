@@ -42,7 +42,7 @@ n_run, utt_off, utt_T = i32([beam] * B), i32([b * T for b in range(B)]), i32([T]
 step_t = i32([step])
 qkv = torch.randn(R, 3072, device=dev)
 q2 = torch.randn(R, 1024, device=dev)
-kc = torch.randn(nl, B, 16, 16, lmax * beam, 4, device=dev)        # keys transposed in 16-byte groups
+kc = torch.randn(nl, B, 16, 8, lmax * beam, 8, device=dev)        # keys transposed in 32-byte groups
 vc = torch.randn(nl, B, 16, lmax * beam, 64, device=dev)
 anc = torch.randint(0, beam, (2, R, lmax), dtype=torch.uint8, device=dev)
 if len(sys.argv) > 2 and sys.argv[2] == 'shared':

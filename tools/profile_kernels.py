@@ -45,7 +45,7 @@ if "ctc" in which:
 if "attn" in which:
     lmax, nl = T + 1, 2
     qkv, q2 = torch.randn(R, 3072, device=dev), torch.randn(R, 1024, device=dev)
-    kc = torch.randn(nl, B, 16, 16, lmax * beam, 4, device=dev)
+    kc = torch.randn(nl, B, 16, 8, lmax * beam, 8, device=dev)
     vc = torch.randn(nl, B, 16, lmax * beam, 64, device=dev)
     anc = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
     ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
