@@ -402,6 +402,7 @@ __device__ __forceinline__ float ctc_logpsi(const AvsrBeamState& st, const int* 
 }
 
 constexpr int MAXB = 8;
+constexpr int FAST_MAXS = 12;             // pre-beam candidates per hyp handled by the fast path of the fusion kernel
 
 __global__ void __launch_bounds__(256)
 beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ dec_logp, const int* __restrict__ part_ids,
@@ -425,7 +426,63 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     const int step = *st.step;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- per-thread top-`beam` over the flattened [nrun, V] fused scores
+    // ---- fast path.  Only the pre-beam candidates and eos have a CTC score other than logzero (batch_beam_search.py:229-247:
+    // the partial scorer fills everything else with -1e10), so the top-`beam` of the flattened [nrun, V] fused scores are
+    // found among those <= nrun * (S + 1) entries whenever `beam` of them beat the best score any other entry could have.
+    __shared__ float fw[MAXB * (FAST_MAXS + 1)];
+    __shared__ int fi[MAXB * (FAST_MAXS + 1)];
+    __shared__ int s_fast;
+    if (tid == 0) s_fast = 0;
+    __syncthreads();
+    if (S <= FAST_MAXS && warp == 0) {
+        const int ncand = nrun * (S + 1);
+        float bound = -INFINITY;                     // upper bound of every entry that is NOT a candidate (dec_logp <= 0)
+        for (int h = 0; h < nrun; ++h)
+            bound = fmaxf(bound, __fadd_rn(__fmul_rn(w_ctc, __fsub_rn(LOGZERO, st.s_prev[base + h])), st.score[base + h]));
+        for (int c = lane; c < ncand; c += 32) {
+            const int h = c / (S + 1), s = c - h * (S + 1);
+            const int row = base + h;
+            const int v = (s < S) ? part_ids[row * S + s] : st.eos;
+            float w = -INFINITY;
+            int ix = 0x7fffffff;
+            if (!(s < S && (v == st.eos || v == st.blank))) {        // eos is listed once; blank scores logzero like a non-candidate
+                const float lpsi = (s < S) ? psi[row * S + s] : rsum_last[row];
+                const float cs = __fsub_rn(lpsi, st.s_prev[row]);
+                w = __fadd_rn(__fadd_rn(__fmul_rn(w_dec, dec_logp[(long long)row * V + v]), __fmul_rn(w_ctc, cs)), st.score[row]);
+                ix = h * V + v;
+            }
+            fw[c] = w;
+            fi[c] = ix;
+        }
+        __syncwarp();
+        bool ok = true;
+        for (int j = 0; j < beam; ++j) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff, bo = -1;
+            for (int c = lane; c < ncand; c += 32) {
+                const float v = fw[c];
+                const int ix = fi[c];
+                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; bo = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int oo = __shfl_xor_sync(0xffffffffu, bo, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bo = oo; }
+            }
+            if (!(bv > bound)) ok = false;           // a non-candidate could tie or win: take the exhaustive path
+            if (lane == 0) {
+                selv[j] = bv; seli[j] = bi;
+                if (bo >= 0) { fw[bo] = -INFINITY; fi[bo] = 0x7fffffff; }
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && ok) s_fast = 1;
+    }
+    __syncthreads();
+    if (!s_fast) {
+    // ---- exhaustive path: per-thread top-`beam` over the flattened [nrun, V] fused scores
     float lv[MAXB];
     int li[MAXB];
 #pragma unroll
@@ -476,6 +533,8 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
             if (bo >= 0) { cval[bo] = -INFINITY; cidx[bo] = 0x7fffffff; }
         }
         __syncthreads();
+    }
+
     }
 
     // ---- bookkeeping (serial over <= beam candidates)

@@ -142,13 +142,14 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
 }
 
 // One CTA per output row (see splitk_epilogue.cuh).
-__global__ void __launch_bounds__(256)
+template <int P>
+__global__ void __launch_bounds__(768)
 splitk_epilogue_kernel(const SplitKEpi e) {
     extern __shared__ float rowbuf[];
     __shared__ float red[32];
     pdl_trigger();
     pdl_wait();
-    avsr_splitk_epilogue_row(e, blockIdx.x, rowbuf, red);
+    avsr_splitk_epilogue_row<P>(e, blockIdx.x, rowbuf, red);
 }
 
 int g_sms = 0;
@@ -209,6 +210,11 @@ extern "C" int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N,
     AVSR_REQUIRE(!ln_g || (ln_b && N * 4 <= 48 * 1024), "avsr_splitk_epilogue: LayerNorm needs gamma/beta and N <= 12288");
     const size_t smem = ln_g ? (size_t)N * 4 : 0;
     SplitKEpi e = {part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps, ln_out, ld_ln, row_active, (__nv_bfloat16*)split_out};
-    AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel, dim3(M), dim3(256), smem, stream, e));
+    // one thread per 4 columns up to 768 threads.  (Splitting a column group's partial sums over 2 or 4 threads, P > 1, cuts
+    // the loads per thread but measured slower on B200 at these sizes: 5.8 vs 4.0 us for N = 1024, 16 splits - the row-wide
+    // reductions of the LayerNorm then run over 1024 mostly idle threads.)
+    int threads = ((N + 3) / 4 + 31) / 32 * 32;
+    threads = threads < 256 ? 256 : (threads > 768 ? 768 : threads);
+    AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel<1>, dim3(M), dim3(threads), smem, stream, e));
     return AVSR_OK;
 }

@@ -27,6 +27,10 @@ struct SplitKEpi {
 };
 
 // rowbuf: N floats of shared memory (only touched when ln_g != nullptr); red: 32 floats of shared memory.
+// P (1, 2 or 4; blockDim.x % P == 0): threads that share one group of four columns.  Each sums a contiguous range of the
+// splits (few loads per thread, all in flight at once: one L2 round trip) and the P sums are combined with xor shuffles in
+// a fixed tree, so every thread of the group holds the bit-identical total; thread 0 of the group finishes the columns.
+template <int P = 1>
 __device__ __forceinline__ void avsr_splitk_epilogue_row(const SplitKEpi& e, int row, float* rowbuf, float* red) {
     const float* part = e.part;
     const int nsplit = e.nsplit, M = e.M, N = e.N, act = e.act;
@@ -44,12 +48,18 @@ __device__ __forceinline__ void avsr_splitk_epilogue_row(const SplitKEpi& e, int
     float lsum = 0.f;
     const long long zstride = (long long)M * N;
     if ((N & 3) == 0 && (ldr & 3) == 0 && (ldo & 3) == 0) {
-        // vector path: 4 columns per thread, the nsplit partial loads of a column group are issued 4 at a time
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
-            const float* p = part + (long long)row * N + c;
+        // vector path: 4 columns per group of P threads
+        const int sub = threadIdx.x % P, grp = threadIdx.x / P, ngrp = blockDim.x / P;
+        const int zper = (nsplit + P - 1) / P;
+        const int z0 = sub * zper, z1 = min(nsplit, z0 + zper);
+        const int ncol_iter = (N / 4 + ngrp - 1) / ngrp;              // same trip count for every thread (shuffles inside)
+        for (int it = 0; it < ncol_iter; ++it) {
+            const int c = (grp + it * ngrp) * 4;
+            const bool live = c < N;
+            const float* p = part + (long long)row * N + (live ? c : 0);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            int z = 0;
-            for (; z + 4 <= nsplit; z += 4) {
+            int z = z0;
+            for (; z + 4 <= z1; z += 4) {
                 const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p + (z + 0) * zstride));
                 const float4 a1 = __ldcg(reinterpret_cast<const float4*>(p + (z + 1) * zstride));
                 const float4 a2 = __ldcg(reinterpret_cast<const float4*>(p + (z + 2) * zstride));
@@ -59,10 +69,18 @@ __device__ __forceinline__ void avsr_splitk_epilogue_row(const SplitKEpi& e, int
                 v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
                 v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
             }
-            for (; z < nsplit; ++z) {
+            for (; z < z1; ++z) {
                 const float4 a0 = __ldcg(reinterpret_cast<const float4*>(p + z * zstride));
                 v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
             }
+            if (P > 1) {
+#pragma unroll
+                for (int o = 1; o < P; o <<= 1) {
+                    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+                }
+            }
+            if (!live || sub != 0) continue;
             if (bias) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias + c);
                 v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
@@ -81,13 +99,13 @@ __device__ __forceinline__ void avsr_splitk_epilogue_row(const SplitKEpi& e, int
         // LayerNorm of the finished row (values of this thread's columns are still in rowbuf; same thread re-reads them)
         const float mean = block_sum(lsum, red) / (float)N;
         float lvar = 0.f;
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        for (int c = (sub == 0 ? grp * 4 : N); c < N; c += ngrp * 4) {
             const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
             const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
             lvar += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         }
         const float rstd = rsqrtf(block_sum(lvar, red) / (float)N + ln_eps);
-        for (int c = threadIdx.x * 4; c < N; c += blockDim.x * 4) {
+        for (int c = (sub == 0 ? grp * 4 : N); c < N; c += ngrp * 4) {
             const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
             const float4 g4 = *reinterpret_cast<const float4*>(ln_g + c);
             const float4 b4 = *reinterpret_cast<const float4*>(ln_b + c);
