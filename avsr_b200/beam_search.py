@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, NamedTuple, Optional, Sequence, Union
 
 import numpy as np
@@ -76,6 +77,10 @@ class BatchedBeamSearch:
         self.w_ctc = float(np.float32(ctc_weight))
         self.use_graph = use_graph
         self.fuse_epilogue = False
+        # stage the layer's cross-attention K/V in L2 ahead of the source attention (AVSR_L2_PREFETCH=0: dev A/B switch)
+        # (measured SLOWER on B200, 477 vs 461 ms per 32-utterance pass, so it is off unless AVSR_L2_PREFETCH=1)
+        self.l2_prefetch = os.environ.get("AVSR_L2_PREFETCH", "0") == "1"
+        self._skip = frozenset()      # dev aid (tools/ablate_step.py): kernel groups left out of _step for timing ablations
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
         self.last_session = None
         self._sessions = {}
@@ -120,11 +125,6 @@ class BatchedBeamSearch:
         s["vc"] = torch.empty(nl, B, 16, lmax * beam, 64, dtype=torch.float32, device=dev)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
-        # scratch of the key-chunked step attention (csrc/decode.cu): partial (sum e*v, max, sum) per chunk + merge tickets
-        nch = lib.avsr_dec_attn_chunks(lmax)
-        s["att_po"] = torch.empty(B, 16, nch, beam, 64, dtype=torch.float32, device=dev)
-        s["att_pms"] = torch.empty(B, 16, nch, beam, 2, dtype=torch.float32, device=dev)
-        s["att_tickets"] = i32(B, 16)
         shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
         if self.precision == "bf16x3":
             # activations of the step in compact bf16x3 form [a1|a2|a3] (operands of csrc/gemm_x3.cu)
@@ -165,6 +165,8 @@ class BatchedBeamSearch:
         """partial sums of act[R,K] @ W[N,K]^T into s['part']; returns the number of K splits."""
         lib = L.load()
         R = s["R"]
+        if "gemm" in self._skip:
+            return lib.avsr_gemm_x3_splits(R, N, K) if self.precision == "bf16x3" else lib.avsr_sgemm_skinny_splits(R, N, K)
         if self.precision == "bf16x3":
             ns = lib.avsr_gemm_x3_splits(R, N, K)
             L.check(lib.avsr_gemm_x3_splitk(L.ptr(s[key_a + "3"]), L.ll(3 * K), L.ptr(lay[name + "3"]), L.ll(3 * K), R, N, K,
@@ -176,7 +178,7 @@ class BatchedBeamSearch:
                     "avsr_sgemm_skinny")
         return ns
 
-    def _linear(self, s, key_a, lay, name, N, K, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, key_out=None):
+    def _linear(self, s, key_a, lay, name, N, K, bias, act=L.ACT_NONE, residual=None, out=None, ln=None, key_out=None, prefetch=None):
         """One nn.Linear of the step plus its glue: act[R,K] @ W[N,K]^T + bias ; act ; + residual -> out ; LayerNorm -> the
         operand of the next projection (fp32 s[key_out] on the CUDA-core path, compact bf16x3 s[key_out + '3'] on the
         tensor-core path).  Split-K projection + row-wise epilogue kernel.  ``fuse_epilogue=True`` runs both in ONE launch
@@ -198,9 +200,13 @@ class BatchedBeamSearch:
                                            L.ptr(s["gbar"]), L.stream()), "avsr_gemm_x3_fused")
             return
         ns = self._proj(s, key_a, lay, name, N, K)
-        L.check(lib.avsr_splitk_epilogue(L.ptr(s["part"]), ns, R, N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
-                                         L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(ln_out), L.ll(1024),
-                                         L.ptr(s["row_active"]), L.ptr(split), L.stream()), "avsr_splitk_epilogue")
+        if "epi" in self._skip:
+            return
+        pf_bytes = prefetch.numel() * prefetch.element_size() if (prefetch is not None and self.l2_prefetch) else 0
+        L.check(lib.avsr_splitk_epilogue_pf(L.ptr(s["part"]), ns, R, N, L.ptr(bias), act, L.ptr(residual), L.ll(1024),
+                                            L.ptr(out), L.ll(N), L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(ln_out), L.ll(1024),
+                                            L.ptr(s["row_active"]), L.ptr(split), L.ptr(prefetch) if pf_bytes else None, L.ll(pf_bytes),
+                                            L.stream()), "avsr_splitk_epilogue")
 
     def _step(self, s):
         """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
@@ -217,20 +223,24 @@ class BatchedBeamSearch:
         kvld = nl * 2 * 1024
         att_f32 = None if tc else L.ptr(s["att"])
         att_split = L.ptr(s["att3"]) if tc else None
-        scratch = (L.ptr(s["att_po"]), L.ptr(s["att_pms"]), L.ptr(s["att_tickets"]))
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93); the attention kernel sums the split-K partials of q | k | v itself
             ns = self._proj(s, "a", lay, "wqkv", 3072, 1024)
-            L.check(lib.avsr_dec_attn_step(0, L.ptr(s["part"]), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]),
-                                           L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R,
-                                           L.ptr(s["step"]), att_f32, lmax, L.ll(0), att_split, *scratch, st()), "avsr_dec_attn_step(self)")
-            self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a")
+            if "self" not in self._skip:
+                L.check(lib.avsr_dec_attn_step(0, L.ptr(s["part"]), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]),
+                                               L.ptr(s["vc"][li]), L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]),
+                                               L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32, L.ll(0), att_split, st()),
+                        "avsr_dec_attn_step(self)")
+            # (its row epilogue also asks the L2 for this layer's cross K/V, which the source attention streams two kernels later)
+            self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a",
+                         prefetch=s["ckv_t"][li])
             # source attention over the precomputed K/V of the utterance's frames (decoder_layer.py:97-107)
             ns = self._proj(s, "a", lay, "wq2", 1024, 1024)
             ck, cv = s["ckv_t"][li, 0], s["ckv_t"][li, 1]
-            L.check(lib.avsr_dec_attn_step(1, L.ptr(s["part"]), L.ll(1024), ns, L.ptr(lay["bq2"]), L.ptr(ck), L.ptr(cv), None, lmax,
-                                           L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32,
-                                           s["tmax"], L.ll(s["F"]), att_split, *scratch, st()), "avsr_dec_attn_step(src)")
+            if "cross" not in self._skip:
+                L.check(lib.avsr_dec_attn_step(1, L.ptr(s["part"]), L.ll(1024), ns, L.ptr(lay["bq2"]), L.ptr(ck), L.ptr(cv), None, lmax,
+                                               L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
+                                               att_f32, L.ll(s["F"]), att_split, st()), "avsr_dec_attn_step(src)")
             self._linear(s, "att", lay, "wo2", 1024, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
             self._linear(s, "a", lay, "w1", 3072, 1024, lay["b1"], act=L.ACT_RELU, key_out="ffn")
@@ -238,6 +248,8 @@ class BatchedBeamSearch:
             self._linear(s, "ffn", lay, "w2", 1024, 3072, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
         # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
         ns = self._proj(s, "a", {"out": w.out_w, "out3": getattr(w, "out_w3", None)}, "out", V, 1024)
+        if "tail" in self._skip:
+            return
         L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
                                              L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
         # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
@@ -245,6 +257,8 @@ class BatchedBeamSearch:
                                             beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
                                             L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
                 "avsr_ctc_prefix_prebeam")
+        if "advance" in self._skip:
+            return
         # fusion, top-k, hypothesis bookkeeping, end detection (batch_beam_search.py:222-349)
         L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
                                                 L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc), st()),

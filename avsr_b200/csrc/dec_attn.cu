@@ -3,8 +3,11 @@
 // form: the reference re-projects K and V of every cached token / source frame at every step (decoder.py:153-183).
 //
 // HBM-streaming design:
-//   * CTA (128 threads) = (utterance, head, chunk of 128 keys).  All live hyps of the utterance are served by the same CTA,
-//     so a K / V row shared by several hyps is read from HBM once.
+//   * CTA (128 threads) = (utterance, head): the whole grid (512 CTAs for 32 utterances) is resident at once, so there are no
+//     waves of CTAs that each pay the full dependent chain (wait -> query -> loads -> softmax -> merge), which is what bounds
+//     a launch this short.  All live hyps of the utterance are served by the same CTA, so a K / V row shared by several hyps
+//     is read from HBM once.  The keys are processed in tiles of 128; the K registers of tile i+1 are requested as soon as
+//     the scores of tile i are done and the V tile of i+1 as soon as the P.V product of tile i is done.
 //   * K is stored TRANSPOSED in 32-byte groups, K^T[j][row][8] (j = dim / 8): thread = key, its loads are coalesced across
 //     the warp (whole 32-byte sectors per row, also when only every beam-th row of the self-attention cache is live) and put
 //     the 64-float key in registers; the dot products with the (few) queries are plain FMAs against broadcast
@@ -16,10 +19,9 @@
 //   * mode 0 (self-attention): a hyp finds its history through the ancestry table anc[row][pos] = slot; the CTA builds the
 //     list of DISTINCT (pos, slot) rows its live hyps reference, each with the bit mask of the hyps that use it (beams
 //     mostly share their ancestors), and streams exactly those rows, 128 at a time.  k / v of the current position are
-//     appended by the CTA that owns the chunk containing it.
-//   * softmax statistics per tile (exact max, then exponentials), running (max, sum, sum e*v) across the tiles of a CTA,
-//     partial results of the chunks merged in chunk order by the last CTA of the (utterance, head) group (atomic ticket):
-//     the result never depends on scheduling.
+//     appended to the cache first.
+//   * softmax statistics per tile (exact max, then exponentials), running (max, sum, sum e*v) across the tiles in tile
+//     order: the result never depends on scheduling.
 //   * The query (and the current k, v) can be taken straight from the split-K partial sums of the projection that produced
 //     them (sum over splits in a fixed order + bias), which saves one epilogue launch per attention.
 //   * The body is instantiated for the exact number of live hyps: no per-hyp guards in the inner loops.
@@ -30,7 +32,7 @@ namespace {
 constexpr int D = 1024;
 constexpr int HEADS = 16;
 constexpr int DH = 64;
-constexpr int CK = 128;                  // positions (self) / frames (cross) per chunk = keys per tile = threads per CTA
+constexpr int CK = 128;                  // keys per tile = threads per CTA
 constexpr int NHW = 8;                   // half-warps per CTA
 constexpr int VR = CK / NHW;             // V rows per half-warp and tile (16 consecutive keys)
 constexpr int KG = 8;                    // floats per key group (32 bytes = one sector)
@@ -44,7 +46,7 @@ struct AttnArgs {
     const float* q_in; long long ldq; int nsplit; const float* q_bias;
     float* kc; float* vc; const unsigned char* anc; int lmax;
     const int* n_run; const int* utt_off; const int* utt_T; int beam; int R; const int* step_p;
-    float* out; long long n_frames; __nv_bfloat16* out_split; float* part_o; float* part_ms; int* tickets; int nch;
+    float* out; long long n_frames; __nv_bfloat16* out_split;
 };
 
 template <int NH>
@@ -56,7 +58,7 @@ struct AttnSmem {
     float s_redm[4][NH], s_reds[4][NH];
     float s_run[2][NH];                  // running max / sum over the tiles of this CTA
     int s_wcnt[4];
-    int s_last;
+    int s_nrows;
 };
 
 // K of one key: 16 x 16-byte loads, two per 32-byte group.  MODE 0 uses plain loads (this CTA may just have written the row).
@@ -80,12 +82,10 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
                                           const float* kbase, const float* vbase, long long nr, int T_utt, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = tid >> 4, l16 = tid & 15;
-    const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z;
+    const int utt = blockIdx.x, head = blockIdx.y;
     const int beam = a.beam, R = a.R, nsplit = a.nsplit;
     const int row0 = utt * beam;
-    const int p0 = chunk * CK;
-    const int n = (MODE == 1) ? T_utt : step + 1;
-    const int nact = (n + CK - 1) / CK;
+    const int n = (MODE == 1) ? T_utt : step + 1;    // keys (mode 1) / positions (mode 0)
     const float* q_in = a.q_in;
     const long long ldq = a.ldq;
     const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(vtile) + (uint32_t)((hw * VR) * DH + 4 * l16) * 4u;   // this thread's V slots
@@ -126,7 +126,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
             *reinterpret_cast<float4*>(sub == 0 ? &sm.qs[h][4 * j] : &sm.qpart[h][4 * j]) = v;
         }
     }
-    if (MODE == 0 && step >= p0 && step < p0 + CK) {
+    if (MODE == 0) {
         for (int g = tid; g < 2 * G; g += CK) {
             const int kv = g / G, gg = g % G;
             const int h = gg / (DH / 4), j = gg % (DH / 4);
@@ -145,37 +145,42 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         }
     }
     // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
-    int nrows = (MODE == 1) ? min(CK, T_utt - p0) : 0;
+    int nrows = (MODE == 1) ? T_utt : 0;
     if (MODE == 0) {
-        const int p = p0 + tid;
-        unsigned msk[NH];
+        int total = 0;
+        for (int pb = 0; pb < n; pb += CK) {
+            const int p = pb + tid;
+            unsigned msk[NH];
 #pragma unroll
-        for (int s = 0; s < NH; ++s) msk[s] = 0u;
-        if (p < n) {
+            for (int s = 0; s < NH; ++s) msk[s] = 0u;
+            if (p < n) {
 #pragma unroll
-            for (int h = 0; h < NHT; ++h) {
-                const int slot = (p < step) ? (int)a.anc[((long long)(step & 1) * R + row0 + h) * a.lmax + p] : h;
+                for (int h = 0; h < NHT; ++h) {
+                    const int slot = (p < step) ? (int)a.anc[((long long)(step & 1) * R + row0 + h) * a.lmax + p] : h;
 #pragma unroll
-                for (int s = 0; s < NH; ++s) msk[s] |= (slot == s) ? (1u << h) : 0u;
+                    for (int s = 0; s < NH; ++s) msk[s] |= (slot == s) ? (1u << h) : 0u;
+                }
             }
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < NH; ++s) cnt += msk[s] != 0u;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            __syncthreads();                         // s_wcnt of the previous round has been read; the appended k / v are visible
+            if (lane == 31) sm.s_wcnt[warp] = incl;
+            __syncthreads();
+            int base = total + incl - cnt;
+            for (int w = 0; w < warp; ++w) base += sm.s_wcnt[w];
+            total += sm.s_wcnt[0] + sm.s_wcnt[1] + sm.s_wcnt[2] + sm.s_wcnt[3];
+#pragma unroll
+            for (int s = 0; s < NH; ++s)
+                if (msk[s] != 0u) rlist[base++] = ((unsigned)(p * beam + s) << 8) | msk[s];
         }
-        int cnt = 0;
-#pragma unroll
-        for (int s = 0; s < NH; ++s) cnt += msk[s] != 0u;
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) sm.s_wcnt[warp] = incl;
-        __syncthreads();                             // also: the appended k / v are visible to the whole CTA
-        int base = incl - cnt;
-        for (int w = 0; w < warp; ++w) base += sm.s_wcnt[w];
-        nrows = sm.s_wcnt[0] + sm.s_wcnt[1] + sm.s_wcnt[2] + sm.s_wcnt[3];
-#pragma unroll
-        for (int s = 0; s < NH; ++s)
-            if (msk[s] != 0u) rlist[base++] = ((unsigned)(p * beam + s) << 8) | msk[s];
+        nrows = total;
     }
     if (tid < NHT) { sm.s_run[0][tid] = -INFINITY; sm.s_run[1][tid] = 0.f; }
     __syncthreads();                                 // qs / qpart, rlist, s_run ready
@@ -196,20 +201,33 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
 #pragma unroll
     for (int h = 0; h < NHT; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
 
-    const int ntiles = (nrows + CK - 1) / CK;        // mode 1: always 1
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int t0 = tile * CK;
-        unsigned my = 0xffu;                         // hyp mask of this thread's key
-        const bool kvalid = t0 + tid < nrows;
-        const int nv = min(VR, nrows - t0 - hw * VR);                // valid V rows of this half-warp in this tile (may be <= 0)
+    const int ntiles = (nrows + CK - 1) / CK;
+    // requests of one tile: K of this thread's key into registers, the half-warp's 16 V rows into shared memory
+    auto request_k = [&](int t0) {
+        const bool ok = t0 + tid < nrows;
+        if (MODE == 0) load_k<0>(kreg, kbase, nr, ok ? (long long)(rlist[t0 + tid] >> 8) : 0, ok);
+        else load_k<1>(kreg, kbase, nr, t0 + tid, ok);
+    };
+    auto request_v = [&](int t0) {
+        const int nv = nrows - t0 - hw * VR;
         if (MODE == 0) {
-            my = kvalid ? rlist[t0 + tid] : 0u;
-            load_k<0>(kreg, kbase, nr, (long long)(my >> 8), kvalid);
 #pragma unroll
             for (int i = 0; i < VR; ++i)
                 if (i < nv) cp_async16(vt_s + i * DH * 4, vbase + (long long)(rlist[t0 + hw * VR + i] >> 8) * DH + 4 * l16);
+        } else {
+            const float* vsrc = vbase + (long long)(t0 + hw * VR) * DH + 4 * l16;
+#pragma unroll
+            for (int i = 0; i < VR; ++i)
+                if (i < nv) cp_async16(vt_s + i * DH * 4, vsrc + i * DH);
         }
-        if (tile == 0) __syncthreads();              // finished query visible (the loads above are already in flight)
+    };
+    if (MODE == 0) { request_k(0); request_v(0); }  // mode 1: tile 0 was requested before griddepcontrol.wait
+    __syncthreads();                                 // finished query visible (the loads above are already in flight)
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int t0 = tile * CK;
+        const bool kvalid = t0 + tid < nrows;
+        const unsigned my = (MODE == 0) ? (kvalid ? rlist[t0 + tid] : 0u) : 0xffu;     // hyp mask of this thread's key
+        const int nv = min(VR, nrows - t0 - hw * VR);                // valid V rows of this half-warp in this tile (may be <= 0)
         // ---- scores of this thread's key against every live hyp
         float s[NHT];
 #pragma unroll
@@ -223,6 +241,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
                 s[h] = fmaf(q.z, kreg[j].z, s[h]); s[h] = fmaf(q.w, kreg[j].w, s[h]);
             }
         }
+        if (tile + 1 < ntiles) request_k(t0 + CK);   // the key registers are free: next tile's keys fly during softmax and P.V
 #pragma unroll
         for (int h = 0; h < NHT; ++h) {
             s[h] = (kvalid && ((my >> h) & 1u)) ? s[h] * 0.125f : -INFINITY;
@@ -284,6 +303,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
                 }
             }
         }
+        if (tile + 1 < ntiles) request_v(t0 + CK);   // this thread's V slots are free again
     }
     // ---- merge the eight half-warp accumulators (fixed order); they all refer to the same running max
 #pragma unroll
@@ -295,58 +315,24 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         if (a.out) a.out[row * D + head * DH + d] = v;
         if (a.out_split) avsr_split3c_store(a.out_split + row * 3 * D, D, head * DH + d, v);
     };
-    const long long grp = (long long)utt * HEADS + head;
-    const int nch = a.nch;
-    float* po = a.part_o + ((grp * nch + chunk) * beam) * DH;
-    float* pms = a.part_ms + ((grp * nch + chunk) * beam) * 2;
     for (int i = tid; i < NHT * DH; i += CK) {
         const int h = i / DH, d = i % DH;
         float o = 0.f;
 #pragma unroll
         for (int w = 0; w < NHW; ++w) o += sm.s_o[w][h][d];
-        if (nact == 1) store_out(h, d, o / sm.s_run[1][h]);
-        else {
-            po[i] = o;
-            if (d == 0) { pms[2 * h] = sm.s_run[0][h]; pms[2 * h + 1] = sm.s_run[1][h]; }
-        }
-    }
-    if (nact == 1) return;
-    // ---- several chunks: the last CTA of the group to arrive merges all partials in chunk order
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int t = atomicAdd(&a.tickets[grp], 1);
-        sm.s_last = (t == nact - 1) ? 1 : 0;
-        if (sm.s_last) a.tickets[grp] = 0;           // re-armed for the next launch
-    }
-    __syncthreads();
-    if (!sm.s_last) return;
-    __threadfence();
-    for (int i = tid; i < NHT * DH; i += CK) {
-        const int h = i / DH, d = i % DH;
-        float M = -INFINITY;
-        for (int c = 0; c < nact; ++c) M = fmaxf(M, __ldcg(a.part_ms + ((grp * nch + c) * beam + h) * 2));
-        float S = 0.f, o = 0.f;
-        for (int c = 0; c < nact; ++c) {
-            const float* q = a.part_ms + ((grp * nch + c) * beam + h) * 2;
-            const float f = expf(__ldcg(q) - M);
-            S = fmaf(__ldcg(q + 1), f, S);
-            o = fmaf(__ldcg(a.part_o + ((grp * nch + c) * beam) * DH + i), f, o);
-        }
-        store_out(h, d, o / S);
+        store_out(h, d, o / sm.s_run[1][h]);
     }
 }
 
 template <int MODE, int NH>
 __global__ void __launch_bounds__(CK, (NH <= 4) ? 4 : 2)
 dec_attn_stream_kernel(const AttnArgs a) {
-    extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target)
+    extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target), then rlist
     __shared__ __align__(16) AttnSmem<NH> sm;
-    __shared__ unsigned rlist[(MODE == 0) ? CK * NH : 1];          // (row index << 8) | hyp mask, row = pos * beam + slot
+    unsigned* rlist = reinterpret_cast<unsigned*>(vtile + CK * DH); // mode 0: (row index << 8) | hyp mask, row = pos * beam + slot
     const int tid = threadIdx.x;
     const int hw = tid >> 4, l16 = tid & 15;
-    const int utt = blockIdx.x, head = blockIdx.y, chunk = blockIdx.z;
-    const int p0 = chunk * CK;
+    const int utt = blockIdx.x, head = blockIdx.y;
     pdl_trigger();
 
     // K^T base (groups [j][row][8]) and V base ([row][64]) of this (utterance, head); nr = rows per j plane
@@ -361,10 +347,10 @@ dec_attn_stream_kernel(const AttnArgs a) {
         const long long uoff = a.utt_off[utt];
         kbase = a.kc + (long long)head * nr * DH + uoff * KG;
         vbase = a.vc + (long long)head * nr * DH + uoff * DH;
-        // whole tile requested before the wait; rows past the end of the utterance are skipped
-        load_k<1>(kreg, kbase, nr, p0 + tid, p0 + tid < T_utt);
-        const int nv = T_utt - p0 - hw * VR;
-        const float* vsrc = vbase + (long long)(p0 + hw * VR) * DH + 4 * l16;
+        // first tile requested before the wait; rows past the end of the utterance are skipped
+        load_k<1>(kreg, kbase, nr, tid, tid < T_utt);
+        const int nv = T_utt - hw * VR;
+        const float* vsrc = vbase + (long long)(hw * VR) * DH + 4 * l16;
         const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(vtile) + (uint32_t)((hw * VR) * DH + 4 * l16) * 4u;
 #pragma unroll
         for (int i = 0; i < VR; ++i)
@@ -377,8 +363,7 @@ dec_attn_stream_kernel(const AttnArgs a) {
     pdl_wait();
     const int nh = a.n_run[utt];
     const int step = *a.step_p;
-    const int n = (MODE == 1) ? T_utt : step + 1;
-    if (nh == 0 || p0 >= n) { cp_async_wait_all(); return; }
+    if (nh == 0) { cp_async_wait_all(); return; }
 #define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step)
     if (NH <= 4) {
         switch (nh) {
@@ -404,9 +389,6 @@ dec_attn_stream_kernel(const AttnArgs a) {
 
 }  // namespace
 
-// Chunks of scratch per (utterance, head) the caller must provide for up to max_keys positions / frames.
-extern "C" int avsr_dec_attn_chunks(int max_keys) { return (max_keys + CK - 1) / CK; }
-
 // mode 0: self-attention step.  Query / current k / current v = columns [0,1024) / [1024,2048) / [2048,3072) of q_in
 //   ([R, ldq] fp32).  kc / vc = this layer's caches; with row = pos*beam + slot and nr = lmax*beam, key element
 //   (utt, head, row, d) is at ((utt*16 + head)*8 + d/8)*nr*8 + row*8 + d%8 (transposed in 32-byte groups) and value
@@ -417,14 +399,11 @@ extern "C" int avsr_dec_attn_chunks(int max_keys) { return (max_keys + CK - 1) /
 //   frame*8 + d%8, value element at (head*n_frames + frame)*64 + d (the layout avsr_kv_head_major writes).
 // nsplit > 0: q_in holds the split-K partial sums part[z][R][ldq] of the projection (z < nsplit); they are summed in a fixed
 //   order and q_bias[ldq] is added.  nsplit == 0: q_in is the finished projection.
-// out (fp32 [R,1024]) and / or out_split (compact bf16x3 [R, 3*1024]).  Scratch (nch = avsr_dec_attn_chunks(max_keys)):
-// part_o [R/beam][16][nch][beam][64], part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once by the
-// caller (the kernel re-arms them).
+// out (fp32 [R,1024]) and / or out_split (compact bf16x3 [R, 3*1024]).
 extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                                   const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
-                                  int R, const int* step, float* out, int max_keys, long long n_frames, void* out_split,
-                                  float* part_o, float* part_ms, int* tickets, cudaStream_t stream) {
-    AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && max_keys > 0, "avsr_dec_attn_step: bad arguments");
+                                  int R, const int* step, float* out, long long n_frames, void* out_split, cudaStream_t stream) {
+    AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && lmax > 0, "avsr_dec_attn_step: bad arguments");
     AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T && n_frames > 0), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
     AVSR_REQUIRE(beam <= 8 && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max 8)", beam);
     AVSR_REQUIRE(nsplit >= 0 && (nsplit == 0 || q_bias), "avsr_dec_attn_step: partial-sum input needs the bias");
@@ -432,19 +411,25 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
                      ((uintptr_t)vc & 15) == 0,
                  "avsr_dec_attn_step: q_in / q_bias / vc must be 16-byte aligned, kc 32-byte aligned and ldq a multiple of 4");
     AVSR_REQUIRE(mode == 1 || (long long)lmax * beam < (1 << 24), "avsr_dec_attn_step: cache too long");
-    const int nch = (max_keys + CK - 1) / CK;
-    AVSR_REQUIRE(nch == 1 || (part_o && part_ms && tickets), "avsr_dec_attn_step: %d keys need the chunk scratch buffers", max_keys);
-    AVSR_REQUIRE(nch <= 65535, "avsr_dec_attn_step: too many keys");
-    const dim3 grid(R / beam, HEADS, nch);
-    static bool configured = false;
-    if (!configured) {                                // static + dynamic shared memory of the 8-slot variants exceeds 48 KB
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_stream_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK * DH * 4));
-        configured = true;
+    const int nslots = beam <= 4 ? 4 : 8;
+    // V tile + (self-attention) the list of distinct history rows, at most lmax * beam entries
+    const size_t smem = (size_t)CK * DH * sizeof(float) + (mode == 0 ? (size_t)lmax * nslots * sizeof(unsigned) : 0);
+    AVSR_REQUIRE(smem <= 160 * 1024, "avsr_dec_attn_step: %d positions do not fit the shared-memory row list", lmax);
+    static size_t configured[4] = {0, 0, 0, 0};
+    const int ki = (mode == 0 ? 0 : 2) + (nslots == 4 ? 0 : 1);
+    if (smem > configured[ki]) {
+        const int lim = 160 * 1024;
+        cudaError_t e = cudaSuccess;
+        if (ki == 0) e = cudaFuncSetAttribute(dec_attn_stream_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        else if (ki == 1) e = cudaFuncSetAttribute(dec_attn_stream_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        else if (ki == 2) e = cudaFuncSetAttribute(dec_attn_stream_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        else e = cudaFuncSetAttribute(dec_attn_stream_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        AVSR_CHECK_CUDA(e);
+        configured[ki] = lim;
     }
+    const dim3 grid(R / beam, HEADS);
     const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, n_frames,
-                        (__nv_bfloat16*)out_split, part_o, part_ms, tickets, nch};
-    const size_t smem = (size_t)CK * DH * sizeof(float);
+                        (__nv_bfloat16*)out_split};
     if (mode == 0) {
         if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 4>, grid, dim3(CK), smem, stream, a));
         else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 8>, grid, dim3(CK), smem, stream, a));

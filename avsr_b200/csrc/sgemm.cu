@@ -142,12 +142,25 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
 }
 
 // One CTA per output row (see splitk_epilogue.cuh).
+// pf / pf_bytes: optional span that a LATER kernel of the step streams (the cross-attention K/V of the layer, written before
+// the chain of step kernels started).  Before waiting for its producer, CTA b asks the L2 to fetch its 1/gridDim share in
+// 32 KB pieces (cp.async.bulk.prefetch.L2, fire and forget): the decode step is a chain of latency-bound launches during
+// which HBM is mostly idle, so the span is L2-resident by the time the attention kernel asks for it.
 template <int P>
 __global__ void __launch_bounds__(768)
-splitk_epilogue_kernel(const SplitKEpi e) {
+splitk_epilogue_kernel(const SplitKEpi e, const char* pf, long long pf_bytes) {
     extern __shared__ float rowbuf[];
     __shared__ float red[32];
     pdl_trigger();
+    if (pf != nullptr) {
+        constexpr long long PIECE = 32 * 1024;
+        const long long share = ((pf_bytes + gridDim.x - 1) / gridDim.x + PIECE - 1) / PIECE * PIECE;
+        const long long lo = (long long)blockIdx.x * share, hi = min(pf_bytes, lo + share);
+        for (long long o = lo + (long long)threadIdx.x * PIECE; o < hi; o += (long long)blockDim.x * PIECE) {
+            const unsigned n = (unsigned)min(PIECE, hi - o) & ~15u;
+            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf + o), "r"(n) : "memory");
+        }
+    }
     pdl_wait();
     avsr_splitk_epilogue_row<P>(e, blockIdx.x, rowbuf, red);
 }
@@ -204,7 +217,16 @@ extern "C" int avsr_sgemm_skinny(const float* A, long long lda, const float* W, 
 extern "C" int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
                                     long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
                                     float* ln_out, long long ld_ln, const int* row_active, void* split_out, cudaStream_t stream) {
+    return avsr_splitk_epilogue_pf(part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps, ln_out, ld_ln, row_active,
+                                   split_out, nullptr, 0, stream);
+}
+
+extern "C" int avsr_splitk_epilogue_pf(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
+                                       long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
+                                       float* ln_out, long long ld_ln, const int* row_active, void* split_out, const void* l2_prefetch,
+                                       long long l2_prefetch_bytes, cudaStream_t stream) {
     AVSR_REQUIRE(part && M > 0 && N > 0 && nsplit >= 1, "avsr_splitk_epilogue: bad arguments");
+    AVSR_REQUIRE(!l2_prefetch || (((uintptr_t)l2_prefetch & 15) == 0 && l2_prefetch_bytes > 0), "avsr_splitk_epilogue: prefetch span must be 16-byte aligned");
     AVSR_REQUIRE(out || ln_out || split_out, "avsr_splitk_epilogue: no output");
     AVSR_REQUIRE(!ln_out || ln_g, "avsr_splitk_epilogue: ln_out needs gamma/beta");
     AVSR_REQUIRE(!ln_g || (ln_b && N * 4 <= 48 * 1024), "avsr_splitk_epilogue: LayerNorm needs gamma/beta and N <= 12288");
@@ -215,6 +237,6 @@ extern "C" int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N,
     // reductions of the LayerNorm then run over 1024 mostly idle threads.)
     int threads = ((N + 3) / 4 + 31) / 32 * 32;
     threads = threads < 256 ? 256 : (threads > 768 ? 768 : threads);
-    AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel<1>, dim3(M), dim3(threads), smem, stream, e));
+    AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel<1>, dim3(M), dim3(threads), smem, stream, e, (const char*)l2_prefetch, l2_prefetch_bytes));
     return AVSR_OK;
 }

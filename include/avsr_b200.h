@@ -143,6 +143,12 @@ int avsr_sgemm_skinny(const float* A, long long lda, const float* W, long long l
 int avsr_splitk_epilogue(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
                          long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
                          float* ln_out, long long ld_ln, const int* row_active, void* split_out, avsr_stream_t stream);
+/* The same, and before it waits for its producer the kernel asks the L2 to fetch [l2_prefetch, +l2_prefetch_bytes): a span a
+ * later kernel of the decode step streams (the layer's cross-attention K/V; must not be written by the chain itself). */
+int avsr_splitk_epilogue_pf(const float* part, int nsplit, int M, int N, const float* bias, int act, const float* residual,
+                            long long ldr, float* out, long long ldo, const float* ln_g, const float* ln_b, float ln_eps,
+                            float* ln_out, long long ld_ln, const int* row_active, void* split_out, const void* l2_prefetch,
+                            long long l2_prefetch_bytes, avsr_stream_t stream);
 int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_stream_t stream);
 /* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
@@ -156,14 +162,11 @@ int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, co
  *   are appended at (pos = *step, slot = own slot).
  * mode 1 = source attention over the utterance's precomputed K/V (n_frames packed frames of all utterances): key element
  *   (head, frame, d) at (head*8 + d/8)*n_frames*8 + frame*8 + d%8, value element at (head*n_frames + frame)*64 + d.
- * nsplit > 0: q_in = split-K partial sums part[z][R][ldq] of the projection, summed here in split order + q_bias.
- * Scratch (caller-owned, nch = avsr_dec_attn_chunks(max_keys)): part_o [R/beam][16][nch][beam][64] fp32,
- * part_ms [R/beam][16][nch][beam][2] fp32, tickets [R/beam][16] int32 zeroed once. */
-int avsr_dec_attn_chunks(int max_keys);
+ * nsplit > 0: q_in = split-K partial sums part[z][R][ldq] of the projection, summed here in a fixed order + q_bias.
+ * One CTA per (utterance, head) walks all keys in tiles of 128. */
 int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                        const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
-                       const int* step, float* out, int max_keys, long long n_frames, void* out_split, float* part_o,
-                       float* part_ms, int* tickets, avsr_stream_t stream);
+                       const int* step, float* out, long long n_frames, void* out_split, avsr_stream_t stream);
 /* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span).  k_transposed:
  * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][8][F][8] (transposed in 32-byte groups), the
  * key layout avsr_dec_attn_step mode 1 reads. */

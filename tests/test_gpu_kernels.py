@@ -308,19 +308,14 @@ def test_dec_attn_step_self(L, beam, step, nsplit):
     anc[:, :, :shared] = anc[:, ::beam, :shared].repeat_interleave(beam, 1)
     anc = anc.cuda()
     step_t = torch.tensor([step], dtype=torch.int32, device="cuda")
-    nch = lib.avsr_dec_attn_chunks(lmax)
-    po = torch.empty(B, 16, nch, beam, 64, device="cuda")
-    pms = torch.empty(B, 16, nch, beam, 2, device="cuda")
-    tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
     out = torch.full((R, 1024), 7.0, device="cuda")
     out6 = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device="cuda")
     kc0, vc0 = kc_log.clone(), vc.clone()
-    for _ in range(2):                                   # twice: the merge tickets must re-arm themselves
+    for _ in range(2):                                   # twice: the second call re-reads the k / v the first one appended
         L.check(lib.avsr_dec_attn_step(0, L.ptr(q_in), L.ll(3072), nsplit, L.ptr(q_bias), L.ptr(kc), L.ptr(vc), L.ptr(anc), lmax,
-                                       L.ptr(n_run), None, None, beam, R, L.ptr(step_t), L.ptr(out), lmax, L.ll(0), L.ptr(out6),
-                                       L.ptr(po), L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(self)")
+                                       L.ptr(n_run), None, None, beam, R, L.ptr(step_t), L.ptr(out), L.ll(0), L.ptr(out6),
+                                       L.stream()), "dec_attn_step(self)")
     torch.cuda.synchronize()
-    assert tick.abs().sum().item() == 0
     kc = to_log(kc)
     a = anc[step & 1].cpu().long()
     tol = 2e-5 if nsplit == 0 else 1e-4                  # the partial-sum form adds the rounding of the split sums
@@ -365,17 +360,12 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
     utt_off = torch.from_numpy(offs).cuda()
     utt_T = torch.tensor(lengths, dtype=torch.int32, device="cuda")
     step_t = torch.tensor([3], dtype=torch.int32, device="cuda")
-    nch = lib.avsr_dec_attn_chunks(tmax)
-    po = torch.empty(B, 16, nch, beam, 64, device="cuda")
-    pms = torch.empty(B, 16, nch, beam, 2, device="cuda")
-    tick = torch.zeros(B, 16, dtype=torch.int32, device="cuda")
     out = torch.full((R, 1024), 7.0, device="cuda")
     for _ in range(2):
         L.check(lib.avsr_dec_attn_step(1, L.ptr(q_in), L.ll(1024), nsplit, L.ptr(q_bias), L.ptr(kc_phys), L.ptr(vc), None, tmax + 1, L.ptr(n_run),
-                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), tmax, L.ll(Fr), None,
-                                       L.ptr(po), L.ptr(pms), L.ptr(tick), L.stream()), "dec_attn_step(src)")
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), L.ll(Fr), None, L.stream()),
+                "dec_attn_step(src)")
     torch.cuda.synchronize()
-    assert tick.abs().sum().item() == 0
     tol = 2e-5 if nsplit == 0 else 1e-4
     for b in range(B):
         K, Vv = kc[:, offs[b]:offs[b] + lengths[b]], vc[:, offs[b]:offs[b] + lengths[b]]

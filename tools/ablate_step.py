@@ -1,0 +1,58 @@
+"""Dev aid: in-situ cost of the kernel groups of ONE decode position (CUDA-graph replays, programmatic dependent launch
+intact).  Decodes the bench batch up to a chosen position with the real path, then freezes the beam state (the
+fusion / advance kernels are left out, so every replay recomputes the same position) and times the position with one kernel
+group removed at a time.  The outputs of ablated runs are meaningless; only the times are used.
+
+    python tools/ablate_step.py [position=187] [B=32] [T=375]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avsr_b200 import synth
+from avsr_b200.model import AVSRCocktailB200
+
+pos = int(sys.argv[1]) if len(sys.argv) > 1 else 187
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 375
+sd = synth.make_state_dict(0)
+m = AVSRCocktailB200(sd, beam_size=3)
+bs = m.beam_search
+x = torch.randn(B * T, 1024, device="cuda")
+x = torch.nn.functional.layer_norm(x, (1024,))
+bs.decode_batch(x, [T] * B, max_steps=pos)          # real decode up to `pos` (realistic caches / ancestry tables)
+s = bs.last_session
+torch.cuda.synchronize()
+print(f"position {int(s['step'].item())}, live hyps per utterance {s['n_run'].tolist()[:8]}...")
+
+
+def time_step(skip, n=8, reps=6):
+    bs._skip = frozenset(skip) | {"advance"}
+    bs._step(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            bs._step(s)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (n * reps) * 1e3
+
+
+full = time_step(set())
+print(f"full position (without fusion/advance): {full:8.1f} us")
+for name, skip in (("self-attention x6", {"self"}), ("source attention x6", {"cross"}), ("both attentions", {"self", "cross"}),
+                   ("row epilogues x24", {"epi"}), ("projections x37", {"gemm"}), ("projections + epilogues", {"gemm", "epi"}),
+                   ("softmax/top-S + CTC", {"tail"}), ("everything but projections+epilogues", {"self", "cross", "tail"}),
+                   ("everything but attention", {"gemm", "epi", "tail"})):
+    t = time_step(skip)
+    print(f"  without {name:40s}: {t:8.1f} us   (group costs {full - t:7.1f} us in place)")
+bs._skip = frozenset()

@@ -50,10 +50,6 @@ if len(sys.argv) > 2 and sys.argv[2] == 'shared':
 ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
 att = torch.empty(R, 1024, device=dev)
 att6 = torch.empty(R, 3072, device=dev, dtype=torch.bfloat16)
-nch = lib.avsr_dec_attn_chunks(lmax)
-po, pms = torch.empty(B, 16, nch, beam, 64, device=dev), torch.empty(B, 16, nch, beam, 2, device=dev)
-tick = torch.zeros(B, 16, dtype=torch.int32, device=dev)
-scr = (L.ptr(po), L.ptr(pms), L.ptr(tick))
 li = {"i": 0}
 # the attention kernels take q (and the current k, v) from the split-K partial sums of their projection, as in the real step
 NSQ, NSC = lib.avsr_gemm_x3_splits(R, 3072, 1024), lib.avsr_gemm_x3_splits(R, 1024, 1024)
@@ -64,14 +60,14 @@ q2_p, q2_b = torch.randn(NSC, R, 1024, device=dev), torch.randn(1024, device=dev
 def self_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv_p), L.ll(3072), NSQ, L.ptr(qkv_b), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run),
-                                   L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, lmax, L.ll(0), L.ptr(att6), *scr, L.stream()), "self")
+                                   L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(0), L.ptr(att6), L.stream()), "self")
 
 
 def cross_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(1, L.ptr(q2_p), L.ll(1024), NSC, L.ptr(q2_b), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
-                                   L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, T, L.ll(B * T),
-                                   L.ptr(att6), *scr, L.stream()), "cross")
+                                   L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(B * T),
+                                   L.ptr(att6), L.stream()), "cross")
 
 
 print(f"step={step}  R={R}")
