@@ -42,43 +42,65 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
     }
 }
 
-// logits = sum_z part[z][row] + bias ; logp = log_softmax(logits) -> dec_logp[row] ; part_ids[row] = top-S token ids.
-__global__ void __launch_bounds__(256)
+// logits = sum_z part[z][row] + bias ; logp = log_softmax(logits) -> dec_logp[row] ; part_ids[row] = top-S token ids
+// (value descending, ties to the lower id).  One CTA (512 threads) per row; a thread keeps its <= ITER strided logits in
+// registers for all three passes (max, sum of exponentials, top-S), so the row is read once and nothing is staged.
+constexpr int LSM_THREADS = 512;
+
+template <int ITER>
+__global__ void __launch_bounds__(LSM_THREADS)
 dec_logits_lsm_topk_kernel(const float* __restrict__ part, int nsplit, int R, int V, const float* __restrict__ bias,
                            const int* __restrict__ n_run, int beam, float* __restrict__ logp, int* __restrict__ part_ids, int S) {
-    extern __shared__ float rowv[];
     __shared__ float red[32];
-    __shared__ int redi[32];
-    const int row = blockIdx.x;
+    __shared__ float s_v[LSM_THREADS / 32];
+    __shared__ int s_i[LSM_THREADS / 32];
+    __shared__ int s_win;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     pdl_trigger();
+    // the bias does not depend on the previous kernel
+    float v[ITER];
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int c = tid + k * LSM_THREADS;
+        v[k] = (c < V) ? __ldg(bias + c) : 0.f;
+    }
     pdl_wait();
     if ((row % beam) >= n_run[row / beam]) return;
     float mx = -INFINITY;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-        float v = 0.f;
-        for (int z = 0; z < nsplit; ++z) v += part[((long long)z * R + row) * V + c];
-        v += bias[c];
-        rowv[c] = v;
-        mx = fmaxf(mx, v);
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int c = tid + k * LSM_THREADS;
+        if (c < V) {
+            float a = 0.f;
+            for (int z = 0; z < nsplit; ++z) a += part[((long long)z * R + row) * V + c];
+            v[k] = a + v[k];
+            mx = fmaxf(mx, v[k]);
+        } else {
+            v[k] = -INFINITY;
+        }
     }
     mx = block_max(mx, red);
-    float s = 0.f;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) s += expf(rowv[c] - mx);
-    s = block_sum(s, red);
-    const float lse = logf(s);
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-        const float v = (rowv[c] - mx) - lse;
-        rowv[c] = v;
-        logp[(long long)row * V + c] = v;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) sum += expf(v[k] - mx);            // padding: exp(-inf) = 0
+    sum = block_sum(sum, red);
+    const float lse = logf(sum);
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+        const int c = tid + k * LSM_THREADS;
+        if (c < V) {
+            v[k] = (v[k] - mx) - lse;
+            logp[(long long)row * V + c] = v[k];
+        }
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int k = 0; k < S; ++k) {
+    // ---- S rounds of block arg-max over the register values; the winner drops its entry
+    for (int r = 0; r < S; ++r) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
-        for (int c = threadIdx.x; c < V; c += blockDim.x) {
-            const float v = rowv[c];
-            if (v > bv) { bv = v; bi = c; }
+#pragma unroll
+        for (int k = 0; k < ITER; ++k) {
+            const int c = tid + k * LSM_THREADS;
+            if (v[k] > bv) { bv = v[k]; bi = c; }                     // ascending c: the lowest id wins ties
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -86,23 +108,24 @@ dec_logits_lsm_topk_kernel(const float* __restrict__ part, int nsplit, int R, in
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { red[w] = bv; redi[w] = bi; }
+        if (lane == 0) { s_v[w] = bv; s_i[w] = bi; }
         __syncthreads();
         if (w == 0) {
-            bv = lane < 8 ? red[lane] : -INFINITY;
-            bi = lane < 8 ? redi[lane] : 0x7fffffff;
+            bv = lane < LSM_THREADS / 32 ? s_v[lane] : -INFINITY;
+            bi = lane < LSM_THREADS / 32 ? s_i[lane] : 0x7fffffff;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
+            for (int o = 8; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            if (lane == 0) {
-                part_ids[row * S + k] = bi;
-                rowv[bi] = -INFINITY;
-            }
+            if (lane == 0) { part_ids[row * S + r] = bi; s_win = bi; }
         }
         __syncthreads();
+        const int win = s_win;
+#pragma unroll
+        for (int k = 0; k < ITER; ++k)
+            if (tid + k * LSM_THREADS == win) v[k] = -INFINITY;
     }
 }
 
@@ -135,9 +158,15 @@ extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* l
 extern "C" int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam,
                                         float* logp, int* part_ids, int S, cudaStream_t stream) {
     AVSR_REQUIRE(part && bias && n_run && logp && part_ids && R > 0 && V > 0 && S > 0 && S <= V, "avsr_dec_logits_lsm_topk: bad arguments");
-    AVSR_REQUIRE((size_t)V * 4 <= 48 * 1024, "avsr_dec_logits_lsm_topk: vocabulary %d too large for the shared-memory row", V);
-    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_logits_lsm_topk_kernel, dim3(R), dim3(256), (size_t)V * 4, stream, part, nsplit, R, V, bias, n_run, beam,
-                                    logp, part_ids, S));
+    AVSR_REQUIRE(V <= 16 * LSM_THREADS, "avsr_dec_logits_lsm_topk: vocabulary %d too large (max %d)", V, 16 * LSM_THREADS);
+    const int iter = (V + LSM_THREADS - 1) / LSM_THREADS;
+#define AVSR_LSM(IT)                                                                                                              \
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_logits_lsm_topk_kernel<IT>, dim3(R), dim3(LSM_THREADS), 0, stream, part, nsplit, R, V, bias, n_run, \
+                                    beam, logp, part_ids, S))
+    if (iter <= 4) AVSR_LSM(4);
+    else if (iter <= 10) AVSR_LSM(10);
+    else AVSR_LSM(16);
+#undef AVSR_LSM
     return AVSR_OK;
 }
 

@@ -233,7 +233,7 @@ extern "C" int avsr_splitk_epilogue_pf(const float* part, int nsplit, int M, int
     const size_t smem = ln_g ? (size_t)N * 4 : 0;
     SplitKEpi e = {part, nsplit, M, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps, ln_out, ld_ln, row_active, (__nv_bfloat16*)split_out};
     // one thread per 4 columns up to 768 threads.  (Splitting a column group's partial sums over 2 or 4 threads, P > 1, cuts
-    // the loads per thread but measured slower on B200 at these sizes: 5.8 vs 4.0 us for N = 1024, 16 splits - the row-wide
+    // the loads per thread but measured slower on B200 at these sizes: 4.9 (P = 2) / 5.8 (P = 4) vs 4.0 us for N = 1024, 16 splits - the row-wide
     // reductions of the LayerNorm then run over 1024 mostly idle threads.)
     int threads = ((N + 3) / 4 + 31) / 32 * 32;
     threads = threads < 256 ? 256 : (threads > 768 ? 768 : threads);

@@ -25,7 +25,13 @@ x = torch.nn.functional.layer_norm(x, (1024,))
 bs.decode_batch(x, [T] * B, max_steps=pos)          # real decode up to `pos` (realistic caches / ancestry tables)
 s = bs.last_session
 torch.cuda.synchronize()
-print(f"position {int(s['step'].item())}, live hyps per utterance {s['n_run'].tolist()[:8]}...")
+step_now = int(s['step'].item())
+print(f"position {step_now}, live hyps per utterance {s['n_run'].tolist()[:8]}...")
+anc = s["anc"][step_now & 1].view(B, 3, -1)[:, :, :step_now].cpu().numpy()
+import numpy as np
+distinct = np.array([[len(set(anc[b, :, p])) for p in range(step_now)] for b in range(B)])
+print(f"distinct history rows per utterance: mean {distinct.sum(1).mean() + 3:.0f} of {3 * (step_now + 1)} "
+      f"(positions with 1 / 2 / 3 distinct ancestors: {[(distinct == k).mean().round(3) for k in (1, 2, 3)]})")
 
 
 def time_step(skip, n=8, reps=6):
