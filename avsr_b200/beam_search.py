@@ -123,6 +123,10 @@ class BatchedBeamSearch:
         # [layer][utt][head][8][pos*beam+slot][8], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
         s["kc"] = torch.empty(nl, B, 16, 8, lmax * beam, 8, dtype=torch.float32, device=dev)
         s["vc"] = torch.empty(nl, B, 16, lmax * beam, 64, dtype=torch.float32, device=dev)
+        # dense copy of the converged history prefix (all live hyps share the ancestor): consecutive positions = consecutive rows
+        s["kd"] = torch.empty(nl, B, 16, 8, lmax, 8, dtype=torch.float32, device=dev)
+        s["vd"] = torch.empty(nl, B, 16, lmax, 64, dtype=torch.float32, device=dev)
+        s["conv_len"] = i32(2, B)
         s["r_buf"] = torch.empty(2, R * S, tmax, 2, dtype=torch.float32, device=dev)
         lib = L.load()
         shapes = ((3072, 1024), (1024, 1024), (1024, 3072), (V, 1024))
@@ -216,6 +220,9 @@ class BatchedBeamSearch:
         st = L.stream
         tc = self.precision == "bf16x3"
         l0 = w.layers[0]
+        # newly converged history positions -> dense self-attention caches (all layers)
+        L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
+                                           L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
         L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
                                       L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]),
                                       None if tc else L.ptr(s["a"]), L.ptr(s["a3"]) if tc else None, st()), "avsr_dec_embed_ln")
@@ -229,7 +236,8 @@ class BatchedBeamSearch:
             if "self" not in self._skip:
                 L.check(lib.avsr_dec_attn_step(0, L.ptr(s["part"]), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]),
                                                L.ptr(s["vc"][li]), L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]),
-                                               L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32, L.ll(0), att_split, st()),
+                                               L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32, L.ll(0), att_split,
+                                               L.ptr(s["kd"][li]), L.ptr(s["vd"][li]), L.ptr(s["conv_len"]), st()),
                         "avsr_dec_attn_step(self)")
             # (its row epilogue also asks the L2 for this layer's cross K/V, which the source attention streams two kernels later)
             self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a",
@@ -240,7 +248,7 @@ class BatchedBeamSearch:
             if "cross" not in self._skip:
                 L.check(lib.avsr_dec_attn_step(1, L.ptr(s["part"]), L.ll(1024), ns, L.ptr(lay["bq2"]), L.ptr(ck), L.ptr(cv), None, lmax,
                                                L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]),
-                                               att_f32, L.ll(s["F"]), att_split, st()), "avsr_dec_attn_step(src)")
+                                               att_f32, L.ll(s["F"]), att_split, None, None, None, st()), "avsr_dec_attn_step(src)")
             self._linear(s, "att", lay, "wo2", 1024, 1024, lay["bo2"], residual=s["x"], out=s["x"], ln=(lay["n3_g"], lay["n3_b"]), key_out="a")
             # feed-forward (decoder_layer.py:112-116)
             self._linear(s, "a", lay, "w1", 3072, 1024, lay["b1"], act=L.ACT_RELU, key_out="ffn")
@@ -287,7 +295,7 @@ class BatchedBeamSearch:
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
         s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))
         s["utt_off"].copy_(torch.from_numpy(offs))
-        for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev"):
+        for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev", "conv_len"):
             s[k].zero_()
         s["n_run"].fill_(1)
         s["row_active"].zero_()

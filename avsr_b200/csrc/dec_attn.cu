@@ -45,6 +45,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 struct AttnArgs {
     const float* q_in; long long ldq; int nsplit; const float* q_bias;
     float* kc; float* vc; const unsigned char* anc; int lmax;
+    const float* kd; const float* vd; const int* conv_len;      // mode 0: dense copy of the converged history prefix (may be null)
     const int* n_run; const int* utt_off; const int* utt_T; int beam; int R; const int* step_p;
     float* out; long long n_frames; __nv_bfloat16* out_split;
 };
@@ -63,7 +64,7 @@ struct AttnSmem {
 
 // K of one key: 16 x 16-byte loads, two per 32-byte group.  MODE 0 uses plain loads (this CTA may just have written the row).
 template <int MODE>
-__device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbase, long long nr, long long r, bool ok) {
+__device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbase, long long nr, long long r, bool ok) {   // nr = rows per plane
 #pragma unroll
     for (int j = 0; j < DH / KG; ++j) {
         kreg[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -145,10 +146,21 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         }
     }
     // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
+    // Positions [0, C) of the history are "converged": every live hyp has the same ancestor there, and that row has been
+    // copied to the dense caches kd / vd (avsr_dec_cache_promote), where consecutive positions are consecutive rows.  Only
+    // the positions from C on go through the (pos, slot) list.
+    int C = 0;
+    const float* kdb = nullptr;
+    const float* vdb = nullptr;
+    if (MODE == 0 && a.conv_len != nullptr) {
+        C = a.conv_len[((step + 1) & 1) * (R / beam) + utt];
+        kdb = a.kd + (long long)(utt * HEADS + head) * a.lmax * DH;
+        vdb = a.vd + (long long)(utt * HEADS + head) * a.lmax * DH;
+    }
     int nrows = (MODE == 1) ? T_utt : 0;
     if (MODE == 0) {
         int total = 0;
-        for (int pb = 0; pb < n; pb += CK) {
+        for (int pb = C; pb < n; pb += CK) {
             const int p = pb + tid;
             unsigned msk[NH];
 #pragma unroll
@@ -180,7 +192,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
             for (int s = 0; s < NH; ++s)
                 if (msk[s] != 0u) rlist[base++] = ((unsigned)(p * beam + s) << 8) | msk[s];
         }
-        nrows = total;
+        nrows = C + total;
     }
     if (tid < NHT) { sm.s_run[0][tid] = -INFINITY; sm.s_run[1][tid] = 0.f; }
     __syncthreads();                                 // qs / qpart, rlist, s_run ready
@@ -204,18 +216,29 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     const int ntiles = (nrows + CK - 1) / CK;
     // requests of one tile: K of this thread's key into registers, the half-warp's 16 V rows into shared memory
     auto request_k = [&](int t0) {
-        const bool ok = t0 + tid < nrows;
-        if (MODE == 0) load_k<0>(kreg, kbase, nr, ok ? (long long)(rlist[t0 + tid] >> 8) : 0, ok);
-        else load_k<1>(kreg, kbase, nr, t0 + tid, ok);
+        const int g = t0 + tid;
+        const bool ok = g < nrows;
+        if (MODE == 0) {
+            if (g < C) load_k<0>(kreg, kdb, a.lmax, g, true);
+            else load_k<0>(kreg, kbase, nr, ok ? (long long)(rlist[g - C] >> 8) : 0, ok);
+        } else {
+            load_k<1>(kreg, kbase, nr, g, ok);
+        }
     };
     auto request_v = [&](int t0) {
-        const int nv = nrows - t0 - hw * VR;
+        const int g0 = t0 + hw * VR;
+        const int nv = nrows - g0;
         if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < VR; ++i)
-                if (i < nv) cp_async16(vt_s + i * DH * 4, vbase + (long long)(rlist[t0 + hw * VR + i] >> 8) * DH + 4 * l16);
+            for (int i = 0; i < VR; ++i) {
+                if (i < nv) {
+                    const int g = g0 + i;
+                    const float* src = (g < C) ? vdb + (long long)g * DH : vbase + (long long)(rlist[g - C] >> 8) * DH;
+                    cp_async16(vt_s + i * DH * 4, src + 4 * l16);
+                }
+            }
         } else {
-            const float* vsrc = vbase + (long long)(t0 + hw * VR) * DH + 4 * l16;
+            const float* vsrc = vbase + (long long)g0 * DH + 4 * l16;
 #pragma unroll
             for (int i = 0; i < VR; ++i)
                 if (i < nv) cp_async16(vt_s + i * DH * 4, vsrc + i * DH);
@@ -226,7 +249,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     for (int tile = 0; tile < ntiles; ++tile) {
         const int t0 = tile * CK;
         const bool kvalid = t0 + tid < nrows;
-        const unsigned my = (MODE == 0) ? (kvalid ? rlist[t0 + tid] : 0u) : 0xffu;     // hyp mask of this thread's key
+        const unsigned my = (MODE == 0 && t0 + tid >= C) ? (kvalid ? rlist[t0 + tid - C] : 0u) : 0xffu;     // hyp mask of this thread's key
         const int nv = min(VR, nrows - t0 - hw * VR);                // valid V rows of this half-warp in this tile (may be <= 0)
         // ---- scores of this thread's key against every live hyp
         float s[NHT];
@@ -387,6 +410,68 @@ dec_attn_stream_kernel(const AttnArgs a) {
 #undef AVSR_BODY
 }
 
+// Promotion of converged history positions to the dense caches.  A position p < *step is converged for an utterance when
+// all its live hyps have the same ancestor slot there; it stays converged for all descendants (new hyps copy their parent's
+// ancestry), so the row (pos, slot) can be copied once to row `pos` of the dense caches and read from there from now on:
+// the self-attention then streams consecutive rows instead of every beam-th row of the per-slot cache (whose 32-byte keys
+// cost a full 128-byte DRAM line each).  CTA = (utterance, layer); conv_len is double-buffered on step parity because the
+// CTAs of one utterance (one per layer) all read the old value.  At most PROMOTE_MAX positions per call.
+constexpr int PROMOTE_MAX = 32;
+
+__global__ void __launch_bounds__(256)
+dec_cache_promote_kernel(const float* __restrict__ kc, const float* __restrict__ vc, float* __restrict__ kd, float* __restrict__ vd,
+                         long long sparse_layer_stride, long long dense_layer_stride, const unsigned char* __restrict__ anc, int lmax,
+                         const int* __restrict__ n_run, int beam, int R, const int* __restrict__ step_p, int* __restrict__ conv_len) {
+    __shared__ int s_cnt;
+    __shared__ unsigned char s_slot[PROMOTE_MAX];
+    const int utt = blockIdx.x, layer = blockIdx.y, B = R / beam;
+    const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const int step = *step_p;
+    const int nh = n_run[utt];
+    const int C = conv_len[(step & 1) * B + utt];
+    if (tid < 32) {
+        const int p = C + tid;
+        bool ok = nh > 0 && p < step;
+        unsigned char s0 = 0;
+        if (ok) {
+            const unsigned char* ar = anc + ((long long)(step & 1) * R + utt * beam) * lmax + p;
+            s0 = ar[0];
+            for (int h = 1; h < nh; ++h) ok = ok && (ar[(long long)h * lmax] == s0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int cnt = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;      // leading converged positions
+        if (tid < cnt) s_slot[tid] = s0;
+        if (tid == 0) {
+            s_cnt = cnt;
+            if (layer == 0) conv_len[((step + 1) & 1) * B + utt] = C + cnt;
+        }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt == 0) return;
+    const long long nr = (long long)lmax * beam;
+    const float* kcl = kc + layer * sparse_layer_stride + (long long)utt * HEADS * nr * DH;
+    const float* vcl = vc + layer * sparse_layer_stride + (long long)utt * HEADS * nr * DH;
+    float* kdl = kd + layer * dense_layer_stride + (long long)utt * HEADS * lmax * DH;
+    float* vdl = vd + layer * dense_layer_stride + (long long)utt * HEADS * lmax * DH;
+    // per (position, head): 16 key pieces + 16 value pieces of 16 bytes
+    for (int i = tid; i < cnt * HEADS * 32; i += 256) {
+        const int piece = i & 15, kv = (i >> 4) & 1, head = (i >> 5) % HEADS, pi = i / (32 * HEADS);
+        const int p = C + pi;
+        const long long rs = (long long)p * beam + s_slot[pi];
+        if (kv == 0) {
+            const int j = piece >> 1, half = piece & 1;
+            const float4 v = *reinterpret_cast<const float4*>(kcl + (long long)head * nr * DH + ((long long)j * nr + rs) * KG + half * 4);
+            *reinterpret_cast<float4*>(kdl + (long long)head * lmax * DH + ((long long)j * lmax + p) * KG + half * 4) = v;
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(vcl + (long long)head * nr * DH + rs * DH + piece * 4);
+            *reinterpret_cast<float4*>(vdl + (long long)head * lmax * DH + (long long)p * DH + piece * 4) = v;
+        }
+    }
+}
+
 }  // namespace
 
 // mode 0: self-attention step.  Query / current k / current v = columns [0,1024) / [1024,2048) / [2048,3072) of q_in
@@ -400,9 +485,16 @@ dec_attn_stream_kernel(const AttnArgs a) {
 // nsplit > 0: q_in holds the split-K partial sums part[z][R][ldq] of the projection (z < nsplit); they are summed in a fixed
 //   order and q_bias[ldq] is added.  nsplit == 0: q_in is the finished projection.
 // out (fp32 [R,1024]) and / or out_split (compact bf16x3 [R, 3*1024]).
+// kd / vd / conv_len (mode 0, optional): dense caches of the converged history prefix maintained by avsr_dec_cache_promote,
+//   key element (utt, head, pos, d) at ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at
+//   ((utt*16 + head)*lmax + pos)*64 + d; conv_len [2][R/beam], the kernel reads conv_len[(*step + 1) & 1][utt].
 extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                                   const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
-                                  int R, const int* step, float* out, long long n_frames, void* out_split, cudaStream_t stream) {
+                                  int R, const int* step, float* out, long long n_frames, void* out_split, const float* kd,
+                                  const float* vd, const int* conv_len, cudaStream_t stream) {
+    AVSR_REQUIRE((kd != nullptr) == (vd != nullptr) && (kd != nullptr) == (conv_len != nullptr) && (mode == 0 || kd == nullptr),
+                 "avsr_dec_attn_step: kd / vd / conv_len go together (self-attention only)");
+    AVSR_REQUIRE(((uintptr_t)kd & 31) == 0 && ((uintptr_t)vd & 15) == 0, "avsr_dec_attn_step: kd / vd alignment");
     AVSR_REQUIRE(q_in && kc && vc && n_run && step && (out || out_split) && R > 0 && beam > 0 && lmax > 0, "avsr_dec_attn_step: bad arguments");
     AVSR_REQUIRE(mode == 0 ? (anc != nullptr) : (utt_off && utt_T && n_frames > 0), "avsr_dec_attn_step: missing index arrays for mode %d", mode);
     AVSR_REQUIRE(beam <= 8 && R % beam == 0, "avsr_dec_attn_step: beam %d unsupported (max 8)", beam);
@@ -428,8 +520,8 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
         configured[ki] = lim;
     }
     const dim3 grid(R / beam, HEADS);
-    const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, n_frames,
-                        (__nv_bfloat16*)out_split};
+    const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, kd, vd, conv_len, n_run, utt_off, utt_T, beam, R, step, out,
+                        n_frames, (__nv_bfloat16*)out_split};
     if (mode == 0) {
         if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 4>, grid, dim3(CK), smem, stream, a));
         else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 8>, grid, dim3(CK), smem, stream, a));
@@ -437,5 +529,20 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
         if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 4>, grid, dim3(CK), smem, stream, a));
         else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 8>, grid, dim3(CK), smem, stream, a));
     }
+    return AVSR_OK;
+}
+
+// Copies the newly converged history positions of every utterance from the per-slot caches (all n_layers layers, layer
+// stride = B*16*lmax*beam*64 floats) to the dense caches (layer stride B*16*lmax*64) and advances
+// conv_len[(*step + 1) & 1][utt] = conv_len[*step & 1][utt] + promoted.  Call once per position, before the layers run.
+extern "C" int avsr_dec_cache_promote(const float* kc, const float* vc, float* kd, float* vd, int n_layers, const unsigned char* anc,
+                                      int lmax, const int* n_run, int beam, int R, const int* step, int* conv_len,
+                                      cudaStream_t stream) {
+    AVSR_REQUIRE(kc && vc && kd && vd && anc && n_run && step && conv_len && n_layers > 0 && lmax > 0 && beam > 0 && R > 0 && R % beam == 0,
+                 "avsr_dec_cache_promote: bad arguments");
+    const long long B = R / beam;
+    const long long sls = B * HEADS * (long long)lmax * beam * DH, dls = B * HEADS * (long long)lmax * DH;
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_cache_promote_kernel, dim3((unsigned)B, n_layers), dim3(256), 0, stream, kc, vc, kd, vd, sls, dls, anc,
+                                    lmax, n_run, beam, R, step, conv_len));
     return AVSR_OK;
 }

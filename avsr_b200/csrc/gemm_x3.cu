@@ -24,6 +24,7 @@
 // One CTA per work item (m-tile, n-tile, k-split): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
 // epilogue.  The kernel is launched with programmatic dependent launch: the weight tiles of the first pipeline stages are
 // requested BEFORE griddepcontrol.wait, i.e. while the kernel that produces the activations is still running.
+#include <stdlib.h>
 #include "common.cuh"
 #include "splitk_epilogue.cuh"
 #include "tc_ptx.cuh"
@@ -253,6 +254,9 @@ int plan(int R, int N, int K, int* nb, int* tiles_m, int* tiles_n, int* splits) 
     *tiles_n = cdiv(R, *nb);
     const int nkb = K / BK;
     int s = sm_count() / (*tiles_m * *tiles_n);
+    static int min_kb = -1;                           // dev knob: at least this many k blocks per CTA (AVSR_X3_MIN_KB)
+    if (min_kb < 0) { const char* e = getenv("AVSR_X3_MIN_KB"); min_kb = e ? atoi(e) : 1; if (min_kb < 1) min_kb = 1; }
+    if (s > nkb / min_kb) s = nkb / min_kb;
     if (s > nkb) s = nkb;
     if (s < 1) s = 1;
     *splits = s;

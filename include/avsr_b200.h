@@ -163,10 +163,19 @@ int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, co
  * mode 1 = source attention over the utterance's precomputed K/V (n_frames packed frames of all utterances): key element
  *   (head, frame, d) at (head*8 + d/8)*n_frames*8 + frame*8 + d%8, value element at (head*n_frames + frame)*64 + d.
  * nsplit > 0: q_in = split-K partial sums part[z][R][ldq] of the projection, summed here in a fixed order + q_bias.
- * One CTA per (utterance, head) walks all keys in tiles of 128. */
+ * One CTA per (utterance, head) walks all keys in tiles of 128.  kd / vd / conv_len: optional dense caches of the converged
+ * history prefix (mode 0 only, see avsr_dec_cache_promote); pass NULL to read everything through the ancestry table. */
 int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                        const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
-                       const int* step, float* out, long long n_frames, void* out_split, avsr_stream_t stream);
+                       const int* step, float* out, long long n_frames, void* out_split, const float* kd, const float* vd,
+                       const int* conv_len, avsr_stream_t stream);
+/* Dense copy of the CONVERGED history prefix (positions where all live hyps of an utterance share their ancestor): copies the
+ * newly converged rows of all layers from the per-slot caches to kd / vd (key element (layer, utt, head, pos, d) at
+ * layer*B*16*lmax*64 + ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at layer*B*16*lmax*64 +
+ * ((utt*16 + head)*lmax + pos)*64 + d) and advances conv_len[(*step + 1) & 1][utt].  avsr_dec_attn_step (mode 0) then
+ * streams consecutive rows for that prefix.  Call once per position before the layers run. */
+int avsr_dec_cache_promote(const float* kc, const float* vc, float* kd, float* vd, int n_layers, const unsigned char* anc, int lmax,
+                           const int* n_run, int beam, int R, const int* step, int* conv_len, avsr_stream_t stream);
 /* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span).  k_transposed:
  * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][8][F][8] (transposed in 32-byte groups), the
  * key layout avsr_dec_attn_step mode 1 reads. */

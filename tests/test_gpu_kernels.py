@@ -284,9 +284,10 @@ def _as_partials(x, nsplit, seed):
     return part.contiguous(), bias
 
 
-@pytest.mark.parametrize("beam,step,nsplit", [(3, 0, 0), (3, 5, 6), (3, 127, 0), (3, 128, 3), (5, 300, 0), (3, 375, 6), (8, 140, 2),
-                                              (4, 260, 0)])
-def test_dec_attn_step_self(L, beam, step, nsplit):
+@pytest.mark.parametrize("beam,step,nsplit,dense", [(3, 0, 0, False), (3, 5, 6, True), (3, 127, 0, False), (3, 128, 3, True),
+                                                    (5, 300, 0, True), (3, 375, 6, True), (8, 140, 2, False), (4, 260, 0, True),
+                                                    (3, 200, 0, False)])
+def test_dec_attn_step_self(L, beam, step, nsplit, dense):
     """Self-attention of one decode position over a random cache and a random ancestry table (decoder_layer.py:82-93,
     attention.py:38-106 restated in torch fp32): streaming kernel incl. the distinct-row list, the multi-chunk merge, the
     k/v append and the query taken from split-K partial sums."""
@@ -311,11 +312,42 @@ def test_dec_attn_step_self(L, beam, step, nsplit):
     out = torch.full((R, 1024), 7.0, device="cuda")
     out6 = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device="cuda")
     kc0, vc0 = kc_log.clone(), vc.clone()
+    kd = vd = conv = None
+    if dense:
+        # dense caches of the converged prefix, filled by the promotion kernel in a few calls (at most 32 positions each); the
+        # per-slot rows of promoted positions are then poisoned: the attention must read the dense copies
+        kd = torch.zeros(1, B, 16, 8, lmax, 8, device="cuda")
+        vd = torch.zeros(1, B, 16, lmax, 64, device="cuda")
+        conv = torch.zeros(2, B, dtype=torch.int32, device="cuda")
+        for _ in range(step // 32 + 2):
+            L.check(lib.avsr_dec_cache_promote(L.ptr(kc), L.ptr(vc), L.ptr(kd), L.ptr(vd), 1, L.ptr(anc), lmax, L.ptr(n_run), beam, R,
+                                               L.ptr(step_t), L.ptr(conv), L.stream()), "promote")
+            conv[step & 1] = conv[(step + 1) & 1]            # next call continues where this one stopped
+        torch.cuda.synchronize()
+        cl = conv[(step + 1) & 1].cpu().tolist()
+        a_now = anc[step & 1].cpu().long()
+        for b in range(B):
+            nh = int(n_run[b])
+            want_c = 0
+            while nh > 0 and want_c < step and len({int(a_now[b * beam + h, want_c]) for h in range(nh)}) == 1:
+                want_c += 1
+            assert cl[b] == want_c, (b, cl[b], want_c)
+            if cl[b] > 0:
+                slots = a_now[b * beam, :cl[b]]
+                kd_log = kd[0, b].permute(0, 2, 1, 3).reshape(16, lmax, 64)
+                assert torch.equal(kd_log[:, :cl[b]], kc_log[b][:, torch.arange(cl[b]), slots])
+                assert torch.equal(vd[0, b][:, :cl[b]], vc[b][:, torch.arange(cl[b]), slots])
+                kcl = to_log(kc)
+                kcl[b, :, :cl[b]] = float("nan")
+                kc = to_phys(kcl)
+                vc[b, :, :cl[b]] = float("nan")
+        vc = vc.contiguous().view(B, 16, lmax * beam, 64)
     for _ in range(2):                                   # twice: the second call re-reads the k / v the first one appended
         L.check(lib.avsr_dec_attn_step(0, L.ptr(q_in), L.ll(3072), nsplit, L.ptr(q_bias), L.ptr(kc), L.ptr(vc), L.ptr(anc), lmax,
                                        L.ptr(n_run), None, None, beam, R, L.ptr(step_t), L.ptr(out), L.ll(0), L.ptr(out6),
-                                       L.stream()), "dec_attn_step(self)")
+                                       L.ptr(kd), L.ptr(vd), L.ptr(conv), L.stream()), "dec_attn_step(self)")
     torch.cuda.synchronize()
+    vc = vc.view(B, 16, lmax, beam, 64)
     kc = to_log(kc)
     a = anc[step & 1].cpu().long()
     tol = 2e-5 if nsplit == 0 else 1e-4                  # the partial-sum form adds the rounding of the split sums
@@ -337,10 +369,11 @@ def test_dec_attn_step_self(L, beam, step, nsplit):
             assert (out[row] - want).abs().max().item() < tol, (b, h)
             o3 = out6[row].float().view(3, 1024)
             assert (o3[0] + o3[1] + o3[2] - want).abs().max().item() < tol
-    # positions other than the current one are never written
+    # positions other than the current one are never written (poisoned rows of the dense variant stay poisoned)
     keep = torch.ones(lmax, dtype=torch.bool)
     keep[step] = False
-    assert torch.equal(kc[:, :, keep], kc0[:, :, keep]) and torch.equal(vc[:, :, keep], vc0[:, :, keep])
+    same = lambda x, y: bool(((x == y) | (x != x)).all())
+    assert same(kc[:, :, keep], kc0[:, :, keep]) and same(vc[:, :, keep], vc0[:, :, keep])
 
 
 @pytest.mark.parametrize("beam,lengths,nsplit", [(3, [375, 12, 130, 257], 0), (5, [128, 129, 1, 375], 16), (3, [400, 384, 385, 900], 4)])
@@ -363,8 +396,8 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
     out = torch.full((R, 1024), 7.0, device="cuda")
     for _ in range(2):
         L.check(lib.avsr_dec_attn_step(1, L.ptr(q_in), L.ll(1024), nsplit, L.ptr(q_bias), L.ptr(kc_phys), L.ptr(vc), None, tmax + 1, L.ptr(n_run),
-                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), L.ll(Fr), None, L.stream()),
-                "dec_attn_step(src)")
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), L.ptr(out), L.ll(Fr), None, None, None, None,
+                                       L.stream()), "dec_attn_step(src)")
     torch.cuda.synchronize()
     tol = 2e-5 if nsplit == 0 else 1e-4
     for b in range(B):

@@ -29,6 +29,11 @@ step_now = int(s['step'].item())
 print(f"position {step_now}, live hyps per utterance {s['n_run'].tolist()[:8]}...")
 anc = s["anc"][step_now & 1].view(B, 3, -1)[:, :, :step_now].cpu().numpy()
 import numpy as np
+one = np.array([[anc[b, 0, p] for p in range(step_now) if len(set(anc[b, :, p])) == 1] for b in range(B)], dtype=object)
+allv = np.concatenate([np.asarray(o, dtype=np.int64) for o in one])
+print("slot of the single surviving ancestor (share of positions):", [round(float((allv == k).mean()), 3) for k in range(3)])
+runs = np.concatenate([np.diff(np.asarray(o, dtype=np.int64)) != 0 for o in one])
+print(f"adjacent converged positions whose survivor sits in a different slot: {runs.mean():.3f}")
 distinct = np.array([[len(set(anc[b, :, p])) for p in range(step_now)] for b in range(B)])
 print(f"distinct history rows per utterance: mean {distinct.sum(1).mean() + 3:.0f} of {3 * (step_now + 1)} "
       f"(positions with 1 / 2 / 3 distinct ancestors: {[(distinct == k).mean().round(3) for k in (1, 2, 3)]})")

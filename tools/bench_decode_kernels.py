@@ -12,6 +12,12 @@ from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
+if os.environ.get("AVSR_L2_GRAN"):
+    from cuda import cudart
+    torch.zeros(1, device=dev)
+    print("cudaLimitMaxL2FetchGranularity before:", cudart.cudaDeviceGetLimit(cudart.cudaLimit.cudaLimitMaxL2FetchGranularity))
+    print("set:", cudart.cudaDeviceSetLimit(cudart.cudaLimit.cudaLimitMaxL2FetchGranularity, int(os.environ["AVSR_L2_GRAN"])))
+    print("after:", cudart.cudaDeviceGetLimit(cudart.cudaLimit.cudaLimitMaxL2FetchGranularity))
 B, beam, T, V = 32, 3, 375, 5049
 step = int(sys.argv[1]) if len(sys.argv) > 1 else 187
 R, S, lmax, nl = B * beam, 4, T + 1, 6
@@ -60,14 +66,14 @@ q2_p, q2_b = torch.randn(NSC, R, 1024, device=dev), torch.randn(1024, device=dev
 def self_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv_p), L.ll(3072), NSQ, L.ptr(qkv_b), L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run),
-                                   L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(0), L.ptr(att6), L.stream()), "self")
+                                   L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(0), L.ptr(att6), None, None, None, L.stream()), "self")
 
 
 def cross_attn():
     l = li["i"] % nl; li["i"] += 1
     L.check(lib.avsr_dec_attn_step(1, L.ptr(q2_p), L.ll(1024), NSC, L.ptr(q2_b), L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax,
                                    L.ptr(n_run), L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(B * T),
-                                   L.ptr(att6), L.stream()), "cross")
+                                   L.ptr(att6), None, None, None, L.stream()), "cross")
 
 
 print(f"step={step}  R={R}")

@@ -50,13 +50,13 @@ if "attn" in which:
     anc = torch.zeros(2, R, lmax, dtype=torch.uint8, device=dev)
     ckv = torch.randn(nl, 2, 16, B * T, 64, device=dev)
     att6 = torch.empty(R, 3072, device=dev, dtype=torch.bfloat16)
-        for it in range(3):
+    for it in range(3):
         l = it % nl
         flush.zero_()
         L.check(lib.avsr_dec_attn_step(0, L.ptr(qkv), L.ll(3072), 0, None, L.ptr(kc[l]), L.ptr(vc[l]), L.ptr(anc), lmax, L.ptr(n_run),
-                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(0), L.ptr(att6), L.stream()), "self")
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(0), L.ptr(att6), None, None, None, L.stream()), "self")
         L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), 0, None, L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, lmax, L.ptr(n_run),
-                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(B * T), L.ptr(att6), L.stream()), "cross")
+                                       L.ptr(utt_off), L.ptr(utt_T), beam, R, L.ptr(step_t), None, L.ll(B * T), L.ptr(att6), None, None, None, L.stream()), "cross")
     torch.cuda.synchronize()
 
 if "gemm" in which:
