@@ -4,6 +4,7 @@
 // (src/nets/batch_beam_search.py:86-110,208-349), end_detect (src/nets/e2e_asr_common.py:18-48).
 // The reference runs ~16.7k ATen ops + per-hyp host syncs per step here; this file does it in two launches per step
 // for all utterances at once, with the hypothesis state resident on the device.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -157,13 +158,19 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int bl
 // registers.  With more than one time split the partial sums are published and the last CTA of a (utterance, column
 // group) to finish (ticket) adds them in split order, takes the logarithm and writes the scores.
 constexpr int FV_MAXH = 8;
-constexpr int FV_THREADS = 256;
-constexpr int FV_CG = FV_THREADS * 4;     // columns per group
-constexpr int FV_UT = 8;                  // rows per batch (two batches in flight)
+constexpr int FV_THREADS = 160;
+constexpr int FV_CG = FV_THREADS * 4;     // most columns a group can have (the plan sizes the groups to fill the SMs)
+constexpr int FV_UT = 12;                 // rows per batch (two batches in flight)
 constexpr int FV_NHP = 5;                 // hyps accumulated per pass over the block (beam <= 5: the block is read once)
 constexpr int FV_ES = 8;                  // row stride of the E table in shared memory (floats): one or two 16-byte reads per row
 constexpr int FV_NSPECIAL = 1024;
 constexpr float FV_TINY = 1e-30f;
+
+__device__ __forceinline__ float fv_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 
 // rows t .. t+FV_UT-1 of this thread's four columns; rows past the end are clamped (their weight is skipped by the consumer)
 __device__ __forceinline__ void fv_load(const float* __restrict__ lpc, int ldp, int t, int t_last, float4 (&x)[FV_UT]) {
@@ -183,8 +190,10 @@ __device__ __forceinline__ void fv_consume(const float* __restrict__ s_E, int t,
                 const float4 e1 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES + 4);
                 ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
             }
-            // ex2.approx(x * log2 e): relative error ~2^-21, far below the rounding of the fp32 sum itself
-            const float pr[4] = {__expf(x[u].x), __expf(x[u].y), __expf(x[u].z), __expf(x[u].w)};
+            // ex2.approx.ftz(x * log2 e): one FMUL + one MUFU per posterior (__expf adds a denormal-range fix-up: a compare and
+            // two more multiplies).  Relative error ~2^-21, far below the rounding of the fp32 sum itself; posteriors below
+            // e^-87 flush to zero, where the IEEE result (< 1e-38) could not change a sum that is checked against 1e-30.
+            const float pr[4] = {fv_exp(x[u].x), fv_exp(x[u].y), fv_exp(x[u].z), fv_exp(x[u].w)};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -225,7 +234,7 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
                        const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
                        const int* __restrict__ last_tok, const int* __restrict__ rprev_idx, const float* __restrict__ r_buf,
                        int tmax, const int* __restrict__ step_p, const float* __restrict__ s_prev, float* __restrict__ scores,
-                       int ncg, int tsplit, float* __restrict__ part, int* __restrict__ tickets) {
+                       int ncg, int cgw, int tsplit, float* __restrict__ part, int* __restrict__ tickets) {
     extern __shared__ __align__(16) float sm[];     // s_E [T][FV_ES], s_rs [T][nh] (r_sum), s_pb [T][nh] (blank-ending)
     __shared__ float s_M[FV_MAXH];
     __shared__ float s_red[FV_THREADS / 32][FV_MAXH];
@@ -249,7 +258,7 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
     const int t_lo = start + z * per, t_hi = min(T, t_lo + per);
     if (tid == 0) s_nspecial = 0;
     // this thread's columns c0 .. c0+3 (columns >= V lie in the row padding or are clamped; they are dropped at the end)
-    const int c0 = cg * FV_CG + 4 * tid;
+    const int c0 = (4 * tid < cgw) ? cg * cgw + 4 * tid : ldp;    // cgw = columns per group (multiple of 4); spare threads idle
     const float* lpc = lp + min(c0, ldp - 4);
     // ---- first batch of log-posteriors: requested now, consumed after the preamble below (its latency is hidden)
     float4 xa[FV_UT];
@@ -650,8 +659,16 @@ extern "C" int avsr_ctc_prefix_full_plan(int B, int V, int* ncg, int* tsplit) {
     int sms = 0, dev = 0;
     AVSR_CHECK_CUDA(cudaGetDevice(&dev));
     AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    *ncg = cdiv(V, FV_CG);
-    int ts = (2 * sms) / (B * *ncg);                 // two CTAs per SM, all resident at once
+    // two CTAs per SM, all resident at once: column groups first (at least 128 busy threads each), then time splits
+    const int v4 = cdiv(V, 4);
+    int g = (2 * sms) / B;
+    const int gmin = cdiv(v4, FV_THREADS), gmax = cdiv(v4, 128) > gmin ? cdiv(v4, 128) : gmin;
+    g = g < gmin ? gmin : (g > gmax ? gmax : g);
+    *ncg = g;
+    int ts = (2 * sms) / (B * *ncg);
+    static int force = -1;                            // dev knob AVSR_CTC_TSPLIT
+    if (force < 0) { const char* e = getenv("AVSR_CTC_TSPLIT"); force = e ? atoi(e) : 0; }
+    if (force > 0) ts = force;
     *tsplit = ts < 1 ? 1 : (ts > 16 ? 16 : ts);
     return AVSR_OK;
 }
@@ -677,8 +694,9 @@ extern "C" int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank
         configured = 160 * 1024;
     }
     dim3 grid(ncg * tsplit, B);
+    const int cgw = cdiv(cdiv(V, 4), ncg) * 4;       // columns per group
     ctc_prefix_full_kernel<<<grid, FV_THREADS, smem, stream>>>(logp, V, ldp, blank, eos, utt_off, utt_T, n_run, beam, B * beam, S, last_tok,
-                                                               rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, tsplit, part, tickets);
+                                                               rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, cgw, tsplit, part, tickets);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

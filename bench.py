@@ -153,17 +153,25 @@ def _kernel_rooflines(model, peaks):
     dev = model.device
     out = {}
 
-    def timeit(fn, n=20, warm=3):
+    def timeit(fn, n=20, warm=3, reps=4):
+        """n launches captured in ONE CUDA graph (as in the decode loop: no host launch overhead between them), replayed
+        `reps` times between two CUDA events on the launching stream."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            fn()
+        for _ in range(reps):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n * 1e-3
+        return e0.elapsed_time(e1) / (n * reps) * 1e-3
 
     # (1) decode-step skinny fp32 GEMM (dominant kernel of the step): FFN w_1 [3072,1024], R = 96 rows, cycling over the 6
     #     layers' weights so that they stream from HBM as in the real step (373 MB of decoder weights > L2)

@@ -194,7 +194,7 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
                     scores = torch.zeros(R, V, device="cuda")
                     ncg, ts = C.c_int(0), C.c_int(0)
                     L.check(lib.avsr_ctc_prefix_full_plan(1, V, C.byref(ncg), C.byref(ts)), "plan")
-                    assert ts.value == 16 and ncg.value == -(-V // 1024)           # one utterance: the time axis is split 16 ways
+                    assert ts.value == 16 and ncg.value == -(-V // 512)            # one utterance: the time axis is split 16 ways
                     fpart = torch.empty(1, ts.value, beam, V, device="cuda")
                     ftick = torch.zeros(1, ncg.value, dtype=torch.int32, device="cuda")
                     for _ in range(2):                                             # twice: the tickets must re-arm themselves
