@@ -55,6 +55,11 @@ __global__ void __launch_bounds__(256)
 im2col_frontend_kernel(const float* __restrict__ video, const int* __restrict__ frame_t, const int* __restrict__ frame_T,
                        __nv_bfloat16* __restrict__ out, int f0) {
     __shared__ float rows[5][7][96];       // [dt][dy][x + 3], x in [-3, 91)
+    __shared__ int koff[256];              // k = (dt*7 + dy)*7 + dx -> (dt*7 + dy)*96 + dx, -1 for the padding columns
+    if (threadIdx.x < 256) {
+        const int k = threadIdx.x;
+        koff[k] = k < 245 ? (k / 7) * 96 + (k % 7) : -1;
+    }
     const int f = f0 + blockIdx.x / 44, oy = blockIdx.x % 44;
     const int t = frame_t[f], T = frame_T[f];
     for (int i = threadIdx.x; i < 5 * 7 * 96; i += blockDim.x) {
@@ -65,14 +70,23 @@ im2col_frontend_kernel(const float* __restrict__ video, const int* __restrict__ 
         rows[dt][dy][xx] = v;
     }
     __syncthreads();
+    // 8 consecutive k per thread = one 16-byte store; k -> offset in `rows` through a small table (no divisions per element)
     __nv_bfloat16* o = out + ((long long)(blockIdx.x) * 44) * 256;
-    for (int i = threadIdx.x; i < 44 * 128; i += blockDim.x) {
-        const int ox = i / 128, k = (i % 128) * 2;
-        float v0 = 0.f, v1 = 0.f;
-        if (k < 245) { const int dt = k / 49, dy = (k / 7) % 7, dx = k % 7; v0 = rows[dt][dy][ox * 2 + dx]; }
-        if (k + 1 < 245) { const int k1 = k + 1; const int dt = k1 / 49, dy = (k1 / 7) % 7, dx = k1 % 7; v1 = rows[dt][dy][ox * 2 + dx]; }
-        __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-        *reinterpret_cast<__nv_bfloat162*>(o + (long long)ox * 256 + k) = p;
+    const float* rflat = &rows[0][0][0];
+    for (int i = threadIdx.x; i < 44 * 32; i += blockDim.x) {
+        const int ox = i >> 5, k0 = (i & 31) * 8;
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int off = koff[k0 + u];
+            v[u] = off >= 0 ? rflat[off + ox * 2] : 0.f;
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+        pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(o + (long long)ox * 256 + k0) = pk;
     }
 }
 
