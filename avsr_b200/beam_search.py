@@ -81,6 +81,11 @@ class BatchedBeamSearch:
         # (measured SLOWER on B200, 477 vs 461 ms per 32-utterance pass, so it is off unless AVSR_L2_PREFETCH=1)
         self.l2_prefetch = os.environ.get("AVSR_L2_PREFETCH", "0") == "1"
         self._skip = frozenset()      # dev aid (tools/ablate_step.py): kernel groups left out of _step for timing ablations
+        # bf16x3 path, opt-in (AVSR_CHAIN=1): a projection launch also finishes the rows of the previous projection (its own
+        # operand), 54 launches per position instead of 78.  Measured SLOWER on B200 (873 vs 815 us per position): releasing
+        # the operand rows through a device counter (threadfence + proxy fence + atomic + acquire spin) costs more than the
+        # programmatic-dependent-launch boundary it replaces, so the default keeps the separate row-epilogue launches.
+        self.chain = os.environ.get("AVSR_CHAIN", "0") == "1"
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
         self.last_session = None
         self._sessions = {}
@@ -145,6 +150,10 @@ class BatchedBeamSearch:
         else:
             n_part = max(lib.avsr_sgemm_skinny_splits(R, n, k) * R * n for n, k in shapes)
         s["part"] = torch.empty(n_part, dtype=torch.float32, device=dev)
+        # chained projections (csrc/gemm_x3.cu): consecutive projections alternate between two partial-sum buffers, and a
+        # pair of device counters releases the operand rows that a launch finishes for itself
+        s["part2"] = torch.empty(n_part, dtype=torch.float32, device=dev) if self.precision == "bf16x3" else None
+        s["ready"] = torch.zeros(2, dtype=torch.int32, device=dev)
         # per-utterance precomputed tensors
         s["ldp"] = (V + 31) // 32 * 32              # posterior row pitch: 128-byte aligned rows (V = 5049 -> 5056)
         s["logp"] = torch.zeros(F, s["ldp"], dtype=torch.float32, device=dev)
@@ -212,8 +221,97 @@ class BatchedBeamSearch:
                                             L.ptr(s["row_active"]), L.ptr(split), L.ptr(prefetch) if pf_bytes else None, L.ll(pf_bytes),
                                             L.stream()), "avsr_splitk_epilogue")
 
+    def _step_chain(self, s):
+        """The bf16x3 position with chained projections: every nn.Linear whose input is the row-wise glue of the previous one
+        (bias / residual / LayerNorm / ReLU, decoder_layer.py:58-121) finishes those rows inside its own launch
+        (avsr_gemm_x3_chain), so a position is 54 launches instead of 78."""
+        lib = L.load()
+        w = self.w
+        R, beam, S, V, lmax = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab, s["lmax"]
+        st = L.stream
+        nl = w.n_layers
+        parts = (s["part"], s["part2"])
+        state = {"cur": 0, "rq": 0}
+
+        def proj(key_a, w3, N, K, pro=None):
+            """act[R,K] @ W^T -> partial sums in the other buffer; pro = row glue of the previous projection to finish first:
+            dict(N, bias, act, residual, out, ln, split)."""
+            prev, cur = parts[state["cur"]], parts[state["cur"] ^ 1]
+            state["cur"] ^= 1
+            if pro is None:
+                L.check(lib.avsr_gemm_x3_splitk(L.ptr(s[key_a]), L.ll(3 * K), L.ptr(w3), L.ll(3 * K), R, N, K, L.ptr(cur), st()),
+                        "avsr_gemm_x3_splitk")
+            else:
+                g, b = pro.get("ln") or (None, None)
+                ns_prev = lib.avsr_gemm_x3_splits(R, pro["N"], pro["K"])
+                L.check(lib.avsr_gemm_x3_chain(L.ptr(s[key_a]), L.ll(3 * K), L.ptr(w3), L.ll(3 * K), R, N, K, L.ptr(cur),
+                                               L.ptr(prev), ns_prev, pro["N"], L.ptr(pro["bias"]), pro.get("act", L.ACT_NONE),
+                                               L.ptr(pro.get("residual")), L.ll(1024), L.ptr(pro.get("out")), L.ll(pro["N"]), L.ptr(g),
+                                               L.ptr(b), C.c_float(1e-12), L.ptr(s["row_active"]), L.ptr(s[key_a]), L.ptr(s["ready"]),
+                                               state["rq"], st()), "avsr_gemm_x3_chain")
+                state["rq"] ^= 1
+            return cur, lib.avsr_gemm_x3_splits(R, N, K)
+
+        l0 = w.layers[0]
+        L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), nl, L.ptr(s["anc"]), lmax,
+                                           L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
+        L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
+                                      L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), None, L.ptr(s["a3"]), st()),
+                "avsr_dec_embed_ln")
+        att_split = L.ptr(s["att3"])
+        pending = None           # row glue of the last projection that the next chained projection has to finish
+        for li, lay in enumerate(w.layers):
+            # self-attention (decoder_layer.py:82-93); q | k | v come straight from the split-K partial sums
+            part, ns = proj("a3", lay["wqkv3"], 3072, 1024, pending)
+            L.check(lib.avsr_dec_attn_step(0, L.ptr(part), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]), L.ptr(s["vc"][li]),
+                                           L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R,
+                                           L.ptr(s["step"]), None, L.ll(0), att_split, L.ptr(s["kd"][li]), L.ptr(s["vd"][li]),
+                                           L.ptr(s["conv_len"]), st()), "avsr_dec_attn_step(self)")
+            proj("att3", lay["wo3"], 1024, 1024)
+            # source attention (decoder_layer.py:97-107): its query projection first finishes x += wo(att) + bo ; LayerNorm n2
+            part, ns = proj("a3", lay["wq23"], 1024, 1024, dict(N=1024, K=1024, bias=lay["bo"], residual=s["x"], out=s["x"],
+                                                                ln=(lay["n2_g"], lay["n2_b"])))
+            L.check(lib.avsr_dec_attn_step(1, L.ptr(part), L.ll(1024), ns, L.ptr(lay["bq2"]), L.ptr(s["ckv_t"][li, 0]),
+                                           L.ptr(s["ckv_t"][li, 1]), None, lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]),
+                                           beam, R, L.ptr(s["step"]), None, L.ll(s["F"]), att_split, None, None, None, st()),
+                    "avsr_dec_attn_step(src)")
+            proj("att3", lay["wo23"], 1024, 1024)
+            # feed-forward (decoder_layer.py:112-116)
+            proj("a3", lay["w13"], 3072, 1024, dict(N=1024, K=1024, bias=lay["bo2"], residual=s["x"], out=s["x"],
+                                                    ln=(lay["n3_g"], lay["n3_b"])))
+            proj("ffn3", lay["w23"], 1024, 3072, dict(N=3072, K=1024, bias=lay["b1"], act=L.ACT_RELU))
+            nxt = (w.layers[li + 1]["n1_g"], w.layers[li + 1]["n1_b"]) if li + 1 < nl else (w.after_g, w.after_b)
+            pending = dict(N=1024, K=3072, bias=lay["b2"], residual=s["x"], out=s["x"], ln=nxt)
+        # output layer (decoder.py:176-181) finishes the last feed-forward + after_norm first
+        part, ns = proj("a3", w.out_w3, V, 1024, pending)
+        self._tail(s, part, ns)
+
+    def _tail(self, s, part, ns):
+        """log_softmax + pre-beam, CTC prefix scores, fusion / top-k / bookkeeping (batch_beam_search.py:222-349)."""
+        lib = L.load()
+        w = self.w
+        R, beam, S, V = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab
+        st = L.stream
+        if "tail" in self._skip:
+            return
+        L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(part), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
+                                             L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
+        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, s["ldp"], w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
+                                            beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
+                                            L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
+                "avsr_ctc_prefix_prebeam")
+        if "advance" in self._skip:
+            return
+        L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
+                                                L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc), st()),
+                "avsr_beam_fuse_topk_advance")
+        L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
+                "avsr_beam_step_advance")
+
     def _step(self, s):
         """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
+        if self.precision == "bf16x3" and self.chain and not self.fuse_epilogue and not self._skip - {"advance", "tail"}:
+            return self._step_chain(s)
         lib = L.load()
         w = self.w
         R, beam, S, V, lmax = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab, s["lmax"]
@@ -256,23 +354,7 @@ class BatchedBeamSearch:
             self._linear(s, "ffn", lay, "w2", 1024, 3072, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
         # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
         ns = self._proj(s, "a", {"out": w.out_w, "out3": getattr(w, "out_w3", None)}, "out", V, 1024)
-        if "tail" in self._skip:
-            return
-        L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(s["part"]), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
-                                             L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
-        # CTC prefix scores of the pre-beam candidates (ctc_prefix_score.py:68-187)
-        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, s["ldp"], w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
-                                            beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
-                                            L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
-                "avsr_ctc_prefix_prebeam")
-        if "advance" in self._skip:
-            return
-        # fusion, top-k, hypothesis bookkeeping, end detection (batch_beam_search.py:222-349)
-        L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
-                                                L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc), st()),
-                "avsr_beam_fuse_topk_advance")
-        L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
-                "avsr_beam_step_advance")
+        self._tail(s, s["part"], ns)
 
     # ------------------------------------------------------------------------------------------ public API
     def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int]):

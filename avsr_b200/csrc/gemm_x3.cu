@@ -74,9 +74,22 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
     __threadfence();
 }
 
+// Spin (one thread) until the rows-ready counter of this launch reaches `rows`; traps instead of hanging.
+__device__ __forceinline__ void wait_rows_ready(const unsigned* ctr, unsigned rows) {
+    unsigned v;
+    for (uint32_t i = 0;; ++i) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= rows) break;
+        if (i > (1u << 26)) __trap();
+        __nanosleep(20);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, int R, int N, int K, int NB,
-               float* __restrict__ part, int splits, int tiles_m, int tiles_n, int fuse, const SplitKEpi epi, unsigned* gbar) {
+               float* __restrict__ part, int splits, int tiles_m, int tiles_n, int fuse, const SplitKEpi epi, unsigned* gbar,
+               int pro_on, const SplitKEpi pro, unsigned* ready, int rq) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -139,6 +152,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     }
                     pdl_wait();
                     waited = true;
+                    if (pro_on) wait_rows_ready(ready + rq, (unsigned)pro.M);      // the operand rows are finished by this launch
                     for (int i = 0; i < npre; ++i) {
                         uint8_t* sa = smem + i * STAGE_BYTES + 3 * W_TILE;
 #pragma unroll
@@ -199,6 +213,21 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int quad = warp & 3;
         uint32_t acc_phase = 0;
         pdl_wait();                                   // the partial-sum buffer may still be read by the previous consumer
+        if (pro_on) {
+            // ---- prologue: finish rows of the PREVIOUS projection (split-K sum, bias, activation, residual, LayerNorm, bf16x3
+            //      split) - they are this projection's operand.  One row per CTA; a device counter tells every CTA's TMA
+            //      producer when all rows are there.  The counter of the next chained launch is re-armed here.
+            const int gt = threadIdx.x - 64;
+            if (blockIdx.x == 0 && gt == 0) ready[rq ^ 1] = 0u;
+            unsigned done = 0;
+            for (int row = blockIdx.x; row < pro.M; row += gridDim.x, ++done) avsr_splitk_epilogue_row_group<128>(pro, row, rowbuf, red, gt, 1);
+            if (done) {
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores -> visible to the TMA loads of other CTAs
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (gt == 0) atomicAdd(ready + rq, done);
+            }
+        }
         for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
             int m0, n0, kb0, kb1;
             item_coords(item, m0, n0, kb0, kb1);
@@ -278,7 +307,8 @@ extern "C" int avsr_gemm_x3_splits(int R, int N, int K) {
 }
 
 static int x3_launch(const void* A3, long long lda, const void* W3, long long ldw, int R, int N, int K, float* part, int fuse,
-                     const SplitKEpi& epi, unsigned* gbar, cudaStream_t stream) {
+                     const SplitKEpi& epi, unsigned* gbar, cudaStream_t stream, int pro_on = 0, const SplitKEpi* pro = nullptr,
+                     unsigned* ready = nullptr, int rq = 0) {
     AVSR_REQUIRE(A3 && W3 && part, "avsr_gemm_x3: null operand");
     AVSR_REQUIRE(R > 0 && N > 0 && K > 0 && (K % BK) == 0, "avsr_gemm_x3: bad shape R=%d N=%d K=%d (K must be a multiple of 64)", R, N, K);
     int nb, tiles_m, tiles_n, splits;
@@ -295,8 +325,10 @@ static int x3_launch(const void* A3, long long lda, const void* W3, long long ld
     }
     const int items = tiles_m * tiles_n * splits;
     const int grid = items < sm_count() ? items : sm_count();
+    AVSR_REQUIRE(!pro_on || items <= sm_count(), "avsr_gemm_x3_chain: %d work items exceed one CTA per SM (R=%d N=%d)", items, R, N);
+    SplitKEpi none = {};
     AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tw, ta, R, N, K, nb, part, splits,
-                                    tiles_m, tiles_n, fuse, epi, gbar));
+                                    tiles_m, tiles_n, fuse, epi, gbar, pro_on, pro_on ? *pro : none, ready, rq));
     return AVSR_OK;
 }
 
@@ -324,4 +356,25 @@ extern "C" int avsr_gemm_x3_fused(const void* A3, long long lda, const void* W3,
                  tiles_m * tiles_n * splits, R, N);
     SplitKEpi e = {part, splits, R, N, bias, act, residual, ldr, out, ldo, ln_g, ln_b, ln_eps, ln_out, ld_ln, row_active, (__nv_bfloat16*)split_out};
     return x3_launch(A3, lda, W3, ldw, R, N, K, part, 1, e, gbar, stream);
+}
+
+// Chained form: before the projection loads its operand A3, the SAME launch finishes the rows of the previous projection
+// that produce it (arguments as avsr_splitk_epilogue: p_part [p_nsplit][R][p_N] partial sums -> bias, activation, residual,
+// out, LayerNorm -> split_out, which must be A3's buffer), one row per CTA, and a device counter releases the TMA loads
+// once all R rows are there.  That removes the row-epilogue launch between two projections.  ready = two zero-initialised
+// uint32 owned by the caller; consecutive chained launches on a stream alternate parity = 0, 1, 0, ... (each launch re-arms
+// the other counter).  part must not alias p_part.  Needs tiles * splits <= number of SMs.
+extern "C" int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long ldw, int R, int N, int K, float* part,
+                                  const float* p_part, int p_nsplit, int p_N, const float* p_bias, int p_act, const float* p_residual,
+                                  long long p_ldr, float* p_out, long long p_ldo, const float* p_ln_g, const float* p_ln_b, float p_ln_eps,
+                                  const int* row_active, void* p_split_out, unsigned* ready, int parity, cudaStream_t stream) {
+    AVSR_REQUIRE(p_part && p_nsplit >= 1 && p_N > 0 && (p_N & 3) == 0 && (p_ldr & 3) == 0 && (p_ldo & 3) == 0 && ready && (parity == 0 || parity == 1),
+                 "avsr_gemm_x3_chain: bad prologue arguments");
+    AVSR_REQUIRE(p_part != part, "avsr_gemm_x3_chain: the partial-sum buffers of consecutive projections must differ");
+    AVSR_REQUIRE(p_out || p_split_out, "avsr_gemm_x3_chain: the prologue has no output");
+    AVSR_REQUIRE(!p_ln_g || (p_ln_b && p_N * 4 <= ROWBUF_BYTES), "avsr_gemm_x3_chain: LayerNorm needs gamma/beta and N <= 3072");
+    SplitKEpi e = {};
+    SplitKEpi pro = {p_part, p_nsplit, R, p_N, p_bias, p_act, p_residual, p_ldr, p_out, p_ldo, p_ln_g, p_ln_b, p_ln_eps, nullptr, 0, row_active,
+                     (__nv_bfloat16*)p_split_out};
+    return x3_launch(A3, lda, W3, ldw, R, N, K, part, 0, e, nullptr, stream, 1, &pro, ready, parity);
 }

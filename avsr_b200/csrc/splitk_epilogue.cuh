@@ -143,3 +143,102 @@ __device__ __forceinline__ void avsr_splitk_epilogue_row(const SplitKEpi& e, int
         if (split_out) avsr_split3c_store(split_out + (long long)row * 3 * N, N, c, y);
     }
 }
+
+// ---- the same row epilogue on a GROUP of GT threads of a CTA (named barrier `bar`; tid = index inside the group), for the
+// projection kernel that finishes the rows of the PREVIOUS projection before it loads them as its own operand
+// (csrc/gemm_x3.cu).  Vector path only: N, ldr, ldo multiples of 4.
+template <int GT>
+__device__ __forceinline__ float avsr_group_sum(float v, float* red, int tid, int bar) {
+    const int lane = tid & 31, w = tid >> 5;
+    v = warp_sum(v);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(GT) : "memory");
+    if (lane == 0) red[w] = v;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(GT) : "memory");
+    float r = (lane < GT / 32) ? red[lane] : 0.f;
+    return warp_sum(r);
+}
+
+template <int GT>
+__device__ __forceinline__ void avsr_splitk_epilogue_row_group(const SplitKEpi& e, int row, float* rowbuf, float* red, int tid, int bar) {
+    if (e.row_active != nullptr && e.row_active[row] == 0) return;
+    const int nsplit = e.nsplit, N = e.N, act = e.act;
+    const long long zstride = (long long)e.M * N;
+    float lsum = 0.f;
+    // two column groups per pass, eight splits of both requested before the first add: the partial sums of a 1024-wide row
+    // with 16 splits cost two L2 round trips per thread (this runs on the critical path of the projection that follows)
+    for (int c0 = tid * 4; c0 < N; c0 += GT * 8) {
+        const int c1 = c0 + GT * 4;
+        const bool two = c1 < N;
+        const float* p0 = e.part + (long long)row * N + c0;
+        const float* p1 = e.part + (long long)row * N + (two ? c1 : c0);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        int z = 0;
+        for (; z + 8 <= nsplit; z += 8) {
+            float4 t0[8], t1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                t0[u] = __ldcg(reinterpret_cast<const float4*>(p0 + (z + u) * zstride));
+                t1[u] = __ldcg(reinterpret_cast<const float4*>(p1 + (z + u) * zstride));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v0.x += t0[u].x; v0.y += t0[u].y; v0.z += t0[u].z; v0.w += t0[u].w;
+                v1.x += t1[u].x; v1.y += t1[u].y; v1.z += t1[u].z; v1.w += t1[u].w;
+            }
+        }
+        {
+            float4 t0[8], t1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = z + u < nsplit;
+                t0[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p0 + (z + u) * zstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                t1[u] = ok ? __ldcg(reinterpret_cast<const float4*>(p1 + (z + u) * zstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (z + u < nsplit) {
+                    v0.x += t0[u].x; v0.y += t0[u].y; v0.z += t0[u].z; v0.w += t0[u].w;
+                    v1.x += t1[u].x; v1.y += t1[u].y; v1.z += t1[u].z; v1.w += t1[u].w;
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (g == 1 && !two) break;
+            const int c = g == 0 ? c0 : c1;
+            float4 v = g == 0 ? v0 : v1;
+            if (e.bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(e.bias + c);
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            }
+            if (act == AVSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            else if (act == AVSR_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if (e.residual) {
+                const float4 r4 = *reinterpret_cast<const float4*>(e.residual + (long long)row * e.ldr + c);
+                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+            }
+            if (e.out) *reinterpret_cast<float4*>(e.out + (long long)row * e.ldo + c) = v;
+            if (e.ln_g) { *reinterpret_cast<float4*>(rowbuf + c) = v; lsum += (v.x + v.y) + (v.z + v.w); }
+            else if (e.split_out) avsr_split3c_store4(e.split_out + (long long)row * 3 * N, N, c, v);
+        }
+    }
+    if (e.ln_g == nullptr) return;
+    // LayerNorm of the finished row (every thread re-reads only the columns it wrote)
+    const float mean = avsr_group_sum<GT>(lsum, red, tid, bar) / (float)N;
+    float lvar = 0.f;
+    for (int c = tid * 4; c < N; c += GT * 4) {
+        const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
+        const float d0 = t.x - mean, d1 = t.y - mean, d2 = t.z - mean, d3 = t.w - mean;
+        lvar += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(avsr_group_sum<GT>(lvar, red, tid, bar) / (float)N + e.ln_eps);
+    for (int c = tid * 4; c < N; c += GT * 4) {
+        const float4 t = *reinterpret_cast<const float4*>(rowbuf + c);
+        const float4 g4 = *reinterpret_cast<const float4*>(e.ln_g + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(e.ln_b + c);
+        const float4 y = make_float4((t.x - mean) * rstd * g4.x + b4.x, (t.y - mean) * rstd * g4.y + b4.y,
+                                     (t.z - mean) * rstd * g4.z + b4.z, (t.w - mean) * rstd * g4.w + b4.w);
+        if (e.ln_out) *reinterpret_cast<float4*>(e.ln_out + (long long)row * e.ld_ln + c) = y;
+        if (e.split_out) avsr_split3c_store4(e.split_out + (long long)row * 3 * N, N, c, y);
+    }
+}

@@ -110,6 +110,14 @@ int avsr_gemm_x3_fused(const void* A3, long long lda, const void* W3, long long 
                        const float* bias, int act, const float* residual, long long ldr, float* out, long long ldo,
                        const float* ln_g, const float* ln_b, float ln_eps, float* ln_out, long long ld_ln,
                        const int* row_active, void* split_out, unsigned* gbar, avsr_stream_t stream);
+/* Chained form: the launch first finishes the rows of the PREVIOUS projection that produce its operand (arguments p_* as
+ * avsr_splitk_epilogue; p_split_out must be A3's buffer), one row per CTA, then runs the projection; no row-epilogue launch
+ * in between.  ready = two zero-initialised uint32 (caller-owned); consecutive chained launches on a stream alternate
+ * parity 0, 1, 0, ...; part must not alias p_part; needs tiles * splits <= number of SMs. */
+int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long ldw, int R, int N, int K, float* part,
+                       const float* p_part, int p_nsplit, int p_N, const float* p_bias, int p_act, const float* p_residual,
+                       long long p_ldr, float* p_out, long long p_ldo, const float* p_ln_g, const float* p_ln_b, float p_ln_eps,
+                       const int* row_active, void* p_split_out, unsigned* ready, int parity, avsr_stream_t stream);
 /* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
 int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */

@@ -71,6 +71,17 @@ def test_beam_search_vs_reference_golden(state_dict, gpu_model, golden, T, beam,
     assert isinstance(d["yseq"], list) and isinstance(d["score"], float) and set(d["scores"]) == {"decoder", "ctc"}
 
 
+@pytest.mark.parametrize("beam,graph", [(3, True), (5, False)])
+def test_chained_projections_match_reference_golden(gpu_model, golden, beam, graph):
+    """Opt-in variant of the bf16x3 position (avsr_gemm_x3_chain: a projection launch first finishes the rows of the previous
+    projection): same token-identical n-best as the default sequence of launches."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam, use_graph=graph)
+    bs.chain = True
+    for T in (30, 12):
+        _check_nbest(bs(torch.from_numpy(golden[f"enc_T{T}"]).cuda()), golden, T, beam)
+
+
 @pytest.mark.parametrize("beam", [3, 5])
 def test_beam_search_vs_reference_cfg0_T375(gpu_model, golden_cfg0, beam):
     """BASELINE.json configs[0] at full size: T=375 frames, decode from the reference's encoder output, n-best
@@ -221,3 +232,26 @@ def test_ctc_prefix_kernels_vs_reference_golden(golden_ctc):
                     rprev = i32(list(range(len(picks))) + [0] * (R - len(picks)))
                     s_prev = torch.cat([psi2[:len(picks), 0], torch.zeros(R - len(picks), device="cuda")])
                 n_hyp = len(picks)
+
+
+@pytest.mark.gpu
+def test_sharded_evaluation_driver_equals_single_runs(gpu_model):
+    """evaluate_sharded (length-bucketed batches, the eval_lrs2 loop of script/evaluation.py:387-404) on a mixed-length
+    set: every utterance must get the token ids of its own `inference()` call, and the corpus WER must follow from them."""
+    from avsr_b200 import evaluation as E
+    from avsr_b200 import sharding as S
+    lengths = [14, 9, 22, 5, 17]
+    samples = [synth.make_inputs(900 + i, t) for i, t in enumerate(lengths)]
+    load = lambda i: (samples[i][0][0], samples[i][1][0])
+    want = []
+    for v, a in samples:
+        ids = gpu_model.inference(v.cuda(), a.cuda())
+        want.append(E.strip_sos_eos([gpu_model.sos] + ids, gpu_model.eos))
+    refs = [" ".join(str(t) for t in w) for w in want]
+    refs[2] = refs[2] + " 7"                               # one deletion in utterance 2
+    res = E.evaluate_sharded(gpu_model, lengths, load, references=refs, max_utts=2, max_frames=40, device="cuda")
+    assert res.n_batches >= 3
+    assert [res.hyp_tokens[i] for i in range(len(lengths))] == want
+    assert res.edits == 1 and res.ref_words == sum(len(r.split()) for r in refs)
+    assert res.wer == pytest.approx(1 / res.ref_words)
+    assert S.shard_utterances(lengths, 1) == [[2, 4, 0, 1, 3]]
