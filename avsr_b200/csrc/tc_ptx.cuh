@@ -48,6 +48,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// im2col-mode load of an NHWC activation tensor {C, W, H, N}: `pixelsPerColumn` consecutive base pixels starting at (w, h, n) -
+// walking W, then H, then N inside the map's bounding box - each shifted by the filter offset (w_off, h_off); out-of-image
+// pixels are zero-filled.  The box lands in shared memory exactly like a 2D [pixels x channels] tile.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t w_off, uint16_t h_off) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(w_off),
+          "h"(h_off)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -128,4 +139,8 @@ EncodeTiledFn get_encode_fn();
 // rank-2 bf16 map: inner dim = cols (contiguous), outer = rows; box {box_cols, box_rows}; 128B swizzle; OOB -> 0.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
                       uint32_t box_cols);
+// im2col map of a bf16 NHWC tensor [n, h, w, c] for a 3x3 / stride 1 / pad 1 convolution: boxes of `pixels` output pixels x
+// `channels` input channels; 128B swizzle; out-of-image -> 0.
+int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t pixels,
+                             uint32_t channels);
 }  // namespace tc

@@ -12,6 +12,7 @@ the HBM-bound helpers of csrc/elementwise.cu.  The residual stream is kept in fp
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -40,6 +41,9 @@ class Encoder:
         L.load()
         self.w = EncoderWeights(state_dict, self.device)
         self._ws = {}
+        # stride-1 3x3 convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit
+        # im2col + GEMM for all of them (dev A/B switch; the stride-2 convolutions always take the explicit path)
+        self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
@@ -62,11 +66,15 @@ class Encoder:
         s, C_out = blk["stride"], blk["cout"]
         Ho = (H + 2 - 3) // s + 1
         M = nf * Ho * Ho
-        col = self._buf("col", (M, 9 * C_in), torch.bfloat16)
-        L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(nf), H, H, C_in, 3, s, L.stream()), "avsr_im2col2d")
         t1 = self._buf("blk_t1", (M, C_out), torch.bfloat16)
-        self._conv_gemm(col, blk["conv1_w"], M, C_out, 9 * C_in, bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"],
-                        out_bf16=t1, ld_bf16=C_out)
+        ep1 = dict(bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"], out_bf16=t1, ld_bf16=C_out)
+        if s == 1 and self.implicit_conv:
+            # stride-1 3x3 convolutions run as implicit GEMMs: the TMA unit gathers the patches, nothing is materialised
+            L.conv3x3_bf16(x, blk["conv1_w"], nf, H, H, C_in, C_out, L.make_epilogue(**ep1))
+        else:
+            col = self._buf("col", (M, 9 * C_in), torch.bfloat16)
+            L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(nf), H, H, C_in, 3, s, L.stream()), "avsr_im2col2d")
+            self._conv_gemm(col, blk["conv1_w"], M, C_out, 9 * C_in, **ep1)
         if "down_w" in blk:
             colr = self._buf("col", (M, C_in), torch.bfloat16)
             L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(colr), L.ll(nf), H, H, C_in, 1, s, L.stream()), "avsr_im2col2d")
@@ -74,11 +82,15 @@ class Encoder:
             self._conv_gemm(colr, blk["down_w"], M, C_out, C_in, bias=blk["down_b"], out_bf16=res, ld_bf16=C_out)
         else:
             res = x.view(M, C_out)
-        col2 = self._buf("col", (M, 9 * C_out), torch.bfloat16)
-        L.check(lib.avsr_im2col2d(L.ptr(t1), L.ptr(col2), L.ll(nf), Ho, Ho, C_out, 3, 1, L.stream()), "avsr_im2col2d")
         out = self._buf("blk_out_" + tag, (M, C_out), torch.bfloat16)
-        self._conv_gemm(col2, blk["conv2_w"], M, C_out, 9 * C_out, bias=blk["conv2_b"], act=L.ACT_PRELU, prelu=blk["prelu2"],
-                        residual=res, ldr=C_out, act_after_residual=True, out_bf16=out, ld_bf16=C_out)
+        ep2 = dict(bias=blk["conv2_b"], act=L.ACT_PRELU, prelu=blk["prelu2"], residual=res, ldr=C_out, act_after_residual=True,
+                   out_bf16=out, ld_bf16=C_out)
+        if self.implicit_conv:
+            L.conv3x3_bf16(t1, blk["conv2_w"], nf, Ho, Ho, C_out, C_out, L.make_epilogue(**ep2))
+        else:
+            col2 = self._buf("col", (M, 9 * C_out), torch.bfloat16)
+            L.check(lib.avsr_im2col2d(L.ptr(t1), L.ptr(col2), L.ll(nf), Ho, Ho, C_out, 3, 1, L.stream()), "avsr_im2col2d")
+            self._conv_gemm(col2, blk["conv2_w"], M, C_out, 9 * C_out, **ep2)
         return out.view(nf, Ho, Ho, C_out), Ho
 
     def _video_frontend(self, video_packed, frame_t, frame_T, F, taps=None):
