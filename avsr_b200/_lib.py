@@ -129,10 +129,10 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, ep: Epil
           "avsr_gemm_bf16_tc")
 
 
-def conv3x3_bf16(x: torch.Tensor, w: torch.Tensor, nf: int, H: int, W: int, Cin: int, Cout: int, ep: Epilogue):
-    """3x3 / stride 1 / pad 1 convolution of NHWC bf16 `x` [nf,H,W,Cin] with w [Cout, 9*Cin] as an implicit GEMM (no im2col)."""
+def conv2d_bf16(x: torch.Tensor, w: torch.Tensor, nf: int, H: int, W: int, Cin: int, Cout: int, ks: int, stride: int, ep: Epilogue):
+    """ks x ks / stride / pad ks//2 convolution of NHWC bf16 `x` [nf,H,W,Cin] with w [Cout, ks*ks*Cin] as an implicit GEMM."""
     lib = load()
-    check(lib.avsr_conv3x3_bf16_tc(ptr(x), ptr(w), ll(nf), H, W, Cin, Cout, C.byref(ep), stream()), "avsr_conv3x3_bf16_tc")
+    check(lib.avsr_conv2d_bf16_tc(ptr(x), ptr(w), ll(nf), H, W, Cin, Cout, ks, stride, C.byref(ep), stream()), "avsr_conv2d_bf16_tc")
 
 
 def sgemm(a: torch.Tensor, w: torch.Tensor, M: int, N: int, K: int, ep: Epilogue, lda=None, ldw=None):

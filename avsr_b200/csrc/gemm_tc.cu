@@ -167,10 +167,10 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 // splits > 1: split-K. Work item = (z, m-tile, n-tile); item z covers k-blocks [z*kb_per_split, (z+1)*kb_per_split) and
 // stores its raw fp32 partial sums at ep.out_f32 + z*M*ld_f32 (the caller reduces them in a fixed order).
-// Implicit-GEMM convolution (3x3, stride 1, pad 1, NHWC): A is never materialised; row m = output pixel (n, y, x) and
-// k block kb = (filter tap, 64-channel slice), fetched by an im2col-mode TMA load of the activation tensor itself.
+// Implicit-GEMM convolution (ks x ks, stride s, pad ks/2, NHWC): A is never materialised; row m = output pixel (n, y, x) of the
+// Ho x Wo output and k block kb = (filter tap, 64-channel slice), fetched by an im2col-mode TMA load of the activation tensor.
 struct ConvA {
-    int on, H, W, C;
+    int on, Ho, Wo, C, ks, stride;
 };
 
 template <int BN>
@@ -227,10 +227,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int kb0 = z * kb_per_split, kb1 = min(num_kb_total, kb0 + kb_per_split);
                 int cn = 0, cy = 0, cx = 0, cpb = 1;
                 if (conv.on) {
-                    const int hw = conv.H * conv.W;
+                    const int hw = conv.Ho * conv.Wo, pad = conv.ks / 2;
                     cn = m0 / hw;
-                    cy = (m0 - cn * hw) / conv.W;
-                    cx = m0 - cn * hw - cy * conv.W;
+                    cy = (m0 - cn * hw) / conv.Wo;
+                    cx = m0 - cn * hw - cy * conv.Wo;
+                    cy = cy * conv.stride - pad;     // base pixel of the first output pixel, in input coordinates
+                    cx = cx * conv.stride - pad;
                     cpb = conv.C / BK;               // k blocks per filter tap
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -239,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     if (conv.on) {
                         const int tap = kb / cpb, c0 = (kb - tap * cpb) * BK;
-                        tc::tma_load_im2col_4d(sa, &tmA, &full[stage], c0, cx - 1, cy - 1, cn, (uint16_t)(tap % 3), (uint16_t)(tap / 3));
+                        tc::tma_load_im2col_4d(sa, &tmA, &full[stage], c0, cx, cy, cn, (uint16_t)(tap % conv.ks), (uint16_t)(tap / conv.ks));
                     } else
                     tc::tma_load_2d(sa, &tmA, &full[stage], kb * BK, m0);
                     tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], kb * BK, n0);
@@ -343,7 +345,7 @@ int g_sm_count = 0;
 
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, int splits, cudaStream_t stream,
-           const ConvA& conv = ConvA{0, 0, 0, 0}) {
+           const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0}) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -407,8 +409,8 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t pixels,
-                             uint32_t channels) {
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, int ks, int stride,
+                          uint32_t pixels, uint32_t channels) {
     static EncodeIm2colFn fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;
@@ -427,9 +429,10 @@ int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* base, uint64_t n, uin
     }
     cuuint64_t gdim[4] = {c, w, h, n};
     cuuint64_t gstr[3] = {c * 2, w * c * 2, h * w * c * 2};
-    int lower[2] = {-1, -1};                 // {W, H}: the filter's base pixel starts one pixel outside the image (pad 1) ...
-    int upper[2] = {-1, -1};                 // ... and stops pad - (3 - 1) = -1 from the far edge: W x H base positions
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const int pad = ks / 2;
+    int lower[2] = {-pad, -pad};             // {W, H}: the filter's base pixel starts `pad` pixels outside the image ...
+    int upper[2] = {-pad, -pad};             // ... and stops pad - (ks - 1) = -pad from the far edge
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};       // the base pixel advances by the conv stride
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lower, upper, channels, pixels, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -442,29 +445,32 @@ int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* base, uint64_t n, uin
 }
 }  // namespace tc
 
-// 3x3 / stride 1 / pad 1 convolution of an NHWC bf16 tensor as an implicit GEMM on the tensor cores (BasicBlock convs,
-// src/nets/backend/backbones/resnet.py:56-69): out[(f, y, x), :] = epilogue(sum_{ky,kx,c} in[f, y+ky-1, x+kx-1, c] *
-// Wt[:, (ky*3 + kx)*C + c]).  in [F, H, W, C] bf16, Wt [Cout, 9*C] bf16 (the layout the explicit im2col path uses), the
-// epilogue's outputs are [F*H*W, Cout].  C % 64 == 0.  The patch matrix is never written to memory.
-extern "C" int avsr_conv3x3_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, const AvsrEpilogue* ep,
-                                    cudaStream_t stream) {
-    AVSR_REQUIRE(in && Wt && ep && F > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "avsr_conv3x3_bf16_tc: bad arguments");
-    AVSR_REQUIRE((C % BK) == 0, "avsr_conv3x3_bf16_tc: C = %d must be a multiple of %d", C, BK);
-    AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_conv3x3_bf16_tc: no output buffer");
-    AVSR_REQUIRE(F * H * W < (1ll << 31), "avsr_conv3x3_bf16_tc: too many output pixels");
+// ks x ks (1 or 3) / stride 1 or 2 / pad ks/2 convolution of an NHWC bf16 tensor as an implicit GEMM on the tensor cores
+// (BasicBlock and downsample convs, src/nets/backend/backbones/resnet.py:30-69): out[(f, y, x), :] = epilogue(sum_{ky,kx,c}
+// in[f, y*s+ky-pad, x*s+kx-pad, c] * Wt[:, (ky*ks + kx)*C + c]).  in [F, H, W, C] bf16, Wt [Cout, ks*ks*C] bf16 (the layout the
+// explicit im2col path uses), the epilogue's outputs are [F*Ho*Wo, Cout].  C % 64 == 0.  The patch matrix is never written.
+extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
+                                   const AvsrEpilogue* ep, cudaStream_t stream) {
+    AVSR_REQUIRE(in && Wt && ep && F > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "avsr_conv2d_bf16_tc: bad arguments");
+    AVSR_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "avsr_conv2d_bf16_tc: ks %d / stride %d unsupported", ks, stride);
+    AVSR_REQUIRE((C % BK) == 0, "avsr_conv2d_bf16_tc: C = %d must be a multiple of %d", C, BK);
+    AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_conv2d_bf16_tc: no output buffer");
+    const int pad = ks / 2;
+    const int Ho = (H + 2 * pad - ks) / stride + 1, Wo = (W + 2 * pad - ks) / stride + 1;
+    AVSR_REQUIRE(F * Ho * Wo < (1ll << 31), "avsr_conv2d_bf16_tc: too many output pixels");
     if (g_sm_count == 0) {
         int dev = 0;
         AVSR_CHECK_CUDA(cudaGetDevice(&dev));
         AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int M = (int)(F * H * W), K = 9 * C;
+    const int M = (int)(F * Ho * Wo), K = ks * ks * C;
     const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((cdiv(M, BM) * cdiv(Cout, 256) >= 2 * g_sm_count) ? 256 : 128));
     CUtensorMap ta, tb;
-    int rc = tc::make_tmap_im2col3x3_bf16(&ta, in, (uint64_t)F, (uint64_t)H, (uint64_t)W, (uint64_t)C, BM, BK);
+    int rc = tc::make_tmap_im2col_bf16(&ta, in, (uint64_t)F, (uint64_t)H, (uint64_t)W, (uint64_t)C, ks, stride, BM, BK);
     if (rc != AVSR_OK) return rc;
     rc = tc::make_tmap_2d_bf16(&tb, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
     if (rc != AVSR_OK) return rc;
-    const ConvA conv = {1, H, W, C};
+    const ConvA conv = {1, Ho, Wo, C, ks, stride};
     if (bn == 64) return launch<64>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     if (bn == 128) return launch<128>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     return launch<256>(ta, tb, M, Cout, K, *ep, 1, stream, conv);

@@ -139,8 +139,8 @@ EncodeTiledFn get_encode_fn();
 // rank-2 bf16 map: inner dim = cols (contiguous), outer = rows; box {box_cols, box_rows}; 128B swizzle; OOB -> 0.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
                       uint32_t box_cols);
-// im2col map of a bf16 NHWC tensor [n, h, w, c] for a 3x3 / stride 1 / pad 1 convolution: boxes of `pixels` output pixels x
-// `channels` input channels; 128B swizzle; out-of-image -> 0.
-int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, uint32_t pixels,
-                             uint32_t channels);
+// im2col map of a bf16 NHWC tensor [n, h, w, c] for a ks x ks / stride / pad ks/2 convolution: boxes of `pixels` output pixels
+// x `channels` input channels; 128B swizzle; out-of-image -> 0.
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, int ks, int stride,
+                          uint32_t pixels, uint32_t channels);
 }  // namespace tc

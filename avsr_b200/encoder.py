@@ -41,8 +41,8 @@ class Encoder:
         L.load()
         self.w = EncoderWeights(state_dict, self.device)
         self._ws = {}
-        # stride-1 3x3 convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit
-        # im2col + GEMM for all of them (dev A/B switch; the stride-2 convolutions always take the explicit path)
+        # 2D convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit im2col + GEMM
+        # (dev A/B switch)
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
 
     # ------------------------------------------------------------------ workspace
@@ -68,25 +68,29 @@ class Encoder:
         M = nf * Ho * Ho
         t1 = self._buf("blk_t1", (M, C_out), torch.bfloat16)
         ep1 = dict(bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"], out_bf16=t1, ld_bf16=C_out)
-        if s == 1 and self.implicit_conv:
-            # stride-1 3x3 convolutions run as implicit GEMMs: the TMA unit gathers the patches, nothing is materialised
-            L.conv3x3_bf16(x, blk["conv1_w"], nf, H, H, C_in, C_out, L.make_epilogue(**ep1))
+        if self.implicit_conv:
+            # the convolutions run as implicit GEMMs: the TMA unit gathers the patches, nothing is materialised
+            L.conv2d_bf16(x, blk["conv1_w"], nf, H, H, C_in, C_out, 3, s, L.make_epilogue(**ep1))
         else:
             col = self._buf("col", (M, 9 * C_in), torch.bfloat16)
             L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(nf), H, H, C_in, 3, s, L.stream()), "avsr_im2col2d")
             self._conv_gemm(col, blk["conv1_w"], M, C_out, 9 * C_in, **ep1)
         if "down_w" in blk:
-            colr = self._buf("col", (M, C_in), torch.bfloat16)
-            L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(colr), L.ll(nf), H, H, C_in, 1, s, L.stream()), "avsr_im2col2d")
             res = self._buf("blk_res", (M, C_out), torch.bfloat16)
-            self._conv_gemm(colr, blk["down_w"], M, C_out, C_in, bias=blk["down_b"], out_bf16=res, ld_bf16=C_out)
+            epd = dict(bias=blk["down_b"], out_bf16=res, ld_bf16=C_out)
+            if self.implicit_conv:
+                L.conv2d_bf16(x, blk["down_w"], nf, H, H, C_in, C_out, 1, s, L.make_epilogue(**epd))
+            else:
+                colr = self._buf("col", (M, C_in), torch.bfloat16)
+                L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(colr), L.ll(nf), H, H, C_in, 1, s, L.stream()), "avsr_im2col2d")
+                self._conv_gemm(colr, blk["down_w"], M, C_out, C_in, **epd)
         else:
             res = x.view(M, C_out)
         out = self._buf("blk_out_" + tag, (M, C_out), torch.bfloat16)
         ep2 = dict(bias=blk["conv2_b"], act=L.ACT_PRELU, prelu=blk["prelu2"], residual=res, ldr=C_out, act_after_residual=True,
                    out_bf16=out, ld_bf16=C_out)
         if self.implicit_conv:
-            L.conv3x3_bf16(t1, blk["conv2_w"], nf, Ho, Ho, C_out, C_out, L.make_epilogue(**ep2))
+            L.conv2d_bf16(t1, blk["conv2_w"], nf, Ho, Ho, C_out, C_out, 3, 1, L.make_epilogue(**ep2))
         else:
             col2 = self._buf("col", (M, 9 * C_out), torch.bfloat16)
             L.check(lib.avsr_im2col2d(L.ptr(t1), L.ptr(col2), L.ll(nf), Ho, Ho, C_out, 3, 1, L.stream()), "avsr_im2col2d")

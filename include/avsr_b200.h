@@ -91,11 +91,12 @@ int avsr_abi_version(void);
  * Wav2Vec2Attention/FeedForward/PositionalConvEmbedding (modeling_wav2vec2.py:326-573). */
 int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue* ep,
                       int bn_hint, avsr_stream_t stream);
-/* 3x3 / stride 1 / pad 1 convolution of an NHWC bf16 tensor as an IMPLICIT GEMM (im2col-mode TMA loads of the activation
- * tensor; the patch matrix is never written): in [F,H,W,C], Wt [Cout, 9*C] with k = (ky*3 + kx)*C + c, outputs
- * [F*H*W, Cout] through the epilogue.  C % 64 == 0.  BasicBlock convolutions, src/nets/backend/backbones/resnet.py:56-69. */
-int avsr_conv3x3_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, const AvsrEpilogue* ep,
-                         avsr_stream_t stream);
+/* ks x ks (1 or 3) / stride 1 or 2 / pad ks/2 convolution of an NHWC bf16 tensor as an IMPLICIT GEMM (im2col-mode TMA loads of
+ * the activation tensor; the patch matrix is never written): in [F,H,W,C], Wt [Cout, ks*ks*C] with k = (ky*ks + kx)*C + c,
+ * outputs [F*Ho*Wo, Cout] through the epilogue.  C % 64 == 0.  BasicBlock / downsample convolutions,
+ * src/nets/backend/backbones/resnet.py:30-69. */
+int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
+                        const AvsrEpilogue* ep, avsr_stream_t stream);
 /* Split-K form for skinny operands: part[z][M][N] fp32 raw partial sums (reduced by avsr_splitk_epilogue). With the
  * "bf16x3" operand layout (avsr_split3 / *_split outputs: [a1|a1|a2|a1|a2|a3] x [w1|w2|w1|w3|w2|w1]) this gives
  * fp32-accurate decoder projections on the tensor cores (src/nets/backend/transformer/decoder_layer.py:58-121). */

@@ -192,29 +192,33 @@ def test_im2col_pool_kernels(L):
     assert (out.float() - x.float().mean(1)).abs().max().item() < 0.02
 
 
-@pytest.mark.parametrize("Fr,H,Cin,Cout", [(3, 22, 64, 64), (5, 11, 128, 128), (7, 6, 256, 256), (9, 3, 512, 512), (40, 22, 64, 64),
-                                           (1, 3, 64, 128)])
-def test_implicit_gemm_conv3x3_equals_im2col_gemm(L, Fr, H, Cin, Cout):
-    """avsr_conv3x3_bf16_tc (im2col-mode TMA, nothing materialised) against the explicit im2col + GEMM path (same k order, same
-    MMAs: bit-identical) and against F.conv2d in fp32 (BasicBlock convolutions, resnet.py:56-69)."""
+@pytest.mark.parametrize("Fr,H,Cin,Cout,ks,stride", [(3, 22, 64, 64, 3, 1), (5, 11, 128, 128, 3, 1), (7, 6, 256, 256, 3, 1),
+                                                     (9, 3, 512, 512, 3, 1), (40, 22, 64, 64, 3, 1), (1, 3, 64, 128, 3, 1),
+                                                     (5, 22, 64, 128, 3, 2), (5, 22, 64, 128, 1, 2), (6, 11, 128, 256, 3, 2),
+                                                     (6, 11, 128, 256, 1, 2), (7, 6, 256, 512, 3, 2), (7, 6, 256, 512, 1, 2)])
+def test_implicit_gemm_conv_equals_im2col_gemm(L, Fr, H, Cin, Cout, ks, stride):
+    """avsr_conv2d_bf16_tc (im2col-mode TMA, nothing materialised) against the explicit im2col + GEMM path (same k order, same
+    MMAs: bit-identical) and against F.conv2d in fp32 (BasicBlock / downsample convolutions, resnet.py:30-69)."""
     lib = L.load()
+    pad = ks // 2
+    Ho = (H + 2 * pad - ks) // stride + 1
     x = _rand(Fr, H, H, Cin, seed=H + Cin).bfloat16()
-    w = (_rand(Cout, 9 * Cin, seed=3) * 0.05).bfloat16()
+    w = (_rand(Cout, ks * ks * Cin, seed=3) * 0.05).bfloat16()
     bias = _rand(Cout, seed=4)
     slope = torch.full((Cout,), 0.25, device="cuda")
-    M = Fr * H * H
+    M = Fr * Ho * Ho
     res = _rand(M, Cout, seed=5).bfloat16()
     out_i = torch.zeros(M, Cout, dtype=torch.bfloat16, device="cuda")
     out_e = torch.zeros(M, Cout, dtype=torch.bfloat16, device="cuda")
     kw = dict(bias=bias, act=L.ACT_PRELU, prelu=slope, residual=res, ldr=Cout, act_after_residual=True, ld_bf16=Cout)
-    L.conv3x3_bf16(x, w, Fr, H, H, Cin, Cout, L.make_epilogue(out_bf16=out_i, **kw))
-    col = torch.empty(M, 9 * Cin, dtype=torch.bfloat16, device="cuda")
-    L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(Fr), H, H, Cin, 3, 1, L.stream()), "im2col2d")
-    L.gemm_bf16(col, w, M, Cout, 9 * Cin, L.make_epilogue(out_bf16=out_e, **kw))
+    L.conv2d_bf16(x, w, Fr, H, H, Cin, Cout, ks, stride, L.make_epilogue(out_bf16=out_i, **kw))
+    col = torch.empty(M, ks * ks * Cin, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(Fr), H, H, Cin, ks, stride, L.stream()), "im2col2d")
+    L.gemm_bf16(col, w, M, Cout, ks * ks * Cin, L.make_epilogue(out_bf16=out_e, **kw))
     torch.cuda.synchronize()
     assert torch.equal(out_i, out_e), (out_i.float() - out_e.float()).abs().max().item()
-    wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)                        # [Cout, Cin, ky, kx]
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1).permute(0, 2, 3, 1).reshape(M, Cout) + res.float()
+    wt = w.float().view(Cout, ks, ks, Cin).permute(0, 3, 1, 2)                      # [Cout, Cin, ky, kx]
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=pad, stride=stride).permute(0, 2, 3, 1).reshape(M, Cout) + res.float()
     y = torch.where(y >= 0, y, 0.25 * y)
     assert (out_i.float() - y).abs().max().item() < 0.05 * max(1.0, y.abs().max().item() / 8)
 
