@@ -203,8 +203,11 @@ def _kernel_rooflines(model, peaks):
             L.check(lib.avsr_sgemm_skinny(L.ptr(a), L.ll(K), L.ptr(w), L.ll(K), R, N, K, L.ptr(part), ns, L.stream()), "skinny")
         kname = f"sgemm_tn_kernel<96,64,16,6,4> split-K {ns} (decoder step projections)"
     t = timeit(skinny, n=48)
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture summarised in
+    # profiles/ncu_r01_kernels.txt (19.53 MB read, 0 written: the bf16x3 weights, 6 B per parameter; partial sums stay in L2)
     out["decoder_step_projection"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                      "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
+                                      "frac": byts / t / 1e9 / peaks["hbm"],
+                                      "traffic": 19.53e6 if model.beam_search.precision == "bf16x3" else None, "us_per_launch": t * 1e6,
                                       "shape": f"[{R},{K}]x[{N},{K}]^T", "kernel": kname, "gflops_fp32_equiv": 2.0 * R * N * K / t / 1e9}
     # (2) encoder FFN GEMM on tcgen05: [12000,1024]x[4096,1024]^T, bias + GELU, bf16 out
     M = BATCH * T_FRAMES
@@ -251,10 +254,32 @@ def _kernel_rooflines(model, peaks):
     t = timeit(ctc_full, n=12)
     byts = BATCH * (4.0 * T * V + 4.0 * nh * V + 16.0 * T * nh)
     out["ctc_prefix_full_vocab"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                    "frac": byts / t / 1e9 / peaks["hbm"], "traffic": None, "us_per_launch": t * 1e6,
+                                    "frac": byts / t / 1e9 / peaks["hbm"], "traffic": 247.1e6, "us_per_launch": t * 1e6,
                                     "shape": f"{BATCH} utt x {nh} hyps x T={T} x V={V}, {ncg.value} column groups x {ts.value} time splits per "
                                              f"utterance; 3 posterior blocks of 242 MB used in turn (each launch reads from HBM)"}
     del logps
+    # (4) source attention of one decode position (csrc/dec_attn.cu): the K/V of all 32 utterances, 6 layers used in turn
+    #     (590 MB > L2).  Algorithmic bytes per launch = 2 * sum(T) * 1024 * 4 (every frame's K and V row read once).
+    R = BATCH * BEAM
+    Fr = BATCH * T
+    ckv = torch.randn(6, 2, 16, Fr, 64, device=dev)
+    q2 = torch.randn(R, 1024, device=dev)
+    att3 = torch.empty(R, 3 * 1024, device=dev, dtype=torch.bfloat16)
+    n_run3, step_t = i32([nh] * BATCH), i32([187])
+    li = {"i": 0}
+
+    def cross():
+        l = li["i"] % 6
+        li["i"] += 1
+        L.check(lib.avsr_dec_attn_step(1, L.ptr(q2), L.ll(1024), 0, None, L.ptr(ckv[l, 0]), L.ptr(ckv[l, 1]), None, T + 1, L.ptr(n_run3),
+                                       L.ptr(utt_off), L.ptr(utt_T), nh, R, L.ptr(step_t), None, L.ll(Fr), L.ptr(att3), None, None, None,
+                                       L.stream()), "cross")
+    t = timeit(cross, n=24)
+    byts = 2.0 * Fr * 1024 * 4
+    out["decode_source_attention"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                      "frac": byts / t / 1e9 / peaks["hbm"], "traffic": 103.1e6, "us_per_launch": t * 1e6,
+                                      "shape": f"{BATCH} utt x {nh} hyps x 16 heads x T={T} frames, fp32 K/V, one CTA per (utterance, head)"}
+    del ckv
     return out
 
 
