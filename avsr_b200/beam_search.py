@@ -92,8 +92,15 @@ class BatchedBeamSearch:
         L.load()
 
     # ------------------------------------------------------------------------------------------ session buffers
+    T_BUCKET = 16        # sessions (buffers + the captured graph) are shared by all batches whose longest utterance rounds up to the same multiple
+
     def _session(self, B: int, tmax: int, F: int):
-        key = (B, tmax, F)
+        """Buffers and CUDA graph for batches of B utterances of at most `tmax` frames (rounded up to a multiple of T_BUCKET):
+        everything is sized for B * tmax frames, so mixed-length batches of an evaluation run reuse a handful of sessions
+        instead of allocating and capturing one per (lengths) combination."""
+        tmax = -(-tmax // self.T_BUCKET) * self.T_BUCKET
+        F = B * tmax                       # capacity in frames; a batch uses the first sum(lengths) of them
+        key = (B, tmax)
         s = self._sessions.get(key)
         if s is not None:
             return s
@@ -372,7 +379,7 @@ class BatchedBeamSearch:
             L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
             L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
-        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), n, 1, L.stream()), "avsr_kv_head_major")
+        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), L.ll(s["F"]), n, 1, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
         offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
         s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))

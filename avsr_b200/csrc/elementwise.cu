@@ -54,11 +54,11 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int N, const float*
 __global__ void __launch_bounds__(256)
 im2col_frontend_kernel(const float* __restrict__ video, const int* __restrict__ frame_t, const int* __restrict__ frame_T,
                        __nv_bfloat16* __restrict__ out, int f0) {
-    __shared__ float rows[5][7][96];       // [dt][dy][x + 3], x in [-3, 91)
-    __shared__ int koff[256];              // k = (dt*7 + dy)*7 + dx -> (dt*7 + dy)*96 + dx, -1 for the padding columns
+    __shared__ float rows[5][7][97];       // [dt][dy][x + 3], x in [-3, 91); odd pitch: the 35 patch rows start in different banks
+    __shared__ int koff[256];              // k = (dt*7 + dy)*7 + dx -> (dt*7 + dy)*97 + dx, -1 for the padding columns
     if (threadIdx.x < 256) {
         const int k = threadIdx.x;
-        koff[k] = k < 245 ? (k / 7) * 96 + (k % 7) : -1;
+        koff[k] = k < 245 ? (k / 7) * 97 + (k % 7) : -1;
     }
     const int f = f0 + blockIdx.x / 44, oy = blockIdx.x % 44;
     const int t = frame_t[f], T = frame_T[f];
@@ -209,11 +209,11 @@ split3_kernel(const float* __restrict__ in, long long ldi, __nv_bfloat16* __rest
     avsr_split3_store(out + r * 6 * K, K, c, in[r * ldi + c]);
 }
 
-// [F, ncol] -> [ncol/64][F][64]: float4 per thread.  kt_period > 0: 64-column blocks whose index b has (b / 16) % kt_period == 0
+// [F, ncol] -> [ncol/64][Fs][64] (Fs = rows each 64-column block has room for, >= F): float4 per thread.  kt_period > 0: 64-column blocks whose index b has (b / 16) % kt_period == 0
 // (the K halves of [k | v] pairs of 16 heads) are written transposed in 32-byte groups, [b][8][F][8], the layout the decode
 // step's attention reads keys in (csrc/dec_attn.cu).
 __global__ void __launch_bounds__(256)
-kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int ncol, int kt_period) {
+kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, long long Fs, int ncol, int kt_period) {
     const long long total = F * (ncol / 4);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long f = i / (ncol / 4);
@@ -221,9 +221,9 @@ kv_head_major_kernel(const float* __restrict__ in, float* __restrict__ out, long
         const float4 v = *reinterpret_cast<const float4*>(in + f * ncol + c);
         const int b = c / 64;
         if (kt_period > 0 && ((b / 16) % kt_period) == 0)
-            *reinterpret_cast<float4*>(out + (long long)b * F * 64 + ((long long)((c % 64) >> 3) * F + f) * 8 + (c & 4)) = v;
+            *reinterpret_cast<float4*>(out + (long long)b * Fs * 64 + ((long long)((c % 64) >> 3) * Fs + f) * 8 + (c & 4)) = v;
         else
-            *reinterpret_cast<float4*>(out + ((long long)b * F + f) * 64 + (c % 64)) = v;
+            *reinterpret_cast<float4*>(out + ((long long)b * Fs + f) * 64 + (c % 64)) = v;
     }
 }
 
@@ -309,11 +309,12 @@ extern "C" int avsr_split3(const float* in, long long ldi, void* out, long long 
     return AVSR_OK;
 }
 
-extern "C" int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, int k_transposed, cudaStream_t stream) {
-    AVSR_REQUIRE(in && out && F > 0 && ncol > 0 && (ncol & 63) == 0, "avsr_kv_head_major: bad arguments");
+extern "C" int avsr_kv_head_major(const float* in, float* out, long long F, long long F_capacity, int ncol, int k_transposed,
+                                  cudaStream_t stream) {
+    AVSR_REQUIRE(in && out && F > 0 && F_capacity >= F && ncol > 0 && (ncol & 63) == 0, "avsr_kv_head_major: bad arguments");
     AVSR_REQUIRE(!k_transposed || (ncol % 2048) == 0, "avsr_kv_head_major: k_transposed needs [k(1024) | v(1024)] column pairs");
     const long long total = F * (ncol / 4);
-    kv_head_major_kernel<<<GRID1D(total), 256, 0, stream>>>(in, out, F, ncol, k_transposed ? 2 : 0);
+    kv_head_major_kernel<<<GRID1D(total), 256, 0, stream>>>(in, out, F, F_capacity, ncol, k_transposed ? 2 : 0);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

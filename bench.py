@@ -138,7 +138,8 @@ def run_reference(args):
 
 
 def _config(n_gpus):
-    return {"workload": f"configs[1]: {BATCH} synthetic 15 s utterances per GPU (T={T_FRAMES} frames 88x88 gray + 104-dim stacked fbank), "
+    tag = "configs[1]" if (BATCH, T_FRAMES, BEAM) == (32, 375, 3) else "non-default shape"
+    return {"workload": f"{tag}: {BATCH} synthetic {T_FRAMES / FPS:g} s utterances per GPU (T={T_FRAMES} frames 88x88 gray + 104-dim stacked fbank), "
                         f"AV-HuBERT-large encoder (bf16 tensor-core GEMMs, fp32 residual stream) + joint CTC/attention beam search "
                         f"(beam {BEAM}, ctc_weight 0.1, fp32), random-init weights: every utterance decodes all {T_FRAMES} positions",
             "utterances_per_gpu": BATCH, "frames": T_FRAMES, "beam": BEAM, "parallelism": f"utterance-sharded x{n_gpus}",
@@ -400,16 +401,21 @@ def run_b200(args):
 
 
 def main():
+    global BEAM, T_FRAMES, BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--beam", type=int, default=BEAM, help="dev: beam size (default = configs[1]: 3; configs[3] uses 5)")
+    ap.add_argument("--frames", type=int, default=T_FRAMES, help="dev: frames per utterance (default 375 = 15 s; configs[3]: 250)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="dev: utterances per GPU (default 32)")
     ap.add_argument("--rooflines-only", action="store_true", help="dev aid: only the isolated kernel timings (not a bench line)")
     ap.add_argument("--profile-decode-steps", type=int, default=0,
                     help="profiling aid: run ONE pass with the decode truncated to this many positions and exit (not a bench value)")
     args = ap.parse_args()
+    BEAM, T_FRAMES, BATCH = args.beam, args.frames, args.batch
     if args.impl == "reference":
         run_reference(args)
     else:

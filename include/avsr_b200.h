@@ -190,10 +190,12 @@ int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, c
  * streams consecutive rows for that prefix.  Call once per position before the layers run. */
 int avsr_dec_cache_promote(const float* kc, const float* vc, float* kd, float* vd, int n_layers, const unsigned char* anc, int lmax,
                            const int* n_run, int beam, int R, const int* step, int* conv_len, avsr_stream_t stream);
-/* [F, ncol] fp32 -> [ncol/64][F][64] (head-major K/V: every (utterance, head) reads one contiguous span).  k_transposed:
+/* [F, ncol] fp32 -> [ncol/64][F_capacity][64] (head-major K/V: every (utterance, head) reads one contiguous span; the
+ * destination has room for F_capacity >= F frames per block so one allocation serves batches of different sizes).  k_transposed:
  * columns are [k(1024) | v(1024)] pairs and the K blocks are written [block][8][F][8] (transposed in 32-byte groups), the
  * key layout avsr_dec_attn_step mode 1 reads. */
-int avsr_kv_head_major(const float* in, float* out, long long F, int ncol, int k_transposed, avsr_stream_t stream);
+int avsr_kv_head_major(const float* in, float* out, long long F, long long F_capacity, int ncol, int k_transposed,
+                       avsr_stream_t stream);
 int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const float* bias, const int* n_run, int beam, float* logp,
                              int* part_ids, int S, avsr_stream_t stream);
 /* CTCPrefixScoreTH.__call__ (src/nets/ctc_prefix_score.py:68-187): pre-beam and full-vocabulary modes.  logp = CTC
