@@ -104,7 +104,7 @@ class BatchedBeamSearch:
         s = self._sessions.get(key)
         if s is not None:
             return s
-        if len(self._sessions) > 4:
+        if len(self._sessions) >= 16:         # a full evaluation run needs ~10 length buckets x a few batch sizes
             self._sessions.clear()
         dev, beam, S, V = self.device, self.beam_size, self.pre_beam_size, self.n_vocab
         R = B * beam
