@@ -88,23 +88,29 @@ class BatchedBeamSearch:
         self.chain = os.environ.get("AVSR_CHAIN", "0") == "1"
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
         self.last_session = None
+        self.last_sessions = []
         self._sessions = {}
+        self._streams = []
+        # independent groups of utterances decoded concurrently on separate streams (AVSR_DECODE_GROUPS).  Default 1: on B200
+        # two concurrent chains measured SLOWER (449 vs 373 ms per 32-utterance pass; 3 groups 524, 4 groups 587): the
+        # projection launches of the chains each want one CTA with ~200 KB of shared memory on every SM and serialise.
+        self.n_groups = max(1, int(os.environ.get("AVSR_DECODE_GROUPS", "1")))
         L.load()
 
     # ------------------------------------------------------------------------------------------ session buffers
     T_BUCKET = 16        # sessions (buffers + the captured graph) are shared by all batches whose longest utterance rounds up to the same multiple
 
-    def _session(self, B: int, tmax: int, F: int):
+    def _session(self, B: int, tmax: int, F: int, slot: int = 0):
         """Buffers and CUDA graph for batches of B utterances of at most `tmax` frames (rounded up to a multiple of T_BUCKET):
         everything is sized for B * tmax frames, so mixed-length batches of an evaluation run reuse a handful of sessions
         instead of allocating and capturing one per (lengths) combination."""
         tmax = -(-tmax // self.T_BUCKET) * self.T_BUCKET
         F = B * tmax                       # capacity in frames; a batch uses the first sum(lengths) of them
-        key = (B, tmax)
+        key = (B, tmax, slot)              # slot: concurrent groups of one decode_batch call never share buffers
         s = self._sessions.get(key)
         if s is not None:
             return s
-        if len(self._sessions) >= 16:         # a full evaluation run needs ~10 length buckets x a few batch sizes
+        if len(self._sessions) >= 24:         # a full evaluation run needs ~10 length buckets x a few batch sizes x groups
             self._sessions.clear()
         dev, beam, S, V = self.device, self.beam_size, self.pre_beam_size, self.n_vocab
         R = B * beam
@@ -115,6 +121,8 @@ class BatchedBeamSearch:
         s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
         s["utt_T"], s["utt_off"] = i32(B), i32(B)
         s["step"], s["any_running"] = i32(1), i32(1)
+        s["poll"] = torch.zeros(1, dtype=torch.int32).pin_memory()      # host copy of any_running (async poll)
+        s["poll_event"] = torch.cuda.Event()
         s["n_run"], s["row_active"], s["last_tok"], s["rprev_idx"] = i32(B), i32(R), i32(R), i32(R)
         for k in ("score", "dec_sc", "ctc_sc", "s_prev", "rsum_last"):
             s[k] = f32(R)
@@ -394,48 +402,100 @@ class BatchedBeamSearch:
         s["best_all"].fill_(float("-inf"))
 
     def decode_batch(self, x_packed: torch.Tensor, lengths: Sequence[int], max_steps: Optional[int] = None) -> List[List[Hypothesis]]:
-        """x_packed [sum(T),1024] fp32 encoder outputs (utterances back to back) -> n-best list per utterance."""
+        """x_packed [sum(T),1024] fp32 encoder outputs (utterances back to back) -> n-best list per utterance.
+
+        With `self.n_groups` > 1 the utterances are decoded in independent groups on separate CUDA streams (every utterance
+        evolves independently of its batch, so the split does not change any result; measured slower on B200, see __init__)."""
         L.require_cuda(x_packed, torch.float32, "encoder output")
         lengths = [int(t) for t in lengths]
         if x_packed.dim() != 2 or x_packed.shape[1] != 1024 or x_packed.shape[0] != sum(lengths) or min(lengths) < 1:
             raise RuntimeError(f"bad decode input: x {tuple(x_packed.shape)}, lengths {lengths}")
-        B, tmax, F = len(lengths), max(lengths), x_packed.shape[0]
-        s = self._session(B, tmax, F)
-        self.last_session = s
-        self.prepare(s, x_packed, lengths)
-        n_steps = tmax if max_steps is None else min(tmax, max_steps)
-        self._step(s)                                   # position 0 eagerly (also warms every kernel up)
-        done_steps = 1
-        if n_steps > 1:
-            chunk = self.POLL_EVERY
-            if self.use_graph and s["graph"] is None:
-                torch.cuda.synchronize()
-                # ONE graph holds POLL_EVERY positions (every kernel reads the position and liveness from device memory), so
-                # the kernels of consecutive positions chain through programmatic dependent launch inside the graph and
-                # the host only replays + polls.  Capture runs no kernels; state is untouched.
-                g = torch.cuda.CUDAGraph()
-                n0 = L.launch_count
-                with torch.cuda.graph(g):
-                    for _ in range(chunk):
-                        self._step(s)
-                s["launches_per_graph"] = L.launch_count - n0
-                L.launch_count = n0
-                s["graph"] = g
-            while done_steps < n_steps:
-                n = min(chunk, n_steps - done_steps)
-                if self.use_graph and (n == chunk or max_steps is None):
-                    # a replay past the last position only runs no-op kernels (every utterance has n_run == 0 by then)
-                    s["graph"].replay()
-                    self.graph_launches += s["launches_per_graph"]
-                else:
-                    for _ in range(n):
-                        self._step(s)
-                done_steps += n
-                if int(s["any_running"].item()) == 0:
-                    break
-        if int(s["overflow"].item()) != 0:
-            raise RuntimeError("ended-hypothesis table overflowed")
-        return self._collect(s, lengths, truncated=max_steps is not None)
+        B = len(lengths)
+        G = max(1, min(self.n_groups, B))
+        if G == 1:
+            return self._decode_groups([(x_packed, lengths)], max_steps)[0]
+        # contiguous groups of (almost) equal size; the packed rows of a group are contiguous
+        bounds = [round(g * B / G) for g in range(G + 1)]
+        offs = [0]
+        for t in lengths:
+            offs.append(offs[-1] + t)
+        parts = [(x_packed[offs[bounds[g]]:offs[bounds[g + 1]]], lengths[bounds[g]:bounds[g + 1]]) for g in range(G)]
+        out = []
+        for r in self._decode_groups(parts, max_steps):
+            out += r
+        return out
+
+    def _decode_groups(self, parts, max_steps):
+        """parts: [(x_packed_g, lengths_g)]; each group gets its own session (buffers + graph) and stream."""
+        G = len(parts)
+        main = torch.cuda.current_stream()
+        if len(self._streams) < G:
+            self._streams += [torch.cuda.Stream(device=self.device) for _ in range(G - len(self._streams))]
+        streams = [main] if G == 1 else self._streams[:G]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        chunk = self.POLL_EVERY
+        sess, nsteps, done = [], [], []
+        self.last_sessions = sess
+        # ---- set-up per group: posteriors, cross K/V, position 0 eagerly (also warms the kernels up), graph capture
+        for g, (xg, lg) in enumerate(parts):
+            tmax = max(lg)
+            s = self._session(len(lg), tmax, xg.shape[0], slot=g)
+            self.last_session = s
+            with torch.cuda.stream(streams[g]):
+                streams[g].wait_event(ready)
+                self.prepare(s, xg, lg)
+                n = tmax if max_steps is None else min(tmax, max_steps)
+                self._step(s)
+                if n > 1 and self.use_graph and s["graph"] is None:
+                    torch.cuda.synchronize()
+                    # ONE graph holds POLL_EVERY positions (every kernel reads the position and liveness from device memory),
+                    # so the kernels of consecutive positions chain through programmatic dependent launch inside the graph
+                    # and the host only replays + polls.  Capture runs no kernels; state is untouched.
+                    gr = torch.cuda.CUDAGraph()
+                    n0 = L.launch_count
+                    with torch.cuda.graph(gr):
+                        for _ in range(chunk):
+                            self._step(s)
+                    s["launches_per_graph"] = L.launch_count - n0
+                    L.launch_count = n0
+                    s["graph"] = gr
+            sess.append(s)
+            nsteps.append(n)
+            done.append(1)
+        # ---- position loop: one graph replay per group and round, then one poll per group
+        active = [n > 1 for n in nsteps]
+        while any(active):
+            for g in range(G):
+                if not active[g]:
+                    continue
+                s = sess[g]
+                n = min(chunk, nsteps[g] - done[g])
+                with torch.cuda.stream(streams[g]):
+                    if self.use_graph and (n == chunk or max_steps is None):
+                        # a replay past the last position only runs no-op kernels (every utterance has n_run == 0 by then)
+                        s["graph"].replay()
+                        self.graph_launches += s["launches_per_graph"]
+                    else:
+                        for _ in range(n):
+                            self._step(s)
+                    s["poll"].copy_(s["any_running"], non_blocking=True)
+                    s["poll_event"].record(streams[g])
+                done[g] += n
+            for g in range(G):
+                if active[g]:
+                    sess[g]["poll_event"].synchronize()
+                    if done[g] >= nsteps[g] or int(sess[g]["poll"][0]) == 0:
+                        active[g] = False
+        out = []
+        for g, (xg, lg) in enumerate(parts):
+            with torch.cuda.stream(streams[g]):
+                if int(sess[g]["overflow"].item()) != 0:
+                    raise RuntimeError("ended-hypothesis table overflowed")
+                out.append(self._collect(sess[g], lg, truncated=max_steps is not None))
+            if G > 1:
+                main.wait_stream(streams[g])
+        return out
 
     def _collect(self, s, lengths, truncated=False) -> List[List[Hypothesis]]:
         """Backtrace the ended hypotheses on the host (one D2H at the end instead of the reference's per-step syncs)."""

@@ -377,9 +377,9 @@ def run_b200(args):
     if rank == 0:
         roof = _kernel_rooflines(model, peaks)
         cpu = cpu_reference_sample(sd) if world == 1 and not args.no_cpu_baseline else None
-        s = model.beam_search.last_session
-        d2h = sum(s[k].numel() * s[k].element_size() for k in ("hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j",
-                                                                "end_len", "end_score", "end_dec", "end_ctc")) + 8 * ((T_FRAMES // 16) + 2)
+        d2h = sum(s[k].numel() * s[k].element_size() for s in model.beam_search.last_sessions
+                  for k in ("hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j", "end_len", "end_score", "end_dec", "end_ctc"))
+        d2h += len(model.beam_search.last_sessions) * 8 * ((T_FRAMES // 16) + 2)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -114,6 +114,18 @@ def test_batched_decode_equals_single_runs(gpu_model, golden):
     assert all(abs(float(a.score) - float(b.score)) < 1e-4 for a, b in zip(out[2], single))
 
 
+def test_concurrent_decode_groups_equal_single_runs(gpu_model, golden):
+    """decode_batch with the utterances split into groups on separate streams (n_groups > 1): same n-best as one chain."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=3)
+    bs.n_groups = 2
+    x12, x30 = torch.from_numpy(golden["enc_T12"]).cuda(), torch.from_numpy(golden["enc_T30"]).cuda()
+    out = bs.decode_batch(torch.cat([x30, x12, x12, x30], 0), [30, 12, 12, 30])
+    assert len(bs.last_sessions) == 2
+    for o, T in zip(out, (30, 12, 12, 30)):
+        _check_nbest(o, golden, T, 3)
+
+
 def test_batched_encoder_equals_single_runs(gpu_model):
     """Padded mixed-length batch == per-utterance runs (temporal conv / pos-conv / attention stop at utterance ends)."""
     enc = gpu_model.encoder

@@ -20,6 +20,7 @@ T = int(sys.argv[3]) if len(sys.argv) > 3 else 375
 sd = synth.make_state_dict(0)
 m = AVSRCocktailB200(sd, beam_size=3)
 bs = m.beam_search
+bs.n_groups = 1                       # one chain: this tool looks at a single session
 x = torch.randn(B * T, 1024, device="cuda")
 x = torch.nn.functional.layer_norm(x, (1024,))
 bs.decode_batch(x, [T] * B, max_steps=pos)          # real decode up to `pos` (realistic caches / ancestry tables)

@@ -19,6 +19,7 @@ vp = v.reshape(B * T, 88, 88).contiguous()
 for it in range(2):
     t0 = ev(); x = enc.forward_packed(vp, a, [T] * B); t1 = ev()
     bs = m.beam_search
+    bs.n_groups = 1                   # one chain: this tool looks at a single session
     s = bs._session(B, T, B * T); bs.last_session = s
     t2 = ev(); bs.prepare(s, x, [T] * B); t3 = ev()
     nb = bs.decode_batch(x, [T] * B); t4 = ev()
