@@ -41,6 +41,7 @@ class Encoder:
         L.load()
         self.w = EncoderWeights(state_dict, self.device)
         self._ws = {}
+        self._copy_stream = None
         # 2D convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit im2col + GEMM
         # (dev A/B switch)
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
@@ -97,13 +98,19 @@ class Encoder:
             self._conv_gemm(col2, blk["conv2_w"], M, C_out, 9 * C_out, **ep2)
         return out.view(nf, Ho, Ho, C_out), Ho
 
-    def _video_frontend(self, video_packed, frame_t, frame_T, F, taps=None):
-        """[F,88,88] fp32 -> trunk features [F,512] bf16 (resnet.py:126-164)."""
+    def _video_frontend(self, video_packed, frame_t, frame_T, F, taps=None, ready=None):
+        """[F,88,88] fp32 -> trunk features [F,512] bf16 (resnet.py:126-164).  ready: optional CUDA events, one per chunk of
+        CHUNK_FRAMES frames, recorded when that chunk of `video_packed` has arrived from the host (chunked upload that
+        overlaps the frontend of the previous chunks); a chunk also needs the two-frame halo of its neighbours."""
         lib = L.load()
         w = self.w
         feat = self._buf("trunk_out", (F, 512), torch.bfloat16)
-        for f0 in range(0, F, self.CHUNK_FRAMES):
+        for ci, f0 in enumerate(range(0, F, self.CHUNK_FRAMES)):
             nf = min(self.CHUNK_FRAMES, F - f0)
+            if ready is not None:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ready[ci])
+                cur.wait_event(ready[min(ci + 1, len(ready) - 1)])
             M0 = nf * 44 * 44
             col = self._buf("col", (M0, 256), torch.bfloat16)
             L.check(lib.avsr_im2col_frontend(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(col), L.stream()),
@@ -122,7 +129,8 @@ class Encoder:
         return feat
 
     # ------------------------------------------------------------------ forward
-    def forward_packed(self, video_packed: torch.Tensor, audio: torch.Tensor, lengths: Sequence[int], taps=None) -> torch.Tensor:
+    def forward_packed(self, video_packed: torch.Tensor, audio: torch.Tensor, lengths: Sequence[int], taps=None,
+                       video_ready=None) -> torch.Tensor:
         """video_packed [F,88,88] fp32 (valid frames of all utterances back to back), audio [B,104,Tpad] fp32.
         Returns the encoder output for the packed frames, [F,1024] fp32."""
         lib = L.load()
@@ -150,7 +158,7 @@ class Encoder:
         frame_T = torch.tensor(fT, dtype=torch.int32, device=dev)
 
         # --- modality front-ends (avhubert.py:187-198) and concat-fusion (avhubert.py:486-502)
-        trunk = self._video_frontend(video_packed, frame_t, frame_T, F, taps)
+        trunk = self._video_frontend(video_packed, frame_t, frame_T, F, taps, ready=video_ready)
         if taps is not None:
             taps["trunk"] = trunk.float()
         feats = self._buf("feats", (F, 2048), torch.float32)
@@ -218,13 +226,32 @@ class Encoder:
         B, _, T = input_features.shape
         if lengths is None:
             lengths = [T] * B
-        video = video.to(self.device, torch.float32)
-        audio = input_features.to(self.device, torch.float32).contiguous()
-        if all(t == T for t in lengths):
-            vp = video.reshape(B * T, 88, 88).contiguous()
+        audio = input_features.to(self.device, torch.float32, non_blocking=True).contiguous()
+        ready = None
+        if (video.device.type == "cpu" and video.is_pinned() and video.dtype == torch.float32 and video.is_contiguous()
+                and all(t == T for t in lengths)):
+            # pinned host frames: upload in frontend-sized chunks on a copy stream, the frontend of chunk c runs while chunk
+            # c + 2 is still on the PCIe / C2C link
+            vp = self._buf("video_in", (B * T, 88, 88), torch.float32)
+            src = video.view(B * T, 88, 88)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())      # the buffer may still be read by the previous pass
+            ready = []
+            with torch.cuda.stream(self._copy_stream):
+                for f0 in range(0, B * T, self.CHUNK_FRAMES):
+                    f1 = min(B * T, f0 + self.CHUNK_FRAMES)
+                    vp[f0:f1].copy_(src[f0:f1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    ready.append(ev)
         else:
-            vp = torch.cat([video[b, 0, :t] for b, t in enumerate(lengths)], 0).contiguous()
-        packed = self.forward_packed(vp, audio, lengths)
+            video = video.to(self.device, torch.float32)
+            if all(t == T for t in lengths):
+                vp = video.reshape(B * T, 88, 88).contiguous()
+            else:
+                vp = torch.cat([video[b, 0, :t] for b, t in enumerate(lengths)], 0).contiguous()
+        packed = self.forward_packed(vp, audio, lengths, video_ready=ready)
         if all(t == T for t in lengths):
             padded = packed.view(B, T, 1024)
         else:

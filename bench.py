@@ -349,9 +349,8 @@ def run_b200(args):
     step_dev = lambda: model.infer_batch(video_d, audio_d)
 
     def step_e2e():
-        v = video_h.to(dev, non_blocking=True)
-        a = audio_h.to(dev, non_blocking=True)
-        nb = model.infer_batch(v, a)
+        # the public call with HOST (pinned) inputs: infer_batch uploads them itself, chunk by chunk under the video frontend
+        nb = model.infer_batch(video_h, audio_h)
         return [h[0].yseq.tolist() for h in nb]          # host-side 1-best token ids (what evaluation.py consumes)
 
     for _ in range(args.warmup):

@@ -267,3 +267,20 @@ def test_sharded_evaluation_driver_equals_single_runs(gpu_model):
     assert res.edits == 1 and res.ref_words == sum(len(r.split()) for r in refs)
     assert res.wer == pytest.approx(1 / res.ref_words)
     assert S.shard_utterances(lengths, 1) == [[2, 4, 0, 1, 3]]
+
+
+def test_pinned_host_inputs_are_uploaded_in_chunks(gpu_model):
+    """infer_batch / encoder with pinned HOST video (chunked upload on a copy stream under the video frontend) gives the
+    bit-identical encoder output of the same call with device-resident inputs."""
+    enc = gpu_model.encoder
+    old = enc.CHUNK_FRAMES
+    enc.CHUNK_FRAMES = 8                         # several chunks + halo frames across chunk borders
+    try:
+        vids, auds = zip(*[synth.make_inputs(40 + i, 13) for i in range(3)])
+        video, audio = torch.cat(vids, 0), torch.cat(auds, 0)
+        ref = enc(input_features=audio.cuda(), video=video.cuda()).last_hidden_state
+        for _ in range(2):                       # twice: the upload buffer is reused
+            got = enc(input_features=audio.pin_memory(), video=video.pin_memory()).last_hidden_state
+            assert torch.equal(got, ref)
+    finally:
+        enc.CHUNK_FRAMES = old
