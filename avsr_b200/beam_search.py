@@ -184,7 +184,7 @@ class BatchedBeamSearch:
             setattr(st, name, s[name].data_ptr())
         st.d_end = D_END
         s["state"] = st
-        s["graph"] = None
+        s["graph"] = s["graph1"] = None
         self._sessions[key] = s
         return s
 
@@ -458,8 +458,12 @@ class BatchedBeamSearch:
                         for _ in range(chunk):
                             self._step(s)
                     s["launches_per_graph"] = L.launch_count - n0
+                    # ... and a one-position graph for the last (tmax - 1) % POLL_EVERY positions of an utterance
+                    gr1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr1):
+                        self._step(s)
                     L.launch_count = n0
-                    s["graph"] = gr
+                    s["graph"], s["graph1"] = gr, gr1
             sess.append(s)
             nsteps.append(n)
             done.append(1)
@@ -472,10 +476,13 @@ class BatchedBeamSearch:
                 s = sess[g]
                 n = min(chunk, nsteps[g] - done[g])
                 with torch.cuda.stream(streams[g]):
-                    if self.use_graph and (n == chunk or max_steps is None):
-                        # a replay past the last position only runs no-op kernels (every utterance has n_run == 0 by then)
+                    if self.use_graph and n == chunk:
                         s["graph"].replay()
                         self.graph_launches += s["launches_per_graph"]
+                    elif self.use_graph and max_steps is None:
+                        for _ in range(n):
+                            s["graph1"].replay()
+                        self.graph_launches += n * (s["launches_per_graph"] // chunk)
                     else:
                         for _ in range(n):
                             self._step(s)
@@ -498,34 +505,41 @@ class BatchedBeamSearch:
         return out
 
     def _collect(self, s, lengths, truncated=False) -> List[List[Hypothesis]]:
-        """Backtrace the ended hypotheses on the host (one D2H at the end instead of the reference's per-step syncs)."""
+        """Backtrace the ended hypotheses on the host (one D2H at the end instead of the reference's per-step syncs), all
+        hypotheses of the batch at once: one vectorised step per position instead of a Python loop per token."""
         tok = s["hist_tok"].cpu().numpy()
         prev = s["hist_prev"].cpu().numpy()
         r2j = s["run2j"].cpu().numpy()
         n_end = s["n_ended"].cpu().numpy()
         e_step, e_j, e_len = s["end_step"].cpu().numpy(), s["end_j"].cpu().numpy(), s["end_len"].cpu().numpy()
         e_sc, e_dec, e_ctc = s["end_score"].cpu(), s["end_dec"].cpu(), s["end_ctc"].cpu()
-        out = []
-        for b in range(s["B"]):
-            hyps = []
-            for e in range(int(n_end[b])):
-                i, j = int(e_step[b, e]), int(e_j[b, e])
-                toks = []
-                ii, jj = i, j
-                while True:
-                    toks.append(int(tok[b, ii, jj]))
-                    if ii == 0:
-                        break
-                    p = int(prev[b, ii, jj])
-                    jj = int(r2j[b, ii - 1, p])
-                    ii -= 1
-                yseq = [self.sos] + toks[::-1]
-                if int(e_len[b, e]) == len(yseq) + 1:        # eos appended at the last position (batch_beam_search.py:321-337)
-                    yseq.append(self.eos)
-                hyps.append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e],
-                                       scores={"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}, states={}))
-            hyps.sort(key=lambda h: float(h.score), reverse=True)     # stable, like sorted() in beam_search.py:378
-            out.append(hyps)
+        B = s["B"]
+        hb = np.concatenate([np.full(int(n_end[b]), b, dtype=np.int64) for b in range(B)]) if B else np.zeros(0, np.int64)
+        he = np.concatenate([np.arange(int(n_end[b]), dtype=np.int64) for b in range(B)]) if B else np.zeros(0, np.int64)
+        n = len(hb)
+        out = [[] for _ in range(B)]
+        if n == 0:
+            return out
+        last = e_step[hb, he].astype(np.int64)            # position of the hypothesis' last token
+        jj = e_j[hb, he].astype(np.int64)
+        toks = np.zeros((n, int(last.max()) + 1), dtype=np.int64)
+        for ii in range(int(last.max()), -1, -1):
+            live = last >= ii                             # hypotheses that have a token at position ii
+            if ii < int(last.max()):
+                # step from position ii + 1 to its parent: candidate index at ii of the running slot it extended
+                up = last >= ii + 1
+                p = prev[hb[up], ii + 1, jj[up]]
+                jj[up] = r2j[hb[up], ii, p]
+            toks[live, ii] = tok[hb[live], ii, jj[live]]
+        for k in range(n):
+            b, e = int(hb[k]), int(he[k])
+            yseq = [self.sos] + toks[k, :last[k] + 1].tolist()
+            if int(e_len[b, e]) == len(yseq) + 1:        # eos appended at the last position (batch_beam_search.py:321-337)
+                yseq.append(self.eos)
+            out[b].append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e],
+                                     scores={"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}, states={}))
+        for b in range(B):
+            out[b].sort(key=lambda h: float(h.score), reverse=True)     # stable, like sorted() in beam_search.py:378
         return out
 
     def forward(self, x: torch.Tensor, maxlenratio: float = 0.0, minlenratio: float = 0.0) -> List[Hypothesis]:

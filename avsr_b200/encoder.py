@@ -42,6 +42,7 @@ class Encoder:
         self.w = EncoderWeights(state_dict, self.device)
         self._ws = {}
         self._copy_stream = None
+        self._idx_cache = {}
         # 2D convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit im2col + GEMM
         # (dev A/B switch)
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
@@ -145,17 +146,23 @@ class Encoder:
             raise RuntimeError(f"bad encoder input shapes: video {tuple(video_packed.shape)}, audio {tuple(audio.shape)}, lengths {lengths}")
         if min(lengths) < 1 or max(lengths) > Tpad:
             raise RuntimeError("utterance lengths must be in [1, T]")
-        fb, ft, fT, offs = [], [], [], []
-        o = 0
-        for b, t in enumerate(lengths):
-            offs.append(o)
-            fb += [b] * t
-            ft += list(range(t))
-            fT += [t] * t
-            o += t
-        frame_b = torch.tensor(fb, dtype=torch.int32, device=dev)
-        frame_t = torch.tensor(ft, dtype=torch.int32, device=dev)
-        frame_T = torch.tensor(fT, dtype=torch.int32, device=dev)
+        # per-frame index arrays (utterance, position, utterance length) and the attention work list; cached per length tuple
+        key = tuple(lengths)
+        idx = self._idx_cache.get(key)
+        if idx is None:
+            if len(self._idx_cache) > 64:
+                self._idx_cache.clear()
+            ln = torch.tensor(lengths, dtype=torch.int64)
+            offs_t = torch.cumsum(ln, 0) - ln
+            fb_t = torch.repeat_interleave(torch.arange(B, dtype=torch.int64), ln)
+            ft_t = torch.arange(F, dtype=torch.int64) - offs_t[fb_t]
+            work = [(int(offs_t[b]), t, q0) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
+            idx = dict(frame_b=fb_t.to(torch.int32).to(dev), frame_t=ft_t.to(torch.int32).to(dev), frame_T=ln[fb_t].to(torch.int32).to(dev),
+                       n_work=len(work), work_off=torch.tensor([x[0] for x in work], dtype=torch.int32, device=dev),
+                       work_T=torch.tensor([x[1] for x in work], dtype=torch.int32, device=dev),
+                       work_q0=torch.tensor([x[2] for x in work], dtype=torch.int32, device=dev))
+            self._idx_cache[key] = idx
+        frame_b, frame_t, frame_T = idx["frame_b"], idx["frame_t"], idx["frame_T"]
 
         # --- modality front-ends (avhubert.py:187-198) and concat-fusion (avhubert.py:486-502)
         trunk = self._video_frontend(video_packed, frame_t, frame_T, F, taps, ready=video_ready)
@@ -186,10 +193,7 @@ class Encoder:
             taps["posconv"] = h.clone()
 
         # --- 24 pre-LN transformer layers (avhubert.py:747-768)
-        work = [(offs[b], t, q0) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
-        work_off = torch.tensor([x[0] for x in work], dtype=torch.int32, device=dev)
-        work_T = torch.tensor([x[1] for x in work], dtype=torch.int32, device=dev)
-        work_q0 = torch.tensor([x[2] for x in work], dtype=torch.int32, device=dev)
+        work_off, work_T, work_q0, n_work = idx["work_off"], idx["work_T"], idx["work_q0"], idx["n_work"]
         Fld = (F + 7) // 8 * 8
         a = self._buf("ln_out", (F, 1024), torch.bfloat16)
         qk = self._buf("qk", (F, 2048), torch.bfloat16)
@@ -201,7 +205,7 @@ class Encoder:
             L.gemm_bf16(a, lay["wqk"], F, 2048, 1024, L.make_epilogue(bias=lay["bqk"], out_bf16=qk, ld_bf16=2048))
             L.gemm_bf16(lay["wv"], a, 1024, F, 1024, L.make_epilogue(bias=lay["bv"], bias_mode=2, out_bf16=vt, ld_bf16=Fld))
             L.check(lib.avsr_attention_varlen(L.ptr(qk), L.ptr(vt), L.ll(Fld), L.ptr(ao), L.ll(F), L.ptr(work_off), L.ptr(work_T),
-                                              L.ptr(work_q0), len(work), max(lengths), L.stream()), "avsr_attention_varlen")
+                                              L.ptr(work_q0), n_work, max(lengths), L.stream()), "avsr_attention_varlen")
             L.gemm_bf16(ao, lay["wo"], F, 1024, 1024, L.make_epilogue(bias=lay["bo"], residual=h, ldr=1024, out_f32=h, ld_f32=1024))
             L.layernorm(h, lay["ln2_g"], lay["ln2_b"], 1e-5, out_bf16=a)
             L.gemm_bf16(a, lay["w1"], F, 4096, 1024, L.make_epilogue(bias=lay["b1"], act=L.ACT_GELU, out_bf16=ff, ld_bf16=4096))
