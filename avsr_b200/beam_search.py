@@ -309,12 +309,11 @@ class BatchedBeamSearch:
         st = L.stream
         if "tail" in self._skip:
             return
-        L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(part), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
-                                             L.ptr(s["part_ids"]), S, st()), "avsr_dec_logits_lsm_topk")
-        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, s["ldp"], w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
-                                            beam, R, S, L.ptr(s["last_tok"]), L.ptr(s["part_ids"]), L.ptr(s["rprev_idx"]),
-                                            L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
-                "avsr_ctc_prefix_prebeam")
+        # one launch: output-layer log_softmax + pre-beam top-S and the CTC prefix scores of those candidates
+        L.check(lib.avsr_dec_tail(L.ptr(part), ns, L.ptr(w.out_b), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["logp"]), V, s["ldp"],
+                                  w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]), beam, R, S, L.ptr(s["last_tok"]),
+                                  L.ptr(s["rprev_idx"]), L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]),
+                                  L.ptr(s["rsum_last"]), st()), "avsr_dec_tail")
         if "advance" in self._skip:
             return
         L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),

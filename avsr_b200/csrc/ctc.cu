@@ -6,6 +6,7 @@
 // for all utterances at once, with the hypothesis state resident on the device.
 #include <stdlib.h>
 #include "common.cuh"
+#include "dec_tail.cuh"
 
 namespace {
 
@@ -37,36 +38,39 @@ __device__ __forceinline__ float lse2_chain(float a, float b) {
 constexpr int PB_THREADS = 128;
 constexpr int PB_MAXS = 12;
 
-__global__ void __launch_bounds__(PB_THREADS)
-ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int blank, const int* __restrict__ utt_off,
-                          const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
-                          const int* __restrict__ last_tok, const int* __restrict__ part_ids, const int* __restrict__ rprev_idx,
-                          float* __restrict__ r_buf, int tmax, int pitch, const int* __restrict__ step_p, float* __restrict__ psi,
-                          float* __restrict__ rsum_last) {
-    extern __shared__ float pb_sm[];                 // xs [S][pitch], xb [pitch], phi [pitch], pbk [pitch]
-    __shared__ float s_rmax[3][PB_MAXS], s_rsum[3][PB_MAXS];
-    const int row = blockIdx.x, utt = row / beam;
+struct PrebeamArgs {
+    const float* logp; int V, ldp, blank;
+    const int* utt_off; const int* utt_T; const int* n_run; int beam, R, S;
+    const int* last_tok; const int* rprev_idx; float* r_buf; int tmax, pitch; const int* step_p;
+    float* psi; float* rsum_last;
+};
+
+// One hypothesis row on a CTA of NT threads.  pb_sm: (S + 3) * pitch floats = xs [S][pitch], xb [pitch], phi [pitch],
+// pbk [pitch]; ids: the row's S candidate tokens (global or shared memory).  The caller has already filled xb (blank column,
+// which does not depend on the previous kernel) and made sure the row is live.
+template <int NT>
+__device__ __forceinline__ void ctc_prebeam_row(const PrebeamArgs& a, int row, float* pb_sm, const int* ids,
+                                                float (*s_rmax)[PB_MAXS], float (*s_rsum)[PB_MAXS]) {
+    constexpr int NR = NT - 32;                      // threads of the reduction warps
+    constexpr int NRW = NR / 32;
+    const int utt = row / a.beam;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, pitch = a.pitch, R = a.R, tmax = a.tmax;
     float* xs = pb_sm;
     float* xb = pb_sm + (size_t)S * pitch;
     float* phi = xb + pitch;
     float* pbk = phi + pitch;
-    pdl_trigger();
-    // the posteriors were written before the chain of step kernels started: the blank column is fetched before the wait
-    const int T = utt_T[utt];
-    const float* lp = logp + (long long)utt_off[utt] * ldp;
-    for (int t = tid; t < T; t += PB_THREADS) xb[t] = __ldg(lp + (long long)t * ldp + blank);
-    pdl_wait();
-    if ((row % beam) >= n_run[utt]) return;
-    const int step = *step_p;
+    const int T = a.utt_T[utt];
+    const float* lp = a.logp + (long long)a.utt_off[utt] * a.ldp;
+    const int step = *a.step_p;
     const int cur = step & 1;
     const int start = step > 1 ? step : 1;
-    const int last = last_tok[row];
-    const float2* rp = reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + (step > 0 ? rprev_idx[row] : 0)) * tmax;
+    const int last = a.last_tok[row];
+    const float2* rp = reinterpret_cast<const float2*>(a.r_buf) + ((long long)cur * R * S + (step > 0 ? a.rprev_idx[row] : 0)) * tmax;
 
     // ---- phase A
-    for (int t = tid; t < T; t += PB_THREADS) {
-        for (int s = 0; s < S; ++s) xs[s * pitch + t] = __ldg(lp + (long long)t * ldp + part_ids[row * S + s]);
+    for (int t = tid; t < T; t += NT) {
+        for (int s = 0; s < S; ++s) xs[s * pitch + t] = __ldg(lp + (long long)t * a.ldp + ids[s]);
         if (step > 0) {
             const float2 p = rp[t];
             phi[t] = lse2(p.x, p.y);
@@ -89,10 +93,9 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int bl
     if (warp == 0) {
         if (lane < S) {
             const int s = lane;
-            const int c = part_ids[row * S + s];
-            const float* ph = (c == last) ? pbk : phi;
+            const float* ph = (ids[s] == last) ? pbk : phi;
             const float* x = xs + s * pitch;
-            float2* ro = reinterpret_cast<float2*>(r_buf) + ((long long)(cur ^ 1) * R * S + (long long)row * S + s) * tmax;
+            float2* ro = reinterpret_cast<float2*>(a.r_buf) + ((long long)(cur ^ 1) * R * S + (long long)row * S + s) * tmax;
             float rn = (step == 0) ? x[0] : LOGZERO;
             float rb = LOGZERO;
             ro[start - 1] = make_float2(rn, rb);
@@ -109,33 +112,82 @@ ctc_prefix_prebeam_kernel(const float* __restrict__ logp, int V, int ldp, int bl
     }
     const int tt = tid - 32, w3 = warp - 1;
     for (int s = 0; s < S; ++s) {
-        const float* ph = (part_ids[row * S + s] == last) ? pbk : phi;
+        const float* ph = (ids[s] == last) ? pbk : phi;
         const float* x = xs + s * pitch;
         float mx = -INFINITY;
-        for (int t = start + tt; t < T; t += PB_THREADS - 32) mx = fmaxf(mx, ph[t - 1] + x[t]);
+        for (int t = start + tt; t < T; t += NR) mx = fmaxf(mx, ph[t - 1] + x[t]);
         mx = warp_max(mx);
         if (lane == 0) s_rmax[w3][s] = mx;
     }
-    asm volatile("bar.sync 1, 96;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NR) : "memory");
     for (int s = 0; s < S; ++s) {
-        const float* ph = (part_ids[row * S + s] == last) ? pbk : phi;
+        const float* ph = (ids[s] == last) ? pbk : phi;
         const float* x = xs + s * pitch;
         const float r0 = (step == 0) ? x[0] : LOGZERO;                       // r[start-1, 0]
-        const float M = fmaxf(fmaxf(s_rmax[0][s], s_rmax[1][s]), fmaxf(s_rmax[2][s], r0));
+        float M = r0;
+#pragma unroll
+        for (int w = 0; w < NRW; ++w) M = fmaxf(M, s_rmax[w][s]);
         float sum = 0.f;
-        for (int t = start + tt; t < T; t += PB_THREADS - 32) sum += expf(ph[t - 1] + x[t] - M);
+        for (int t = start + tt; t < T; t += NR) sum += expf(ph[t - 1] + x[t] - M);
         sum = warp_sum(sum);
         if (lane == 0) s_rsum[w3][s] = sum;
     }
-    asm volatile("bar.sync 1, 96;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NR) : "memory");
     if (tt < S) {
         const int s = tt;
         const float r0 = (step == 0) ? xs[s * pitch] : LOGZERO;
-        const float M = fmaxf(fmaxf(s_rmax[0][s], s_rmax[1][s]), fmaxf(s_rmax[2][s], r0));
-        const float sum = ((s_rsum[0][s] + s_rsum[1][s]) + s_rsum[2][s]) + expf(r0 - M);
-        psi[row * S + s] = M + logf(sum);
+        float M = r0;
+#pragma unroll
+        for (int w = 0; w < NRW; ++w) M = fmaxf(M, s_rmax[w][s]);
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NRW; ++w) sum += s_rsum[w][s];
+        sum += expf(r0 - M);
+        a.psi[row * S + s] = M + logf(sum);
     }
-    if (tt == 32) rsum_last[row] = phi[T - 1];
+    if (tt == 32) a.rsum_last[row] = phi[T - 1];
+}
+
+__global__ void __launch_bounds__(PB_THREADS)
+ctc_prefix_prebeam_kernel(const PrebeamArgs a, const int* __restrict__ part_ids) {
+    extern __shared__ float pb_sm[];
+    __shared__ float s_rmax[PB_THREADS / 32 - 1][PB_MAXS], s_rsum[PB_THREADS / 32 - 1][PB_MAXS];
+    const int row = blockIdx.x, utt = row / a.beam;
+    pdl_trigger();
+    // the posteriors were written before the chain of step kernels started: the blank column is fetched before the wait
+    const int T = a.utt_T[utt];
+    const float* lp = a.logp + (long long)a.utt_off[utt] * a.ldp;
+    float* xb = pb_sm + (size_t)a.S * a.pitch;
+    for (int t = threadIdx.x; t < T; t += PB_THREADS) xb[t] = __ldg(lp + (long long)t * a.ldp + a.blank);
+    pdl_wait();
+    if ((row % a.beam) >= a.n_run[utt]) return;
+    ctc_prebeam_row<PB_THREADS>(a, row, pb_sm, part_ids + row * a.S, s_rmax, s_rsum);
+}
+
+// Fused tail of a decode position, one CTA (512 threads) per hypothesis row: output-layer log_softmax + pre-beam top-S
+// (dec_tail.cuh) and, for the S candidates just found, the CTC prefix scores - one launch instead of two on the critical
+// chain (the candidates stay in shared memory).
+template <int ITER>
+__global__ void __launch_bounds__(LSM_THREADS)
+dec_tail_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias, float* __restrict__ dec_logp,
+                int* __restrict__ part_ids, const PrebeamArgs a) {
+    extern __shared__ float pb_sm[];
+    __shared__ LsmSmem lsm;
+    __shared__ int s_ids[PB_MAXS];
+    __shared__ float s_rmax[LSM_THREADS / 32 - 1][PB_MAXS], s_rsum[LSM_THREADS / 32 - 1][PB_MAXS];
+    const int row = blockIdx.x, utt = row / a.beam;
+    pdl_trigger();
+    float v[ITER];
+    lsm_load_bias<ITER>(v, bias, a.V);
+    const int T = a.utt_T[utt];
+    const float* lp = a.logp + (long long)a.utt_off[utt] * a.ldp;
+    float* xb = pb_sm + (size_t)a.S * a.pitch;
+    for (int t = threadIdx.x; t < T; t += LSM_THREADS) xb[t] = __ldg(lp + (long long)t * a.ldp + a.blank);
+    pdl_wait();
+    if ((row % a.beam) >= a.n_run[utt]) return;
+    lsm_topk_row<ITER>(v, lsm, part, nsplit, a.R, a.V, row, dec_logp, part_ids + row * a.S, s_ids, a.S);
+    __syncthreads();
+    ctc_prebeam_row<LSM_THREADS>(a, row, pb_sm, s_ids, s_rmax, s_rsum);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -632,22 +684,62 @@ __global__ void beam_step_advance_kernel(int* step, const int* n_run, int B, int
 
 }  // namespace
 
-extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run,
-                                       int beam, int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx,
-                                       float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, cudaStream_t stream) {
-    AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && part_ids && rprev_idx && r_buf && step && psi && rsum_last,
+static int prebeam_args(PrebeamArgs* a, size_t* smem, const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T,
+                        const int* n_run, int beam, int R, int S, const int* last_tok, const int* rprev_idx, float* r_buf, int tmax,
+                        const int* step, float* psi, float* rsum_last) {
+    AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && rprev_idx && r_buf && step && psi && rsum_last,
                  "avsr_ctc_prefix_prebeam: null argument");
     AVSR_REQUIRE(R > 0 && S > 0 && S <= PB_MAXS && beam > 0 && tmax > 0 && ldp >= V, "avsr_ctc_prefix_prebeam: bad sizes (S <= %d)", PB_MAXS);
     const int pitch = tmax | 1;                       // odd pitch: the S chains read their columns without bank conflicts
-    const size_t smem = (size_t)(S + 3) * pitch * sizeof(float);
-    AVSR_REQUIRE(smem <= 200 * 1024, "avsr_ctc_prefix_prebeam: %d frames x %d candidates do not fit shared memory", tmax, S);
+    *smem = (size_t)(S + 3) * pitch * sizeof(float);
+    AVSR_REQUIRE(*smem <= 200 * 1024, "avsr_ctc_prefix_prebeam: %d frames x %d candidates do not fit shared memory", tmax, S);
+    *a = PrebeamArgs{logp, V, ldp, blank, utt_off, utt_T, n_run, beam, R, S, last_tok, rprev_idx, r_buf, tmax, pitch, step, psi, rsum_last};
+    return AVSR_OK;
+}
+
+extern "C" int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run,
+                                       int beam, int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx,
+                                       float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, cudaStream_t stream) {
+    AVSR_REQUIRE(part_ids, "avsr_ctc_prefix_prebeam: null argument");
+    PrebeamArgs a;
+    size_t smem;
+    int rc = prebeam_args(&a, &smem, logp, V, ldp, blank, utt_off, utt_T, n_run, beam, R, S, last_tok, rprev_idx, r_buf, tmax, step, psi,
+                          rsum_last);
+    if (rc != AVSR_OK) return rc;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_prebeam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
-    AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_prebeam_kernel, dim3(R), dim3(PB_THREADS), smem, stream, logp, V, ldp, blank, utt_off,
-                                    utt_T, n_run, beam, R, S, last_tok, part_ids, rprev_idx, r_buf, tmax, pitch, step, psi, rsum_last));
+    AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_prebeam_kernel, dim3(R), dim3(PB_THREADS), smem, stream, a, part_ids));
+    return AVSR_OK;
+}
+
+// avsr_dec_logits_lsm_topk followed by avsr_ctc_prefix_prebeam in ONE launch (one CTA per hypothesis row): part [nsplit][R][V]
+// partial logits + bias -> dec_logp [R][V], part_ids [R][S] (pre-beam candidates) -> psi [R][S], rsum_last [R] and the new
+// forward variables in r_buf; the remaining arguments as in the two stand-alone calls.
+extern "C" int avsr_dec_tail(const float* part, int nsplit, const float* bias, float* dec_logp, int* part_ids, const float* logp, int V,
+                             int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam, int R, int S,
+                             const int* last_tok, const int* rprev_idx, float* r_buf, int tmax, const int* step, float* psi,
+                             float* rsum_last, cudaStream_t stream) {
+    AVSR_REQUIRE(part && bias && dec_logp && part_ids && nsplit >= 1, "avsr_dec_tail: null argument");
+    AVSR_REQUIRE(V <= 16 * LSM_THREADS, "avsr_dec_tail: vocabulary %d too large (max %d)", V, 16 * LSM_THREADS);
+    PrebeamArgs a;
+    size_t smem;
+    int rc = prebeam_args(&a, &smem, logp, V, ldp, blank, utt_off, utt_T, n_run, beam, R, S, last_tok, rprev_idx, r_buf, tmax, step, psi,
+                          rsum_last);
+    if (rc != AVSR_OK) return rc;
+    const int iter = (V + LSM_THREADS - 1) / LSM_THREADS;
+    static bool configured = false;
+    if (!configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_tail_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_tail_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_tail_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (iter <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_tail_kernel<4>, dim3(R), dim3(LSM_THREADS), smem, stream, part, nsplit, bias, dec_logp, part_ids, a));
+    else if (iter <= 10) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_tail_kernel<10>, dim3(R), dim3(LSM_THREADS), smem, stream, part, nsplit, bias, dec_logp, part_ids, a));
+    else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_tail_kernel<16>, dim3(R), dim3(LSM_THREADS), smem, stream, part, nsplit, bias, dec_logp, part_ids, a));
     return AVSR_OK;
 }
 

@@ -7,6 +7,7 @@
 // that computed them; a hyp finds its history through anc[row][p] = slot (within its utterance) that holds position p,
 // so beam reordering never copies the cache (reference copies per-hyp caches in batch_beam_search.py:250-284).
 #include "common.cuh"
+#include "dec_tail.cuh"
 
 namespace {
 
@@ -42,91 +43,19 @@ dec_embed_ln_kernel(const float* __restrict__ emb, const float* __restrict__ pe,
     }
 }
 
-// logits = sum_z part[z][row] + bias ; logp = log_softmax(logits) -> dec_logp[row] ; part_ids[row] = top-S token ids
-// (value descending, ties to the lower id).  One CTA (512 threads) per row; a thread keeps its <= ITER strided logits in
-// registers for all three passes (max, sum of exponentials, top-S), so the row is read once and nothing is staged.
-constexpr int LSM_THREADS = 512;
-
+// Output-layer log_softmax + pre-beam top-S, one CTA per row (device code in dec_tail.cuh).
 template <int ITER>
 __global__ void __launch_bounds__(LSM_THREADS)
 dec_logits_lsm_topk_kernel(const float* __restrict__ part, int nsplit, int R, int V, const float* __restrict__ bias,
                            const int* __restrict__ n_run, int beam, float* __restrict__ logp, int* __restrict__ part_ids, int S) {
-    __shared__ float red[32];
-    __shared__ float s_v[LSM_THREADS / 32];
-    __shared__ int s_i[LSM_THREADS / 32];
-    __shared__ int s_win;
-    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    __shared__ LsmSmem sm;
+    const int row = blockIdx.x;
     pdl_trigger();
-    // the bias does not depend on the previous kernel
     float v[ITER];
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-        const int c = tid + k * LSM_THREADS;
-        v[k] = (c < V) ? __ldg(bias + c) : 0.f;
-    }
+    lsm_load_bias<ITER>(v, bias, V);
     pdl_wait();
     if ((row % beam) >= n_run[row / beam]) return;
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-        const int c = tid + k * LSM_THREADS;
-        if (c < V) {
-            float a = 0.f;
-            for (int z = 0; z < nsplit; ++z) a += part[((long long)z * R + row) * V + c];
-            v[k] = a + v[k];
-            mx = fmaxf(mx, v[k]);
-        } else {
-            v[k] = -INFINITY;
-        }
-    }
-    mx = block_max(mx, red);
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) sum += expf(v[k] - mx);            // padding: exp(-inf) = 0
-    sum = block_sum(sum, red);
-    const float lse = logf(sum);
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) {
-        const int c = tid + k * LSM_THREADS;
-        if (c < V) {
-            v[k] = (v[k] - mx) - lse;
-            logp[(long long)row * V + c] = v[k];
-        }
-    }
-    // ---- S rounds of block arg-max over the register values; the winner drops its entry
-    for (int r = 0; r < S; ++r) {
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-#pragma unroll
-        for (int k = 0; k < ITER; ++k) {
-            const int c = tid + k * LSM_THREADS;
-            if (v[k] > bv) { bv = v[k]; bi = c; }                     // ascending c: the lowest id wins ties
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { s_v[w] = bv; s_i[w] = bi; }
-        __syncthreads();
-        if (w == 0) {
-            bv = lane < LSM_THREADS / 32 ? s_v[lane] : -INFINITY;
-            bi = lane < LSM_THREADS / 32 ? s_i[lane] : 0x7fffffff;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) { part_ids[row * S + r] = bi; s_win = bi; }
-        }
-        __syncthreads();
-        const int win = s_win;
-#pragma unroll
-        for (int k = 0; k < ITER; ++k)
-            if (tid + k * LSM_THREADS == win) v[k] = -INFINITY;
-    }
+    lsm_topk_row<ITER>(v, sm, part, nsplit, R, V, row, logp, part_ids + row * S, nullptr, S);
 }
 
 // log_softmax over rows of a [rows, V] fp32 matrix, in place (CTC head: src/nets/backend/ctc.py:163-170).

@@ -204,6 +204,11 @@ int avsr_dec_logits_lsm_topk(const float* part, int nsplit, int R, int V, const 
 int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam,
                             int R, int S, const int* last_tok, const int* part_ids, const int* rprev_idx, float* r_buf, int tmax,
                             const int* step, float* psi, float* rsum_last, avsr_stream_t stream);
+/* avsr_dec_logits_lsm_topk + avsr_ctc_prefix_prebeam in ONE launch (one CTA per hypothesis row; the pre-beam candidates stay
+ * in shared memory): the tail of a decode position, decoder.py:176-181 + batch_beam_search.py:229-235 + ctc_prefix_score.py:68-187. */
+int avsr_dec_tail(const float* part, int nsplit, const float* bias, float* dec_logp, int* part_ids, const float* logp, int V, int ldp,
+                  int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam, int R, int S, const int* last_tok,
+                  const int* rprev_idx, float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, avsr_stream_t stream);
 /* Full-vocabulary mode.  avsr_ctc_prefix_full_plan gives the work split (*ncg column groups x *tsplit time splits per
  * utterance); caller-owned scratch: part [B][tsplit][beam][V] fp32 (may be NULL when tsplit == 1), tickets [B][ncg] int32
  * zeroed once. */
