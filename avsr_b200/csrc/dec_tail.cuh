@@ -31,14 +31,27 @@ template <int ITER>
 __device__ __forceinline__ void lsm_topk_row(float (&v)[ITER], LsmSmem& sm, const float* __restrict__ part, int nsplit, int R, int V,
                                              int row, float* __restrict__ logp, int* __restrict__ ids_g, int* ids_s, int S) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // partial sums: split-major so that the ITER loads of one split are all in flight (nsplit round trips, not ITER * nsplit)
+    float acc[ITER];
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) acc[k] = 0.f;
+    for (int z = 0; z < nsplit; ++z) {
+        const float* pz = part + ((long long)z * R + row) * V;
+        float t[ITER];
+#pragma unroll
+        for (int k = 0; k < ITER; ++k) {
+            const int c = tid + k * LSM_THREADS;
+            t[k] = (c < V) ? pz[c] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < ITER; ++k) acc[k] += t[k];
+    }
     float mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < ITER; ++k) {
         const int c = tid + k * LSM_THREADS;
         if (c < V) {
-            float a = 0.f;
-            for (int z = 0; z < nsplit; ++z) a += part[((long long)z * R + row) * V + c];
-            v[k] = a + v[k];
+            v[k] = acc[k] + v[k];
             mx = fmaxf(mx, v[k]);
         } else {
             v[k] = -INFINITY;

@@ -142,6 +142,69 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
 }
 
 // One CTA per output row (see splitk_epilogue.cuh).
+// ---- fast row epilogue for the decode step: exactly one group of four columns per thread (N = 4 * blockDim).  The chain of
+// dependent launches makes the kernel's own critical path matter, so every load is requested as early as it can be: bias /
+// gamma / beta (static) before griddepcontrol.wait; row_active, the residual and ALL partial sums right after it, the
+// partial sums through in-order loads followed by an "issue barrier" (an empty volatile asm that owns the loaded registers)
+// because ptxas otherwise sinks the loads between the adds and keeps only ~4 in flight (4-5 L2 round trips instead of one).
+__device__ __forceinline__ float4 ldcg_f4_inorder(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+template <int MAXT, int BATCH>
+__global__ void __launch_bounds__(MAXT)
+splitk_epilogue_fast_kernel(const SplitKEpi e) {
+    extern __shared__ float rowbuf[];
+    __shared__ float red[32];
+    const int row = blockIdx.x, c = threadIdx.x * 4, N = e.N, nsplit = e.nsplit;
+    pdl_trigger();
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + c)) : zero4;
+    float4 g4 = zero4, be4 = zero4;
+    if (e.ln_g) {
+        g4 = __ldg(reinterpret_cast<const float4*>(e.ln_g + c));
+        be4 = __ldg(reinterpret_cast<const float4*>(e.ln_b + c));
+    }
+    pdl_wait();
+    const int active = e.row_active ? e.row_active[row] : 1;
+    const float4 r4 = e.residual ? *reinterpret_cast<const float4*>(e.residual + (long long)row * e.ldr + c) : zero4;
+    const long long zstride = (long long)e.M * N;
+    const float* p = e.part + (long long)row * N + c;
+    const int rt_zero = e.act >> 16;                  // 0 at run time (act is a small enum), opaque at compile time
+    float4 v = zero4;
+    for (int z = 0; z < nsplit; z += BATCH) {
+        float4 t[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) t[u] = ldcg_f4_inorder(p + (long long)min(z + u, nsplit - 1) * zstride);
+        // the first add depends on EVERY load of the batch (an OR over one word of each, masked to zero by a value the
+        // compiler cannot know), so all loads are in flight before anything waits: one L2 round trip per batch
+        int dep = 0;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) dep |= __float_as_int(t[u].x);
+        v.x += __int_as_float(dep & rt_zero);
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)
+            if (z + u < nsplit) { v.x += t[u].x; v.y += t[u].y; v.z += t[u].z; v.w += t[u].w; }
+    }
+    if (!active) return;                              // uniform for the CTA
+    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+    if (e.act == AVSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    else if (e.act == AVSR_ACT_GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+    v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+    if (e.out) *reinterpret_cast<float4*>(e.out + (long long)row * e.ldo + c) = v;
+    if (e.ln_g == nullptr) {
+        if (e.split_out) avsr_split3c_store4(e.split_out + (long long)row * 3 * N, N, c, v);
+        return;
+    }
+    const float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)N;
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float rstd = rsqrtf(block_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3), red) / (float)N + e.ln_eps);
+    const float4 y = make_float4(d0 * rstd * g4.x + be4.x, d1 * rstd * g4.y + be4.y, d2 * rstd * g4.z + be4.z, d3 * rstd * g4.w + be4.w);
+    if (e.ln_out) *reinterpret_cast<float4*>(e.ln_out + (long long)row * e.ld_ln + c) = y;
+    if (e.split_out) avsr_split3c_store4(e.split_out + (long long)row * 3 * N, N, c, y);
+}
+
 // pf / pf_bytes: optional span that a LATER kernel of the step streams (the cross-attention K/V of the layer, written before
 // the chain of step kernels started).  Before waiting for its producer, CTA b asks the L2 to fetch its 1/gridDim share in
 // 32 KB pieces (cp.async.bulk.prefetch.L2, fire and forget): the decode step is a chain of latency-bound launches during
@@ -237,6 +300,17 @@ extern "C" int avsr_splitk_epilogue_pf(const float* part, int nsplit, int M, int
     // reductions of the LayerNorm then run over 1024 mostly idle threads.)
     int threads = ((N + 3) / 4 + 31) / 32 * 32;
     threads = threads < 256 ? 256 : (threads > 768 ? 768 : threads);
+    const bool vec = (N & 3) == 0 && (ldr & 3) == 0 && (ldo & 3) == 0 && (ld_ln & 3) == 0;
+    if (vec && l2_prefetch == nullptr && N / 4 == threads && N == 4 * threads) {
+        // one column group per thread: the fast kernel with every load requested up front
+        if (threads <= 256 && nsplit <= 16)
+            AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_fast_kernel<256, 16>, dim3(M), dim3(threads), 0, stream, e));
+        else if (threads <= 256)
+            AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_fast_kernel<256, 20>, dim3(M), dim3(threads), 0, stream, e));
+        else
+            AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_fast_kernel<768, 8>, dim3(M), dim3(threads), 0, stream, e));
+        return AVSR_OK;
+    }
     AVSR_CHECK_CUDA(avsr_launch_pdl(splitk_epilogue_kernel<1>, dim3(M), dim3(threads), smem, stream, e, (const char*)l2_prefetch, l2_prefetch_bytes));
     return AVSR_OK;
 }

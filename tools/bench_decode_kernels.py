@@ -112,3 +112,17 @@ def ctc():
     L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(logp), V, V, 0, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, R, S, L.ptr(last), L.ptr(part_ids),
                                         L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(psi), L.ptr(rsum), L.stream()), "ctc")
 print(f"ctc prebeam: {timeit(ctc):8.1f} us")
+
+# floor of a dependent launch in the chain: a trivial kernel (one thread bumps the step counter) and a small row kernel
+step2, nrun2, anyr = i32([0]), i32([beam] * B), i32([0])
+def adv():
+    L.check(lib.avsr_beam_step_advance(L.ptr(step2), L.ptr(nrun2), B, L.ptr(anyr), L.stream()), "adv")
+print(f"launch floor (1-thread kernel in the PDL chain): {timeit(adv):8.2f} us")
+emb, pe = torch.randn(V, 1024, device=dev), torch.randn(5000, 1024, device=dev)
+g1, b1 = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+xx, a3 = torch.empty(R, 1024, device=dev), torch.empty(R, 3 * 1024, device=dev, dtype=torch.bfloat16)
+lt = i32([5] * R)
+def emb_ln():
+    L.check(lib.avsr_dec_embed_ln(L.ptr(emb), L.ptr(pe), L.ptr(lt), L.ptr(n_run), beam, R, L.ptr(step_t), L.ptr(g1), L.ptr(b1),
+                                  C.c_float(1e-12), L.ptr(xx), None, L.ptr(a3), L.stream()), "embed")
+print(f"embed + LayerNorm row kernel (96 CTAs x 256 threads): {timeit(emb_ln):8.2f} us")
