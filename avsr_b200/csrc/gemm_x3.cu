@@ -38,11 +38,15 @@ namespace {
 constexpr int BM = 128;                   // output features per tile (TMEM lanes)
 constexpr int BK = 64;
 constexpr int W_TILE = BM * BK * 2;       // 16 KB
-constexpr int A_TILE = 128 * BK * 2;      // room for NB <= 128 activation rows
-constexpr int STAGE_BYTES = 3 * W_TILE + 3 * A_TILE;
+constexpr int A_TILE_MAX = 128 * BK * 2;  // NB <= 128 activation rows; a stage holds 3 weight tiles + 3 tiles of NB rows
+constexpr int STAGE_MAX = 3 * W_TILE + 3 * A_TILE_MAX;
 constexpr int STAGES = 2;
 constexpr int ROWBUF_BYTES = 3072 * 4;    // LayerNorm row of the fused tail (N <= 3072)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + ROWBUF_BYTES;
+constexpr int SMEM_MAX = STAGES * STAGE_MAX + 1024 + 256 + ROWBUF_BYTES;
+// Shared memory actually requested: stages sized by the real NB and the LayerNorm row only when a row tail / prologue runs
+// in the launch.  At NB = 96 that is 170 KB instead of 205 KB, which leaves room for one CTA of the neighbouring attention
+// kernel on the same SM: the projection's prologue (and the attention's K/V prefetch) can then overlap the other kernel.
+static inline int smem_bytes(int nb, bool rowbuf) { return STAGES * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + (rowbuf ? ROWBUF_BYTES : 0); }
 constexpr int NUM_THREADS = 64 + 4 * 32;
 constexpr int TMEM_COLS = 128;
 
@@ -92,6 +96,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                int pro_on, const SplitKEpi pro, unsigned* ready, int rq) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int A_TILE = NB * BK * 2, STAGE_BYTES = 3 * W_TILE + 3 * A_TILE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -320,14 +325,14 @@ static int x3_launch(const void* A3, long long lda, const void* W3, long long ld
     if (rc != AVSR_OK) return rc;
     static bool configured = false;
     if (!configured) {
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         configured = true;
     }
     const int items = tiles_m * tiles_n * splits;
     const int grid = items < sm_count() ? items : sm_count();
     AVSR_REQUIRE(!pro_on || items <= sm_count(), "avsr_gemm_x3_chain: %d work items exceed one CTA per SM (R=%d N=%d)", items, R, N);
     SplitKEpi none = {};
-    AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tw, ta, R, N, K, nb, part, splits,
+    AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes(nb, fuse || pro_on), stream, tw, ta, R, N, K, nb, part, splits,
                                     tiles_m, tiles_n, fuse, epi, gbar, pro_on, pro_on ? *pro : none, ready, rq));
     return AVSR_OK;
 }
