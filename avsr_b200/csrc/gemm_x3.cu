@@ -46,7 +46,9 @@ constexpr int SMEM_MAX = STAGES * STAGE_MAX + 1024 + 256 + ROWBUF_BYTES;
 // Shared memory actually requested: stages sized by the real NB and the LayerNorm row only when a row tail / prologue runs
 // in the launch.  At NB = 96 that is 170 KB instead of 205 KB, which leaves room for one CTA of the neighbouring attention
 // kernel on the same SM: the projection's prologue (and the attention's K/V prefetch) can then overlap the other kernel.
-static inline int smem_bytes(int nb, bool rowbuf) { return STAGES * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + (rowbuf ? ROWBUF_BYTES : 0); }
+static inline int smem_bytes(int nb, bool rowbuf, int nstages) {
+    return nstages * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + (rowbuf ? ROWBUF_BYTES : 0);
+}
 constexpr int NUM_THREADS = 64 + 4 * 32;
 constexpr int TMEM_COLS = 128;
 
@@ -93,16 +95,16 @@ __device__ __forceinline__ void wait_rows_ready(const unsigned* ctr, unsigned ro
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, int R, int N, int K, int NB,
                float* __restrict__ part, int splits, int tiles_m, int tiles_n, int fuse, const SplitKEpi epi, unsigned* gbar,
-               int pro_on, const SplitKEpi pro, unsigned* ready, int rq) {
+               int pro_on, const SplitKEpi pro, unsigned* ready, int rq, int nstages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int A_TILE = NB * BK * 2, STAGE_BYTES = 3 * W_TILE + 3 * A_TILE;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + nstages * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
-    float* rowbuf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
+    float* rowbuf = reinterpret_cast<float*>(smem + nstages * STAGE_BYTES + 256);
     __shared__ float red[32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,7 +150,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 if (!waited) {
                     // weights do not depend on the previous kernel: fill the pipeline with them first, then wait for the
                     // grid that produces the activations, then complete the same stages with the activation tiles
-                    const int npre = min(STAGES, kb1 - kb0);
+                    const int npre = min(nstages, kb1 - kb0);
                     for (int i = 0; i < npre; ++i) {
                         uint8_t* sw = smem + i * STAGE_BYTES;
                         tc::mbar_arrive_expect_tx(&full[i], stage_tx);
@@ -164,8 +166,8 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         for (int j = 0; j < 3; ++j) tc::tma_load_2d(sa + j * A_TILE, &tmA, &full[i], (kb0 + i) * BK + j * K, n0);
                     }
                     kb = kb0 + npre;
-                    stage = npre % STAGES;
-                    phase = (npre == STAGES) ? 1u : 0u;
+                    stage = npre % nstages;
+                    phase = (npre == nstages) ? 1u : 0u;
                 }
                 for (; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -175,7 +177,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     for (int j = 0; j < 3; ++j) tc::tma_load_2d(sw + j * W_TILE, &tmW, &full[stage], kb * BK + j * K, m0);
 #pragma unroll
                     for (int j = 0; j < 3; ++j) tc::tma_load_2d(sw + 3 * W_TILE + j * A_TILE, &tmA, &full[stage], kb * BK + j * K, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
             if (!waited) pdl_wait();
@@ -208,7 +210,7 @@ gemm_x3_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                         tc::umma_bf16(tmem_base, w1 + 2 * k, a1 + 2 * k, idesc, 1u);
                     }
                     tc::umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 tc::umma_commit(tfull);
                 acc_phase ^= 1;
@@ -332,8 +334,11 @@ static int x3_launch(const void* A3, long long lda, const void* W3, long long ld
     const int grid = items < sm_count() ? items : sm_count();
     AVSR_REQUIRE(!pro_on || items <= sm_count(), "avsr_gemm_x3_chain: %d work items exceed one CTA per SM (R=%d N=%d)", items, R, N);
     SplitKEpi none = {};
-    AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes(nb, fuse || pro_on), stream, tw, ta, R, N, K, nb, part, splits,
-                                    tiles_m, tiles_n, fuse, epi, gbar, pro_on, pro_on ? *pro : none, ready, rq));
+    // (a single stage for the projections whose CTAs have one k block each - 86 KB, so that three attention CTAs fit beside
+    // one on an SM - measured slower: 339 vs 330 ms per pass; two CTAs of the projection itself then share SMs)
+    const int nstages = STAGES;
+    AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes(nb, fuse || pro_on, nstages), stream, tw, ta, R, N, K, nb, part, splits,
+                                    tiles_m, tiles_n, fuse, epi, gbar, pro_on, pro_on ? *pro : none, ready, rq, nstages));
     return AVSR_OK;
 }
 
