@@ -48,8 +48,19 @@ struct PrebeamArgs {
 // One hypothesis row on a CTA of NT threads.  pb_sm: (S + 3) * pitch floats = xs [S][pitch], xb [pitch], phi [pitch],
 // pbk [pitch]; ids: the row's S candidate tokens (global or shared memory).  The caller has already filled xb (blank column,
 // which does not depend on the previous kernel) and made sure the row is live.
+struct PrebeamRowState {        // beam state of the row, requested by the caller right after griddepcontrol.wait
+    int step, last, rprev;
+};
+__device__ __forceinline__ PrebeamRowState prebeam_row_state(const PrebeamArgs& a, int row) {
+    PrebeamRowState st;
+    st.step = *a.step_p;
+    st.last = a.last_tok[row];
+    st.rprev = a.rprev_idx[row];
+    return st;
+}
+
 template <int NT>
-__device__ __forceinline__ void ctc_prebeam_row(const PrebeamArgs& a, int row, float* pb_sm, const int* ids,
+__device__ __forceinline__ void ctc_prebeam_row(const PrebeamArgs& a, int row, const PrebeamRowState& rs, float* pb_sm, const int* ids,
                                                 float (*s_rmax)[PB_MAXS], float (*s_rsum)[PB_MAXS]) {
     constexpr int NR = NT - 32;                      // threads of the reduction warps
     constexpr int NRW = NR / 32;
@@ -62,11 +73,11 @@ __device__ __forceinline__ void ctc_prebeam_row(const PrebeamArgs& a, int row, f
     float* pbk = phi + pitch;
     const int T = a.utt_T[utt];
     const float* lp = a.logp + (long long)a.utt_off[utt] * a.ldp;
-    const int step = *a.step_p;
+    const int step = rs.step;
     const int cur = step & 1;
     const int start = step > 1 ? step : 1;
-    const int last = a.last_tok[row];
-    const float2* rp = reinterpret_cast<const float2*>(a.r_buf) + ((long long)cur * R * S + (step > 0 ? a.rprev_idx[row] : 0)) * tmax;
+    const int last = rs.last;
+    const float2* rp = reinterpret_cast<const float2*>(a.r_buf) + ((long long)cur * R * S + (step > 0 ? rs.rprev : 0)) * tmax;
 
     // ---- phase A
     for (int t = tid; t < T; t += NT) {
@@ -160,8 +171,10 @@ ctc_prefix_prebeam_kernel(const PrebeamArgs a, const int* __restrict__ part_ids)
     float* xb = pb_sm + (size_t)a.S * a.pitch;
     for (int t = threadIdx.x; t < T; t += PB_THREADS) xb[t] = __ldg(lp + (long long)t * a.ldp + a.blank);
     pdl_wait();
-    if ((row % a.beam) >= a.n_run[utt]) return;
-    ctc_prebeam_row<PB_THREADS>(a, row, pb_sm, part_ids + row * a.S, s_rmax, s_rsum);
+    const int nrun = a.n_run[utt];
+    const PrebeamRowState rs = prebeam_row_state(a, row);
+    if ((row % a.beam) >= nrun) return;
+    ctc_prebeam_row<PB_THREADS>(a, row, rs, pb_sm, part_ids + row * a.S, s_rmax, s_rsum);
 }
 
 // Fused tail of a decode position, one CTA (512 threads) per hypothesis row: output-layer log_softmax + pre-beam top-S
@@ -184,10 +197,12 @@ dec_tail_kernel(const float* __restrict__ part, int nsplit, const float* __restr
     float* xb = pb_sm + (size_t)a.S * a.pitch;
     for (int t = threadIdx.x; t < T; t += LSM_THREADS) xb[t] = __ldg(lp + (long long)t * a.ldp + a.blank);
     pdl_wait();
-    if ((row % a.beam) >= a.n_run[utt]) return;
+    const int nrun = a.n_run[utt];
+    const PrebeamRowState rs = prebeam_row_state(a, row);       // in flight while the logits are reduced
+    if ((row % a.beam) >= nrun) return;
     lsm_topk_row<ITER>(v, lsm, part, nsplit, a.R, a.V, row, dec_logp, part_ids + row * a.S, s_ids, a.S);
     __syncthreads();
-    ctc_prebeam_row<LSM_THREADS>(a, row, pb_sm, s_ids, s_rmax, s_rsum);
+    ctc_prebeam_row<LSM_THREADS>(a, row, rs, pb_sm, s_ids, s_rmax, s_rsum);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbas
 // Everything after griddepcontrol.wait, for exactly NHT live hyps (NH = hyp slots of the beam).
 template <int MODE, int NH, int NHT>
 __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, unsigned* rlist, float* vtile, float4 (&kreg)[DH / 4],
-                                          const float* kbase, const float* vbase, long long nr, int T_utt, int step) {
+                                          const float* kbase, const float* vbase, long long nr, int T_utt, int step, int conv) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y;
@@ -90,6 +90,27 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     const float* q_in = a.q_in;
     const long long ldq = a.ldq;
     const uint32_t vt_s = (uint32_t)__cvta_generic_to_shared(vtile) + (uint32_t)((hw * VR) * DH + 4 * l16) * 4u;   // this thread's V slots
+
+    // Positions [0, C) of the history are "converged": every live hyp has the same ancestor there, and that row has been
+    // copied to the dense caches kd / vd (avsr_dec_cache_promote), where consecutive positions are consecutive rows.  Only
+    // the positions from C on go through the (pos, slot) list.
+    int C = 0;
+    const float* kdb = nullptr;
+    const float* vdb = nullptr;
+    if (MODE == 0 && a.conv_len != nullptr) {
+        C = conv;
+        kdb = a.kd + (long long)(utt * HEADS + head) * a.lmax * DH;
+        vdb = a.vd + (long long)(utt * HEADS + head) * a.lmax * DH;
+    }
+    // A first tile that lies entirely in the dense prefix needs nothing but C: its K / V are requested now, before the query
+    // is gathered and the row list is built, so that their latency overlaps both.
+    bool early = false;
+    if (MODE == 0 && C >= CK) {
+        early = true;
+        load_k<0>(kreg, kdb, a.lmax, tid, true);
+#pragma unroll
+        for (int i = 0; i < VR; ++i) cp_async16(vt_s + i * DH * 4, vdb + (long long)(hw * VR + i) * DH + 4 * l16);
+    }
 
     // ---- query: 16-byte groups, all split-K terms of a group requested at once (two threads share a group when there are
     //      few hyps); the current k / v of the chunk that owns this position go straight to the cache
@@ -146,17 +167,6 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         }
     }
     // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
-    // Positions [0, C) of the history are "converged": every live hyp has the same ancestor there, and that row has been
-    // copied to the dense caches kd / vd (avsr_dec_cache_promote), where consecutive positions are consecutive rows.  Only
-    // the positions from C on go through the (pos, slot) list.
-    int C = 0;
-    const float* kdb = nullptr;
-    const float* vdb = nullptr;
-    if (MODE == 0 && a.conv_len != nullptr) {
-        C = a.conv_len[((step + 1) & 1) * (R / beam) + utt];
-        kdb = a.kd + (long long)(utt * HEADS + head) * a.lmax * DH;
-        vdb = a.vd + (long long)(utt * HEADS + head) * a.lmax * DH;
-    }
     int nrows = (MODE == 1) ? T_utt : 0;
     if (MODE == 0) {
         int total = 0;
@@ -244,7 +254,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
                 if (i < nv) cp_async16(vt_s + i * DH * 4, vsrc + i * DH);
         }
     };
-    if (MODE == 0) { request_k(0); request_v(0); }  // mode 1: tile 0 was requested before griddepcontrol.wait
+    if (MODE == 0 && !early) { request_k(0); request_v(0); }  // mode 1: tile 0 was requested before griddepcontrol.wait
     __syncthreads();                                 // finished query visible (the loads above are already in flight)
     for (int tile = 0; tile < ntiles; ++tile) {
         const int t0 = tile * CK;
@@ -384,10 +394,18 @@ dec_attn_stream_kernel(const AttnArgs a) {
         vbase = a.vc + (long long)(utt * HEADS + head) * nr * DH;
     }
     pdl_wait();
+    // everything the body needs from the beam state is requested in ONE round trip (both parities of conv_len: which one
+    // applies depends on *step)
     const int nh = a.n_run[utt];
     const int step = *a.step_p;
+    int conv0 = 0, conv1 = 0;
+    if (MODE == 0 && a.conv_len != nullptr) {
+        conv0 = a.conv_len[utt];
+        conv1 = a.conv_len[a.R / a.beam + utt];
+    }
     if (nh == 0) { cp_async_wait_all(); return; }
-#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step)
+    const int conv = ((step + 1) & 1) ? conv1 : conv0;
+#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step, conv)
     if (NH <= 4) {
         switch (nh) {
             case 1: AVSR_BODY(1); break;

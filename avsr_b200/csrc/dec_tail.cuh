@@ -35,16 +35,19 @@ __device__ __forceinline__ void lsm_topk_row(float (&v)[ITER], LsmSmem& sm, cons
     float acc[ITER];
 #pragma unroll
     for (int k = 0; k < ITER; ++k) acc[k] = 0.f;
-    for (int z = 0; z < nsplit; ++z) {
+    for (int z = 0; z < nsplit; z += 2) {             // two splits per pass: 2 * ITER independent loads in flight
         const float* pz = part + ((long long)z * R + row) * V;
-        float t[ITER];
+        const float* pz1 = pz + (long long)R * V;
+        const bool two = z + 1 < nsplit;
+        float t[ITER], u[ITER];
 #pragma unroll
         for (int k = 0; k < ITER; ++k) {
             const int c = tid + k * LSM_THREADS;
             t[k] = (c < V) ? pz[c] : 0.f;
+            u[k] = (c < V && two) ? pz1[c] : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < ITER; ++k) acc[k] += t[k];
+        for (int k = 0; k < ITER; ++k) { acc[k] += t[k]; if (two) acc[k] += u[k]; }
     }
     float mx = -INFINITY;
 #pragma unroll

@@ -336,7 +336,9 @@ static int x3_launch(const void* A3, long long lda, const void* W3, long long ld
     SplitKEpi none = {};
     // (a single stage for the projections whose CTAs have one k block each - 86 KB, so that three attention CTAs fit beside
     // one on an SM - measured slower: 339 vs 330 ms per pass; two CTAs of the projection itself then share SMs)
-    const int nstages = STAGES;
+    static int one_stage = -1;                        // dev knob AVSR_X3_ONE_STAGE=1
+    if (one_stage < 0) { const char* e = getenv("AVSR_X3_ONE_STAGE"); one_stage = (e && atoi(e) == 1) ? 1 : 0; }
+    const int nstages = (one_stage && items <= sm_count() && cdiv(K / BK, splits) <= 1) ? 1 : STAGES;
     AVSR_CHECK_CUDA(avsr_launch_pdl(gemm_x3_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes(nb, fuse || pro_on, nstages), stream, tw, ta, R, N, K, nb, part, splits,
                                     tiles_m, tiles_n, fuse, epi, gbar, pro_on, pro_on ? *pro : none, ready, rq, nstages));
     return AVSR_OK;
