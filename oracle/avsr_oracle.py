@@ -369,7 +369,8 @@ def beam_search(sd: SD, x: torch.Tensor, beam_size: int = 3, ctc_weight: float =
     S = int(pre_beam_ratio * beam_size)                                     # beam_search.py:91
     maxlen = T if maxlenratio == 0 else (-int(maxlenratio) if maxlenratio < 0 else max(1, int(maxlenratio * T)))
     logp_ctc = ctc_log_softmax(sd, x.unsqueeze(0))[0]                       # scorers/ctc.py:96
-    kvdec = KVDecoder(sd, x) if kv_cache else None
+    ctc_only = ctc_weight == 1.0       # decoder dropped (weight 0, beam_search.py:72-75), no pre-beam (avhubert_avsr_model.py:35)
+    kvdec = KVDecoder(sd, x) if (kv_cache and not ctc_only) else None
 
     # running hyps (all the same length)
     yseqs = [[sos]]
@@ -385,12 +386,17 @@ def beam_search(sd: SD, x: torch.Tensor, beam_size: int = 3, ctc_weight: float =
     for i in range(n_steps):
         n = len(yseqs)
         ys = torch.tensor(yseqs, dtype=torch.int64)
-        if kv_cache:
-            dec, new_state = kvdec.step(ys[:, -1], i, dec_state)
+        if ctc_only:
+            dec, new_state = torch.zeros(n, Vv), None
+            weighted = torch.zeros(n, Vv)
+            part = None                                                     # batch_beam_search.py:219: no pre-beam
         else:
-            dec, new_state = decoder_batch_score(sd, ys, dec_state, x.unsqueeze(0).expand(n, T, Dm))
-        weighted = torch.zeros(n, Vv) + w_dec * dec                         # batch_beam_search.py:222-227
-        part = torch.topk(dec, S, dim=-1)[1]                                # :235
+            if kv_cache:
+                dec, new_state = kvdec.step(ys[:, -1], i, dec_state)
+            else:
+                dec, new_state = decoder_batch_score(sd, ys, dec_state, x.unsqueeze(0).expand(n, T, Dm))
+            weighted = torch.zeros(n, Vv) + w_dec * dec                     # batch_beam_search.py:222-227
+            part = torch.topk(dec, S, dim=-1)[1]                            # :235
         ctc, log_psi, rn, rb = ctc_prefix_scores(logp_ctc, rn_prev, rb_prev, s_prev,
                                                  [y[-1] for y in yseqs], len(yseqs[0]) - 1, part, blank, eos)
         weighted = weighted + w_ctc * ctc                                   # :240-241
@@ -401,7 +407,7 @@ def beam_search(sd: SD, x: torch.Tensor, beam_size: int = 3, ctc_weight: float =
         prev = torch.div(top, Vv, rounding_mode="trunc")
         tok = top % Vv
         if trace is not None:
-            trace.append(dict(dec=dec.clone(), part=part.clone(), ctc=ctc.clone(), weighted=weighted.clone(),
+            trace.append(dict(dec=dec.clone(), part=None if part is None else part.clone(), ctc=ctc.clone(), weighted=weighted.clone(),
                               prev=prev.clone(), tok=tok.clone()))
         n_yseqs, n_score, n_dsc, n_csc, keep_prev, keep_tok = [], [], [], [], [], []
         for pj, tj in zip(prev.tolist(), tok.tolist()):
@@ -429,13 +435,18 @@ def beam_search(sd: SD, x: torch.Tensor, beam_size: int = 3, ctc_weight: float =
         dsc = torch.stack([n_dsc[j] for j in run])
         csc = torch.stack([n_csc[j] for j in run])
         pidx = torch.tensor([keep_prev[j] for j in run])
-        if kv_cache:
+        if ctc_only:
+            dec_state = None
+        elif kv_cache:
             dec_state = [(k[pidx], v[pidx]) for k, v in new_state]
         else:
             dec_state = [c[pidx] for c in new_state]
         cols = []
         for j in run:
             pj, tj = keep_prev[j], keep_tok[j]
+            if ctc_only:
+                cols.append(tj)                                             # full vocabulary: the state column is the token
+                continue
             hit = (part[pj] == tj).nonzero()
             cols.append(int(hit[-1]) if hit.numel() else S - 1)              # idmap -1 -> last column (eos quirk)
         cols_t = torch.tensor(cols)

@@ -119,3 +119,21 @@ def test_end_detect():
     assert not O.end_detect(ended, 7)        # length 5 is the best itself (diff 0)
     assert not O.end_detect(ended[:3], 8)    # length 8 missing
     assert not O.end_detect([], 3)
+
+
+def test_ctc_only_beam_search_matches_reference(state_dict, golden):
+    """ctc_weight = 1.0 (decoder scorer dropped, full-vocabulary CTC prefix scoring every step): oracle vs the n-best of the
+    unmodified reference (tests/golden/ctc_only.npz, oracle/gen_golden_ctc_only.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import avsr_oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctc_only.npz"))
+    for T, beam in ((12, 3), (12, 5), (30, 3)):
+        x = torch.from_numpy(golden[f"enc_T{T}"])
+        hyps = O.beam_search(state_dict, x, beam, ctc_weight=1.0)
+        ys, sc, ln = g[f"nbest_T{T}_b{beam}_yseq"], g[f"nbest_T{T}_b{beam}_score"], g[f"nbest_T{T}_b{beam}_len"]
+        assert len(hyps) == len(sc)
+        for k, h in enumerate(hyps):
+            assert h.yseq == ys[k, :ln[k]].tolist(), (T, beam, k)
+            assert abs(h.score - sc[k]) < 1e-3 * ln[k]
