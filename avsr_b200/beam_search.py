@@ -63,16 +63,20 @@ class BatchedBeamSearch:
             raise RuntimeError("avsr_b200 beam search needs a CUDA device (no CPU fallback)")
         if not (1 <= beam_size <= 8):
             raise RuntimeError("beam_size must be in [1, 8]")
-        if ctc_weight in (0.0, 1.0):
-            raise RuntimeError("ctc_weight 0.0 / 1.0 (single-scorer search) is not wired yet; use 0 < ctc_weight < 1")
+        if ctc_weight == 0.0:
+            raise RuntimeError("ctc_weight 0.0 (attention-only search) is not wired; use 0 < ctc_weight <= 1")
+        # ctc_weight == 1.0: the reference drops the decoder scorer (weight 0, beam_search.py:72-75) and the pre-beam
+        # (avhubert_avsr_model.py:35): every step scores the FULL vocabulary with CTCPrefixScoreTH (ctc_prefix_score.py:115-119)
+        self.ctc_only = ctc_weight == 1.0
         if token_list is not None and len(token_list) != weights.V:
             raise RuntimeError(f"token_list has {len(token_list)} entries, model vocabulary is {weights.V}")
         self.beam_size = beam_size
-        self.pre_beam_size = int(pre_beam_ratio * beam_size)        # beam_search.py:91
+        self.pre_beam_size = 1 if self.ctc_only else int(pre_beam_ratio * beam_size)        # beam_search.py:91 (ctc-only: chains of the survivors only)
         self.n_vocab = weights.V
         self.sos, self.eos = weights.sos, weights.eos
         self.token_list = token_list
         self.weights = {"decoder": 1.0 - ctc_weight, "ctc": ctc_weight, "lm": 0.0, "length_bonus": 0.0}
+        self.scorers = ("ctc",) if self.ctc_only else ("decoder", "ctc")
         self.w_dec = float(np.float32(1.0 - ctc_weight))
         self.w_ctc = float(np.float32(ctc_weight))
         self.use_graph = use_graph
@@ -139,6 +143,15 @@ class BatchedBeamSearch:
         s["ffn"] = f32(R, 3072)
         s["dec_logp"] = f32(R, V)
         s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
+        if self.ctc_only:
+            lib0 = L.load()
+            s["ctc_full"] = f32(R, V)
+            s["rc_last"], s["rc_chain"], s["rc_tok"] = i32(R), i32(R), i32(R)
+            s["iota"] = torch.arange(R, dtype=torch.int32, device=dev)
+            ncg, ts = C.c_int(0), C.c_int(0)
+            L.check(lib0.avsr_ctc_prefix_full_plan(B, V, C.byref(ncg), C.byref(ts)), "avsr_ctc_prefix_full_plan")
+            s["fpart"] = torch.empty(B, ts.value, beam, V, dtype=torch.float32, device=dev)
+            s["ftick"] = i32(B, ncg.value)
         # self-attention caches, one contiguous span per (utterance, head): keys transposed in 32-byte groups
         # [layer][utt][head][8][pos*beam+slot][8], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
         s["kc"] = torch.empty(nl, B, 16, 8, lmax * beam, 8, dtype=torch.float32, device=dev)
@@ -322,8 +335,33 @@ class BatchedBeamSearch:
         L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
                 "avsr_beam_step_advance")
 
+    def _step_ctc_only(self, s):
+        """One position of the single-scorer search (ctc_weight = 1.0): full-vocabulary CTC prefix scores of every live hyp
+        (the HBM-bound kernel), fusion / top-k / bookkeeping over all n_h * V entries, then the forward variables of the
+        survivors recomputed on their chosen token (CTCPrefixScorer.select_state, scorers/ctc.py:40-63, without ever
+        materialising r[T, 2, n_h, V])."""
+        lib = L.load()
+        w = self.w
+        R, beam, V = s["R"], self.beam_size, self.n_vocab
+        st = L.stream
+        L.check(lib.avsr_ctc_prefix_full(L.ptr(s["logp"]), V, s["ldp"], w.blank, self.eos, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]),
+                                         L.ptr(s["n_run"]), beam, s["B"], 1, L.ptr(s["last_tok"]), L.ptr(s["iota"]), L.ptr(s["r_buf"]),
+                                         s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["ctc_full"]), L.ptr(s["fpart"]),
+                                         L.ptr(s["ftick"]), st()), "avsr_ctc_prefix_full")
+        L.check(lib.avsr_beam_fuse_topk_advance_full(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["ctc_full"]), C.c_float(0.0),
+                                                     C.c_float(1.0), L.ptr(s["rc_last"]), L.ptr(s["rc_chain"]), L.ptr(s["rc_tok"]), st()),
+                "avsr_beam_fuse_topk_advance_full")
+        L.check(lib.avsr_ctc_prefix_prebeam(L.ptr(s["logp"]), V, s["ldp"], w.blank, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), L.ptr(s["n_run"]),
+                                            beam, R, 1, L.ptr(s["rc_last"]), L.ptr(s["rc_tok"]), L.ptr(s["rc_chain"]), L.ptr(s["r_buf"]),
+                                            s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["rsum_last"]), st()),
+                "avsr_ctc_prefix_prebeam(recompute)")
+        L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
+                "avsr_beam_step_advance")
+
     def _step(self, s):
         """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
+        if self.ctc_only:
+            return self._step_ctc_only(s)
         if self.precision == "bf16x3" and self.chain and not self.fuse_epilogue and not self._skip - {"advance", "tail"}:
             return self._step_chain(s)
         lib = L.load()
@@ -393,6 +431,9 @@ class BatchedBeamSearch:
         s["utt_off"].copy_(torch.from_numpy(offs))
         for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev", "conv_len"):
             s[k].zero_()
+        if self.ctc_only:
+            s["psi"].zero_()                          # log_psi of the empty prefix
+            s["dec_logp"].zero_()                     # the dropped decoder scorer contributes 0 * 0
         s["n_run"].fill_(1)
         s["row_active"].zero_()
         s["row_active"].view(B, beam)[:, 0] = 1
@@ -535,8 +576,8 @@ class BatchedBeamSearch:
             yseq = [self.sos] + toks[k, :last[k] + 1].tolist()
             if int(e_len[b, e]) == len(yseq) + 1:        # eos appended at the last position (batch_beam_search.py:321-337)
                 yseq.append(self.eos)
-            out[b].append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e],
-                                     scores={"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}, states={}))
+            scores = {"ctc": e_ctc[b, e]} if self.ctc_only else {"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}
+            out[b].append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e], scores=scores, states={}))
         for b in range(B):
             out[b].sort(key=lambda h: float(h.score), reverse=True)     # stable, like sorted() in beam_search.py:378
         return out

@@ -482,7 +482,9 @@ constexpr int FAST_MAXS = 12;             // pre-beam candidates per hyp handled
 
 __global__ void __launch_bounds__(256)
 beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ dec_logp, const int* __restrict__ part_ids,
-                              const float* __restrict__ psi, const float* __restrict__ rsum_last, float w_dec, float w_ctc) {
+                              const float* __restrict__ psi, const float* __restrict__ rsum_last, float w_dec, float w_ctc,
+                              const float* __restrict__ ctc_full, int* __restrict__ rc_last, int* __restrict__ rc_chain,
+                              int* __restrict__ rc_tok) {
     __shared__ float cval[256 * MAXB];
     __shared__ int cidx[256 * MAXB];
     __shared__ float redv[8];
@@ -510,7 +512,7 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     __shared__ int s_fast;
     if (tid == 0) s_fast = 0;
     __syncthreads();
-    if (S <= FAST_MAXS && warp == 0) {
+    if (ctc_full == nullptr && S <= FAST_MAXS && warp == 0) {
         const int ncand = nrun * (S + 1);
         float bound = -INFINITY;                     // upper bound of every entry that is NOT a candidate (dec_logp <= 0)
         for (int h = 0; h < nrun; ++h)
@@ -567,13 +569,18 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     for (int i = tid; i < total; i += 256) {
         const int h = i / V, v = i - h * V;
         const int row = base + h;
-        float lpsi = LOGZERO;
-        if (v == st.eos) lpsi = rsum_last[row];
-        else if (v != st.blank) {
-            for (int s = 0; s < S; ++s)
-                if (part_ids[row * S + s] == v) lpsi = psi[row * S + s];
+        float cs;
+        if (ctc_full != nullptr) {
+            cs = ctc_full[(long long)row * V + v];               // full-vocabulary CTC scores (log_psi - s_prev) of this hyp
+        } else {
+            float lpsi = LOGZERO;
+            if (v == st.eos) lpsi = rsum_last[row];
+            else if (v != st.blank) {
+                for (int s = 0; s < S; ++s)
+                    if (part_ids[row * S + s] == v) lpsi = psi[row * S + s];
+            }
+            cs = __fsub_rn(lpsi, st.s_prev[row]);
         }
-        const float cs = __fsub_rn(lpsi, st.s_prev[row]);
         const float w = __fadd_rn(__fadd_rn(__fmul_rn(w_dec, dec_logp[(long long)row * V + v]), __fmul_rn(w_ctc, cs)), st.score[row]);
         if (w > lv[beam - 1]) {                       // strict: on ties the lower flat index (seen first) stays
             int k = beam - 1;
@@ -618,7 +625,11 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
         const int T = st.utt_T[b];
         const bool is_last = (step == T - 1);
         float o_dec[MAXB], o_ctc[MAXB], o_sp[MAXB];
-        for (int h = 0; h < nrun; ++h) { o_dec[h] = st.dec_sc[base + h]; o_ctc[h] = st.ctc_sc[base + h]; o_sp[h] = st.s_prev[base + h]; }
+        int o_last[MAXB], o_chain[MAXB];
+        for (int h = 0; h < nrun; ++h) {
+            o_dec[h] = st.dec_sc[base + h]; o_ctc[h] = st.ctc_sc[base + h]; o_sp[h] = st.s_prev[base + h];
+            o_last[h] = st.last_tok[base + h]; o_chain[h] = st.rprev_idx[base + h];
+        }
         int n_tok[MAXB], n_ridx[MAXB];
         float n_score[MAXB], n_dec[MAXB], n_ctc[MAXB], n_sp[MAXB];
         int cnt = 0;
@@ -627,9 +638,13 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
             const int idx = seli[j];
             const int h = idx / V, v = idx - h * V;
             const int row = base + h;
-            int col;
-            const float lpsi = ctc_logpsi(st, part_ids, psi, rsum_last, row, v, &col);
-            const float cs = __fsub_rn(lpsi, o_sp[h]);
+            int col = 0;
+            float lpsi = 0.f, cs;
+            if (ctc_full != nullptr) cs = ctc_full[(long long)row * V + v];
+            else {
+                lpsi = ctc_logpsi(st, part_ids, psi, rsum_last, row, v, &col);
+                cs = __fsub_rn(lpsi, o_sp[h]);
+            }
             const float nd = __fadd_rn(o_dec[h], dec_logp[(long long)row * V + v]);
             const float nc = __fadd_rn(o_ctc[h], cs);
             st.hist_tok[hb + j] = v;
@@ -650,6 +665,14 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
             } else {
                 n_tok[cnt] = v; n_score[cnt] = selv[j]; n_dec[cnt] = nd; n_ctc[cnt] = nc; n_sp[cnt] = lpsi;
                 n_ridx[cnt] = row * S + col;
+                if (ctc_full != nullptr) {
+                    // full-vocabulary mode: the survivor's forward variables are recomputed by the pre-beam kernel on the
+                    // chosen token (S = 1) from its parent's chain; the new chain then sits at the row's own index
+                    rc_last[base + cnt] = o_last[h];
+                    rc_chain[base + cnt] = o_chain[h];
+                    rc_tok[base + cnt] = v;
+                    n_ridx[cnt] = base + cnt;
+                }
                 s_parent[cnt] = h;
                 st.run2j[hb + cnt] = j;
                 ++cnt;
@@ -657,7 +680,8 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
         }
         for (int r = 0; r < cnt; ++r) {
             st.last_tok[base + r] = n_tok[r]; st.score[base + r] = n_score[r]; st.dec_sc[base + r] = n_dec[r];
-            st.ctc_sc[base + r] = n_ctc[r]; st.s_prev[base + r] = n_sp[r]; st.rprev_idx[base + r] = n_ridx[r];
+            st.ctc_sc[base + r] = n_ctc[r]; st.rprev_idx[base + r] = n_ridx[r];
+            if (ctc_full == nullptr) st.s_prev[base + r] = n_sp[r];      // full mode: s_prev = log_psi from the recompute kernel
         }
         // end detection (e2e_asr_common.py:18-48): M = 3 consecutive lengths, each > |D_end| below the best
         bool fin = false;
@@ -814,7 +838,23 @@ extern "C" int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float*
     AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0, "avsr_beam_fuse_topk_advance: beam %d unsupported (max %d)", st->beam, MAXB);
     AVSR_REQUIRE(st->beam <= 255, "avsr_beam_fuse_topk_advance: ancestry slots are 8-bit");
     AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, part_ids, psi, rsum_last,
-                                    w_dec, w_ctc));
+                                    w_dec, w_ctc, (const float*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr));
+    return AVSR_OK;
+}
+
+// Full-vocabulary form (single-scorer search, ctc_weight = 1.0: src/avhubert_avsr/avhubert_avsr_model.py:35 drops the decoder
+// and the pre-beam): fused score = w_dec * dec_logp + w_ctc * ctc_full + previous score over all n_h * V entries, with
+// ctc_full [R][V] from avsr_ctc_prefix_full (dec_logp may be a zero matrix with w_dec = 0).  For every new running hyp the
+// kernel leaves what avsr_ctc_prefix_prebeam (S = 1) needs to recompute its forward variables: rc_last [R] = the parent's
+// last token, rc_chain [R] = the parent's chain index, rc_tok [R] = the chosen token; st->s_prev is not touched (the
+// recompute's psi output is the new log_psi) and st->rprev_idx[row] = row.  The state must have S = 1.
+extern "C" int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const float* dec_logp, const float* ctc_full, float w_dec,
+                                                float w_ctc, int* rc_last, int* rc_chain, int* rc_tok, cudaStream_t stream) {
+    AVSR_REQUIRE(st && dec_logp && ctc_full && rc_last && rc_chain && rc_tok, "avsr_beam_fuse_topk_advance_full: null argument");
+    AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0 && st->S == 1, "avsr_beam_fuse_topk_advance_full: beam %d / S %d unsupported",
+                 st->beam, st->S);
+    AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, (const int*)nullptr,
+                                    (const float*)nullptr, (const float*)nullptr, w_dec, w_ctc, ctc_full, rc_last, rc_chain, rc_tok));
     return AVSR_OK;
 }
 

@@ -220,6 +220,11 @@ int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, 
  * (src/nets/batch_beam_search.py:86-110,222-349; src/nets/e2e_asr_common.py:18-48). */
 int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,
                                 const float* rsum_last, float w_dec, float w_ctc, avsr_stream_t stream);
+/* Full-vocabulary form for the single-scorer search (ctc_weight = 1.0, avhubert_avsr_model.py:35): ctc_full [R][V] from
+ * avsr_ctc_prefix_full replaces the pre-beam candidates; rc_last / rc_chain / rc_tok [R] receive, per new running hyp, the
+ * inputs of the avsr_ctc_prefix_prebeam (S = 1) call that recomputes its forward variables.  The state must have S = 1. */
+int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const float* dec_logp, const float* ctc_full, float w_dec, float w_ctc,
+                                     int* rc_last, int* rc_chain, int* rc_tok, avsr_stream_t stream);
 int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, avsr_stream_t stream);
 
 #ifdef __cplusplus

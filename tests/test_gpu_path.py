@@ -321,3 +321,27 @@ def test_full_size_batch_properties(gpu_model):
         one = gpu_model.beam_search.decode_batch(x[i * T:(i + 1) * T].contiguous(), [T])[0]
         assert [h.yseq.tolist() for h in one] == [h.yseq.tolist() for h in full[i]]
         assert [float(h.score) for h in one] == [float(h.score) for h in full[i]]          # bit-identical
+
+
+@pytest.mark.parametrize("T,beam,graph", [(12, 3, False), (12, 5, True), (30, 3, True)])
+def test_ctc_only_beam_search_vs_reference_golden(gpu_model, golden, T, beam, graph):
+    """ctc_weight = 1.0: the decoder scorer is dropped and every position scores the full vocabulary with the
+    HBM-bound CTC kernel; n-best token-identical to the unmodified reference (tests/golden/ctc_only.npz)."""
+    import os
+    from avsr_b200.beam_search import BatchedBeamSearch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctc_only.npz"))
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam, ctc_weight=1.0, use_graph=graph)
+    x = torch.from_numpy(golden[f"enc_T{T}"]).cuda()
+    nbest = bs(x)
+    ys, sc, ln = g[f"nbest_T{T}_b{beam}_yseq"], g[f"nbest_T{T}_b{beam}_score"], g[f"nbest_T{T}_b{beam}_len"]
+    assert len(nbest) == len(sc)
+    for k, h in enumerate(nbest):
+        assert h.yseq.tolist() == ys[k, :ln[k]].tolist(), (T, beam, k)
+        assert abs(float(h.score) - sc[k]) < 1e-3 * ln[k]
+        assert set(h.scores) == {"ctc"} and abs(float(h.scores["ctc"]) - g[f"nbest_T{T}_b{beam}_ctc"][k]) < 1e-2 * ln[k]
+    # batched: two utterances of different lengths evolve as their own runs
+    x12, x30 = torch.from_numpy(golden["enc_T12"]).cuda(), torch.from_numpy(golden["enc_T30"]).cuda()
+    if T == 12 and beam == 3:
+        out = bs.decode_batch(torch.cat([x30, x12], 0), [30, 12])
+        assert [h.yseq.tolist() for h in out[1]] == [h.yseq.tolist() for h in nbest]
+        assert out[0][0].yseq.tolist() == g["nbest_T30_b3_yseq"][0, :g["nbest_T30_b3_len"][0]].tolist()
