@@ -27,6 +27,7 @@ T_FRAMES = 375          # 15 s at 25 fps
 BATCH = 32
 BEAM = 3
 FPS = 25.0
+CTC_WEIGHT = 0.1
 METRIC = "audio-sec decoded/sec (RTFx)"
 UNIT = "audio-s/s"
 
@@ -138,10 +139,10 @@ def run_reference(args):
 
 
 def _config(n_gpus):
-    tag = "configs[1]" if (BATCH, T_FRAMES, BEAM) == (32, 375, 3) else "non-default shape"
+    tag = "configs[1]" if (BATCH, T_FRAMES, BEAM) == (32, 375, 3) and CTC_WEIGHT == 0.1 else f"non-default shape (ctc_weight {CTC_WEIGHT})"
     return {"workload": f"{tag}: {BATCH} synthetic {T_FRAMES / FPS:g} s utterances per GPU (T={T_FRAMES} frames 88x88 gray + 104-dim stacked fbank), "
                         f"AV-HuBERT-large encoder (bf16 tensor-core GEMMs, fp32 residual stream) + joint CTC/attention beam search "
-                        f"(beam {BEAM}, ctc_weight 0.1, fp32), random-init weights: every utterance decodes all {T_FRAMES} positions",
+                        f"(beam {BEAM}, ctc_weight {CTC_WEIGHT}, fp32), random-init weights: every utterance decodes all {T_FRAMES} positions",
             "utterances_per_gpu": BATCH, "frames": T_FRAMES, "beam": BEAM, "parallelism": f"utterance-sharded x{n_gpus}",
             "l2_policy": "inputs (372 MB video / step) larger than the 126 MB L2"}
 
@@ -300,7 +301,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = _peaks()
     sd = synth.make_state_dict(0)
-    model = AVSRCocktailB200(sd, device=dev, beam_size=BEAM)
+    model = AVSRCocktailB200(sd, device=dev, beam_size=BEAM, ctc_weight=args.ctc_weight)
     # rank r decodes utterances with seeds 1234 + 32 r ... (cfg 2 recipe)
     vids, auds = [], []
     for i in range(BATCH):
@@ -400,7 +401,7 @@ def run_b200(args):
 
 
 def main():
-    global BEAM, T_FRAMES, BATCH
+    global BEAM, T_FRAMES, BATCH, CTC_WEIGHT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -410,11 +411,12 @@ def main():
     ap.add_argument("--beam", type=int, default=BEAM, help="dev: beam size (default = configs[1]: 3; configs[3] uses 5)")
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="dev: frames per utterance (default 375 = 15 s; configs[3]: 250)")
     ap.add_argument("--batch", type=int, default=BATCH, help="dev: utterances per GPU (default 32)")
+    ap.add_argument("--ctc-weight", type=float, default=0.1, help="dev: 1.0 = CTC-only search (full-vocabulary scoring every position)")
     ap.add_argument("--rooflines-only", action="store_true", help="dev aid: only the isolated kernel timings (not a bench line)")
     ap.add_argument("--profile-decode-steps", type=int, default=0,
                     help="profiling aid: run ONE pass with the decode truncated to this many positions and exit (not a bench value)")
     args = ap.parse_args()
-    BEAM, T_FRAMES, BATCH = args.beam, args.frames, args.batch
+    BEAM, T_FRAMES, BATCH, CTC_WEIGHT = args.beam, args.frames, args.batch, args.ctc_weight
     if args.impl == "reference":
         run_reference(args)
     else:
