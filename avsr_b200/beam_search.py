@@ -125,8 +125,9 @@ class BatchedBeamSearch:
         s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
         s["utt_T"], s["utt_off"] = i32(B), i32(B)
         s["step"], s["any_running"] = i32(1), i32(1)
-        s["poll"] = torch.zeros(1, dtype=torch.int32).pin_memory()      # host copy of any_running (async poll)
-        s["poll_event"] = torch.cuda.Event()
+        # host copies of any_running (asynchronous poll, double-buffered: a flag is read one replay late)
+        s["poll"] = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+        s["poll_event"] = [torch.cuda.Event(), torch.cuda.Event()]
         s["n_run"], s["row_active"], s["last_tok"], s["rprev_idx"] = i32(B), i32(R), i32(R), i32(R)
         for k in ("score", "dec_sc", "ctc_sc", "s_prev", "rsum_last"):
             s[k] = f32(R)
@@ -507,11 +508,16 @@ class BatchedBeamSearch:
             sess.append(s)
             nsteps.append(n)
             done.append(1)
-        # ---- position loop: one graph replay per group and round, then one poll per group
+        # ---- position loop: one graph replay per group and round.  The "any utterance still running" flag of a replay is
+        #      read one round LATE, after the next replay has been queued: the GPU never waits for the host between replays
+        #      (a 16-position graph has ~1200 nodes; queueing it takes the host a few hundred microseconds).  If the flag
+        #      says everything had already ended, the replay queued meanwhile only ran no-op kernels.
         active = [n > 1 for n in nsteps]
+        had_prev = [False] * G
+        rnd = 0
         while any(active):
             for g in range(G):
-                if not active[g]:
+                if not active[g] or done[g] >= nsteps[g]:
                     continue
                 s = sess[g]
                 n = min(chunk, nsteps[g] - done[g])
@@ -526,14 +532,21 @@ class BatchedBeamSearch:
                     else:
                         for _ in range(n):
                             self._step(s)
-                    s["poll"].copy_(s["any_running"], non_blocking=True)
-                    s["poll_event"].record(streams[g])
+                    s["poll"][rnd & 1].copy_(s["any_running"], non_blocking=True)
+                    s["poll_event"][rnd & 1].record(streams[g])
                 done[g] += n
             for g in range(G):
-                if active[g]:
-                    sess[g]["poll_event"].synchronize()
-                    if done[g] >= nsteps[g] or int(sess[g]["poll"][0]) == 0:
+                if not active[g]:
+                    continue
+                if had_prev[g]:
+                    sess[g]["poll_event"][(rnd - 1) & 1].synchronize()
+                    if int(sess[g]["poll"][(rnd - 1) & 1][0]) == 0:
                         active[g] = False
+                        continue
+                had_prev[g] = True
+                if done[g] >= nsteps[g]:
+                    active[g] = False                 # everything is queued; _collect synchronises
+            rnd += 1
         out = []
         for g, (xg, lg) in enumerate(parts):
             with torch.cuda.stream(streams[g]):
