@@ -345,3 +345,35 @@ def test_ctc_only_beam_search_vs_reference_golden(gpu_model, golden, T, beam, gr
         out = bs.decode_batch(torch.cat([x30, x12], 0), [30, 12])
         assert [h.yseq.tolist() for h in out[1]] == [h.yseq.tolist() for h in nbest]
         assert out[0][0].yseq.tolist() == g["nbest_T30_b3_yseq"][0, :g["nbest_T30_b3_len"][0]].tolist()
+
+
+@pytest.mark.parametrize("T,beam", [(1, 3), (2, 3), (5, 1), (9, 8), (3, 5)])
+def test_edge_shapes_match_the_oracle(state_dict, gpu_model, T, beam):
+    """Shortest utterances and the extreme beam sizes (1 and 8) against the CPU oracle, from the oracle's fp32 encoder output."""
+    from avsr_b200.beam_search import BatchedBeamSearch
+    from oracle import avsr_oracle as O
+    video, audio = synth.make_inputs(700 + T, T)
+    x = O.encoder_forward(state_dict, audio, video)[0]
+    ref = O.beam_search(state_dict, x, beam, kv_cache=True)
+    bs = BatchedBeamSearch(gpu_model.decoder_weights, beam_size=beam)
+    nbest = bs(x.cuda())
+    assert len(nbest) == len(ref) >= 1
+    for a, b in zip(nbest, ref):
+        if b.score > -1e8:
+            assert a.yseq.tolist() == b.yseq, (T, beam)
+            assert abs(float(a.score) - b.score) < 1e-3 * len(b.yseq)
+
+
+def test_long_utterances_batch_equals_single(gpu_model):
+    """30 s utterances (T = 750, BASELINE.json configs[4] upper end) next to a very short one: batch == single runs, complete
+    hypotheses."""
+    lengths = [750, 3, 401]
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.nn.functional.layer_norm(torch.randn(t, 1024, generator=g), (1024,)).cuda() for t in lengths]
+    bs = gpu_model.beam_search
+    out = bs.decode_batch(torch.cat(xs, 0).contiguous(), lengths)
+    for x, t, hyps in zip(xs, lengths, out):
+        single = bs.decode_batch(x.contiguous(), [t])[0]
+        assert [h.yseq.tolist() for h in hyps] == [h.yseq.tolist() for h in single]
+        assert [float(h.score) for h in hyps] == [float(h.score) for h in single]
+        assert all(len(h.yseq) == t + 2 for h in hyps)
