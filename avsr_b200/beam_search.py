@@ -378,7 +378,6 @@ class BatchedBeamSearch:
                                       L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]),
                                       None if tc else L.ptr(s["a"]), L.ptr(s["a3"]) if tc else None, st()), "avsr_dec_embed_ln")
         nl = w.n_layers
-        kvld = nl * 2 * 1024
         att_f32 = None if tc else L.ptr(s["att"])
         att_split = L.ptr(s["att3"]) if tc else None
         for li, lay in enumerate(w.layers):

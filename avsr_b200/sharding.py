@@ -82,7 +82,7 @@ def gather_hypotheses(utt_ids: Sequence[int], token_seqs: Sequence[Sequence[int]
     Three fixed-shape ``all_gather`` calls (counts, then a padded int32 matrix with a length and an id column); a few KB."""
     if len(utt_ids) != len(token_seqs):
         raise ValueError("utt_ids and token_seqs differ in length")
-    rank, world = _world(group)
+    _, world = _world(group)
     if world == 1:
         return {int(u): [int(t) for t in s] for u, s in zip(utt_ids, token_seqs)}
     dev = torch.device(device)
@@ -140,7 +140,7 @@ def word_edit_distance(ref: Sequence[str], hyp: Sequence[str]) -> int:
 
 def reduce_wer(edits: int, ref_words: int, device="cpu", group=None) -> Tuple[float, int, int]:
     """Corpus WER over all ranks: all_reduce(SUM) of [edit distance, reference words] (int64)."""
-    rank, world = _world(group)
+    _, world = _world(group)
     t = torch.tensor([int(edits), int(ref_words)], dtype=torch.int64, device=torch.device(device))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
