@@ -23,8 +23,8 @@ import torch.distributed as dist
 ENC_FLOPS_PER_FRAME = 1_268_871_168
 ENC_ATTN_FLOPS_PER_FRAME2 = 98_304
 # one decode position of one utterance costs about as much wall time as this many encoder FLOPs (measured on B200 at
-# B=32, beam 3: ~1.2 ms per position for 32 utterances vs ~65 ms for 32 x 489.65 GFLOP of encoder)
-DEC_FLOPS_EQUIV_PER_POSITION = 9.0e9
+# B=32, beam 3: ~0.79 ms per position for 32 utterances vs ~38 ms for 32 x 489.65 GFLOP of encoder)
+DEC_FLOPS_EQUIV_PER_POSITION = 1.0e10
 
 
 def utterance_cost(T: int, decode_positions: Optional[int] = None) -> float:
