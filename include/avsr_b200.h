@@ -227,6 +227,23 @@ int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const float* dec_l
                                      int* rc_last, int* rc_chain, int* rc_tok, avsr_stream_t stream);
 int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, avsr_stream_t stream);
 
+/* ---- input pipeline: the data format on the input side of the path (src/dataset/avhubert_dataset.py) -------------- */
+/* FBanksAndStack.forward (:86-116) over a batch, with cut_or_pad (:22-33) and collate_pad + permute (:277-312, :347) folded
+ * in.  wave = fp32 samples of all utterances back to back; utterance b starts at wave_off[b], has wave_len[b] samples and
+ * is cut or zero-padded to n_samples[b] (= 640 * video frames in DataCollator.__call__, :335) before
+ * python_speech_features.logfbank (25 ms / 10 ms frames, 512-point FFT, 26 mel filters, pre-emphasis 0.97), zero rows up
+ * to a multiple of 4 frames, 4-frame stacking and F.layer_norm over the 104 features.  out = [B][104][Tmax] fp32, zero for
+ * rows >= avsr_fbank_rows(n_samples[b]); Tmax must be >= every utterance's row count. */
+int avsr_fbank_stack_ln(const float* wave, const long long* wave_off, const int* wave_len, const int* n_samples, int B, int Tmax,
+                        float* out, avsr_stream_t stream);
+/* Host helpers (no GPU work): rows FBanksAndStack yields for n samples; the 28 FFT-bin edges of the mel filters. */
+int avsr_fbank_rows(int n_samples);
+int avsr_fbank_bins(int* bins28);
+/* VideoTransform("test") (:225-246): uint8 grey frames [sum(T)][H][W] (utterance b = frames frame_off[b] .. + utt_T[b]) ->
+ * x / 255, CenterCrop(88), Normalize(0.421, 0.165) -> out [B][1][Tmax][88][88] fp32, zero frames behind each utterance. */
+int avsr_video_u8_transform(const unsigned char* frames, const long long* frame_off, const int* utt_T, int B, int Tmax, int H, int W,
+                            float* out, avsr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

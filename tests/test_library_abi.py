@@ -65,3 +65,26 @@ def test_weight_repack_on_cpu_tensors(state_dict):
     y1 = O._bn({k: v.double() if v.is_floating_point() else v for k, v in state_dict.items() if k.startswith(p)}, p + "bn1",
                F.conv2d(x, state_dict[p + "conv1.weight"].double(), None, stride=2, padding=1))
     assert (y0 - y1).abs().max() < 1e-10
+
+
+def test_filterbank_host_helpers_match_oracle():
+    """avsr_fbank_bins / avsr_fbank_rows are host-only: the mel bin edges and frame arithmetic of the CUDA path against the
+    oracle's restatement of python_speech_features."""
+    from oracle import input_oracle as IO
+    lib = _lib.load()
+    bins = (ctypes.c_int * 28)()
+    assert lib.avsr_fbank_bins(bins) == 0
+    assert list(bins) == [int(b) for b in IO.filterbank_bins()]
+    for n in (1, 2, 399, 400, 401, 560, 561, 640, 1040, 16000, 640 * 375, 640 * 375 + 1):
+        assert lib.avsr_fbank_rows(n) == (IO.num_frames(n) + 3) // 4, n
+    assert lib.avsr_fbank_rows(0) == 0
+
+
+def test_input_pipeline_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from avsr_b200 import input_pipeline as P
+    with pytest.raises(RuntimeError):
+        P.fbank_stack_ln_batch([torch.zeros(1000)], device="cpu")
+    with pytest.raises(Exception):
+        P.DataCollator()([{"video": torch.zeros(3, 1, 96, 96, dtype=torch.uint8), "audio": torch.zeros(1920, 1)}])
