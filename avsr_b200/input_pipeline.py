@@ -85,9 +85,10 @@ def fbank_stack_ln_batch(waveforms: Sequence[torch.Tensor], n_samples: Optional[
         wave = host.to(dev, non_blocking=True)
     B = len(flat)
     out = torch.empty(B, N_FEAT, tmax, dtype=torch.float32, device=dev)
+    d_off, d_len, d_n = _i64(offs, dev), _i32(lens, dev), _i32(n_samples, dev)      # named: they must outlive the launch call
     with torch.cuda.device(dev):
-        L.check(lib.avsr_fbank_stack_ln(L.ptr(wave), L.ptr(_i64(offs, dev)), L.ptr(_i32(lens, dev)), L.ptr(_i32(n_samples, dev)), B, tmax,
-                                        L.ptr(out), L.stream()), "avsr_fbank_stack_ln")
+        L.check(lib.avsr_fbank_stack_ln(L.ptr(wave), L.ptr(d_off), L.ptr(d_len), L.ptr(d_n), B, tmax, L.ptr(out), L.stream()),
+                "avsr_fbank_stack_ln")
     return out, rows
 
 
@@ -133,8 +134,9 @@ def video_transform_batch(videos: Sequence[torch.Tensor], device="cuda:0", t_max
         frames = host.to(dev, non_blocking=True)
     B = len(vs)
     out = torch.empty(B, 1, tmax, CROP, CROP, dtype=torch.float32, device=dev)
+    d_off, d_T = _i64(offs, dev), _i32(T, dev)
     with torch.cuda.device(dev):
-        L.check(lib.avsr_video_u8_transform(L.ptr(frames), L.ptr(_i64(offs, dev)), L.ptr(_i32(T, dev)), B, tmax, H, W, L.ptr(out), L.stream()),
+        L.check(lib.avsr_video_u8_transform(L.ptr(frames), L.ptr(d_off), L.ptr(d_T), B, tmax, H, W, L.ptr(out), L.stream()),
                 "avsr_video_u8_transform")
     return out, T
 

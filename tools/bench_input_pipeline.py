@@ -47,6 +47,19 @@ def timed(fn):
 t_a = timed(lambda: P.fbank_stack_ln_batch(waves))
 t_v = timed(lambda: P.video_transform_batch(vids))
 vid_bytes = B * T * (88 * 88 + 88 * 88 * 4)
+
+# kernels alone: inputs already concatenated on the device, index vectors resident
+from avsr_b200 import _lib as L
+lib = L.load()
+wave, frames = torch.cat(waves), torch.cat(vids)
+i64 = lambda v: torch.tensor(v, dtype=torch.int64, device="cuda")
+i32 = lambda v: torch.tensor(v, dtype=torch.int32, device="cuda")
+w_off, w_len, f_off, f_T = i64([b * T * 640 for b in range(B)]), i32([T * 640] * B), i64([b * T for b in range(B)]), i32([T] * B)
+aud = torch.empty(B, 104, T, device="cuda")
+vid = torch.empty(B, 1, T, 88, 88, device="cuda")
+k_a = timed(lambda: L.check(lib.avsr_fbank_stack_ln(L.ptr(wave), L.ptr(w_off), L.ptr(w_len), L.ptr(w_len), B, T, L.ptr(aud), L.stream()), "fbank"))
+k_v = timed(lambda: L.check(lib.avsr_video_u8_transform(L.ptr(frames), L.ptr(f_off), L.ptr(f_T), B, T, 96, 96, L.ptr(vid), L.stream()), "video"))
+print(f"kernels alone: fbank {1e3 * k_a:.1f} us, video {1e3 * k_v:.1f} us ({vid_bytes / (k_v * 1e-3) / 1e9:.0f} GB/s)")
 print(f"fbank+stack+layernorm  B={B} T={T}: {t_a:.3f} ms per batch ({B * T * 640 / 16000 / (t_a * 1e-3):.0f} audio-s/s)")
 print(f"video u8 -> fp32       B={B} T={T}: {t_v:.3f} ms per batch ({vid_bytes / (t_v * 1e-3) / 1e9:.0f} GB/s of crop-in + fp32-out bytes)")
 if not a.no_oracle:
