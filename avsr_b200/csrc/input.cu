@@ -168,6 +168,46 @@ __global__ void __launch_bounds__(256) video_u8_kernel(const unsigned char* __re
     }
 }
 
+
+// torchaudio.functional.add_noise (the mixing AddMultiSpk / AddNoise do, avhubert_dataset.py:160-222): per utterance
+// scale = 10^((10 (log10 Es - log10 En) - snr) / 20), out = wave + scale * noise.  Energies over the first lengths[b] samples.
+// One CTA per utterance and signal accumulates in fp64 in a fixed order (deterministic); the mix is one streaming pass.
+__global__ void __launch_bounds__(1024) wave_energy_kernel(const float* __restrict__ wave, const float* __restrict__ noise,
+                                                           const int* __restrict__ lengths, long long L, double* __restrict__ energy) {
+    __shared__ double red[32];
+    const int b = blockIdx.x, which = blockIdx.y, tid = threadIdx.x;
+    const float* x = (which ? noise : wave) + (size_t)b * L;
+    const long long n = lengths ? min((long long)lengths[b], L) : L;
+    double acc = 0.0;
+    for (long long i = tid; i < n; i += 1024) {
+        const double v = x[i];
+        acc += v * v;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        acc = red[tid];
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (tid == 0) energy[2 * b + which] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) wave_mix_kernel(const float* __restrict__ wave, const float* __restrict__ noise,
+                                                       const float* __restrict__ snr_db, const double* __restrict__ energy, long long L,
+                                                       float* __restrict__ out) {
+    const int b = blockIdx.y;
+    // float32 from here on, like the torch expression: vector_norm(.)**2, log10, 10 ** (. / 20)
+    const float ns = (float)sqrt(energy[2 * b]), nn = (float)sqrt(energy[2 * b + 1]);
+    const float snr0 = 10.f * (log10f(ns * ns) - log10f(nn * nn));
+    const float scale = powf(10.f, (snr0 - snr_db[b]) / 20.f);
+    const float* x = wave + (size_t)b * L;
+    const float* z = noise + (size_t)b * L;
+    float* o = out + (size_t)b * L;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < L; i += (long long)gridDim.x * 256)
+        o[i] = __fadd_rn(x[i], __fmul_rn(scale, z[i]));
+}
+
 }  // namespace
 
 extern "C" int avsr_fbank_rows(int n_samples) {
@@ -205,6 +245,17 @@ extern "C" int avsr_video_u8_transform(const unsigned char* frames, const long l
         video_u8_kernel<true><<<grid, 256, 0, stream>>>(frames, frame_off, utt_T, Tmax, H, W, top, left, out);
     else
         video_u8_kernel<false><<<grid, 256, 0, stream>>>(frames, frame_off, utt_T, Tmax, H, W, top, left, out);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
+}
+
+extern "C" int avsr_add_noise(const float* wave, const float* noise, const float* snr_db, const int* lengths, int B, long long L, float* out,
+                              double* energy, cudaStream_t stream) {
+    AVSR_REQUIRE(wave && noise && snr_db && out && energy && B > 0 && B <= 65535 && L > 0, "avsr_add_noise: bad arguments");
+    wave_energy_kernel<<<dim3(B, 2), 1024, 0, stream>>>(wave, noise, lengths, L, energy);
+    AVSR_LAUNCH_CHECK();
+    const int gx = (int)((L + 256 * 8 - 1) / (256 * 8));
+    wave_mix_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, stream>>>(wave, noise, snr_db, energy, L, out);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

@@ -141,6 +141,35 @@ def video_transform_batch(videos: Sequence[torch.Tensor], device="cuda:0", t_max
     return out, T
 
 
+def add_noise(waveform: torch.Tensor, noise: torch.Tensor, snr: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``torchaudio.functional.add_noise`` for [B, L] (or [L]) CUDA tensors: the interferer / noise mixing of ``AddMultiSpk``
+    and ``AddNoise`` (avhubert_dataset.py:160-222).  Same argument meaning; ``snr`` in dB per row."""
+    squeeze = waveform.dim() == 1
+    if squeeze:
+        waveform, noise, snr = waveform[None], noise[None], snr.reshape(1)
+        lengths = None if lengths is None else lengths.reshape(1)
+    if waveform.dim() != 2 or noise.dim() != 2 or snr.dim() != 1 or (lengths is not None and lengths.dim() != 1):
+        raise ValueError("Input leading dimensions don't match.")
+    if waveform.size(-1) != noise.size(-1):
+        raise ValueError(f"Length dimensions of waveform and noise don't match (got {waveform.size(-1)} and {noise.size(-1)}).")
+    if waveform.shape != noise.shape or snr.numel() != waveform.size(0):
+        raise ValueError("Input leading dimensions don't match.")
+    if not waveform.is_cuda:
+        raise RuntimeError("avsr_b200 input pipeline needs CUDA tensors (no CPU path)")
+    dev = waveform.device
+    w = waveform.to(torch.float32).contiguous()
+    z = noise.to(dev, torch.float32).contiguous()
+    s = snr.to(dev, torch.float32).contiguous()
+    ln = None if lengths is None else lengths.to(dev, torch.int32).contiguous()
+    B, n = w.shape
+    out = torch.empty_like(w)
+    energy = torch.empty(2 * B, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().avsr_add_noise(L.ptr(w), L.ptr(z), L.ptr(s), L.ptr(ln), B, L.ll(n), L.ptr(out), L.ptr(energy), L.stream()),
+                "avsr_add_noise")
+    return out[0] if squeeze else out
+
+
 class FBanksAndStack(torch.nn.Module):
     """Per-utterance form, same call as the reference module: waveform [n,1] -> [rows,104] (on the GPU)."""
 

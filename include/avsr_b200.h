@@ -239,6 +239,10 @@ int avsr_fbank_stack_ln(const float* wave, const long long* wave_off, const int*
 /* Host helpers (no GPU work): rows FBanksAndStack yields for n samples; the 28 FFT-bin edges of the mel filters. */
 int avsr_fbank_rows(int n_samples);
 int avsr_fbank_bins(int* bins28);
+/* torchaudio.functional.add_noise as AddMultiSpk / AddNoise call it (:160-222): wave, noise, out [B][L] fp32, snr_db [B],
+ * lengths [B] or NULL (energies over the first lengths[b] samples), energy = caller-owned scratch of 2*B doubles. */
+int avsr_add_noise(const float* wave, const float* noise, const float* snr_db, const int* lengths, int B, long long L, float* out,
+                   double* energy, avsr_stream_t stream);
 /* VideoTransform("test") (:225-246): uint8 grey frames [sum(T)][H][W] (utterance b = frames frame_off[b] .. + utt_T[b]) ->
  * x / 255, CenterCrop(88), Normalize(0.421, 0.165) -> out [B][1][Tmax][88][88] fp32, zero frames behind each utterance. */
 int avsr_video_u8_transform(const unsigned char* frames, const long long* frame_off, const int* utt_T, int B, int Tmax, int H, int W,

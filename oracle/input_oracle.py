@@ -153,3 +153,20 @@ def collate(videos_u8, waveforms):
         videos[b, :vl[b]] = vids[b]
         audios[b, :al[b]] = auds[b]
     return videos.transpose(0, 2, 1, 3, 4), audios.transpose(0, 2, 1), vl, al
+
+
+def add_noise(waveform, noise, snr, lengths=None):
+    """torchaudio.functional.add_noise (2.x), the mixing ``AddMultiSpk`` / ``AddNoise`` do (avhubert_dataset.py:160-222):
+    waveform, noise [B, L]; snr [B] in dB; energies over the first lengths[b] samples.  float32 from the energies on."""
+    w = np.asarray(waveform, dtype=np.float32)
+    z = np.asarray(noise, dtype=np.float32)
+    if w.shape != z.shape or w.ndim != 2:
+        raise ValueError("waveform and noise must both be [B, L]")
+    L = w.shape[1]
+    mask = np.ones_like(w) if lengths is None else (np.arange(L)[None, :] < np.asarray(lengths)[:, None]).astype(np.float32)
+    es = np.float32(1) * np.sqrt(((w * mask).astype(np.float64) ** 2).sum(1)).astype(np.float32) ** 2
+    en = np.float32(1) * np.sqrt(((z * mask).astype(np.float64) ** 2).sum(1)).astype(np.float32) ** 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        snr0 = np.float32(10) * (np.log10(es) - np.log10(en))
+        scale = np.float32(10) ** ((snr0 - np.asarray(snr, dtype=np.float32)) / np.float32(20))
+        return (w + scale[:, None].astype(np.float32) * z).astype(np.float32)

@@ -146,3 +146,42 @@ def test_pipeline_feeds_the_encoder(P, gpu_model):
     batch = P.DataCollator()(feats)
     out = gpu_model.encoder(input_features=batch["audios"], video=batch["videos"]).last_hidden_state
     assert tuple(out.shape)[0] == 2 and tuple(out.shape)[2] == 1024 and torch.isfinite(out).all()
+
+
+def test_add_noise_matches_torchaudio_and_oracle(P):
+    import torchaudio
+    rng = np.random.default_rng(21)
+    B, n = 5, 160000                                                        # configs[3]: 10 s chunks
+    w = torch.from_numpy((0.3 * rng.standard_normal((B, n))).astype(np.float32))
+    z = torch.from_numpy((0.02 * rng.standard_normal((B, n))).astype(np.float32))
+    snr = torch.tensor([-5.0, 0.0, 5.0, 10.0, 15.0])
+    for lengths in (None, torch.tensor([n, n // 2, 77777, 1000, 1])):
+        want = torchaudio.functional.add_noise(w, z, snr, lengths)
+        got = P.add_noise(w.cuda(), z.cuda(), snr.cuda(), None if lengths is None else lengths.cuda()).cpu()
+        tol = 1e-5 * want.abs().max().item()
+        assert (got - want).abs().max().item() <= tol
+        ora = O.add_noise(w.numpy(), z.numpy(), snr.numpy(), None if lengths is None else lengths.numpy())
+        assert np.abs(got.numpy() - ora).max() <= tol
+    one = P.add_noise(w[0].cuda(), z[0].cuda(), snr[0].cuda())
+    assert one.shape == (n,) and torch.equal(one.cpu(), P.add_noise(w.cuda(), z.cuda(), snr.cuda()).cpu()[0])
+    with pytest.raises(ValueError):
+        P.add_noise(w.cuda(), z[:, :100].cuda(), snr.cuda())
+    with pytest.raises(RuntimeError):
+        P.add_noise(w, z, snr)
+
+
+def test_interferer_mix_then_features(P):
+    """configs[3] shape: a 10 s chunk mixed with two interferers the way AddMultiSpk chains add_noise (:196-222), then the
+    feature kernel; against the oracle chain."""
+    rng = np.random.default_rng(33)
+    n = 160000
+    sp, i1, i2 = [(a * rng.standard_normal(n)).astype(np.float32) for a in (0.2, 0.1, 0.3)]
+    mix_o = O.add_noise(i1[None], i2[None], np.array([5.0], np.float32))
+    out_o = O.add_noise(sp[None], mix_o, np.array([0.0], np.float32))[0]
+    t = lambda a: torch.from_numpy(a).cuda()
+    mix = P.add_noise(t(i1), t(i2), torch.tensor(5.0).cuda())
+    out = P.add_noise(t(sp), mix, torch.tensor(0.0).cuda())
+    assert np.abs(out.cpu().numpy() - out_o).max() < 1e-5
+    feats, rows = P.fbank_stack_ln_batch([out])
+    assert rows == [250]
+    assert np.abs(feats[0].t().cpu().numpy() - O.fbanks_and_stack(out.cpu().numpy())).max() < AUDIO_TOL

@@ -77,3 +77,18 @@ def test_power_spectrum_against_a_direct_dft():
 def test_silent_frames_take_the_eps_floor():
     f = O.logfbank_psf(np.zeros(2000, np.float32))
     assert np.all(f == np.log(np.finfo(float).eps))
+
+
+def test_add_noise_matches_torchaudio():
+    """torchaudio is a library present in the image (not the reference tree); the oracle's mix against its add_noise."""
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    rng = np.random.default_rng(9)
+    w = (0.3 * rng.standard_normal((4, 5000))).astype(np.float32)
+    z = (0.05 * rng.standard_normal((4, 5000))).astype(np.float32)
+    snr = np.array([-5, 0, 10, 15], np.float32)
+    for lengths in (None, np.array([5000, 4000, 123, 1])):
+        want = ta.functional.add_noise(torch.from_numpy(w), torch.from_numpy(z), torch.from_numpy(snr),
+                                       None if lengths is None else torch.from_numpy(lengths)).numpy()
+        got = O.add_noise(w, z, snr, lengths)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
