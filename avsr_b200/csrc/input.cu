@@ -19,6 +19,7 @@ constexpr int FRAME_LEN = 400, FRAME_STEP = 160, NFFT = 512, NFILT = 26, STACK =
 constexpr int CROP = 88;
 
 __constant__ int c_bins[NFILT + 2];
+__device__ double2 g_twiddle[NFFT / 2];       // exp(-2 pi i k / 512), written once from the host (libm cos / sin)
 int h_bins[NFILT + 2];
 bool bins_ready = false;
 
@@ -37,6 +38,11 @@ int ensure_bins() {
     if (!bins_ready) {
         compute_bins(h_bins);
         AVSR_CHECK_CUDA(cudaMemcpyToSymbol(c_bins, h_bins, sizeof(h_bins)));
+        static double2 tw[NFFT / 2];
+        const double pi = 3.14159265358979323846;
+        for (int k = 0; k < NFFT / 2; ++k) tw[k] = make_double2(cos(2.0 * pi * k / NFFT), -sin(2.0 * pi * k / NFFT));
+        tw[NFFT / 4] = make_double2(0.0, -1.0);          // exact quarter turn
+        AVSR_CHECK_CUDA(cudaMemcpyToSymbol(g_twiddle, tw, sizeof(tw)));
         bins_ready = true;
     }
     return AVSR_OK;
@@ -61,11 +67,7 @@ __global__ void __launch_bounds__(256) fbank_stack_ln_kernel(const float* __rest
     }
     const int navail = min(wave_len[b], n);    // cut_or_pad: samples past the waveform read as zero, past n do not exist
     const float* w = wave + wave_off[b];
-    {
-        double s, c;
-        sincospi(-(double)tid / 256.0, &s, &c);
-        tw[tid] = make_double2(c, s);
-    }
+    tw[tid] = g_twiddle[tid];
     for (int i = tid; i < STACK * NFFT; i += 256) {
         const int fr = i >> 9, k = i & (NFFT - 1), f = STACK * r + fr;
         double v = 0.0;
@@ -84,11 +86,13 @@ __global__ void __launch_bounds__(256) fbank_stack_ln_kernel(const float* __rest
     __syncthreads();
 #pragma unroll 1
     for (int s = 1; s <= 9; ++s) {
-        const int half = 1 << (s - 1);
-        for (int j = tid; j < STACK * (NFFT / 2); j += 256) {
-            const int fr = j >> 8, q = j & 255, k = q & (half - 1);
-            const int a = ((q >> (s - 1)) << s) + k, c = a + half;
-            const double2 t = tw[k << (9 - s)], x = buf[fr][c], y = buf[fr][a];
+        // thread = one butterfly position of the stage, applied to the four frames with one twiddle
+        const int half = 1 << (s - 1), k = tid & (half - 1);
+        const int a = ((tid >> (s - 1)) << s) + k, c = a + half;
+        const double2 t = tw[k << (9 - s)];
+#pragma unroll
+        for (int fr = 0; fr < STACK; ++fr) {
+            const double2 x = buf[fr][c], y = buf[fr][a];
             const double tr = t.x * x.x - t.y * x.y, ti = t.x * x.y + t.y * x.x;
             buf[fr][c] = make_double2(y.x - tr, y.y - ti);
             buf[fr][a] = make_double2(y.x + tr, y.y + ti);
