@@ -89,3 +89,55 @@ def make_text_functions(token_list: Sequence[str]) -> Tuple[Callable[[Sequence[i
     """(ids_to_text, normalize) for ``evaluation.evaluate_sharded``, i.e. what eval_lrs2 applies to hypotheses and labels
     (script/evaluation.py:105-107, 392-399): post_process, "<eos>" / "<unk>" removed by the driver, then norm_string."""
     return (lambda ids: ids_to_text(ids, token_list)), norm_string
+
+
+# ------------------------------------------------------------------------------------------------- segments, VTT, stitching
+def fixed_chunks(duration: float, max_length: float = 15) -> List[Tuple[float, float]]:
+    """``InferenceEngine.chunk_video`` without an ASD file (/root/reference/script/evaluation.py:247-270): the clip is cut
+    into ceil(duration / max_length) chunks of a whole number of seconds, on a centisecond grid; returns (start, end) in
+    seconds.  The reference divides by zero for an empty clip; here that is a ValueError."""
+    import math
+    if not duration > 0:
+        raise ValueError("fixed_chunks needs a positive duration")
+    num_chunks = math.ceil(duration / max_length)
+    chunk_size = math.ceil(duration / num_chunks)
+    steps, step_size = int(duration * 100), int(chunk_size * 100)
+    return [(i / 100, min((i + step_size) / 100, duration)) for i in range(0, steps, step_size)]
+
+
+def format_vtt_timestamp(timestamp: float) -> str:
+    """``InferenceEngine.format_vtt_timestamp`` (script/evaluation.py:272-278): HH:MM:SS.mmm, everything truncated."""
+    hours = int(timestamp // 3600)
+    minutes = int((timestamp % 3600) // 60)
+    seconds = int(timestamp % 60)
+    milliseconds = int((timestamp - int(timestamp)) * 1000)
+    return f"{hours:02d}:{minutes:02d}:{seconds:02d}.{milliseconds:03d}"
+
+
+def segment_hypotheses(segments: Sequence[Tuple[float, float]], outputs: Sequence[str], offset: float = 0.0) -> List[dict]:
+    """The list ``infer_video`` returns (script/evaluation.py:327-333): one dict per segment, times shifted by the track's
+    start offset."""
+    if len(segments) != len(outputs):
+        raise ValueError("segments and outputs differ in length")
+    return [{"start_time": s[0] + offset, "end_time": s[1] + offset, "text": o} for s, o in zip(segments, outputs)]
+
+
+def write_vtt(hypotheses: Sequence[dict]) -> str:
+    """The per-speaker .vtt body of ``mcorec_session_infer`` (script/evaluation.py:376-385): ``<unk>`` removed, empty cues
+    dropped, cues in the order given."""
+    parts = ["WEBVTT\n\n"]
+    for hyp in hypotheses:
+        text = hyp["text"].strip().replace("<unk>", "").strip()
+        if len(text) == 0:
+            continue
+        parts.append(f"{format_vtt_timestamp(hyp['start_time'])} --> {format_vtt_timestamp(hyp['end_time'])}\n{text}\n\n")
+    return "".join(parts)
+
+
+def stitch_outputs(start_times: Sequence[float], outputs: Sequence[str], normalize: Optional[Callable[[str], str]] = None) -> str:
+    """Per-video concatenation of the AVCocktail evaluation (script/evaluation.py:449-451): chunk outputs sorted by
+    (start time, text), joined with spaces, ``<unk>`` removed, normalised."""
+    if len(start_times) != len(outputs):
+        raise ValueError("start_times and outputs differ in length")
+    ordered = [o for _, o in sorted(zip(start_times, outputs))]
+    return (normalize or norm_string)(" ".join(ordered).replace("<unk>", ""))

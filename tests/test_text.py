@@ -26,3 +26,27 @@ def test_text_functions_plug_into_the_wer():
     hyp = norm(to_text([2, 3, 4, 5]).replace("<eos>", "").replace("<unk>", ""))
     assert hyp == "IT'S A GOOD DAY"
     assert S.corpus_wer([norm("It's a very good day")], [hyp]) == (1, 5)
+
+
+def test_chunking_and_timestamps_match_reference_outputs():
+    S = json.load(open(os.path.join(ROOT, "tests", "golden", "stitch.json")))
+    for c in S["chunks"]:
+        assert [list(s) for s in X.fixed_chunks(c["duration"], c["max_length"])] == c["segments"], c
+    for t, want in S["timestamps"]:
+        assert X.format_vtt_timestamp(t) == want, t
+    import pytest
+    with pytest.raises(ValueError):
+        X.fixed_chunks(0.0)
+
+
+def test_vtt_and_stitching():
+    hyps = X.segment_hypotheses([(0.0, 4.0), (4.0, 8.5), (8.5, 9.0)], [" HELLO <unk> WORLD ", "<unk>", "IT'S 5%"], offset=3600.25)
+    assert hyps[1] == {"start_time": 3604.25, "end_time": 3608.75, "text": "<unk>"}
+    assert X.write_vtt(hyps) == ("WEBVTT\n\n01:00:00.250 --> 01:00:04.250\nHELLO  WORLD\n\n"
+                                 "01:00:08.750 --> 01:00:09.250\nIT'S 5%\n\n")
+    assert X.write_vtt([]) == "WEBVTT\n\n"
+    # chunk outputs arrive in dataset order; the reference sorts them by (start time, text) before the WER
+    assert X.stitch_outputs([8.0, 0.0, 4.0, 4.0], ["the end.", "Well-known <unk>", "b", "a"]) == "WELL KNOWN A B THE END"
+    import pytest
+    with pytest.raises(ValueError):
+        X.stitch_outputs([0.0], [])
