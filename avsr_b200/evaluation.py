@@ -58,7 +58,7 @@ def pad_batch(samples: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[tor
 
 def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
                      references: Optional[Sequence[str]] = None, ids_to_text: Optional[Callable[[Sequence[int]], str]] = None,
-                     normalize: Optional[Callable[[str], str]] = None, max_utts: int = 32, max_frames: int = 12288,
+                     normalize: Optional[Callable[[str], str]] = None, max_utts: int = 128, max_frames: int = 12288,
                      device="cpu", fps: float = 25.0, group=None) -> EvalResult:
     """Decode utterances 0..N-1 (``lengths[i]`` frames each, inputs from ``load_sample(i)``) on all ranks of the default
     process group and return the corpus result on every rank.

@@ -269,6 +269,28 @@ def test_sharded_evaluation_driver_equals_single_runs(gpu_model):
     assert S.shard_utterances(lengths, 1) == [[2, 4, 0, 1, 3]]
 
 
+def test_large_decode_batches_equal_small_ones(gpu_model):
+    """evaluate_sharded's default batches hold up to 128 utterances (384 hypothesis rows per decode position): the token
+    ids must not depend on how the set was cut into batches."""
+    from avsr_b200 import evaluation as E
+    rng = np.random.default_rng(77)
+    lengths = rng.integers(6, 21, size=150).tolist()
+    samples = {}
+
+    def load(i):
+        if i not in samples:
+            v, a = synth.make_inputs(5000 + i, lengths[i])
+            samples[i] = (v[0], a[0])
+        return samples[i]
+
+    big = E.evaluate_sharded(gpu_model, lengths, load, device="cuda")
+    small = E.evaluate_sharded(gpu_model, lengths, load, max_utts=16, device="cuda")
+    assert big.n_batches == 2 and small.n_batches >= 10
+    assert len(big.hyp_tokens) == 150
+    diff = [i for i in range(150) if big.hyp_tokens[i] != small.hyp_tokens[i]]
+    assert not diff, diff
+
+
 def test_pinned_host_inputs_are_uploaded_in_chunks(gpu_model):
     """infer_batch / encoder with pinned HOST video (chunked upload on a copy stream under the video frontend) gives the
     bit-identical encoder output of the same call with device-resident inputs."""

@@ -1,6 +1,6 @@
 """BASELINE.json configs[2]: an LRS2-test-shaped synthetic set (mixed lengths) sharded by utterance over the ranks.
 
-    python tools/eval_cfg3.py [--n 1243] [--max-utts 32]                                  # one GPU
+    python tools/eval_cfg3.py [--n 1243] [--max-utts 128]                                  # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/eval_cfg3.py
 
 Lengths: T_i = clip(round(25 * LogNormal(ln 1.3, 0.6)), 12, 155) frames, numpy default_rng(2024); inputs
@@ -26,7 +26,7 @@ from avsr_b200.model import AVSRCocktailB200
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1243)
-ap.add_argument("--max-utts", type=int, default=32)
+ap.add_argument("--max-utts", type=int, default=128)
 ap.add_argument("--max-frames", type=int, default=12288)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
