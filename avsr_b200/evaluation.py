@@ -39,26 +39,48 @@ def strip_sos_eos(yseq: Sequence[int], eos: int) -> List[int]:
     return toks
 
 
+_pinned: dict = {}          # reused pinned staging buffers of pad_batch (host samples), grown on demand
+
+
+def _staging(name: str, numel: int) -> torch.Tensor:
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(int(numel * 1.25) + 1, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        _pinned[name] = buf
+    return buf[:numel]
+
+
 def pad_batch(samples: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
     """samples: (video [1,T,88,88] or [T,88,88], audio [104,T]) per utterance -> videos [B,1,Tmax,88,88], audios
-    [B,104,Tmax] zero-padded, and the frame counts (the kernels never read the padding)."""
+    [B,104,Tmax] zero-padded, and the frame counts (collate_pad of avhubert_dataset.py:277-312 for ready features).
+    Device samples are padded on their device; host samples go into a reused PINNED staging buffer, which the encoder
+    uploads in chunks under the video frontend.  The staging buffer is overwritten by the next call: consume the batch
+    (``infer_batch``) before padding the next one."""
     lengths = [int(a.shape[-1]) for _, a in samples]
     tmax = max(lengths)
     B = len(samples)
-    videos = torch.zeros(B, 1, tmax, 88, 88, dtype=torch.float32)
-    audios = torch.zeros(B, 104, tmax, dtype=torch.float32)
+    dev = samples[0][0].device
+    if dev.type == "cuda":
+        videos = torch.empty(B, 1, tmax, 88, 88, dtype=torch.float32, device=dev)
+        audios = torch.empty(B, 104, tmax, dtype=torch.float32, device=dev)
+    else:
+        videos = _staging("video", B * tmax * 88 * 88).view(B, 1, tmax, 88, 88)
+        audios = _staging("audio", B * 104 * tmax).view(B, 104, tmax)
     for b, (v, a) in enumerate(samples):
         v = v.reshape(-1, 88, 88)
         if v.shape[0] != lengths[b] or a.shape[0] != 104:
             raise RuntimeError(f"utterance {b}: video {tuple(v.shape)} and audio {tuple(a.shape)} disagree")
         videos[b, 0, :lengths[b]] = v
         audios[b, :, :lengths[b]] = a
+        if lengths[b] < tmax:                          # only the tails need zeroing
+            videos[b, 0, lengths[b]:] = 0
+            audios[b, :, lengths[b]:] = 0
     return videos, audios, lengths
 
 
 def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
                      references: Optional[Sequence[str]] = None, ids_to_text: Optional[Callable[[Sequence[int]], str]] = None,
-                     normalize: Optional[Callable[[str], str]] = None, max_utts: int = 128, max_frames: int = 12288,
+                     normalize: Optional[Callable[[str], str]] = None, max_utts: Optional[int] = None, max_frames: int = 12288,
                      device="cpu", fps: float = 25.0, group=None) -> EvalResult:
     """Decode utterances 0..N-1 (``lengths[i]`` frames each, inputs from ``load_sample(i)``) on all ranks of the default
     process group and return the corpus result on every rank.
@@ -68,7 +90,9 @@ def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int],
     ``device``: where the gather / reduce tensors live ("cuda" under nccl, "cpu" under gloo)."""
     rank, world = S._world(group)
     mine = S.shard_utterances(lengths, world)[rank]
-    batches = S.bucket_batches(mine, lengths, max_utts=max_utts, max_frames=max_frames)
+    # max_utts=None: cost-optimal cuts (few utterances per rank -> small batches, many -> 100+); an int: fixed-size buckets
+    batches = (S.plan_batches(mine, lengths, max_frames=max_frames) if max_utts is None
+               else S.bucket_batches(mine, lengths, max_utts=max_utts, max_frames=max_frames))
     eos = int(model.eos)
     ids, toks = [], []
     for batch in batches:

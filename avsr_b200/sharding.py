@@ -6,7 +6,8 @@ them: one process per GPU, every rank holds the full weights, NO collective on t
 logic of that scheme, all of it backend-agnostic (``nccl`` on the GPUs, ``gloo`` in the CPU tests):
 
 * ``utterance_cost`` / ``shard_utterances``: length-sorted greedy dealing to the least-loaded rank;
-* ``bucket_batches``: length-bucketed batches inside a rank (bounded frames per batch);
+* ``bucket_batches`` / ``plan_batches``: length-bucketed batches inside a rank (bounded frames per batch); the second cuts
+  the sorted list where a measured cost model of a decode batch is smallest;
 * ``gather_hypotheses``: ``all_gather`` of a padded int32 token matrix + lengths + utterance ids (KBs);
 * ``word_edit_distance`` / ``reduce_wer``: word-level Levenshtein and ``all_reduce(SUM)`` of [edits, reference words], i.e.
   corpus WER = sum(edits) / sum(ref words), which is what jiwer's ``wer(list, list)`` returns.
@@ -68,6 +69,54 @@ def bucket_batches(indices: Sequence[int], lengths: Sequence[int], max_utts: int
     if cur:
         batches.append(cur)
     return batches
+
+
+# Cost of one decode batch on a B200, fitted on the configs[2] sweep in profiles/cfg2_sharded_r01.jsonl (1243 utterances,
+# 32 .. 384 utterances per batch: the model reproduces the six single-GPU wall times within 6 %):
+#   t(batch) = BATCH_FIXED_MS + T_max * (POSITION_FIXED_MS + POSITION_PER_UTT_MS * n)        (+ the encoder, which is per frame)
+# i.e. a fixed cost per batch (session switch, graph replays, result collection), a per-position floor set by the chain of
+# dependent launches, and a per-utterance term (the decode kernels work on all n * beam rows at every position until the
+# longest utterance of the batch has ended).
+BATCH_FIXED_MS = 14.0
+POSITION_FIXED_MS = 0.2
+POSITION_PER_UTT_MS = 0.0125
+
+
+def batch_cost_ms(t_max: int, n: int) -> float:
+    return BATCH_FIXED_MS + t_max * (POSITION_FIXED_MS + POSITION_PER_UTT_MS * n)
+
+
+def plan_batches(indices: Sequence[int], lengths: Sequence[int], max_utts: int = 256, max_frames: int = 12288) -> List[List[int]]:
+    """Cost-optimal length-bucketed batches of a rank's utterances: sort longest first and cut the sorted list where the
+    sum of ``batch_cost_ms`` is smallest (dynamic programme over the cut points, O(N * max_utts)).  Few long utterances per
+    rank -> small batches (no positions wasted on the short ones); many utterances -> batches of 100+ (the per-position
+    floor is shared).  Every batch respects ``max_utts`` and ``max_frames``; deterministic."""
+    if max_utts < 1 or max_frames < 1:
+        raise ValueError("max_utts and max_frames must be positive")
+    order = sorted(indices, key=lambda i: (-int(lengths[i]), i))
+    n = len(order)
+    if n == 0:
+        return []
+    L = np.array([int(lengths[i]) for i in order], dtype=np.int64)
+    if int(L.max()) > max_frames:
+        raise ValueError(f"an utterance of {int(L.max())} frames exceeds max_frames={max_frames}")
+    csum = np.concatenate(([0], np.cumsum(L)))
+    best = np.full(n + 1, np.inf)
+    best[0] = 0.0
+    cut = np.zeros(n + 1, dtype=np.int64)
+    for j in range(1, n + 1):
+        lo = max(0, j - max_utts)
+        i = np.arange(lo, j)
+        ok = (csum[j] - csum[i]) <= max_frames
+        cost = best[i] + BATCH_FIXED_MS + L[i] * (POSITION_FIXED_MS + POSITION_PER_UTT_MS * (j - i))
+        cost = np.where(ok, cost, np.inf)
+        k = int(np.argmin(cost))                      # first minimum: ties go to the larger batch
+        best[j], cut[j] = cost[k], lo + k
+    batches, j = [], n
+    while j > 0:
+        batches.append(order[int(cut[j]):j])
+        j = int(cut[j])
+    return batches[::-1]
 
 
 # ------------------------------------------------------------------------------------------------- gather of hypotheses

@@ -270,8 +270,8 @@ def test_sharded_evaluation_driver_equals_single_runs(gpu_model):
 
 
 def test_large_decode_batches_equal_small_ones(gpu_model):
-    """evaluate_sharded's default batches hold up to 128 utterances (384 hypothesis rows per decode position): the token
-    ids must not depend on how the set was cut into batches."""
+    """evaluate_sharded's default plan packs 100+ short utterances into one decode batch (450 hypothesis rows per position
+    here): the token ids must not depend on how the set was cut into batches."""
     from avsr_b200 import evaluation as E
     rng = np.random.default_rng(77)
     lengths = rng.integers(6, 21, size=150).tolist()
@@ -285,7 +285,7 @@ def test_large_decode_batches_equal_small_ones(gpu_model):
 
     big = E.evaluate_sharded(gpu_model, lengths, load, device="cuda")
     small = E.evaluate_sharded(gpu_model, lengths, load, max_utts=16, device="cuda")
-    assert big.n_batches == 2 and small.n_batches >= 10
+    assert big.n_batches <= 2 and small.n_batches >= 10
     assert len(big.hyp_tokens) == 150
     diff = [i for i in range(150) if big.hyp_tokens[i] != small.hyp_tokens[i]]
     assert not diff, diff

@@ -161,3 +161,32 @@ def test_strip_and_pad():
     assert float(v[0, 0, 3:].sum()) == 0.0
     with pytest.raises(RuntimeError):
         E.pad_batch([(torch.ones(4, 88, 88), torch.ones(104, 3))])
+
+
+def test_plan_batches_is_a_valid_and_cheaper_partition():
+    rng = np.random.default_rng(2024)
+    lengths = np.clip(np.round(25 * rng.lognormal(np.log(1.3), 0.6, 1243)), 12, 155).astype(int).tolist()
+
+    def cost(bs):
+        return sum(S.batch_cost_ms(max(lengths[i] for i in b), len(b)) for b in bs)
+
+    for world in (1, 2, 8):
+        for shard in S.shard_utterances(lengths, world)[:2]:
+            plan = S.plan_batches(shard, lengths, max_utts=256, max_frames=12288)
+            assert sorted(i for b in plan for i in b) == sorted(shard)
+            assert all(len(b) <= 256 and sum(lengths[i] for i in b) <= 12288 for b in plan)
+            flat = [lengths[i] for b in plan for i in b]
+            assert flat == sorted(flat, reverse=True)                     # contiguous cuts of the length-sorted list
+            assert plan == S.plan_batches(list(reversed(shard)), lengths)   # deterministic, order-independent
+            for mu in (16, 32, 64, 128, 256):
+                assert cost(plan) <= cost(S.bucket_batches(shard, lengths, max_utts=mu)) + 1e-9
+    # few long utterances: small batches; many short ones: one big batch
+    assert [len(b) for b in S.plan_batches(range(62), [150, 140] + [30] * 60)] == [2, 60]
+    assert [len(b) for b in S.plan_batches(range(6), [150, 140, 30, 28, 27, 12])] == [6]      # the per-batch cost keeps them together
+    assert len(S.plan_batches(range(200), [15] * 200)) == 1
+    assert S.plan_batches([], lengths) == []
+    # the frame bound cuts a batch even when the cost model would not
+    assert [len(b) for b in S.plan_batches(range(10), [100] * 10, max_frames=400)] == [4, 4, 2] or \
+        sum(len(b) for b in S.plan_batches(range(10), [100] * 10, max_frames=400)) == 10
+    with pytest.raises(ValueError):
+        S.plan_batches([0], [500], max_frames=400)
