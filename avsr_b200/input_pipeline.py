@@ -17,7 +17,7 @@ raise ``NotImplementedError``.  No CPU fallback: tensors are moved to the model'
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -54,7 +54,7 @@ def _i64(v, dev):
 
 
 def fbank_stack_ln_batch(waveforms: Sequence[torch.Tensor], n_samples: Optional[Sequence[int]] = None, device="cuda:0",
-                         t_max: Optional[int] = None) -> (torch.Tensor, List[int]):
+                         t_max: Optional[int] = None) -> Tuple[torch.Tensor, List[int]]:
     """Batch of waveforms ([n] or [n,1] float32, host or device) -> (audios [B,104,Tmax] fp32 on ``device``, rows per
     utterance).  ``n_samples[b]``: length utterance b is cut / zero-padded to first (default: its own length)."""
     dev = torch.device(device)
@@ -76,13 +76,14 @@ def fbank_stack_ln_batch(waveforms: Sequence[torch.Tensor], n_samples: Optional[
     for n in lens:
         offs.append(acc)
         acc += n
+    # straight into one device buffer: pinned host tensors go by asynchronous DMA, pageable ones through torch's staging,
+    # no host-side concatenation (device-resident inputs are concatenated on the device)
     if all(w.is_cuda for w in flat):
         wave = torch.cat([w.to(dev, torch.float32) for w in flat])
     else:
-        host = torch.empty(acc, dtype=torch.float32, pin_memory=True)
+        wave = torch.empty(acc, dtype=torch.float32, device=dev)
         for w, o, n in zip(flat, offs, lens):
-            host[o:o + n].copy_(w)
-        wave = host.to(dev, non_blocking=True)
+            wave[o:o + n].copy_(w, non_blocking=True)
     B = len(flat)
     out = torch.empty(B, N_FEAT, tmax, dtype=torch.float32, device=dev)
     d_off, d_len, d_n = _i64(offs, dev), _i32(lens, dev), _i32(n_samples, dev)      # named: they must outlive the launch call
@@ -92,7 +93,7 @@ def fbank_stack_ln_batch(waveforms: Sequence[torch.Tensor], n_samples: Optional[
     return out, rows
 
 
-def video_transform_batch(videos: Sequence[torch.Tensor], device="cuda:0", t_max: Optional[int] = None) -> (torch.Tensor, List[int]):
+def video_transform_batch(videos: Sequence[torch.Tensor], device="cuda:0", t_max: Optional[int] = None) -> Tuple[torch.Tensor, List[int]]:
     """Batch of uint8 grey videos ([T,1,H,W] or [T,H,W], one frame size for the batch) -> (videos [B,1,Tmax,88,88] fp32 on
     ``device``, frames per utterance)."""
     dev = torch.device(device)
@@ -128,10 +129,9 @@ def video_transform_batch(videos: Sequence[torch.Tensor], device="cuda:0", t_max
     if all(v.is_cuda for v in vs):
         frames = torch.cat([v.to(dev).contiguous() for v in vs])
     else:
-        host = torch.empty(acc, H, W, dtype=torch.uint8, pin_memory=True)
+        frames = torch.empty(acc, H, W, dtype=torch.uint8, device=dev)
         for v, o, t in zip(vs, offs, T):
-            host[o:o + t].copy_(v)
-        frames = host.to(dev, non_blocking=True)
+            frames[o:o + t].copy_(v, non_blocking=True)
     B = len(vs)
     out = torch.empty(B, 1, tmax, CROP, CROP, dtype=torch.float32, device=dev)
     d_off, d_T = _i64(offs, dev), _i32(T, dev)
