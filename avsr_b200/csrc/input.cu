@@ -4,7 +4,7 @@
 //
 // The reference computes the filterbank on the CPU with python_speech_features 0.6 (numpy, float64 after a float32
 // pre-emphasis).  Here one CTA produces one output row = 4 stacked frames: the four 400-sample frames are zero-padded to
-// 512, transformed by a shared-memory radix-2 FFT in fp64 (B200 keeps a full-rate fp64 pipe; the whole batch is ~1 GFLOP),
+// 512, transformed by a shared-memory FFT (radix-2 stages fused in pairs) in fp64 (B200 keeps a full-rate fp64 pipe; the whole batch is ~1 GFLOP),
 // reduced through the 26 triangular mel filters, floored at DBL_EPSILON, logged, rounded to fp32 exactly where the
 // reference rounds, layer-normed over the 104 values and stored transposed into [B][104][Tmax].  Bytes per row: 3.5 KB of
 // samples in, 416 B out: latency-bound, sized by the number of resident CTAs, not by HBM.
@@ -84,18 +84,41 @@ __global__ void __launch_bounds__(256) fbank_stack_ln_kernel(const float* __rest
         buf[fr][__brev((unsigned)k) >> 23] = make_double2(v, 0.0);
     }
     __syncthreads();
+    // Radix-2 decimation-in-time stages fused in pairs: a thread owns the four points {a, a+h, a+2h, a+3h} of two frames,
+    // applies stage s to (a, a+h), (a+2h, a+3h) and stage s+1 to (a, a+2h), (a+h, a+3h) in registers, so the 32 KB of
+    // spectra cross shared memory five times instead of nine (the kernel is bound by that traffic, profiles/ncu_r01_input.txt).
+    // Same operations in the same order as the unfused stages: bit-identical results.
+    {
+        const int pos = tid & 127, f0 = (tid >> 7) * 2;
 #pragma unroll 1
-    for (int s = 1; s <= 9; ++s) {
-        // thread = one butterfly position of the stage, applied to the four frames with one twiddle
-        const int half = 1 << (s - 1), k = tid & (half - 1);
-        const int a = ((tid >> (s - 1)) << s) + k, c = a + half;
-        const double2 t = tw[k << (9 - s)];
+        for (int s = 1; s <= 7; s += 2) {
+            const int h = 1 << (s - 1), k = pos & (h - 1);
+            const int a = ((pos >> (s - 1)) << (s + 1)) + k;
+            const double2 w1 = tw[k << (9 - s)], w2 = tw[k << (8 - s)], w3 = tw[(k + h) << (8 - s)];
+#pragma unroll
+            for (int fr = f0; fr < f0 + 2; ++fr) {
+                const double2 x0 = buf[fr][a], x1 = buf[fr][a + h], x2 = buf[fr][a + 2 * h], x3 = buf[fr][a + 3 * h];
+                double tr = w1.x * x1.x - w1.y * x1.y, ti = w1.x * x1.y + w1.y * x1.x;
+                const double2 y0 = make_double2(x0.x + tr, x0.y + ti), y1 = make_double2(x0.x - tr, x0.y - ti);
+                tr = w1.x * x3.x - w1.y * x3.y, ti = w1.x * x3.y + w1.y * x3.x;
+                const double2 y2 = make_double2(x2.x + tr, x2.y + ti), y3 = make_double2(x2.x - tr, x2.y - ti);
+                tr = w2.x * y2.x - w2.y * y2.y, ti = w2.x * y2.y + w2.y * y2.x;
+                buf[fr][a] = make_double2(y0.x + tr, y0.y + ti);
+                buf[fr][a + 2 * h] = make_double2(y0.x - tr, y0.y - ti);
+                tr = w3.x * y3.x - w3.y * y3.y, ti = w3.x * y3.y + w3.y * y3.x;
+                buf[fr][a + h] = make_double2(y1.x + tr, y1.y + ti);
+                buf[fr][a + 3 * h] = make_double2(y1.x - tr, y1.y - ti);
+            }
+            __syncthreads();
+        }
+        // last stage (half = 256): thread = butterfly position, all four frames
+        const double2 t = tw[tid];
 #pragma unroll
         for (int fr = 0; fr < STACK; ++fr) {
-            const double2 x = buf[fr][c], y = buf[fr][a];
+            const double2 x = buf[fr][tid + NFFT / 2], y = buf[fr][tid];
             const double tr = t.x * x.x - t.y * x.y, ti = t.x * x.y + t.y * x.x;
-            buf[fr][c] = make_double2(y.x - tr, y.y - ti);
-            buf[fr][a] = make_double2(y.x + tr, y.y + ti);
+            buf[fr][tid + NFFT / 2] = make_double2(y.x - tr, y.y - ti);
+            buf[fr][tid] = make_double2(y.x + tr, y.y + ti);
         }
         __syncthreads();
     }
