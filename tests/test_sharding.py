@@ -190,3 +190,31 @@ def test_plan_batches_is_a_valid_and_cheaper_partition():
         sum(len(b) for b in S.plan_batches(range(10), [100] * 10, max_frames=400)) == 10
     with pytest.raises(ValueError):
         S.plan_batches([0], [500], max_frames=400)
+
+
+def test_plan_batches_is_optimal_on_small_sets():
+    """Exhaustive check: on sets small enough to enumerate every way of cutting the length-sorted list, the dynamic
+    programme returns a cut of minimal model cost (with the utterance and frame bounds in force)."""
+    import itertools
+    rng = random.Random(5)
+    for trial in range(40):
+        n = rng.randint(1, 9)
+        lengths = [rng.choice([12, 20, 33, 60, 110, 155]) for _ in range(n)]
+        max_utts, max_frames = rng.choice([2, 3, 9]), rng.choice([160, 400, 100000])
+        order = sorted(range(n), key=lambda i: (-lengths[i], i))
+        best = None
+        for cuts in itertools.product([0, 1], repeat=n - 1):
+            batches, cur = [], [order[0]]
+            for c, i in zip(cuts, order[1:]):
+                if c:
+                    batches.append(cur)
+                    cur = []
+                cur.append(i)
+            batches.append(cur)
+            if any(len(b) > max_utts or sum(lengths[i] for i in b) > max_frames for b in batches):
+                continue
+            cost = sum(S.batch_cost_ms(max(lengths[i] for i in b), len(b)) for b in batches)
+            best = cost if best is None else min(best, cost)
+        plan = S.plan_batches(range(n), lengths, max_utts=max_utts, max_frames=max_frames)
+        got = sum(S.batch_cost_ms(max(lengths[i] for i in b), len(b)) for b in plan)
+        assert best is not None and abs(got - best) < 1e-9, (lengths, max_utts, max_frames, plan)
