@@ -30,12 +30,12 @@ class Epilogue(C.Structure):
 
 
 class BeamState(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("B", "beam", "S", "V", "lmax", "tmax", "blank", "eos", "cap", "_pad")] + [
+    _fields_ = [(n, C.c_int) for n in ("B", "beam", "S", "V", "lmax", "tmax", "blank", "eos", "cap", "no_end_detect")] + [
         (n, C.c_void_p) for n in (
             "utt_T", "step", "n_run", "row_active", "last_tok", "score", "dec_sc", "ctc_sc", "s_prev", "rprev_idx",
             "anc", "hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j", "end_score", "end_dec",
             "end_ctc", "end_len", "best_len", "best_all", "done", "overflow")
-    ] + [("d_end", C.c_double)]
+    ] + [("d_end", C.c_double), ("utt_maxlen", C.c_void_p)]
 
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_PRELU = 0, 1, 2, 3

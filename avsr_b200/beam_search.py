@@ -63,20 +63,24 @@ class BatchedBeamSearch:
             raise RuntimeError("avsr_b200 beam search needs a CUDA device (no CPU fallback)")
         if not (1 <= beam_size <= 8):
             raise RuntimeError("beam_size must be in [1, 8]")
-        if ctc_weight == 0.0:
-            raise RuntimeError("ctc_weight 0.0 (attention-only search) is not wired; use 0 < ctc_weight <= 1")
+        if not (0.0 <= ctc_weight <= 1.0):
+            raise RuntimeError("ctc_weight must be in [0, 1]")
         # ctc_weight == 1.0: the reference drops the decoder scorer (weight 0, beam_search.py:72-75) and the pre-beam
         # (avhubert_avsr_model.py:35): every step scores the FULL vocabulary with CTCPrefixScoreTH (ctc_prefix_score.py:115-119)
         self.ctc_only = ctc_weight == 1.0
+        # ctc_weight == 0.0: the CTC scorer is dropped instead (no partial scorer left -> no pre-beam, beam_search.py:100-104):
+        # attention-only search, top-k over the decoder's full-vocabulary log-probabilities
+        self.dec_only = ctc_weight == 0.0
         if token_list is not None and len(token_list) != weights.V:
             raise RuntimeError(f"token_list has {len(token_list)} entries, model vocabulary is {weights.V}")
         self.beam_size = beam_size
-        self.pre_beam_size = 1 if self.ctc_only else int(pre_beam_ratio * beam_size)        # beam_search.py:91 (ctc-only: chains of the survivors only)
+        # beam_search.py:91; single-scorer searches have no pre-beam (ctc-only keeps one chain per survivor)
+        self.pre_beam_size = 1 if (self.ctc_only or self.dec_only) else int(pre_beam_ratio * beam_size)
         self.n_vocab = weights.V
         self.sos, self.eos = weights.sos, weights.eos
         self.token_list = token_list
         self.weights = {"decoder": 1.0 - ctc_weight, "ctc": ctc_weight, "lm": 0.0, "length_bonus": 0.0}
-        self.scorers = ("ctc",) if self.ctc_only else ("decoder", "ctc")
+        self.scorers = ("ctc",) if self.ctc_only else (("decoder",) if self.dec_only else ("decoder", "ctc"))
         self.w_dec = float(np.float32(1.0 - ctc_weight))
         self.w_ctc = float(np.float32(ctc_weight))
         self.use_graph = use_graph
@@ -93,6 +97,8 @@ class BatchedBeamSearch:
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
         self.last_session = None
         self.last_sessions = []
+        self.last_stop_positions = []
+        self.last_positions_queued = 0
         self._sessions = {}
         self._streams = []
         # independent groups of utterances decoded concurrently on separate streams (AVSR_DECODE_GROUPS).  Default 1: on B200
@@ -102,20 +108,32 @@ class BatchedBeamSearch:
         L.load()
 
     # ------------------------------------------------------------------------------------------ session buffers
-    T_BUCKET = 16        # sessions (buffers + the captured graph) are shared by all batches whose longest utterance rounds up to the same multiple
+    T_BUCKET = 16        # sessions (buffers + the captured graphs) are shared by all batches whose longest utterance rounds up to the same multiple
+    B_BUCKETS = (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024)
+    SESSION_BYTES = int(os.environ.get("AVSR_SESSION_GB", "48")) << 30     # retained sessions are evicted least-recently-used beyond this
 
-    def _session(self, B: int, tmax: int, F: int, slot: int = 0):
-        """Buffers and CUDA graph for batches of B utterances of at most `tmax` frames (rounded up to a multiple of T_BUCKET):
-        everything is sized for B * tmax frames, so mixed-length batches of an evaluation run reuse a handful of sessions
-        instead of allocating and capturing one per (lengths) combination."""
+    @classmethod
+    def bucket_B(cls, B: int) -> int:
+        """Utterance slots of the session that serves a batch of B utterances: the next bucket size (unused slots are parked
+        with n_run = 0, every kernel skips them), so the batches of an evaluation plan share a handful of sessions and graphs."""
+        for b in cls.B_BUCKETS:
+            if b >= B:
+                return b
+        return -(-B // 256) * 256
+
+    def _session(self, B: int, tmax: int, F: int, slot: int = 0, no_end_detect: bool = False):
+        """Buffers and CUDA graphs for batches of up to bucket_B(B) utterances of at most `tmax` frames (rounded up to a
+        multiple of T_BUCKET): everything is sized for that capacity, so mixed batches of an evaluation run reuse a few
+        sessions instead of allocating and capturing one per (B, lengths) combination.  Sessions are kept least-recently-used
+        within SESSION_BYTES (AVSR_SESSION_GB)."""
+        B = self.bucket_B(B)
         tmax = -(-tmax // self.T_BUCKET) * self.T_BUCKET
         F = B * tmax                       # capacity in frames; a batch uses the first sum(lengths) of them
-        key = (B, tmax, slot)              # slot: concurrent groups of one decode_batch call never share buffers
-        s = self._sessions.get(key)
+        key = (B, tmax, slot, bool(no_end_detect))     # slot: concurrent groups of one decode_batch call never share buffers
+        s = self._sessions.pop(key, None)
         if s is not None:
+            self._sessions[key] = s        # most recently used last
             return s
-        if len(self._sessions) >= 24:         # a full evaluation run needs ~10 length buckets x a few batch sizes x groups
-            self._sessions.clear()
         dev, beam, S, V = self.device, self.beam_size, self.pre_beam_size, self.n_vocab
         R = B * beam
         nl = self.w.n_layers
@@ -123,7 +141,7 @@ class BatchedBeamSearch:
         i32 = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=dev)
         f32 = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
         s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
-        s["utt_T"], s["utt_off"] = i32(B), i32(B)
+        s["utt_T"], s["utt_off"], s["utt_maxlen"] = i32(B), i32(B), i32(B)
         s["step"], s["any_running"] = i32(1), i32(1)
         # host copies of any_running (asynchronous poll, double-buffered: a flag is read one replay late)
         s["poll"] = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
@@ -144,6 +162,9 @@ class BatchedBeamSearch:
         s["ffn"] = f32(R, 3072)
         s["dec_logp"] = f32(R, V)
         s["part_ids"], s["psi"] = i32(R, S), f32(R, S)
+        if self.dec_only:
+            s["ctc_full"] = f32(R, V)                 # the dropped CTC scorer contributes 0 * 0
+            s["rc_last"], s["rc_chain"], s["rc_tok"] = i32(R), i32(R), i32(R)
         if self.ctc_only:
             lib0 = L.load()
             s["ctc_full"] = f32(R, V)
@@ -192,6 +213,8 @@ class BatchedBeamSearch:
         st = L.BeamState()
         st.B, st.beam, st.S, st.V, st.lmax, st.tmax = B, beam, S, V, lmax, tmax
         st.blank, st.eos, st.cap = self.w.blank, self.eos, cap
+        st.no_end_detect = 1 if no_end_detect else 0        # baked into the captured graphs, hence part of the session key
+        st.utt_maxlen = s["utt_maxlen"].data_ptr()
         for name in ("utt_T", "step", "n_run", "row_active", "last_tok", "score", "dec_sc", "ctc_sc", "s_prev", "rprev_idx", "anc",
                      "hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j", "end_score", "end_dec", "end_ctc", "end_len",
                      "best_len", "best_all", "done", "overflow"):
@@ -199,7 +222,13 @@ class BatchedBeamSearch:
         st.d_end = D_END
         s["state"] = st
         s["graph"] = s["graph1"] = None
+        s["bytes"] = sum(v.numel() * v.element_size() for v in s.values() if isinstance(v, torch.Tensor))
         self._sessions[key] = s
+        total = sum(x["bytes"] for x in self._sessions.values())
+        for k in list(self._sessions):
+            if total <= self.SESSION_BYTES or k == key:
+                continue
+            total -= self._sessions.pop(k)["bytes"]           # oldest first; its tensors and graphs are freed with it
         return s
 
     # ------------------------------------------------------------------------------------------ one decode step
@@ -363,8 +392,33 @@ class BatchedBeamSearch:
         """Decoder.batch_score + CTC partial scoring + fusion/top-k/bookkeeping for position *step."""
         if self.ctc_only:
             return self._step_ctc_only(s)
-        if self.precision == "bf16x3" and self.chain and not self.fuse_epilogue and not self._skip - {"advance", "tail"}:
+        if self.precision == "bf16x3" and self.chain and not self.fuse_epilogue and not self.dec_only and not self._skip - {"advance", "tail"}:
             return self._step_chain(s)
+        part, ns = self._decoder_layers(s)
+        if self.dec_only:
+            return self._tail_dec_only(s, part, ns)
+        self._tail(s, part, ns)
+
+    def _tail_dec_only(self, s, part, ns):
+        """Attention-only search (ctc_weight = 0): log_softmax of the output layer, then the full-vocabulary form of the
+        fusion / top-k / bookkeeping kernel with a zero CTC matrix and weight (batch_beam_search.py:208-285 without partial
+        scorers)."""
+        lib = L.load()
+        w = self.w
+        R, beam, V = s["R"], self.beam_size, self.n_vocab
+        st = L.stream
+        L.check(lib.avsr_dec_logits_lsm_topk(L.ptr(part), ns, R, V, L.ptr(w.out_b), L.ptr(s["n_run"]), beam, L.ptr(s["dec_logp"]),
+                                             L.ptr(s["part_ids"]), 1, st()), "avsr_dec_logits_lsm_topk")
+        L.check(lib.avsr_beam_fuse_topk_advance_full(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["ctc_full"]), C.c_float(self.w_dec),
+                                                     C.c_float(0.0), L.ptr(s["rc_last"]), L.ptr(s["rc_chain"]), L.ptr(s["rc_tok"]), st()),
+                "avsr_beam_fuse_topk_advance_full")
+        L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
+                "avsr_beam_step_advance")
+
+    def _decoder_layers(self, s, dense: bool = True):
+        """Decoder.forward_one_step up to the output layer (decoder.py:153-181) for the rows of the session: embedding +
+        positional encoding, six layers, after_norm, output projection.  Returns (partial logits [ns][R][V], ns).
+        dense=False: no converged-prefix caches (the scorer plug-in API drives the kernels without the beam bookkeeping)."""
         lib = L.load()
         w = self.w
         R, beam, S, V, lmax = s["R"], self.beam_size, self.pre_beam_size, self.n_vocab, s["lmax"]
@@ -372,8 +426,9 @@ class BatchedBeamSearch:
         tc = self.precision == "bf16x3"
         l0 = w.layers[0]
         # newly converged history positions -> dense self-attention caches (all layers)
-        L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
-                                           L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
+        if dense:
+            L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
+                                               L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
         L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
                                       L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]),
                                       None if tc else L.ptr(s["a"]), L.ptr(s["a3"]) if tc else None, st()), "avsr_dec_embed_ln")
@@ -387,7 +442,8 @@ class BatchedBeamSearch:
                 L.check(lib.avsr_dec_attn_step(0, L.ptr(s["part"]), L.ll(3072), ns, L.ptr(lay["bqkv"]), L.ptr(s["kc"][li]),
                                                L.ptr(s["vc"][li]), L.ptr(s["anc"]), lmax, L.ptr(s["n_run"]), L.ptr(s["utt_off"]),
                                                L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), att_f32, L.ll(0), att_split,
-                                               L.ptr(s["kd"][li]), L.ptr(s["vd"][li]), L.ptr(s["conv_len"]), st()),
+                                               L.ptr(s["kd"][li]) if dense else None, L.ptr(s["vd"][li]) if dense else None,
+                                               L.ptr(s["conv_len"]) if dense else None, st()),
                         "avsr_dec_attn_step(self)")
             # (its row epilogue also asks the L2 for this layer's cross K/V, which the source attention streams two kernels later)
             self._linear(s, "att", lay, "wo", 1024, 1024, lay["bo"], residual=s["x"], out=s["x"], ln=(lay["n2_g"], lay["n2_b"]), key_out="a",
@@ -404,13 +460,14 @@ class BatchedBeamSearch:
             self._linear(s, "a", lay, "w1", 3072, 1024, lay["b1"], act=L.ACT_RELU, key_out="ffn")
             nxt = (w.layers[li + 1]["n1_g"], w.layers[li + 1]["n1_b"]) if li + 1 < nl else (w.after_g, w.after_b)
             self._linear(s, "ffn", lay, "w2", 1024, 3072, lay["b2"], residual=s["x"], out=s["x"], ln=nxt, key_out="a")
-        # output layer + log_softmax + pre-beam (decoder.py:176-181, batch_beam_search.py:229-235)
+        # output layer (decoder.py:176-181)
         ns = self._proj(s, "a", {"out": w.out_w, "out3": getattr(w, "out_w3", None)}, "out", V, 1024)
-        self._tail(s, s["part"], ns)
+        return s["part"], ns
 
     # ------------------------------------------------------------------------------------------ public API
-    def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int]):
-        """CTC posteriors (scorers/ctc.py:87-99) and the once-per-utterance cross-attention K/V projection."""
+    def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int], maxlens: Optional[Sequence[int]] = None):
+        """CTC posteriors (scorers/ctc.py:87-99) and the once-per-utterance cross-attention K/V projection; resets the beam
+        state.  maxlens: positions per utterance after which eos is appended (default: its frame count, beam_search.py:349-350)."""
         w, V = self.w, self.n_vocab
         F = x_packed.shape[0]
         lib = L.load()
@@ -426,23 +483,50 @@ class BatchedBeamSearch:
         L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
         L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), L.ll(s["F"]), n, 1, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
-        offs = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int32)
-        s["utt_T"].copy_(torch.tensor(list(lengths), dtype=torch.int32))
+        nb = len(lengths)                             # utterances of this batch; slots nb .. B-1 of the session stay parked
+        offs = np.zeros(B, dtype=np.int32)
+        offs[:nb] = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+        lens = np.ones(B, dtype=np.int32)
+        lens[:nb] = lengths
+        s["utt_T"].copy_(torch.from_numpy(lens))
         s["utt_off"].copy_(torch.from_numpy(offs))
+        ml = lens.copy()
+        if maxlens is not None:
+            ml[:nb] = maxlens
+        s["utt_maxlen"].copy_(torch.from_numpy(ml))
+        s["n_utts"] = nb
         for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev", "conv_len"):
             s[k].zero_()
         if self.ctc_only:
             s["psi"].zero_()                          # log_psi of the empty prefix
             s["dec_logp"].zero_()                     # the dropped decoder scorer contributes 0 * 0
-        s["n_run"].fill_(1)
+        if self.dec_only:
+            s["ctc_full"].zero_()
+        s["n_run"].zero_()
+        s["n_run"][:nb] = 1
         s["row_active"].zero_()
-        s["row_active"].view(B, beam)[:, 0] = 1
+        s["row_active"].view(B, beam)[:nb, 0] = 1
         s["last_tok"].fill_(self.sos)
         s["best_len"].fill_(float("-inf"))
         s["best_all"].fill_(float("-inf"))
 
-    def decode_batch(self, x_packed: torch.Tensor, lengths: Sequence[int], max_steps: Optional[int] = None) -> List[List[Hypothesis]]:
+    @staticmethod
+    def max_length(T: int, maxlenratio: float) -> int:
+        """Positions searched for an utterance of T frames (beam_search.py:349-354)."""
+        if maxlenratio == 0:
+            return T
+        if maxlenratio < 0:
+            return -1 * int(maxlenratio)
+        return max(1, int(maxlenratio * T))
+
+    def decode_batch(self, x_packed: torch.Tensor, lengths: Sequence[int], max_steps: Optional[int] = None,
+                     maxlenratio: float = 0.0) -> List[List[Hypothesis]]:
         """x_packed [sum(T),1024] fp32 encoder outputs (utterances back to back) -> n-best list per utterance.
+
+        maxlenratio as in BeamSearch.forward (beam_search.py:330-355): 0 = up to T positions with end detection; > 0 = at
+        most max(1, int(ratio * T)) positions, < 0 = at most -ratio positions, both WITHOUT end detection (:369).  The
+        reference's CTCPrefixScoreTH indexes the frame axis with the prefix length (ctc_prefix_score.py:169-172), so more
+        positions than frames raise there; here they raise a RuntimeError up front.
 
         With `self.n_groups` > 1 the utterances are decoded in independent groups on separate CUDA streams (every utterance
         evolves independently of its batch, so the split does not change any result; measured slower on B200, see __init__)."""
@@ -451,6 +535,9 @@ class BatchedBeamSearch:
         if x_packed.dim() != 2 or x_packed.shape[1] != 1024 or x_packed.shape[0] != sum(lengths) or min(lengths) < 1:
             raise RuntimeError(f"bad decode input: x {tuple(x_packed.shape)}, lengths {lengths}")
         B = len(lengths)
+        self._maxlenratio = float(maxlenratio)
+        if maxlenratio != 0.0 and any(self.max_length(t, maxlenratio) > t for t in lengths):
+            raise RuntimeError(f"maxlenratio {maxlenratio} asks for more positions than an utterance has frames")
         G = max(1, min(self.n_groups, B))
         if G == 1:
             return self._decode_groups([(x_packed, lengths)], max_steps)[0]
@@ -478,14 +565,16 @@ class BatchedBeamSearch:
         sess, nsteps, done = [], [], []
         self.last_sessions = sess
         # ---- set-up per group: posteriors, cross K/V, position 0 eagerly (also warms the kernels up), graph capture
+        mlr = getattr(self, "_maxlenratio", 0.0)
         for g, (xg, lg) in enumerate(parts):
             tmax = max(lg)
-            s = self._session(len(lg), tmax, xg.shape[0], slot=g)
+            s = self._session(len(lg), tmax, xg.shape[0], slot=g, no_end_detect=mlr != 0.0)
             self.last_session = s
+            maxlens = [self.max_length(t, mlr) for t in lg]
             with torch.cuda.stream(streams[g]):
                 streams[g].wait_event(ready)
-                self.prepare(s, xg, lg)
-                n = tmax if max_steps is None else min(tmax, max_steps)
+                self.prepare(s, xg, lg, maxlens)
+                n = max(maxlens) if max_steps is None else min(max(maxlens), max_steps)
                 self._step(s)
                 if n > 1 and self.use_graph and s["graph"] is None:
                     torch.cuda.synchronize()
@@ -512,6 +601,7 @@ class BatchedBeamSearch:
         #      (a 16-position graph has ~1200 nodes; queueing it takes the host a few hundred microseconds).  If the flag
         #      says everything had already ended, the replay queued meanwhile only ran no-op kernels.
         active = [n > 1 for n in nsteps]
+        self.last_positions_queued = 1           # positions the host queued (the search may have stopped earlier: one replay of slack)
         had_prev = [False] * G
         rnd = 0
         while any(active):
@@ -534,6 +624,7 @@ class BatchedBeamSearch:
                     s["poll"][rnd & 1].copy_(s["any_running"], non_blocking=True)
                     s["poll_event"][rnd & 1].record(streams[g])
                 done[g] += n
+                self.last_positions_queued = max(self.last_positions_queued, done[g])
             for g in range(G):
                 if not active[g]:
                     continue
@@ -565,7 +656,8 @@ class BatchedBeamSearch:
         n_end = s["n_ended"].cpu().numpy()
         e_step, e_j, e_len = s["end_step"].cpu().numpy(), s["end_j"].cpu().numpy(), s["end_len"].cpu().numpy()
         e_sc, e_dec, e_ctc = s["end_score"].cpu(), s["end_dec"].cpu(), s["end_ctc"].cpu()
-        B = s["B"]
+        B = s.get("n_utts", s["B"])
+        self.last_stop_positions = (s["done"].cpu().numpy()[:B] - 1).tolist()     # position at which each utterance stopped
         hb = np.concatenate([np.full(int(n_end[b]), b, dtype=np.int64) for b in range(B)]) if B else np.zeros(0, np.int64)
         he = np.concatenate([np.arange(int(n_end[b]), dtype=np.int64) for b in range(B)]) if B else np.zeros(0, np.int64)
         n = len(hb)
@@ -588,7 +680,8 @@ class BatchedBeamSearch:
             yseq = [self.sos] + toks[k, :last[k] + 1].tolist()
             if int(e_len[b, e]) == len(yseq) + 1:        # eos appended at the last position (batch_beam_search.py:321-337)
                 yseq.append(self.eos)
-            scores = {"ctc": e_ctc[b, e]} if self.ctc_only else {"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}
+            scores = ({"ctc": e_ctc[b, e]} if self.ctc_only else
+                      ({"decoder": e_dec[b, e]} if self.dec_only else {"decoder": e_dec[b, e], "ctc": e_ctc[b, e]}))
             out[b].append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=e_sc[b, e], scores=scores, states={}))
         for b in range(B):
             out[b].sort(key=lambda h: float(h.score), reverse=True)     # stable, like sorted() in beam_search.py:378
@@ -596,10 +689,10 @@ class BatchedBeamSearch:
 
     def forward(self, x: torch.Tensor, maxlenratio: float = 0.0, minlenratio: float = 0.0) -> List[Hypothesis]:
         """Reference entry point: x [T, 1024] -> n-best (beam_search.py:330-406)."""
-        if maxlenratio != 0.0 or minlenratio != 0.0:
-            raise RuntimeError("only maxlenratio=0.0 / minlenratio=0.0 (what script/evaluation.py uses) are supported")
+        # minlenratio only feeds a debug log and the retry taken when NO hypothesis ended (:355-358, :380-389); eos is
+        # appended at the last position, so that branch is unreachable and the value has no effect on the result
         x = x.to(self.device, torch.float32).contiguous()
-        return self.decode_batch(x, [x.shape[0]])[0]
+        return self.decode_batch(x, [x.shape[0]], maxlenratio=maxlenratio)[0]
 
     __call__ = forward
 

@@ -622,8 +622,9 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
 
     // ---- bookkeeping (serial over <= beam candidates)
     if (tid == 0) {
-        const int T = st.utt_T[b];
-        const bool is_last = (step == T - 1);
+        // maxlen of the utterance: its frame count, or what maxlenratio asks for (beam_search.py:349-354)
+        const int maxlen = st.utt_maxlen != nullptr ? st.utt_maxlen[b] : st.utt_T[b];
+        const bool is_last = (step == maxlen - 1);
         float o_dec[MAXB], o_ctc[MAXB], o_sp[MAXB];
         int o_last[MAXB], o_chain[MAXB];
         for (int h = 0; h < nrun; ++h) {
@@ -685,7 +686,7 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
         }
         // end detection (e2e_asr_common.py:18-48): M = 3 consecutive lengths, each > |D_end| below the best
         bool fin = false;
-        if (st.n_ended[b] > 0) {
+        if (!st.no_end_detect && st.n_ended[b] > 0) {       // only consulted when maxlenratio == 0 (beam_search.py:369)
             const float* bl = st.best_len + (long long)b * (st.tmax + 4);
             int count = 0;
             for (int m = 0; m < 3; ++m) {
@@ -694,7 +695,7 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
             }
             fin = (count == 3);
         }
-        if (fin || cnt == 0) { cnt = 0; st.done[b] = 1; }
+        if (fin || cnt == 0) { cnt = 0; st.done[b] = step + 1; }   // 1 + the position the search stopped at (beam_search.py:369-374)
         st.n_run[b] = cnt;
         s_newcnt = cnt;
     }

@@ -53,7 +53,7 @@ typedef struct AvsrEpilogue {
  * Replaces the Python Hypothesis / BatchHypothesis lists of src/nets/beam_search.py:13-27 and
  * src/nets/batch_beam_search.py:12-84. */
 typedef struct AvsrBeamState {
-    int B, beam, S, V, lmax, tmax, blank, eos, cap, _pad;
+    int B, beam, S, V, lmax, tmax, blank, eos, cap, no_end_detect;   /* no_end_detect: maxlenratio != 0 (beam_search.py:369) */
     const int* utt_T;       /* [B] frames per utterance (= maxlen, beam_search.py:349-350) */
     const int* step;        /* current position i */
     int* n_run;             /* [B] running hyps; 0 = utterance finished */
@@ -77,9 +77,10 @@ typedef struct AvsrBeamState {
     int* end_len;           /* [B][cap] len(yseq) incl. sos and eos */
     float* best_len;        /* [B][tmax+4] best ended score per yseq length, -inf = none */
     float* best_all;        /* [B] */
-    int* done;              /* [B] */
+    int* done;              /* [B] 0 = still searching, else 1 + the position at which the utterance stopped (end_detect fired or no running hyp left) */
     int* overflow;          /* [1] set if an ended list overflowed */
     double d_end;           /* end_detect threshold log(exp(-10)), e2e_asr_common.py:18 */
+    const int* utt_maxlen;  /* [B] positions after which eos is appended; NULL = utt_T (maxlenratio == 0, beam_search.py:349-354) */
 } AvsrBeamState;
 
 const char* avsr_last_error(void);
