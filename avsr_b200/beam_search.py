@@ -465,23 +465,32 @@ class BatchedBeamSearch:
         return s["part"], ns
 
     # ------------------------------------------------------------------------------------------ public API
-    def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int], maxlens: Optional[Sequence[int]] = None):
+    def prepare(self, s, x_packed: torch.Tensor, lengths: Sequence[int], maxlens: Optional[Sequence[int]] = None,
+                ctc: bool = True, cross_kv: bool = True):
         """CTC posteriors (scorers/ctc.py:87-99) and the once-per-utterance cross-attention K/V projection; resets the beam
         state.  maxlens: positions per utterance after which eos is appended (default: its frame count, beam_search.py:349-350)."""
         w, V = self.w, self.n_vocab
         F = x_packed.shape[0]
         lib = L.load()
         n = w.ckv_w.shape[0]
+        ctc = ctc and not self.dec_only               # attention-only search never reads the posteriors
+        cross_kv = cross_kv and not self.ctc_only     # CTC-only search never runs the decoder
         if self.precision == "bf16x3":
             # fp32-accurate projections on the tensor cores: K' = 6 * 1024 (see weights.split3_weight)
             L.check(lib.avsr_split3(L.ptr(x_packed), L.ll(1024), L.ptr(s["x6"]), L.ll(F), 1024, L.stream()), "avsr_split3")
-            L.gemm_bf16(s["x6"], w.ctc_w6, F, V, 6144, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
-            L.gemm_bf16(s["x6"], w.ckv_w6, F, n, 6144, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+            if ctc:
+                L.gemm_bf16(s["x6"], w.ctc_w6, F, V, 6144, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
+            if cross_kv:
+                L.gemm_bf16(s["x6"], w.ckv_w6, F, n, 6144, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         else:
-            L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
-            L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
-        L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
-        L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), L.ll(s["F"]), n, 1, L.stream()), "avsr_kv_head_major")
+            if ctc:
+                L.sgemm(x_packed, w.ctc_w, F, V, 1024, L.make_epilogue(bias=w.ctc_b, out_f32=s["logp"], ld_f32=s["ldp"]))
+            if cross_kv:
+                L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
+        if ctc:
+            L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
+        if cross_kv:
+            L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), L.ll(s["F"]), n, 1, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size
         nb = len(lengths)                             # utterances of this batch; slots nb .. B-1 of the session stay parked
         offs = np.zeros(B, dtype=np.int32)

@@ -713,6 +713,25 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     for (int r = tid; r < beam; r += 256) st.row_active[base + r] = r < cnt ? 1 : 0;
 }
 
+// Dense score matrix of one CTCPrefixScoreTH.__call__ in pre-beam mode, as the scorer plug-in API has to return it
+// (src/nets/scorers/ctc.py:101-126 -> ctc_prefix_score.py:164-187): every entry logzero, the S candidates of a row psi, then
+// eos = r_sum[T-1] and blank = logzero (in that order, as the reference overwrites them), all minus the row's s_prev.
+__global__ void __launch_bounds__(256)
+ctc_scores_dense_kernel(const float* __restrict__ psi, const float* __restrict__ rsum_last, const float* __restrict__ s_prev,
+                        const int* __restrict__ part_ids, int S, int V, int blank, int eos, float* __restrict__ out) {
+    const int row = blockIdx.x;
+    const float sp = s_prev[row];
+    float* o = out + (long long)row * V;
+    const float lz = __fsub_rn(LOGZERO, sp);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) o[v] = lz;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) o[part_ids[row * S + s]] = __fsub_rn(psi[row * S + s], sp);    // later duplicates win, like index_put
+        o[eos] = __fsub_rn(rsum_last[row], sp);
+        o[blank] = lz;
+    }
+}
+
 __global__ void beam_step_advance_kernel(int* step, const int* n_run, int B, int* any_running) {
     pdl_trigger();
     pdl_wait();
@@ -862,5 +881,16 @@ extern "C" int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const f
 extern "C" int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, cudaStream_t stream) {
     AVSR_REQUIRE(step && n_run && any_running && B > 0, "avsr_beam_step_advance: bad arguments");
     AVSR_CHECK_CUDA(avsr_launch_pdl(beam_step_advance_kernel, dim3(1), dim3(1), 0, stream, step, n_run, B, any_running));
+    return AVSR_OK;
+}
+
+// scores [n][V] = CTCPrefixScoreTH.__call__'s first return value (log_psi - s_prev) from the outputs of
+// avsr_ctc_prefix_prebeam: psi [n][S], rsum_last [n], part_ids [n][S], s_prev [n].
+extern "C" int avsr_ctc_scores_dense(const float* psi, const float* rsum_last, const float* s_prev, const int* part_ids, int n, int S, int V,
+                                     int blank, int eos, float* scores, cudaStream_t stream) {
+    AVSR_REQUIRE(psi && rsum_last && s_prev && part_ids && scores && n > 0 && S > 0 && V > 0 && blank >= 0 && blank < V && eos >= 0 && eos < V,
+                 "avsr_ctc_scores_dense: bad arguments");
+    ctc_scores_dense_kernel<<<n, 256, 0, stream>>>(psi, rsum_last, s_prev, part_ids, S, V, blank, eos, scores);
+    AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

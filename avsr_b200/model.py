@@ -32,8 +32,32 @@ class AVSRCocktailB200:
         self.sos = self.eos = self.odim - 1
         self.blank = 0
         self.token_list = token_list
+        self._decoder_scorer = None
+        self._ctc_head = None
         self.beam_search = BatchedBeamSearch(self.decoder_weights, beam_size=beam_size, ctc_weight=ctc_weight,
                                              token_list=token_list, device=self.device)
+
+    # E2E attributes the reference's own factory reads (src/avhubert_avsr/avhubert_avsr_model.py:12-17: ``model.decoder``,
+    # ``CTCPrefixScorer(model.ctc, model.eos)``): scorer plug-in objects over the same kernels, created on first use so that
+    # they derive from the reference's ScorerInterface when its package has been imported by then (avsr_b200/scorers.py)
+    @property
+    def decoder(self):
+        from . import scorers
+        if not isinstance(self._decoder_scorer, scorers.scorer_classes()[0]):       # also re-made once the reference's interfaces appear
+            self._decoder_scorer = scorers.B200DecoderScorer(self.decoder_weights, self.device)
+        return self._decoder_scorer
+
+    @property
+    def ctc(self):
+        if self._ctc_head is None:
+            from . import scorers
+            self._ctc_head = scorers.B200CTCHead(self.decoder_weights, self.device)
+        return self._ctc_head
+
+    def ctc_prefix_scorer(self):
+        """B200 stand-in for the reference's ``CTCPrefixScorer(model.ctc, model.eos)`` (src/nets/scorers/ctc.py:10-126)."""
+        from . import scorers
+        return scorers.B200CTCPrefixScorer(self.decoder_weights, self.device, eos=self.eos)
 
     def eval(self):
         return self

@@ -107,35 +107,124 @@ def cpu_reference_sample(sd, dec_steps_hi=20, dec_steps_lo=4, T=T_FRAMES):
                        f"{dec_steps_hi} positions in the reference compute pattern (no KV cache), decode extrapolated linearly to {T} positions")
 
 
+def reference_sample(model, bs, BH, beam, T=None, device="cpu"):
+    """One bounded sample of the workload through the UNMODIFIED reference (baseline/reference_arm.py): full encoder,
+    init_hyp, and the stock BatchBeamSearch.search at five prefix lengths spread over 0 .. T-1, integrated over all T positions."""
+    from avsr_b200 import synth
+    from baseline import reference_arm as RA
+    T = T_FRAMES if T is None else T
+    video, audio = synth.make_inputs(1234, T)
+    r = RA.sample_utterance(model, bs, BH, video.to(device), audio.to(device), beam, RA.default_positions(T))
+    r["rtfx"] = (T / FPS) / r["t_utt"]
+    r["sample"] = (f"1 of {BATCH} utterances (T={T}, beam {beam}) through the unmodified reference (baseline/_ref): full encoder + init_hyp + "
+                   f"the stock BatchBeamSearch.search/post_process at positions {r['positions']} (running hypotheses of those lengths "
+                   f"fabricated with the search's own shapes), decode = sum over all {T} positions of the piecewise-linear interpolation")
+    return r
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from avsr_b200 import synth
+    from baseline import reference_arm as RA
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.make_state_dict(0)
     n = args.steps + args.warmup
-    hi = 20 if n <= 6 else (12 if n <= 12 else 8)
     res = []
-    for i in range(n):
-        r = cpu_reference_sample(sd, dec_steps_hi=hi)
-        if i >= args.warmup:
-            res.append(r)
+    why = RA.available()
+    if why is None:
+        kind = "reference"
+        _, _, get_bs, BH = RA.load_modules()
+        model = RA.build_model(sd)
+        bs = get_bs(model, RA.token_list(), ctc_weight=CTC_WEIGHT, beam_size=BEAM)
+        for i in range(n):
+            r = reference_sample(model, bs, BH, BEAM)
+            if i >= args.warmup:
+                res.append(r)
+    else:
+        # the reference copy is missing (it is git-ignored and made by tools/install_ref.sh): the oracle port stands in
+        kind = "port"
+        hi = 20 if n <= 6 else (12 if n <= 12 else 8)
+        for i in range(n):
+            r = cpu_reference_sample(sd, dec_steps_hi=hi)
+            if i >= args.warmup:
+                res.append(r)
     t_utt = float(np.mean([r["t_utt"] for r in res]))
     value = (T_FRAMES / FPS) / t_utt
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": res[0]["sample"], "extrapolated_s_per_utterance": t_utt,
+           "encoder_s": float(np.mean([r["t_enc"] for r in res]))}
+    if kind == "reference":
+        cpu["decode_ms_per_position_at"] = {str(p): float(np.mean([r["per_pos"][j] for r in res]) * 1e3) for j, p in enumerate(res[0]["positions"])}
+        cpu["decode_s"] = float(np.mean([r["t_dec"] for r in res]))
+        cpu["s_per_utterance_min_over_steps"] = float(np.min([r["t_utt"] for r in res]))
+    else:
+        cpu["missing_reference"] = why
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean([r["t_sample"] for r in res])) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": res[0]["sample"],
-                         "extrapolated_s_per_utterance": t_utt, "encoder_s": float(np.mean([r["t_enc"] for r in res])),
-                         "decode_s_per_position": float(np.mean([r["per_step"] for r in res]))},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_library_baseline(sd, dev):
+    """"the kernel to beat" is PyTorch's own cuBLAS / cuDNN / SDPA running the reference modules on the same
+    B200.  The unmodified reference (baseline/_ref) on `dev`: the encoder on the whole batch in fp32 (as shipped) and with
+    ``.to(bfloat16)``, and the stock BatchBeamSearch on ONE utterance (the reference decodes one utterance at a time,
+    script/evaluation.py:102-104) sampled at five prefix lengths.  Reported next to the bench line, never part of it."""
+    from avsr_b200 import synth
+    from baseline import reference_arm as RA
+    why = RA.available()
+    if why is not None:
+        return {"unavailable": why}
+    _, _, get_bs, BH = RA.load_modules()
+    out = {}
+    with torch.no_grad():
+        model = RA.build_model(sd, device=dev)
+        vids, auds = zip(*[synth.make_inputs(1234 + i, T_FRAMES) for i in range(BATCH)])
+        video, audio = torch.cat(vids, 0).to(dev), torch.cat(auds, 0).to(dev)
+
+        def enc_ms(m, v, a, reps=3):
+            chunk = 8                                    # the fp32 Conv3d output of 32 x 375 frames is 5.9 GB per tensor: 8 utterances per call
+            def run():
+                for b0 in range(0, v.shape[0], chunk):
+                    m.encoder(input_features=a[b0:b0 + chunk], video=v[b0:b0 + chunk]).last_hidden_state
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        out["encoder_fp32_ms_per_batch"] = enc_ms(model, video, audio)
+        bs = get_bs(model, RA.token_list(), ctc_weight=CTC_WEIGHT, beam_size=BEAM)
+        r = RA.sample_utterance(model, bs, BH, video[:1], audio[:1], BEAM, RA.default_positions(T_FRAMES))      # warm-up
+        r = RA.sample_utterance(model, bs, BH, video[:1], audio[:1], BEAM, RA.default_positions(T_FRAMES))
+        out["decode_ms_per_position_at"] = {str(p): v * 1e3 for p, v in zip(r["positions"], r["per_pos"])}
+        out["decode_s_per_utterance"] = r["t_dec"] + r["t_init"]
+        out["encoder_fp32_s_per_utterance_b1"] = r["t_enc"]
+        out["rtfx_fp32_one_utterance_at_a_time"] = (T_FRAMES / FPS) / r["t_utt"]
+        enc16 = copy_encoder_bf16(model)
+        out["encoder_bf16_ms_per_batch"] = enc_ms(enc16, video.bfloat16(), audio.bfloat16())
+        out["note"] = ("unmodified reference modules through torch eager (cuBLAS/cuDNN) on this GPU; encoder = the whole "
+                       f"{BATCH} x {T_FRAMES}-frame batch in calls of 8 utterances; decode = stock BatchBeamSearch, one utterance, sampled")
+        del model, enc16
+    torch.cuda.empty_cache()
+    return out
+
+
+def copy_encoder_bf16(model):
+    import copy
+    import types
+    return types.SimpleNamespace(encoder=copy.deepcopy(model.encoder).to(torch.bfloat16))
 
 
 def _config(n_gpus):
@@ -148,12 +237,25 @@ def _config(n_gpus):
 
 
 # ----------------------------------------------------------------------------------------------------- B200 arm
+def _ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels below, from the committed ncu
+    capture: profiles/ncu_traffic.json, written by tools/ncu_summary.py from an `ncu --set full` report."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            pass
+    return {}
+
+
 def _kernel_rooflines(model, peaks):
     """Isolated CUDA-event timings of the three kernels the north star names, at the workload's shapes."""
     from avsr_b200 import _lib as L
     lib = L.load()
     dev = model.device
     out = {}
+    traffic = _ncu_traffic()
 
     def timeit(fn, n=20, warm=3, reps=4):
         """n launches captured in ONE CUDA graph (as in the decode loop: no host launch overhead between them), replayed
@@ -209,7 +311,7 @@ def _kernel_rooflines(model, peaks):
     # profiles/ncu_r01_kernels.txt (19.53 MB read, 0 written: the bf16x3 weights, 6 B per parameter; partial sums stay in L2)
     out["decoder_step_projection"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                                       "frac": byts / t / 1e9 / peaks["hbm"],
-                                      "traffic": 19.53e6 if model.beam_search.precision == "bf16x3" else None, "us_per_launch": t * 1e6,
+                                      "traffic": traffic.get("decoder_step_projection"), "us_per_launch": t * 1e6,
                                       "shape": f"[{R},{K}]x[{N},{K}]^T", "kernel": kname, "gflops_fp32_equiv": 2.0 * R * N * K / t / 1e9}
     # (2) encoder FFN GEMM on tcgen05: [12000,1024]x[4096,1024]^T, bias + GELU, bf16 out
     M = BATCH * T_FRAMES
@@ -220,7 +322,7 @@ def _kernel_rooflines(model, peaks):
     t = timeit(lambda: L.gemm_bf16(x, lay["w1"], M, 4096, 1024, ep), n=20)
     fl = 2.0 * M * 4096 * 1024
     out["encoder_ffn1_gemm_bf16_tcgen05"] = {"bound": "tensor", "achieved": fl / t / 1e12, "peak": peaks["tf"], "unit": "TFLOP/s",
-                                             "frac": fl / t / 1e12 / peaks["tf"], "traffic": None, "us_per_launch": t * 1e6,
+                                             "frac": fl / t / 1e12 / peaks["tf"], "traffic": traffic.get("encoder_ffn1_gemm_bf16_tcgen05"), "us_per_launch": t * 1e6,
                                              "shape": f"[{M},1024]x[4096,1024]^T"}
     # (3) full-vocabulary CTC prefix scoring (cfg 5 / SURVEY 8d): B=32 utterances x 3 hyps, algorithmic bytes
     #     4*T*V + 4*n_h*V + 16*T*n_h per utterance-step
@@ -256,7 +358,7 @@ def _kernel_rooflines(model, peaks):
     t = timeit(ctc_full, n=12)
     byts = BATCH * (4.0 * T * V + 4.0 * nh * V + 16.0 * T * nh)
     out["ctc_prefix_full_vocab"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                    "frac": byts / t / 1e9 / peaks["hbm"], "traffic": 247.1e6, "us_per_launch": t * 1e6,
+                                    "frac": byts / t / 1e9 / peaks["hbm"], "traffic": traffic.get("ctc_prefix_full_vocab"), "us_per_launch": t * 1e6,
                                     "shape": f"{BATCH} utt x {nh} hyps x T={T} x V={V}, {ncg.value} column groups x {ts.value} time splits per "
                                              f"utterance; 3 posterior blocks of 242 MB used in turn (each launch reads from HBM)"}
     del logps
@@ -279,7 +381,7 @@ def _kernel_rooflines(model, peaks):
     t = timeit(cross, n=24)
     byts = 2.0 * Fr * 1024 * 4
     out["decode_source_attention"] = {"bound": "hbm", "achieved": byts / t / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                      "frac": byts / t / 1e9 / peaks["hbm"], "traffic": 103.1e6, "us_per_launch": t * 1e6,
+                                      "frac": byts / t / 1e9 / peaks["hbm"], "traffic": traffic.get("decode_source_attention"), "us_per_launch": t * 1e6,
                                       "shape": f"{BATCH} utt x {nh} hyps x 16 heads x T={T} frames, fp32 K/V, one CTA per (utterance, head)"}
     del ckv
     return out
@@ -302,14 +404,21 @@ def run_b200(args):
     peaks = _peaks()
     sd = synth.make_state_dict(0)
     model = AVSRCocktailB200(sd, device=dev, beam_size=BEAM, ctc_weight=args.ctc_weight)
-    # rank r decodes utterances with seeds 1234 + 32 r ... (cfg 2 recipe)
-    vids, auds = [], []
+    # rank r owns utterances 32 r .. 32 r + 31 of the cfg-2 recipe.  The HOST side of a step is what the reference's
+    # data loader hands over after file decoding: uint8 grey 96x96 mouth crops and the 16 kHz waveform of every utterance
+    # (pinned).  The device-resident features `value` is timed on are those same inputs through the input pipeline
+    # (avsr_b200/input_pipeline.py: x/255, centre crop 88, normalise; log-fbank, stack 4, layer norm), computed once.
+    from avsr_b200 import input_pipeline as P
+    feats = []
     for i in range(BATCH):
-        v, a = synth.make_inputs(1234 + rank * BATCH + i, T_FRAMES)
-        vids.append(v); auds.append(a)
-    video_h = torch.cat(vids, 0).pin_memory()
-    audio_h = torch.cat(auds, 0).pin_memory()
-    video_d, audio_d = video_h.to(dev), audio_h.to(dev)
+        g = torch.Generator().manual_seed(1234 + rank * BATCH + i)
+        frames = torch.randint(0, 256, (T_FRAMES, 1, 96, 96), generator=g, dtype=torch.uint8).pin_memory()
+        wave = (0.1 * torch.randn(T_FRAMES * 640, 1, generator=g)).pin_memory()
+        feats.append({"video": frames, "audio": wave})
+    collator = P.DataCollator(device=str(dev))
+    batch0 = collator(feats)
+    video_d, audio_d = batch0["videos"], batch0["audios"]
+    h2d_bytes = sum(f["video"].numel() + 4 * f["audio"].numel() for f in feats)
     audio_s = BATCH * T_FRAMES / FPS
 
     def sync_all():
@@ -350,9 +459,11 @@ def run_b200(args):
     step_dev = lambda: model.infer_batch(video_d, audio_d)
 
     def step_e2e():
-        # the public call with HOST (pinned) inputs: infer_batch uploads them itself, chunk by chunk under the video frontend
-        nb = model.infer_batch(video_h, audio_h)
-        return [h[0].yseq.tolist() for h in nb]          # host-side 1-best token ids (what evaluation.py consumes)
+        # the public calls a user makes, from HOST buffers: collate (H2D of uint8 frames + waveforms, feature kernels), encode,
+        # decode, and the 1-best token ids back on the host (what evaluation.py consumes)
+        b = collator(feats)
+        nb = model.infer_batch(b["videos"], b["audios"], b["video_lengths"].tolist())
+        return [h[0].yseq.tolist() for h in nb]
 
     for _ in range(args.warmup):
         res = step_dev()
@@ -360,12 +471,13 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     L.launch_count = 0
+    model.beam_search.graph_launches = 0
     ms, res = timed(step_dev, args.steps)
     launches = L.launch_count + model.beam_search.graph_launches
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
-    ms_e2e, toks = timed(step_e2e, max(1, min(args.steps, 3)))
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = args.steps
+    ms_e2e, toks = timed(step_e2e, n_e2e)
     # gather hypotheses (token ids) like a sharded evaluation would; traffic is a few KB
     n_tok = sum(len(h[0].yseq) for h in res)
     if world > 1:
@@ -376,7 +488,9 @@ def run_b200(args):
     e2e = world * audio_s * n_e2e / (ms_e2e * 1e-3)
     if rank == 0:
         roof = _kernel_rooflines(model, peaks)
-        cpu = cpu_reference_sample(sd) if world == 1 and not args.no_cpu_baseline else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = _cpu_baseline_once(sd)
         d2h = sum(s[k].numel() * s[k].element_size() for s in model.beam_search.last_sessions
                   for k in ("hist_tok", "hist_prev", "run2j", "n_ended", "end_step", "end_j", "end_len", "end_score", "end_dec", "end_ctc"))
         d2h += len(model.beam_search.last_sessions) * 8 * ((T_FRAMES // 16) + 2)
@@ -384,17 +498,83 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 encoder GEMMs / f32 decode", "data": "synthetic", "config": _config(world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(video_h.numel() * 4 + audio_h.numel() * 4),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / n_e2e},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
+                    "inputs": "pinned host uint8 96x96 frames + float32 16 kHz waveforms -> DataCollator (input.cu) -> infer_batch -> host token ids"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": dict(roof["decoder_step_projection"], peak_source=peaks["src"]),
             "rooflines": roof,
             "decoded_tokens": int(n_tok),
         }
         if cpu is not None:
-            line["cpu_baseline"] = {"value": cpu["rtfx"], "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu["sample"],
+            line["cpu_baseline"] = {"value": cpu["rtfx"], "unit": UNIT, "cores": os.cpu_count(), "kind": cpu["kind"], "sample": cpu["sample"],
                                     "extrapolated_s_per_utterance": cpu["t_utt"]}
+        if world == 1 and not args.no_gpu_baseline:
+            try:
+                line["gpu_library_baseline"] = gpu_library_baseline(sd, dev)
+            except Exception as e:                    # a reported side number must never cost the bench line
+                line["gpu_library_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_cfg2(args):
+    """--workload cfg2: BASELINE.json configs[2], the LRS2-test-shaped synthetic set (1243 utterances, T = clip(round(25 *
+    LogNormal(ln 1.3, 0.6)), 12, 155) frames, numpy default_rng(2024)) SHARDED by utterance over the ranks
+    through avsr_b200.evaluation.evaluate_sharded: longest-first dealing, cost-planned length-bucketed batches per rank, NCCL
+    gather of the 1-best token ids.  A step = one pass over the whole set (strong scaling: total work fixed); features are
+    resident in HBM (or, with --host-inputs, in host memory: padding + upload inside the timed region)."""
+    import torch.distributed as dist
+    from avsr_b200 import evaluation as E
+    from avsr_b200 import sharding as S
+    from avsr_b200 import synth
+    from avsr_b200.model import AVSRCocktailB200
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.cfg2_utts
+    rng = np.random.default_rng(2024)
+    lengths = np.clip(np.round(25 * rng.lognormal(np.log(1.3), 0.6, n)), 12, 155).astype(int).tolist()
+    model = AVSRCocktailB200(synth.make_state_dict(0), device=dev, beam_size=BEAM)
+    mine = S.shard_utterances(lengths, world)[rank]
+
+    def load(i):
+        v, a = synth.make_inputs(10_000 + i, lengths[i])
+        return (v[0], a[0]) if args.host_inputs else (v[0].to(dev), a[0].to(dev))
+    cache = {i: load(i) for i in mine}
+    times, res = [], None
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = E.evaluate_sharded(model, lengths, lambda i: cache[i], max_frames=args.max_frames, device=dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if it >= args.warmup:
+            times.append(float(ms.item()))
+    if rank == 0:
+        loads = [sum(lengths[i] for i in sh) / FPS for sh in S.shard_utterances(lengths, world)]
+        ms = float(np.mean(times))
+        print(json.dumps({
+            "metric": METRIC, "value": res.audio_seconds / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 encoder GEMMs / f32 decode",
+            "data": "synthetic",
+            "config": {"workload": f"configs[2]: {n} synthetic utterances of 12..155 frames (LogNormal lengths, rng 2024), beam {BEAM}, sharded by "
+                                   f"utterance over {world} GPU(s), cost-planned batches; features {'in host memory' if args.host_inputs else 'resident in HBM'}",
+                       "utterances": n, "audio_s": res.audio_seconds, "batches_rank0": res.n_batches,
+                       "decode_sessions_rank0": len(model.beam_search._sessions), "audio_s_per_rank": [round(x, 1) for x in loads],
+                       "parallelism": f"utterance-sharded x{world}"},
+            "ms_all_steps": times, "hyps": len(res.hyp_tokens)}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -408,6 +588,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-modules-on-this-GPU side measurement")
     ap.add_argument("--beam", type=int, default=BEAM, help="dev: beam size (default = configs[1]: 3; configs[3] uses 5)")
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="dev: frames per utterance (default 375 = 15 s; configs[3]: 250)")
     ap.add_argument("--batch", type=int, default=BATCH, help="dev: utterances per GPU (default 32)")
@@ -415,10 +596,17 @@ def main():
     ap.add_argument("--rooflines-only", action="store_true", help="dev aid: only the isolated kernel timings (not a bench line)")
     ap.add_argument("--profile-decode-steps", type=int, default=0,
                     help="profiling aid: run ONE pass with the decode truncated to this many positions and exit (not a bench value)")
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2"],
+                    help="cfg1 (default) = the headline configs[1] batch per GPU; cfg2 = the sharded LRS2-shaped set (configs[2], strong scaling)")
+    ap.add_argument("--cfg2-utts", type=int, default=1243)
+    ap.add_argument("--max-frames", type=int, default=12288, help="cfg2: packed frames per batch")
+    ap.add_argument("--host-inputs", action="store_true", help="cfg2: features in host memory (pad + upload timed)")
     args = ap.parse_args()
     BEAM, T_FRAMES, BATCH, CTC_WEIGHT = args.beam, args.frames, args.batch, args.ctc_weight
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg2":
+        run_cfg2(args)
     else:
         run_b200(args)
 

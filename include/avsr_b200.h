@@ -210,6 +210,11 @@ int avsr_ctc_prefix_prebeam(const float* logp, int V, int ldp, int blank, const 
 int avsr_dec_tail(const float* part, int nsplit, const float* bias, float* dec_logp, int* part_ids, const float* logp, int V, int ldp,
                   int blank, const int* utt_off, const int* utt_T, const int* n_run, int beam, int R, int S, const int* last_tok,
                   const int* rprev_idx, float* r_buf, int tmax, const int* step, float* psi, float* rsum_last, avsr_stream_t stream);
+/* Dense [n][V] score matrix CTCPrefixScoreTH.__call__ returns in pre-beam mode (log_psi - s_prev; logzero outside the
+ * candidates, eos = r_sum[T-1], blank = logzero; ctc_prefix_score.py:164-187) from avsr_ctc_prefix_prebeam's compact outputs.
+ * Only the scorer plug-in API (src/nets/scorer_interface.py:162-186) needs it; the fused search never materialises it. */
+int avsr_ctc_scores_dense(const float* psi, const float* rsum_last, const float* s_prev, const int* part_ids, int n, int S, int V,
+                          int blank, int eos, float* scores, avsr_stream_t stream);
 /* Full-vocabulary mode.  avsr_ctc_prefix_full_plan gives the work split (*ncg column groups x *tsplit time splits per
  * utterance); caller-owned scratch: part [B][tsplit][beam][V] fp32 (may be NULL when tsplit == 1), tickets [B][ncg] int32
  * zeroed once. */

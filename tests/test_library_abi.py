@@ -21,9 +21,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    # AvsrEpilogue: 13 fields with natural alignment; AvsrBeamState: 10 ints + 25 pointers + 1 double
+    # AvsrEpilogue: 13 fields with natural alignment; AvsrBeamState: 10 ints + 25 pointers + 1 double + 1 pointer (utt_maxlen)
     assert ctypes.sizeof(_lib.Epilogue) == 96
-    assert ctypes.sizeof(_lib.BeamState) == 40 + 25 * 8 + 8
+    assert ctypes.sizeof(_lib.BeamState) == 40 + 25 * 8 + 8 + 8
 
 
 def test_argument_errors_are_reported_not_crashed():
