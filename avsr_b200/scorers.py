@@ -132,7 +132,8 @@ class _DecoderScorerImpl:
         n, Lp = ys.shape
         if n > MAX_HYPS:
             raise RuntimeError(f"B200DecoderScorer scores at most {MAX_HYPS} hypotheses per call, got {n}")
-        L.require_cuda(xs, torch.float32, "encoder output")
+        if not xs.is_cuda or xs.dtype != torch.float32:
+            raise RuntimeError("encoder output must be a float32 CUDA tensor (avsr_b200 has no CPU path)")
         lib = L.load()
         bs = self._bs
         with torch.cuda.device(self.device):
@@ -179,7 +180,8 @@ class _CTCScorerImpl:
 
     def batch_init_state(self, x: torch.Tensor):
         """scorers/ctc.py:87-99: CTC posteriors of the utterance (assuming batch_size = 1, as the reference says)."""
-        L.require_cuda(x, torch.float32, "encoder output")
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("encoder output must be a float32 CUDA tensor (avsr_b200 has no CPU path)")
         T = x.shape[0]
         with torch.cuda.device(self.device):
             s = self._bs._session(1, T, T)
@@ -233,6 +235,8 @@ class _CTCScorerImpl:
         ``scoring_idmap == -1`` quirk) and log_psi[i, new_id]."""
         if state is None:
             return None
+        if not (isinstance(state, tuple) and len(state) == 4):
+            return state[i]                   # a list of per-hypothesis states (BatchBeamSearch._batch_select / unbatchfy)
         ids, psi, rsum, S = state
         i, new_id = int(i), int(new_id)
         hit = np.nonzero(ids[i] == new_id)[0]
@@ -255,7 +259,8 @@ class B200CTCHead:
         self.device = torch.device(device)
 
     def log_softmax(self, hs_pad: torch.Tensor) -> torch.Tensor:
-        L.require_cuda(hs_pad, torch.float32, "hs_pad")
+        if not hs_pad.is_cuda or hs_pad.dtype != torch.float32:
+            raise RuntimeError("hs_pad must be a float32 CUDA tensor (avsr_b200 has no CPU path)")
         lib = L.load()
         w = self.w
         B, T, D = hs_pad.shape

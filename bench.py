@@ -237,6 +237,23 @@ def _config(n_gpus):
 
 
 # ----------------------------------------------------------------------------------------------------- B200 arm
+def _cpu_baseline_once(sd):
+    """cpu_baseline of the B200 line: two bounded samples of the reference's CPU path on the host cores (the first warms up)."""
+    from baseline import reference_arm as RA
+    torch.set_num_threads(os.cpu_count() or 1)
+    if RA.available() is None:
+        _, _, get_bs, BH = RA.load_modules()
+        model = RA.build_model(sd)
+        bs = get_bs(model, RA.token_list(), ctc_weight=CTC_WEIGHT, beam_size=BEAM)
+        reference_sample(model, bs, BH, BEAM)
+        r = reference_sample(model, bs, BH, BEAM)
+        r["kind"] = "reference"
+        return r
+    r = cpu_reference_sample(sd)
+    r["kind"] = "port"
+    return r
+
+
 def _ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels below, from the committed ncu
     capture: profiles/ncu_traffic.json, written by tools/ncu_summary.py from an `ncu --set full` report."""

@@ -125,6 +125,22 @@ int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long 
                        const float* p_part, int p_nsplit, int p_N, const float* p_bias, int p_act, const float* p_residual,
                        long long p_ldr, float* p_out, long long p_ldo, const float* p_ln_g, const float* p_ln_b, float p_ln_eps,
                        const int* row_active, void* p_split_out, unsigned* ready, int parity, avsr_stream_t stream);
+/* Decoder-step projection, second generation (csrc/gemm_x3c.cu): y = act(a W^T + bias) + residual for R rows with the K splits
+ * of an output tile in ONE thread-block cluster, reduced through distributed shared memory in split order (deterministic; no
+ * partial sums in global memory, no separate row-epilogue launch).  Replaces one nn.Linear of DecoderLayer.forward plus the
+ * glue around it (src/nets/backend/transformer/decoder_layer.py:58-121; LayerNorm eps 1e-12, layer_norm.py:12-33).
+ *   operand:  A3 != NULL: compact bf16x3 rows [R, 3K] (pitch lda); else a = LayerNorm(x): x [R, K] fp32 (pitch ldx), stats_in
+ *             [K/128][R][2] = (mean, M2) per 128-column tile of x as an earlier call wrote them via stats_out, ln_g / ln_b [K].
+ *   W3:       compact bf16x3 weights [N, 3K] (pitch ldw), K % 64 == 0.
+ *   outputs:  out [R, N] fp32 (pitch ldo) and / or split_out [R, 3N] compact bf16x3 (N % 4 == 0); stats_out [N/128][R][2] (N % 128 == 0).
+ *             residual [R, N] (pitch ldr) may alias out.  act: AVSR_ACT_NONE or AVSR_ACT_RELU (applied before the residual).
+ * avsr_dec_proj_splits: the cluster size (= K splits) chosen for a shape on the current device. */
+int avsr_dec_proj_splits(int R, int N, int K);
+int avsr_dec_proj_max_clusters(int cluster_size, int nb);   /* resident clusters of that size (operand tiles of nb rows) */
+int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
+                  const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
+                  const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
+                  avsr_stream_t stream);
 /* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
 int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */

@@ -134,11 +134,11 @@ def test_gpu_mixed_batch_stops_per_utterance(gpu_model, golden, eos_golden, prec
     _check(out[0], eos_golden, "s9_T30_b3", get=_part)
     _check(out[1], eos_golden, "s9_T125_b3", get=_part)
     _check(out[3], eos_golden, "s9_T30_b3", get=_part)
+    stops = list(bs.last_stop_positions)
     single = bs(x12)
     assert [h.yseq.tolist() for h in out[2]] == [h.yseq.tolist() for h in single]
     assert [float(h.score) for h in out[2]] == [float(h.score) for h in single]
-    stops = bs.last_stop_positions
-    bs.decode_batch(torch.cat([x30, x125, x12, x30], 0).contiguous(), [30, 125, 12, 30])
+    assert stops[2] == bs.last_stop_positions[0]
     assert stops[0] == stops[3] == int(eos_golden["s9_T30_b3_stop"]) and stops[1] == int(eos_golden["s9_T125_b3_stop"])
 
 

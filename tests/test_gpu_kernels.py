@@ -556,3 +556,82 @@ def test_gemm_x3_fused_epilogue(L, R, N, K, mode):
             back = sp.float().view(R, 3, N).sum(1)
             assert (back[keep] - want[keep]).abs().max().item() < 1e-4
     assert int(gbar[0].item()) == 0 and int(gbar[1].item()) == 3
+
+
+def _tile_stats(x):
+    """(mean, M2) of every 128-column tile of the rows of x -> [K/128][R][2] (what avsr_dec_proj leaves in stats_out)."""
+    R, K = x.shape
+    t = x.double().view(R, K // 128, 128)
+    mean = t.mean(-1)
+    m2 = ((t - mean.unsqueeze(-1)) ** 2).sum(-1)
+    return torch.stack([mean, m2], -1).permute(1, 0, 2).contiguous().float()
+
+
+@pytest.mark.parametrize("R,N,K,mode", [(96, 1024, 1024, "tma_res_stats"), (96, 3072, 1024, "ln_bias"), (96, 3072, 1024, "ln_relu_split"),
+                                        (96, 1024, 3072, "tma_res_stats"), (96, 5049, 1024, "ln_plain"), (96, 3072, 1024, "tma_bias"),
+                                        (160, 1024, 1024, "tma_res_stats"), (160, 3072, 1024, "ln_bias"), (8, 1024, 1024, "ln_bias"),
+                                        (3, 3072, 1024, "tma_bias"), (300, 1024, 3072, "tma_res_stats"), (96, 1024, 1024, "ln_bias")])
+def test_dec_proj_cluster(L, R, N, K, mode):
+    """avsr_dec_proj (csrc/gemm_x3c.cu): cluster split-K reduced through DSMEM, every operand / epilogue mode of a decode
+    position, against float64: fp32-level accuracy, LayerNorm applied while staging, tile statistics, bf16x3 output rows,
+    run-to-run bit identity."""
+    from avsr_b200.weights import split3_weight_compact
+    lib = L.load()
+    ns = lib.avsr_dec_proj_splits(R, N, K)
+    assert 1 <= ns <= min(16, K // 64)
+    w = _rand(N, K, seed=2, scale=0.03)
+    w3 = split3_weight_compact(w)
+    bias = _rand(N, seed=3, scale=0.1)
+    ln = mode.startswith("ln")
+    if ln:
+        x = _rand(R, K, seed=1, scale=2.0) + 0.5
+        g, b = torch.rand(K, device="cuda") * 0.4 + 0.8, _rand(K, seed=5, scale=0.05)
+        stats_in = _tile_stats(x).cuda()
+        a = F.layer_norm(x.double(), (K,), g.double(), b.double(), 1e-12)
+        a3 = None
+    else:
+        a32 = _rand(R, K, seed=1)
+        a3 = _split3c(a32)
+        a = a32.double()
+    ref = a @ w.double().t()
+    fp32_err = ((a.float() @ w.t()).double() - ref).abs().max().item()
+    use_bias = mode != "ln_plain"
+    if use_bias:
+        ref = ref + bias.double()
+    if "relu" in mode:
+        ref = torch.relu(ref)
+    res = None
+    if "res" in mode:
+        res = _rand(R, N, seed=7)
+        ref = ref + res.double()
+    ldo = N
+    out = torch.full((R, ldo), float("nan"), device="cuda") if "split" not in mode else None
+    if res is not None:
+        out = res.clone()                                   # in place, like the residual stream of the decoder step
+    split = torch.zeros(R, 3 * N, dtype=torch.bfloat16, device="cuda") if "split" in mode else None
+    stats = torch.full((N // 128, R, 2), float("nan"), device="cuda") if "stats" in mode else None
+
+    def run(o):
+        L.check(lib.avsr_dec_proj(L.ptr(a3), L.ll(3 * K), L.ptr(x) if ln else None, L.ll(K), L.ptr(stats_in) if ln else None,
+                                  L.ptr(g) if ln else None, L.ptr(b) if ln else None, C.c_float(1e-12), L.ptr(w3), L.ll(3 * K), R, N, K,
+                                  L.ptr(bias) if use_bias else None, L.ACT_RELU if "relu" in mode else L.ACT_NONE,
+                                  L.ptr(o) if res is not None else None, L.ll(N), L.ptr(o), L.ll(ldo), L.ptr(split), L.ptr(stats), L.stream()),
+                "avsr_dec_proj")
+    run(out)
+    torch.cuda.synchronize()
+    tol = max(2e-5 * (K ** 0.5), 4 * fp32_err + 1e-6) * (4.0 if ln else 1.0)
+    if out is not None:
+        assert not torch.isnan(out).any()
+        err = (out.double() - ref).abs().max().item()
+        assert err < tol, (err, fp32_err)
+        if res is not None:
+            again = res.clone()
+            run(again)
+            torch.cuda.synchronize()
+            assert torch.equal(again, out)                  # deterministic reduction order
+    if split is not None:
+        got = split.view(R, 3, N).double().sum(1)
+        assert (got - ref).abs().max().item() < tol
+    if stats is not None:
+        want = _tile_stats(out)
+        assert (stats.cpu() - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
