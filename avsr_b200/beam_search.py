@@ -98,6 +98,7 @@ class BatchedBeamSearch:
         # DSMEM with the LayerNorm applied by the consuming projection (csrc/gemm_x3c.cu, 54 launches per position);
         # "splitk" = round 1's partial sums through L2 + row-epilogue launches (csrc/gemm_x3.cu, 78 launches), kept for A/B runs
         self.proj = os.environ.get("AVSR_PROJ", "cluster")
+        self.weight_prefetch = os.environ.get("AVSR_WEIGHT_PREFETCH", "1") != "0"      # dev A/B switch of the L2 fetch-ahead
         if self.proj not in ("cluster", "splitk"):
             raise RuntimeError(f"AVSR_PROJ must be cluster or splitk, got {self.proj!r}")
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
@@ -426,54 +427,69 @@ class BatchedBeamSearch:
         L.check(lib.avsr_beam_step_advance(L.ptr(s["step"]), L.ptr(s["n_run"]), s["B"], L.ptr(s["any_running"]), st()),
                 "avsr_beam_step_advance")
 
-    def _cproj(self, s, W3, N, K, a3=None, ln=None, bias=None, act=L.ACT_NONE, residual=None, out=None, ldo=None, split=None, stats_out=False):
-        """One cluster projection (avsr_dec_proj): operand = compact bf16x3 rows `a3` or LayerNorm(x) with ln = (gamma, beta)."""
+    def _cproj(self, s, W3, N, K, a3=None, ln=None, bias=None, act=L.ACT_NONE, residual=None, out=None, ldo=None, split=None, stats_out=False,
+               nxt=None):
+        """One cluster projection (avsr_dec_proj): operand = compact bf16x3 rows `a3` or LayerNorm(x) with ln = (gamma, beta).
+        nxt: the weights the NEXT projection of the chain streams; this launch asks the L2 to fetch them."""
         lib = L.load()
         R = s["R"]
         g, b = ln if ln is not None else (None, None)
+        pf = nxt if (nxt is not None and self.weight_prefetch) else None
         L.check(lib.avsr_dec_proj(L.ptr(a3), L.ll(3 * K), L.ptr(s["x"]) if ln is not None else None, L.ll(1024),
                                   L.ptr(s["stats"]) if ln is not None else None, L.ptr(g), L.ptr(b), C.c_float(1e-12), L.ptr(W3), L.ll(3 * K),
                                   R, N, K, L.ptr(bias), act, L.ptr(residual), L.ll(1024), L.ptr(out), L.ll(N if ldo is None else ldo),
-                                  L.ptr(split), L.ptr(s["stats"]) if stats_out else None, L.stream()), "avsr_dec_proj")
+                                  L.ptr(split), L.ptr(s["stats"]) if stats_out else None, L.ptr(pf),
+                                  L.ll(pf.numel() * pf.element_size() if pf is not None else 0), L.stream()), "avsr_dec_proj")
+
+    def _cattn(self, s, mode, q, ldq, kc, vc, dense, li, nxt):
+        """Self (mode 0) / source (mode 1) attention of the position; also starts the L2 fetch of the next projection's weights."""
+        lib = L.load()
+        beam, R, lmax = self.beam_size, s["R"], s["lmax"]
+        pf = nxt if self.weight_prefetch else None
+        use_dense = mode == 0 and dense
+        L.check(lib.avsr_dec_attn_step_pf(mode, L.ptr(q), L.ll(ldq), 0, None, L.ptr(kc), L.ptr(vc), L.ptr(s["anc"]) if mode == 0 else None, lmax,
+                                          L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), None,
+                                          L.ll(0 if mode == 0 else s["F"]), L.ptr(s["att3"]), L.ptr(s["kd"][li]) if use_dense else None,
+                                          L.ptr(s["vd"][li]) if use_dense else None, L.ptr(s["conv_len"]) if use_dense else None, L.ptr(pf),
+                                          L.ll(pf.numel() * pf.element_size() if pf is not None else 0), L.stream()),
+                "avsr_dec_attn_step(self)" if mode == 0 else "avsr_dec_attn_step(src)")
 
     def _decoder_layers_cluster(self, s, dense: bool = True):
         """Decoder.forward_one_step up to the output layer with the cluster projections: 8 launches per layer (6 projections + 2
         attentions).  The residual stream x stays fp32; every projection that updates it also leaves the per-tile LayerNorm
-        statistics, and the projection that consumes LayerNorm(x) normalises while it stages its operand."""
+        statistics, and the projection that consumes LayerNorm(x) normalises while it stages its operand.  Every kernel asks
+        the L2 for the weights of the projection that follows it, so those stream from HBM while the chain is busy elsewhere."""
         lib = L.load()
         w = self.w
         R, beam, V, lmax = s["R"], self.beam_size, self.n_vocab, s["lmax"]
         st = L.stream
         l0 = w.layers[0]
+        nl = w.n_layers
         if dense:
             L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
                                                L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
         L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
                                       L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), None, L.ptr(s["a3"]), st()),
                 "avsr_dec_embed_ln")
-        att3 = L.ptr(s["att3"])
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93): q | k | v finished by the projection, bias included
             if li == 0:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, a3=s["a3"], bias=lay["bqkv"], out=s["qkv"])
             else:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, ln=(lay["n1_g"], lay["n1_b"]), bias=lay["bqkv"], out=s["qkv"])
-            L.check(lib.avsr_dec_attn_step(0, L.ptr(s["qkv"]), L.ll(3072), 0, None, L.ptr(s["kc"][li]), L.ptr(s["vc"][li]), L.ptr(s["anc"]), lmax,
-                                           L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), None, L.ll(0),
-                                           att3, L.ptr(s["kd"][li]) if dense else None, L.ptr(s["vd"][li]) if dense else None,
-                                           L.ptr(s["conv_len"]) if dense else None, st()), "avsr_dec_attn_step(self)")
-            self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], stats_out=True)
+            self._cattn(s, 0, s["qkv"], 3072, s["kc"][li], s["vc"][li], dense, li, lay["wo3"])
+            self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], stats_out=True, nxt=lay["wq23"])
             # source attention (decoder_layer.py:97-107)
             self._cproj(s, lay["wq23"], 1024, 1024, ln=(lay["n2_g"], lay["n2_b"]), bias=lay["bq2"], out=s["q2"])
-            L.check(lib.avsr_dec_attn_step(1, L.ptr(s["q2"]), L.ll(1024), 0, None, L.ptr(s["ckv_t"][li, 0]), L.ptr(s["ckv_t"][li, 1]), None, lmax,
-                                           L.ptr(s["n_run"]), L.ptr(s["utt_off"]), L.ptr(s["utt_T"]), beam, R, L.ptr(s["step"]), None,
-                                           L.ll(s["F"]), att3, None, None, None, st()), "avsr_dec_attn_step(src)")
-            self._cproj(s, lay["wo23"], 1024, 1024, a3=s["att3"], bias=lay["bo2"], residual=s["x"], out=s["x"], stats_out=True)
+            self._cattn(s, 1, s["q2"], 1024, s["ckv_t"][li, 0], s["ckv_t"][li, 1], dense, li, lay["wo23"])
+            self._cproj(s, lay["wo23"], 1024, 1024, a3=s["att3"], bias=lay["bo2"], residual=s["x"], out=s["x"], stats_out=True, nxt=lay["w13"])
             # feed-forward (decoder_layer.py:112-116): ReLU(w_1 LN(x)) goes straight to the bf16x3 operand of w_2
-            self._cproj(s, lay["w13"], 3072, 1024, ln=(lay["n3_g"], lay["n3_b"]), bias=lay["b1"], act=L.ACT_RELU, split=s["ffn3"])
-            self._cproj(s, lay["w23"], 1024, 3072, a3=s["ffn3"], bias=lay["b2"], residual=s["x"], out=s["x"], stats_out=True)
-        # after_norm + output layer (decoder.py:176-181); the bias is added by the softmax kernel that follows
-        self._cproj(s, w.out_w3, V, 1024, ln=(w.after_g, w.after_b), out=s["logits"], ldo=V)
+            self._cproj(s, lay["w13"], 3072, 1024, ln=(lay["n3_g"], lay["n3_b"]), bias=lay["b1"], act=L.ACT_RELU, split=s["ffn3"], nxt=lay["w23"])
+            self._cproj(s, lay["w23"], 1024, 3072, a3=s["ffn3"], bias=lay["b2"], residual=s["x"], out=s["x"], stats_out=True,
+                        nxt=w.layers[li + 1]["wqkv3"] if li + 1 < nl else w.out_w3)
+        # after_norm + output layer (decoder.py:176-181); the bias is added by the softmax kernel that follows.  It fetches
+        # the first projection of the NEXT position (only small kernels run in between)
+        self._cproj(s, w.out_w3, V, 1024, ln=(w.after_g, w.after_b), out=s["logits"], ldo=V, nxt=l0["wqkv3"])
         return s["logits"], 1
 
     def _decoder_layers(self, s, dense: bool = True):

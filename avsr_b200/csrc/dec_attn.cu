@@ -48,6 +48,7 @@ struct AttnArgs {
     const float* kd; const float* vd; const int* conv_len;      // mode 0: dense copy of the converged history prefix (may be null)
     const int* n_run; const int* utt_off; const int* utt_T; int beam; int R; const int* step_p;
     float* out; long long n_frames; __nv_bfloat16* out_split;
+    const char* pf; long long pf_bytes;      // span the next kernel of the chain streams (its weights): fetched into L2 from here
 };
 
 template <int NH>
@@ -367,6 +368,16 @@ dec_attn_stream_kernel(const AttnArgs a) {
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y;
     pdl_trigger();
+    if (a.pf != nullptr && tid == 0) {
+        constexpr long long PIECE = 16 * 1024;
+        const long long ncta = (long long)gridDim.x * gridDim.y, cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        const long long share = ((a.pf_bytes + ncta - 1) / ncta + PIECE - 1) / PIECE * PIECE;
+        const long long lo = cta * share, hi = min(a.pf_bytes, lo + share);
+        for (long long o = lo; o < hi; o += PIECE) {
+            const unsigned n = (unsigned)min(PIECE, hi - o) & ~15u;
+            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf + o), "r"(n) : "memory");
+        }
+    }
 
     // K^T base (groups [j][row][8]) and V base ([row][64]) of this (utterance, head); nr = rows per j plane
     const float* kbase;
@@ -506,10 +517,12 @@ dec_cache_promote_kernel(const float* __restrict__ kc, const float* __restrict__
 // kd / vd / conv_len (mode 0, optional): dense caches of the converged history prefix maintained by avsr_dec_cache_promote,
 //   key element (utt, head, pos, d) at ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at
 //   ((utt*16 + head)*lmax + pos)*64 + d; conv_len [2][R/beam], the kernel reads conv_len[(*step + 1) & 1][utt].
-extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
-                                  const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
-                                  int R, const int* step, float* out, long long n_frames, void* out_split, const float* kd,
-                                  const float* vd, const int* conv_len, cudaStream_t stream) {
+extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
+                                     const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
+                                     int R, const int* step, float* out, long long n_frames, void* out_split, const float* kd,
+                                     const float* vd, const int* conv_len, const void* l2_prefetch, long long l2_prefetch_bytes,
+                                     cudaStream_t stream) {
+    AVSR_REQUIRE(!l2_prefetch || (((uintptr_t)l2_prefetch & 15) == 0 && l2_prefetch_bytes > 0), "avsr_dec_attn_step: prefetch span must be 16-byte aligned");
     AVSR_REQUIRE((kd != nullptr) == (vd != nullptr) && (kd != nullptr) == (conv_len != nullptr) && (mode == 0 || kd == nullptr),
                  "avsr_dec_attn_step: kd / vd / conv_len go together (self-attention only)");
     AVSR_REQUIRE(((uintptr_t)kd & 31) == 0 && ((uintptr_t)vd & 15) == 0, "avsr_dec_attn_step: kd / vd alignment");
@@ -539,7 +552,7 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
     }
     const dim3 grid(R / beam, HEADS);
     const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, kd, vd, conv_len, n_run, utt_off, utt_T, beam, R, step, out,
-                        n_frames, (__nv_bfloat16*)out_split};
+                        n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
     if (mode == 0) {
         if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 4>, grid, dim3(CK), smem, stream, a));
         else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 8>, grid, dim3(CK), smem, stream, a));
@@ -548,6 +561,14 @@ extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, in
         else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 8>, grid, dim3(CK), smem, stream, a));
     }
     return AVSR_OK;
+}
+
+extern "C" int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
+                                  const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
+                                  int R, const int* step, float* out, long long n_frames, void* out_split, const float* kd,
+                                  const float* vd, const int* conv_len, cudaStream_t stream) {
+    return avsr_dec_attn_step_pf(mode, q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, n_run, utt_off, utt_T, beam, R, step, out, n_frames,
+                                 out_split, kd, vd, conv_len, nullptr, 0, stream);
 }
 
 // Copies the newly converged history positions of every utterance from the per-slot caches (all n_layers layers, layer

@@ -74,6 +74,7 @@ struct ProjArgs {
     float* out; long long ldo;
     __nv_bfloat16* split_out;           // compact bf16x3 rows [R][3 N]
     float* stats_out;                   // [N / 128][R][2]
+    const char* pf; long long pf_bytes;  // span the NEXT kernel of the chain streams (its weights): fetched into L2 from here
 };
 
 // three bf16 terms of 8 consecutive fp32 values -> one 16-byte chunk per term
@@ -169,6 +170,19 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            if (p.pf != nullptr) {
+                // the weights of the next projection do not depend on anything: ask the L2 for this CTA's share now (fire and
+                // forget), so that the next kernel's TMA loads find them on chip instead of paying the HBM latency after its wait
+                constexpr long long PIECE = 16 * 1024;
+                const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
+                const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                const long long share = ((p.pf_bytes + ncta - 1) / ncta + PIECE - 1) / PIECE * PIECE;
+                const long long lo = cta * share, hi = min(p.pf_bytes, lo + share);
+                for (long long o = lo; o < hi; o += PIECE) {
+                    const unsigned n = (unsigned)min(PIECE, hi - o) & ~15u;
+                    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf + o), "r"(n) : "memory");
+                }
+            }
             const uint32_t idesc = tc::umma_idesc_bf16(BM, (uint32_t)NB);
             int stage = 0;
             uint32_t phase = 0;
@@ -199,20 +213,51 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const int quad = warp & 3;
         pdl_wait();                                    // x / stats / residual are written by the previous kernels of the chain
         if (p.ln_mode) {
+            // Everything this phase needs from global memory is requested in as few dependent round trips as possible: the
+            // fp32 rows of the first k block and the row statistics go out together; the rows of k block i + 1 are requested
+            // before k block i is converted and stored.
+            const int ch = et & 7;                     // 16-byte chunk = 8 consecutive columns; fixed per thread
+            const int rbase = et >> 3;                 // this thread's rows: rbase + 16 i
+            constexpr int MAXI = MAX_NB / 16;
+            const int NI = NB / 16;
+            float4 xa[MAXI][2], xb[MAXI][2], ga[4], gb[4];
+            auto load = [&](float4 (&xr)[MAXI][2], float4 (&gv)[4], int kb) {
+                const int c0 = kb * BK + ch * 8;
+                gv[0] = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0)); gv[1] = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0 + 4));
+                gv[2] = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0)); gv[3] = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0 + 4));
+#pragma unroll
+                for (int i = 0; i < MAXI; ++i) {
+                    const int row = n0 + rbase + 16 * i;
+                    if (i < NI && row < R) {
+                        const float* xp = p.x + (long long)row * p.ldx + c0;
+                        xr[i][0] = __ldcg(reinterpret_cast<const float4*>(xp));
+                        xr[i][1] = __ldcg(reinterpret_cast<const float4*>(xp + 4));
+                    } else {
+                        xr[i][0] = xr[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            };
+            load(xa, ga, kb0);
             // ---- row statistics: merge the (mean, M2) of the K / 128 column tiles of every row in tile order
             if (et < NB) {
                 const int row = n0 + et;
                 float mean = 0.f, rstd = 0.f;
                 if (row < R) {
-                    const int nt = K / 128;
+                    const int nt = K / 128;            // <= 8 (checked on the host): one batch of loads, one L2 round trip
+                    float2 st[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        st[u] = (u < nt) ? __ldcg(reinterpret_cast<const float2*>(p.stats_in + ((long long)u * R + row) * 2)) : make_float2(0.f, 0.f);
                     float ms = 0.f;
-                    for (int t = 0; t < nt; ++t) ms += __ldcg(p.stats_in + ((long long)t * R + row) * 2);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) ms += st[u].x;
                     mean = ms / (float)nt;
+                    // Chan's merge of equal-sized tiles in tile order: M2 = sum_t (M2_t + 128 (mean_t - mean)^2)
                     float m2 = 0.f;
-                    for (int t = 0; t < nt; ++t) {
-                        const float2 st = __ldcg(reinterpret_cast<const float2*>(p.stats_in + ((long long)t * R + row) * 2));
-                        const float d = st.x - mean;
-                        m2 += st.y + 128.f * d * d;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float d = st[u].x - mean;
+                        if (u < nt) m2 += st[u].y + 128.f * d * d;
                     }
                     rstd = rsqrtf(m2 / (float)K + p.ln_eps);
                 }
@@ -222,42 +267,42 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             asm volatile("bar.sync 1, 128;" ::: "memory");
             // ---- stage LayerNorm(x) of this CTA's k blocks as three bf16 terms in the UMMA layout: a tile is NB rows of
             //      128 bytes (64 bf16), 16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4) (128-byte swizzle)
-            const int ch = et & 7;                     // 16-byte chunk = 8 consecutive columns; fixed per thread
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
+            auto process = [&](const float4 (&xr)[MAXI][2], const float4 (&gv)[4], int kb) {
                 if (kb - kb0 >= STAGES) mbar_wait(&empty[stage], phase ^ 1);
-                const int c0 = kb * BK + ch * 8;
-                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0 + 4));
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0 + 4));
-                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float g[8] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w};
+                const float b[8] = {gv[2].x, gv[2].y, gv[2].z, gv[2].w, gv[3].x, gv[3].y, gv[3].z, gv[3].w};
                 uint8_t* sa = smem + stage * STAGE_BYTES + 3 * W_TILE;
-                for (int r = et >> 3; r < NB; r += 16) {
-                    const int row = n0 + r;
-                    float v[8];
-                    if (row < R) {
-                        const float4 x0 = __ldcg(reinterpret_cast<const float4*>(p.x + (long long)row * p.ldx + c0));
-                        const float4 x1 = __ldcg(reinterpret_cast<const float4*>(p.x + (long long)row * p.ldx + c0 + 4));
-                        const float xin[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int i = 0; i < MAXI; ++i) {
+                    if (i < NI) {
+                        const int r = rbase + 16 * i;
+                        const float xin[8] = {xr[i][0].x, xr[i][0].y, xr[i][0].z, xr[i][0].w, xr[i][1].x, xr[i][1].y, xr[i][1].z, xr[i][1].w};
                         const float mean = s_mean[r], rstd = s_rstd[r];
+                        float v[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = (xin[i] - mean) * rstd * g[i] + b[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                        for (int j = 0; j < 8; ++j) v[j] = (n0 + r < R) ? (xin[j] - mean) * rstd * g[j] + b[j] : 0.f;
+                        uint4 c1, c2, c3;
+                        split3_chunk(v, c1, c2, c3);
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(sa + off) = c1;
+                        *reinterpret_cast<uint4*>(sa + A_TILE + off) = c2;
+                        *reinterpret_cast<uint4*>(sa + 2 * A_TILE + off) = c3;
                     }
-                    uint4 c1, c2, c3;
-                    split3_chunk(v, c1, c2, c3);
-                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
-                    *reinterpret_cast<uint4*>(sa + off) = c1;
-                    *reinterpret_cast<uint4*>(sa + A_TILE + off) = c2;
-                    *reinterpret_cast<uint4*>(sa + 2 * A_TILE + off) = c3;
                 }
                 tc::fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int kb = kb0; kb < kb1; kb += 2) {
+                if (kb + 1 < kb1) load(xb, gb, kb + 1);
+                process(xa, ga, kb);
+                if (kb + 1 < kb1) {
+                    if (kb + 2 < kb1) load(xa, ga, kb + 2);
+                    process(xb, gb, kb + 1);
+                }
             }
         }
         // ---- accumulator tile -> shared memory as [row][feature] fp32 (conflict-free: a register = a row, lanes = features)
@@ -368,11 +413,14 @@ int sm_count() {
 
 size_t smem_bytes(int nb) { return (size_t)STAGES * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + 2 * MAX_NB * sizeof(float); }
 
+int g_force_splits = 0;
 bool g_configured = false;
 int configure() {
     if (!g_configured) {
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_NB)));
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const char* e = getenv("AVSR_X3C_SPLITS");
+        if (e) g_force_splits = atoi(e);
         g_configured = true;
     }
     return AVSR_OK;
@@ -410,8 +458,7 @@ int max_active_clusters(int cs, int nb) {
 
 // K splits (= cluster size) for a projection: as many CTAs as fit in ONE wave of co-resident clusters.
 int plan_splits(int R, int N, int K, int nb) {
-    static int force = -1;                             // dev knob AVSR_X3C_SPLITS
-    if (force < 0) { const char* e = getenv("AVSR_X3C_SPLITS"); force = e ? atoi(e) : 0; }
+    const int force = g_force_splits;                  // dev knob (avsr_dec_proj_force_splits / AVSR_X3C_SPLITS)
     const int tiles = cdiv(N, BM);
     const int nkb = K / BK;
     int smax = sm_count() / tiles;
@@ -442,6 +489,15 @@ extern "C" int avsr_dec_proj_max_clusters(int cluster_size, int nb) {
     return max_active_clusters(cluster_size, nb);
 }
 
+// Dev knob: force the cluster size (= K splits) of every following avsr_dec_proj call (0 = plan automatically).  A forced
+// size whose clusters do not all fit at once simply runs in more than one wave.
+extern "C" int avsr_dec_proj_force_splits(int splits) {
+    if (splits < 0 || splits > MAX_CLUSTER) return AVSR_ERR_ARG;
+    if (configure() != AVSR_OK) return AVSR_ERR_CUDA;
+    g_force_splits = splits;
+    return AVSR_OK;
+}
+
 // One decoder-step projection with its glue:  y = act(a W^T + bias) + residual  for R rows.
 //   operand a:  A3 != NULL: compact bf16x3 rows [R, 3K] (pitch lda elements), loaded with TMA; else a = LayerNorm(x) with
 //               x [R, K] fp32 (pitch ldx), stats_in [K/128][R][2] = (mean, M2) of every 128-column tile of x as a previous call
@@ -449,17 +505,19 @@ extern "C" int avsr_dec_proj_max_clusters(int cluster_size, int nb) {
 //   W3:         compact bf16x3 weights [N, 3K] (pitch ldw).  K % 64 == 0, N % 4 == 0.
 //   outputs:    out [R, N] fp32 (pitch ldo) and / or split_out [R, 3N] compact bf16x3; stats_out [N/128][R][2] (N % 128 == 0)
 //               for a later LayerNorm-mode call.  residual may alias out (each element is read and written by one thread).
+//   l2_prefetch: optional span (the weights of the NEXT projection of the chain) that the kernel asks the L2 to fetch.
 extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
                              const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
                              const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
-                             cudaStream_t stream) {
+                             const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream) {
     AVSR_REQUIRE(W3 && R > 0 && N > 0 && K > 0 && (K % BK) == 0, "avsr_dec_proj: bad shape R=%d N=%d K=%d (K must be a multiple of 64)", R, N, K);
     AVSR_REQUIRE(!split_out || (N & 3) == 0, "avsr_dec_proj: split_out needs N %% 4 == 0");
     AVSR_REQUIRE((A3 != nullptr) != (x != nullptr), "avsr_dec_proj: exactly one of A3 (bf16x3 rows) and x (LayerNorm mode) must be given");
-    AVSR_REQUIRE(x == nullptr || (stats_in && ln_g && ln_b && (K % 128) == 0 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 &&
+    AVSR_REQUIRE(x == nullptr || (stats_in && ln_g && ln_b && (K % 128) == 0 && K <= 1024 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 &&
                                   ((uintptr_t)ln_g & 15) == 0 && ((uintptr_t)ln_b & 15) == 0 && ((uintptr_t)stats_in & 7) == 0),
-                 "avsr_dec_proj: LayerNorm mode needs stats_in / gamma / beta, K %% 128 == 0 and 16-byte aligned rows");
+                 "avsr_dec_proj: LayerNorm mode needs stats_in / gamma / beta, K %% 128 == 0, K <= 1024 and 16-byte aligned rows");
     AVSR_REQUIRE(out || split_out, "avsr_dec_proj: no output");
+    AVSR_REQUIRE(!l2_prefetch || (((uintptr_t)l2_prefetch & 15) == 0 && l2_prefetch_bytes > 0), "avsr_dec_proj: prefetch span must be 16-byte aligned");
     AVSR_REQUIRE(act == AVSR_ACT_NONE || act == AVSR_ACT_RELU, "avsr_dec_proj: activation %d unsupported", act);
     AVSR_REQUIRE(!stats_out || (N % 128) == 0, "avsr_dec_proj: stats_out needs N %% 128 == 0");
     AVSR_REQUIRE((!out || ((uintptr_t)out & 15) == 0) && (!residual || ((uintptr_t)residual & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0) &&
@@ -481,7 +539,7 @@ extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long
         ta = tw;
     }
     ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, bias, act, residual, ldr, out, ldo,
-                  (__nv_bfloat16*)split_out, stats_out};
+                  (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles_m, splits, tiles_n);
     cfg.blockDim = dim3(NUM_THREADS);

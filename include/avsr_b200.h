@@ -134,13 +134,16 @@ int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long 
  *   W3:       compact bf16x3 weights [N, 3K] (pitch ldw), K % 64 == 0.
  *   outputs:  out [R, N] fp32 (pitch ldo) and / or split_out [R, 3N] compact bf16x3 (N % 4 == 0); stats_out [N/128][R][2] (N % 128 == 0).
  *             residual [R, N] (pitch ldr) may alias out.  act: AVSR_ACT_NONE or AVSR_ACT_RELU (applied before the residual).
+ *   l2_prefetch / l2_prefetch_bytes: optional span (the weights of the NEXT projection of the chain, 16-byte aligned) that the
+ *             kernel asks the L2 to fetch while it runs, so the next launch does not pay the HBM latency after its wait.
  * avsr_dec_proj_splits: the cluster size (= K splits) chosen for a shape on the current device. */
 int avsr_dec_proj_splits(int R, int N, int K);
+int avsr_dec_proj_force_splits(int splits);                /* dev knob: 0 = automatic */
 int avsr_dec_proj_max_clusters(int cluster_size, int nb);   /* resident clusters of that size (operand tiles of nb rows) */
 int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
                   const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
                   const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
-                  avsr_stream_t stream);
+                  const void* l2_prefetch, long long l2_prefetch_bytes, avsr_stream_t stream);
 /* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
 int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */
@@ -200,6 +203,12 @@ int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, c
                        const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
                        const int* step, float* out, long long n_frames, void* out_split, const float* kd, const float* vd,
                        const int* conv_len, avsr_stream_t stream);
+/* The same, and every CTA first asks the L2 to fetch its share of [l2_prefetch, +l2_prefetch_bytes): the weights of the
+ * projection that follows the attention in the chain (must not be written by the chain). */
+int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
+                          const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
+                          const int* step, float* out, long long n_frames, void* out_split, const float* kd, const float* vd,
+                          const int* conv_len, const void* l2_prefetch, long long l2_prefetch_bytes, avsr_stream_t stream);
 /* Dense copy of the CONVERGED history prefix (positions where all live hyps of an utterance share their ancestor): copies the
  * newly converged rows of all layers from the per-slot caches to kd / vd (key element (layer, utt, head, pos, d) at
  * layer*B*16*lmax*64 + ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at layer*B*16*lmax*64 +
