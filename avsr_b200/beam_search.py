@@ -99,6 +99,9 @@ class BatchedBeamSearch:
         # "splitk" = round 1's partial sums through L2 + row-epilogue launches (csrc/gemm_x3.cu, 78 launches), kept for A/B runs
         self.proj = os.environ.get("AVSR_PROJ", "cluster")
         self.weight_prefetch = os.environ.get("AVSR_WEIGHT_PREFETCH", "1") != "0"      # dev A/B switch of the L2 fetch-ahead
+        # LayerNorm folded into the consuming projection (avsr_dec_proj_folded: raw rows through TMA, mean / rstd applied to the
+        # finished sums) instead of normalising while the operand is staged; AVSR_LN_FOLD=0 keeps the staged form (A/B switch)
+        self.ln_fold = os.environ.get("AVSR_LN_FOLD", "1") != "0"
         if self.proj not in ("cluster", "splitk"):
             raise RuntimeError(f"AVSR_PROJ must be cluster or splitk, got {self.proj!r}")
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
@@ -113,6 +116,11 @@ class BatchedBeamSearch:
         # projection launches of the chains each want one CTA with ~200 KB of shared memory on every SM and serialise.
         self.n_groups = max(1, int(os.environ.get("AVSR_DECODE_GROUPS", "1")))
         L.load()
+        if self.n_groups > 1 and self.proj == "cluster":
+            # concurrent chains: plan every projection for its share of the SMs so that the chains' clusters are co-resident
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            L.check(L.load().avsr_dec_proj_set_sm_budget(int(os.environ.get("AVSR_SM_BUDGET", sms // self.n_groups))), "avsr_dec_proj_set_sm_budget")
+            L.launch_count -= 1
 
     # ------------------------------------------------------------------------------------------ session buffers
     T_BUCKET = 16        # sessions (buffers + the captured graphs) are shared by all batches whose longest utterance rounds up to the same multiple
@@ -202,6 +210,7 @@ class BatchedBeamSearch:
             # the residual stream (consumed by the LayerNorm of the next projection), dense logits
             s["qkv"], s["q2"] = f32(R, 3072), f32(R, 1024)
             s["stats"] = f32(8, R, 2)
+            s["x3"] = torch.zeros(R, 3 * 1024, dtype=torch.bfloat16, device=dev)      # the residual stream as compact bf16x3 (folded LayerNorm)
             s["logits"] = f32(R, V)
             n_part = max(lib.avsr_gemm_x3_splits(R, n, k) * R * n for n, k in shapes)
             s["gbar"] = torch.zeros(2, dtype=torch.int32, device=dev)          # grid-barrier state of the fused projections
@@ -454,17 +463,29 @@ class BatchedBeamSearch:
                                           L.ll(pf.numel() * pf.element_size() if pf is not None else 0), L.stream()),
                 "avsr_dec_attn_step(self)" if mode == 0 else "avsr_dec_attn_step(src)")
 
+    def _cfold(self, s, W3g, u, c, N, act=L.ACT_NONE, out=None, ldo=None, split=None, nxt=None):
+        """Projection of LayerNorm(x) with the LayerNorm folded in (avsr_dec_proj_folded): operand = the raw rows s['x3']."""
+        lib = L.load()
+        pf = nxt if (nxt is not None and self.weight_prefetch) else None
+        L.check(lib.avsr_dec_proj_folded(L.ptr(s["x3"]), L.ll(3 * 1024), L.ptr(s["stats"]), C.c_float(1e-12), L.ptr(u), L.ptr(c), L.ptr(W3g),
+                                         L.ll(3 * 1024), s["R"], N, 1024, act, None, L.ll(1024), L.ptr(out), L.ll(N if ldo is None else ldo),
+                                         L.ptr(split), None, L.ptr(pf), L.ll(pf.numel() * pf.element_size() if pf is not None else 0),
+                                         L.stream()), "avsr_dec_proj_folded")
+
     def _decoder_layers_cluster(self, s, dense: bool = True):
         """Decoder.forward_one_step up to the output layer with the cluster projections: 8 launches per layer (6 projections + 2
-        attentions).  The residual stream x stays fp32; every projection that updates it also leaves the per-tile LayerNorm
-        statistics, and the projection that consumes LayerNorm(x) normalises while it stages its operand.  Every kernel asks
-        the L2 for the weights of the projection that follows it, so those stream from HBM while the chain is busy elsewhere."""
+        attentions).  The residual stream x stays fp32; every projection that updates it also leaves the row as compact bf16x3
+        (x3) and the per-tile LayerNorm statistics, and the projection that consumes LayerNorm(x) takes x3 through TMA with the
+        LayerNorm folded into its weights and epilogue (ln_fold) or normalises while it stages its operand.  Every kernel asks
+        the L2 for the weights of the projection that follows it."""
         lib = L.load()
         w = self.w
         R, beam, V, lmax = s["R"], self.beam_size, self.n_vocab, s["lmax"]
         st = L.stream
         l0 = w.layers[0]
         nl = w.n_layers
+        fold = self.ln_fold
+        x3 = s["x3"] if fold else None
         if dense:
             L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
                                                L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
@@ -475,21 +496,37 @@ class BatchedBeamSearch:
             # self-attention (decoder_layer.py:82-93): q | k | v finished by the projection, bias included
             if li == 0:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, a3=s["a3"], bias=lay["bqkv"], out=s["qkv"])
+            elif fold:
+                self._cfold(s, lay["wqkv3g"], lay["uqkv"], lay["cqkv"], 3072, out=s["qkv"])
             else:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, ln=(lay["n1_g"], lay["n1_b"]), bias=lay["bqkv"], out=s["qkv"])
             self._cattn(s, 0, s["qkv"], 3072, s["kc"][li], s["vc"][li], dense, li, lay["wo3"])
-            self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], stats_out=True, nxt=lay["wq23"])
+            self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
+                        nxt=lay["wq23g"] if fold else lay["wq23"])
             # source attention (decoder_layer.py:97-107)
-            self._cproj(s, lay["wq23"], 1024, 1024, ln=(lay["n2_g"], lay["n2_b"]), bias=lay["bq2"], out=s["q2"])
+            if fold:
+                self._cfold(s, lay["wq23g"], lay["uq2"], lay["cq2"], 1024, out=s["q2"])
+            else:
+                self._cproj(s, lay["wq23"], 1024, 1024, ln=(lay["n2_g"], lay["n2_b"]), bias=lay["bq2"], out=s["q2"])
             self._cattn(s, 1, s["q2"], 1024, s["ckv_t"][li, 0], s["ckv_t"][li, 1], dense, li, lay["wo23"])
-            self._cproj(s, lay["wo23"], 1024, 1024, a3=s["att3"], bias=lay["bo2"], residual=s["x"], out=s["x"], stats_out=True, nxt=lay["w13"])
+            self._cproj(s, lay["wo23"], 1024, 1024, a3=s["att3"], bias=lay["bo2"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
+                        nxt=lay["w13g"] if fold else lay["w13"])
             # feed-forward (decoder_layer.py:112-116): ReLU(w_1 LN(x)) goes straight to the bf16x3 operand of w_2
-            self._cproj(s, lay["w13"], 3072, 1024, ln=(lay["n3_g"], lay["n3_b"]), bias=lay["b1"], act=L.ACT_RELU, split=s["ffn3"], nxt=lay["w23"])
-            self._cproj(s, lay["w23"], 1024, 3072, a3=s["ffn3"], bias=lay["b2"], residual=s["x"], out=s["x"], stats_out=True,
-                        nxt=w.layers[li + 1]["wqkv3"] if li + 1 < nl else w.out_w3)
-        # after_norm + output layer (decoder.py:176-181); the bias is added by the softmax kernel that follows.  It fetches
-        # the first projection of the NEXT position (only small kernels run in between)
-        self._cproj(s, w.out_w3, V, 1024, ln=(w.after_g, w.after_b), out=s["logits"], ldo=V, nxt=l0["wqkv3"])
+            if fold:
+                self._cfold(s, lay["w13g"], lay["u1"], lay["c1"], 3072, act=L.ACT_RELU, split=s["ffn3"], nxt=lay["w23"])
+            else:
+                self._cproj(s, lay["w13"], 3072, 1024, ln=(lay["n3_g"], lay["n3_b"]), bias=lay["b1"], act=L.ACT_RELU, split=s["ffn3"], nxt=lay["w23"])
+            if li + 1 < nl:
+                nxt = w.layers[li + 1]["wqkv3g"] if fold else w.layers[li + 1]["wqkv3"]
+            else:
+                nxt = w.out_w3g if fold else w.out_w3
+            self._cproj(s, lay["w23"], 1024, 3072, a3=s["ffn3"], bias=lay["b2"], residual=s["x"], out=s["x"], split=x3, stats_out=True, nxt=nxt)
+        # after_norm + output layer (decoder.py:176-181); the output bias is added by the softmax kernel that follows.  It
+        # fetches the first projection of the NEXT position (only small kernels run in between)
+        if fold:
+            self._cfold(s, w.out_w3g, w.out_u, w.out_c, V, out=s["logits"], ldo=V, nxt=l0["wqkv3"])
+        else:
+            self._cproj(s, w.out_w3, V, 1024, ln=(w.after_g, w.after_b), out=s["logits"], ldo=V, nxt=l0["wqkv3"])
         return s["logits"], 1
 
     def _decoder_layers(self, s, dense: bool = True):

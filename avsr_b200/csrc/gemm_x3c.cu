@@ -68,6 +68,9 @@ struct ProjArgs {
     const float* x; long long ldx;
     const float* stats_in;              // [K / 128][R][2] (mean, M2) of each 128-column tile of x
     const float* ln_g; const float* ln_b; float ln_eps;
+    // folded LayerNorm (TMA operand = the RAW rows x as bf16x3, weights pre-multiplied by gamma): the epilogue applies
+    // y = rstd * (acc - mean * fold_u[n]) + fold_c[n], with fold_u = W gamma, fold_c = W beta + bias (both from the host)
+    const float* fold_u;                // fold_c travels as `bias`
     // epilogue
     const float* bias; int act;
     const float* residual; long long ldr;
@@ -335,6 +338,16 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const bool vec = (N & 3) == 0 && (p.ldo & 3) == 0 && (p.ldr & 3) == 0;
         const bool fok = fcol < N;
         const uint32_t red_s = tc::smem_u32(red);
+        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.fold_u != nullptr && fok) {
+            if (vec) u4 = __ldg(reinterpret_cast<const float4*>(p.fold_u + fcol));
+            else {
+                u4.x = __ldg(p.fold_u + fcol);
+                if (fcol + 1 < N) u4.y = __ldg(p.fold_u + fcol + 1);
+                if (fcol + 2 < N) u4.z = __ldg(p.fold_u + fcol + 2);
+                if (fcol + 3 < N) u4.w = __ldg(p.fold_u + fcol + 3);
+            }
+        }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && fok) {
             if (vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + fcol));
@@ -367,6 +380,19 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int z = 0; z < MAX_CLUSTER; ++z)
                 if (z < (int)csize) { v.x += t[z].x; v.y += t[z].y; v.z += t[z].z; v.w += t[z].w; }       // split order: deterministic
+            if (p.fold_u != nullptr) {
+                // LayerNorm of the operand row, applied to the finished sums (see ProjArgs): merge the row's tile statistics
+                // in tile order (lanes 0 .. K/128-1 hold one tile each; xor-shuffle trees are order-independent per lane count)
+                const int nt = K / 128;
+                float2 st = make_float2(0.f, 0.f);
+                if (lane < nt) st = __ldcg(reinterpret_cast<const float2*>(p.stats_in + ((long long)lane * R + row) * 2));
+                const float mean = warp_sum(st.x) / (float)nt;
+                const float d = st.x - mean;
+                const float m2 = warp_sum(lane < nt ? st.y + 128.f * d * d : 0.f);
+                const float rstd = rsqrtf(m2 / (float)K + p.ln_eps);
+                v.x = rstd * (v.x - mean * u4.x); v.y = rstd * (v.y - mean * u4.y);
+                v.z = rstd * (v.z - mean * u4.z); v.w = rstd * (v.w - mean * u4.w);
+            }
             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
             if (p.act == AVSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             v.x += res4.x; v.y += res4.y; v.z += res4.z; v.w += res4.w;
@@ -414,6 +440,7 @@ int sm_count() {
 size_t smem_bytes(int nb) { return (size_t)STAGES * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + 2 * MAX_NB * sizeof(float); }
 
 int g_force_splits = 0;
+int g_sm_budget = 0;                                   // SMs one projection may occupy (0 = all): concurrent decode chains share the GPU
 bool g_configured = false;
 int configure() {
     if (!g_configured) {
@@ -461,13 +488,15 @@ int plan_splits(int R, int N, int K, int nb) {
     const int force = g_force_splits;                  // dev knob (avsr_dec_proj_force_splits / AVSR_X3C_SPLITS)
     const int tiles = cdiv(N, BM);
     const int nkb = K / BK;
-    int smax = sm_count() / tiles;
+    const int budget = (g_sm_budget > 0 && g_sm_budget < sm_count()) ? g_sm_budget : sm_count();
+    const int share = sm_count() / budget;             // chains that run side by side: each needs its clusters resident
+    int smax = budget / tiles;
     if (smax > MAX_CLUSTER) smax = MAX_CLUSTER;
     if (smax > nkb) smax = nkb;
     if (smax < 1) smax = 1;
     if (force > 0) return force < smax ? force : smax;
     for (int s = smax; s > 1; --s)
-        if (max_active_clusters(s, nb) >= tiles) return s;
+        if (max_active_clusters(s, nb) >= tiles * share) return s;
     return 1;
 }
 
@@ -498,6 +527,16 @@ extern "C" int avsr_dec_proj_force_splits(int splits) {
     return AVSR_OK;
 }
 
+// SMs the work of ONE projection launch is planned for (0 = the whole device).  With G decode chains running side by side
+// on separate streams, a budget of sm_count / G keeps every launch's clusters co-resident with the other chains' launches
+// instead of serialising behind them.
+extern "C" int avsr_dec_proj_set_sm_budget(int sms) {
+    if (sms < 0) return AVSR_ERR_ARG;
+    if (configure() != AVSR_OK) return AVSR_ERR_CUDA;
+    g_sm_budget = sms;
+    return AVSR_OK;
+}
+
 // One decoder-step projection with its glue:  y = act(a W^T + bias) + residual  for R rows.
 //   operand a:  A3 != NULL: compact bf16x3 rows [R, 3K] (pitch lda elements), loaded with TMA; else a = LayerNorm(x) with
 //               x [R, K] fp32 (pitch ldx), stats_in [K/128][R][2] = (mean, M2) of every 128-column tile of x as a previous call
@@ -506,13 +545,15 @@ extern "C" int avsr_dec_proj_force_splits(int splits) {
 //   outputs:    out [R, N] fp32 (pitch ldo) and / or split_out [R, 3N] compact bf16x3; stats_out [N/128][R][2] (N % 128 == 0)
 //               for a later LayerNorm-mode call.  residual may alias out (each element is read and written by one thread).
 //   l2_prefetch: optional span (the weights of the NEXT projection of the chain) that the kernel asks the L2 to fetch.
-extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
-                             const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
+static int dec_proj_launch(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
+                             const float* ln_b, float ln_eps, const float* fold_u, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
                              const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
                              const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream) {
     AVSR_REQUIRE(W3 && R > 0 && N > 0 && K > 0 && (K % BK) == 0, "avsr_dec_proj: bad shape R=%d N=%d K=%d (K must be a multiple of 64)", R, N, K);
     AVSR_REQUIRE(!split_out || (N & 3) == 0, "avsr_dec_proj: split_out needs N %% 4 == 0");
     AVSR_REQUIRE((A3 != nullptr) != (x != nullptr), "avsr_dec_proj: exactly one of A3 (bf16x3 rows) and x (LayerNorm mode) must be given");
+    AVSR_REQUIRE(!fold_u || (A3 && stats_in && bias && (K % 128) == 0 && K <= 4096 && ((uintptr_t)fold_u & 15) == 0 && ((uintptr_t)stats_in & 7) == 0),
+                 "avsr_dec_proj_folded: needs bf16x3 rows, stats_in, fold_u / fold_c and K %% 128 == 0 (K <= 4096)");
     AVSR_REQUIRE(x == nullptr || (stats_in && ln_g && ln_b && (K % 128) == 0 && K <= 1024 && (ldx & 3) == 0 && ((uintptr_t)x & 15) == 0 &&
                                   ((uintptr_t)ln_g & 15) == 0 && ((uintptr_t)ln_b & 15) == 0 && ((uintptr_t)stats_in & 7) == 0),
                  "avsr_dec_proj: LayerNorm mode needs stats_in / gamma / beta, K %% 128 == 0, K <= 1024 and 16-byte aligned rows");
@@ -538,7 +579,7 @@ extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long
     } else {
         ta = tw;
     }
-    ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, bias, act, residual, ldr, out, ldo,
+    ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, fold_u, bias, act, residual, ldr, out, ldo,
                   (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles_m, splits, tiles_n);
@@ -556,4 +597,27 @@ extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long
     cfg.numAttrs = 2;
     AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_proj_kernel, tw, ta, p));
     return AVSR_OK;
+}
+
+extern "C" int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
+                             const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
+                             const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
+                             const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream) {
+    return dec_proj_launch(A3, lda, x, ldx, stats_in, ln_g, ln_b, ln_eps, nullptr, W3, ldw, R, N, K, bias, act, residual, ldr, out, ldo, split_out,
+                           stats_out, l2_prefetch, l2_prefetch_bytes, stream);
+}
+
+// LayerNorm FOLDED into the projection: y = act(LayerNorm(x) W^T + bias) + residual computed as
+//     y = act( rstd * (x (gamma . W)^T - mean * fold_u) + fold_c ) + residual,   fold_u[n] = sum_k gamma[k] W[n][k],
+//     fold_c[n] = sum_k beta[k] W[n][k] + bias[n],
+// so the operand is the RAW row x as compact bf16x3 (X3 [R, 3K], written by the projection that produced x through its
+// split_out), loaded with TMA like any other operand, and nothing is normalised on the critical path: mean / rstd come from
+// stats_in [K/128][R][2] in the epilogue.  W3g = compact bf16x3 of gamma . W (weights.fold_layernorm).  K % 128 == 0.
+extern "C" int avsr_dec_proj_folded(const void* X3, long long lda, const float* stats_in, float ln_eps, const float* fold_u, const float* fold_c,
+                                    const void* W3g, long long ldw, int R, int N, int K, int act, const float* residual, long long ldr, float* out,
+                                    long long ldo, void* split_out, float* stats_out, const void* l2_prefetch, long long l2_prefetch_bytes,
+                                    cudaStream_t stream) {
+    AVSR_REQUIRE(fold_u && fold_c, "avsr_dec_proj_folded: fold_u / fold_c missing");
+    return dec_proj_launch(X3, lda, nullptr, 0, stats_in, nullptr, nullptr, ln_eps, fold_u, W3g, ldw, R, N, K, fold_c, act, residual, ldr, out, ldo,
+                           split_out, stats_out, l2_prefetch, l2_prefetch_bytes, stream);
 }

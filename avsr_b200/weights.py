@@ -137,6 +137,21 @@ def split3_weight_compact(w: torch.Tensor) -> torch.Tensor:
     return torch.cat([w1, w2, w3], dim=1).contiguous()
 
 
+def fold_layernorm(w: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm folded into the nn.Linear that consumes it (csrc/gemm_x3c.cu, avsr_dec_proj_folded):
+    LayerNorm(x) W^T + bias = rstd * (x (gamma . W)^T - mean * u) + c with u = W gamma, c = W beta + bias.
+    Returns (compact bf16x3 of gamma . W, u fp32 [N], c fp32 [N]); products and sums in float64."""
+    wd = w.double().cpu()
+    g, b = gamma.double().cpu(), beta.double().cpu()
+    wg = wd * g.unsqueeze(0)
+    u = wg.sum(1)
+    c = wd @ b
+    if bias is not None:
+        c = c + bias.double().cpu()
+    dev = w.device
+    return split3_weight_compact(wg.float().to(dev)), u.float().to(dev).contiguous(), c.float().to(dev).contiguous()
+
+
 class DecoderWeights:
     """Operands of the 6-layer transformer decoder + CTC head: fp32 (CUDA-core path) and bf16x3 (tensor-core path)."""
 
@@ -191,5 +206,12 @@ class DecoderWeights:
             for k in ("wqkv", "wo", "wq2", "wo2", "w1", "w2"):
                 lay[k + "3"] = split3_weight_compact(lay[k])            # per-position projections (gemm_x3)
         self.out_w3 = split3_weight_compact(self.out_w)
+        # LayerNorm-folded operands of the projections that consume a LayerNorm (norm1 -> q|k|v, norm2 -> src q, norm3 -> w_1,
+        # after_norm -> output layer; decoder_layer.py:82-116, decoder.py:176-181)
+        for lay in self.layers:
+            lay["wqkv3g"], lay["uqkv"], lay["cqkv"] = fold_layernorm(lay["wqkv"], lay["bqkv"], lay["n1_g"], lay["n1_b"])
+            lay["wq23g"], lay["uq2"], lay["cq2"] = fold_layernorm(lay["wq2"], lay["bq2"], lay["n2_g"], lay["n2_b"])
+            lay["w13g"], lay["u1"], lay["c1"] = fold_layernorm(lay["w1"], lay["b1"], lay["n3_g"], lay["n3_b"])
+        self.out_w3g, self.out_u, self.out_c = fold_layernorm(self.out_w, None, self.after_g, self.after_b)     # out_b is added by the softmax kernel
         self.ctc_w6 = split3_weight(self.ctc_w)                         # once-per-utterance projections (generic GEMM, K' = 6K)
         self.ckv_w6 = split3_weight(self.ckv_w)

@@ -139,11 +139,21 @@ int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long 
  * avsr_dec_proj_splits: the cluster size (= K splits) chosen for a shape on the current device. */
 int avsr_dec_proj_splits(int R, int N, int K);
 int avsr_dec_proj_force_splits(int splits);                /* dev knob: 0 = automatic */
+int avsr_dec_proj_set_sm_budget(int sms);                  /* SMs one launch is planned for (0 = all): concurrent decode chains */
 int avsr_dec_proj_max_clusters(int cluster_size, int nb);   /* resident clusters of that size (operand tiles of nb rows) */
 int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
                   const float* ln_b, float ln_eps, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
                   const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
                   const void* l2_prefetch, long long l2_prefetch_bytes, avsr_stream_t stream);
+/* LayerNorm FOLDED into the projection (what the decode position uses): y = act(LayerNorm(x) W^T + bias) + residual computed as
+ * y = act(rstd * (x (gamma . W)^T - mean * fold_u) + fold_c) + residual with fold_u[n] = sum_k gamma[k] W[n][k] and
+ * fold_c[n] = sum_k beta[k] W[n][k] + bias[n] (host, float64).  X3 = the RAW rows of x as compact bf16x3 [R, 3K] (written by the
+ * projection that produced x through split_out), W3g = compact bf16x3 of gamma . W; mean / rstd of a row come from stats_in
+ * [K/128][R][2] in the epilogue, so nothing is normalised on the critical path.  K % 128 == 0. */
+int avsr_dec_proj_folded(const void* X3, long long lda, const float* stats_in, float ln_eps, const float* fold_u, const float* fold_c,
+                         const void* W3g, long long ldw, int R, int N, int K, int act, const float* residual, long long ldr, float* out,
+                         long long ldo, void* split_out, float* stats_out, const void* l2_prefetch, long long l2_prefetch_bytes,
+                         avsr_stream_t stream);
 /* fp32 [rows, K] -> bf16 [rows, 6K] in the bf16x3 activation layout. */
 int avsr_split3(const float* in, long long ldi, void* out, long long rows, int K, avsr_stream_t stream);
 /* softmax(q k^T) v per head over packed variable-length utterances (modeling_wav2vec2.py:438-549 via avhubert.py:751). */

@@ -635,3 +635,38 @@ def test_dec_proj_cluster(L, R, N, K, mode):
     if stats is not None:
         want = _tile_stats(out)
         assert (stats.cpu() - want.cpu()).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("R,N,mode", [(96, 1024, "plain"), (96, 3072, "relu_split"), (96, 5049, "nobias"), (160, 3072, "plain"), (5, 1024, "plain")])
+def test_dec_proj_folded_layernorm(L, R, N, mode):
+    """avsr_dec_proj_folded: LayerNorm folded into the projection (raw rows through TMA, mean / rstd applied to the finished
+    sums) against float64 LayerNorm -> Linear, with a row mean that is NOT small against the spread."""
+    from avsr_b200.weights import fold_layernorm
+    lib = L.load()
+    K = 1024
+    x = _rand(R, K, seed=1, scale=2.0) + 1.5                 # |mean| ~ 0.75 sigma: the cancellation the folded form has to survive
+    w = _rand(N, K, seed=2, scale=0.03)
+    bias = None if mode == "nobias" else _rand(N, seed=3, scale=0.1)
+    g, b = torch.rand(K, device="cuda") * 0.4 + 0.8, _rand(K, seed=5, scale=0.05)
+    w3g, u, c = fold_layernorm(w, bias, g, b)
+    x3 = _split3c(x)
+    stats_in = _tile_stats(x).cuda()
+    ref = F.layer_norm(x.double(), (K,), g.double(), b.double(), 1e-12) @ w.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if "relu" in mode:
+        ref = torch.relu(ref)
+    fp32 = F.layer_norm(x, (K,), g, b, 1e-12) @ w.t() + (bias if bias is not None else 0)
+    if "relu" in mode:
+        fp32 = torch.relu(fp32)
+    fp32_err = (fp32.double() - ref).abs().max().item()
+    out = torch.full((R, N), float("nan"), device="cuda") if "split" not in mode else None
+    split = torch.zeros(R, 3 * N, dtype=torch.bfloat16, device="cuda") if "split" in mode else None
+    L.check(lib.avsr_dec_proj_folded(L.ptr(x3), L.ll(3 * K), L.ptr(stats_in), C.c_float(1e-12), L.ptr(u), L.ptr(c), L.ptr(w3g), L.ll(3 * K), R, N, K,
+                                     L.ACT_RELU if "relu" in mode else L.ACT_NONE, None, L.ll(N), L.ptr(out), L.ll(N), L.ptr(split), None, None,
+                                     L.ll(0), L.stream()), "avsr_dec_proj_folded")
+    torch.cuda.synchronize()
+    got = out.double() if out is not None else split.view(R, 3, N).double().sum(1)
+    assert not torch.isnan(got).any()
+    err = (got - ref).abs().max().item()
+    assert err < max(4e-5 * (K ** 0.5), 6 * fp32_err + 1e-6), (err, fp32_err)
