@@ -301,7 +301,22 @@ def _kernel_rooflines(model, peaks):
     R, N, K = BATCH * BEAM, 3072, 1024
     state = {"i": 0}
     byts = 4.0 * (N * K + R * K + R * N)
-    if model.beam_search.precision == "bf16x3":
+    if model.beam_search.precision == "bf16x3" and model.beam_search.proj == "cluster":
+        import ctypes as C
+        ns = lib.avsr_dec_proj_splits(R, N, K)
+        a3 = torch.randn(R, 3 * K, device=dev).bfloat16()
+        o = torch.empty(R, N, device=dev)
+        bias = torch.zeros(N, device=dev)
+        ws = [l["w13"] for l in model.decoder_weights.layers] + [l["wqkv3"] for l in model.decoder_weights.layers]
+
+        def skinny():
+            w = ws[state["i"] % len(ws)]
+            state["i"] += 1
+            L.check(lib.avsr_dec_proj(L.ptr(a3), L.ll(3 * K), None, L.ll(0), None, None, None, C.c_float(1e-12), L.ptr(w), L.ll(3 * K), R, N, K,
+                                      L.ptr(bias), 0, None, L.ll(N), L.ptr(o), L.ll(N), None, None, None, L.ll(0), L.stream()), "dec_proj")
+        kname = (f"dec_proj_kernel: split-K {ns} inside one thread-block cluster, DSMEM reduction + bias in the same launch, compact bf16x3 "
+                 f"operands, 6 MMAs per k step (decoder step projections)")
+    elif model.beam_search.precision == "bf16x3":
         ns = lib.avsr_gemm_x3_splits(R, N, K)
         a3 = torch.randn(R, 3 * K, device=dev).bfloat16()
         part = torch.empty(ns * R * N, device=dev)

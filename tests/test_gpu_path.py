@@ -42,6 +42,18 @@ def test_encoder_vs_reference_golden(gpu_model, golden, T, seed):
     _check_enc(x, torch.from_numpy(golden[f"enc_T{T}"]), f"encoder T={T}")
 
 
+def test_encoder_vs_reference_cfg0_T375(gpu_model, golden_cfg0):
+    """BASELINE.json configs[0] at full size: the bf16 encoder on the 375-frame utterance against the reference's fp32 encoder
+    output (tests/golden/cfg0_T375.npz), alone and as utterance 0 of a 4-utterance batch."""
+    video, audio = synth.make_inputs(1234, 375)
+    ref = torch.from_numpy(golden_cfg0["enc"])
+    x = gpu_model.encoder(input_features=audio.cuda(), video=video.cuda()).last_hidden_state[0]
+    _check_enc(x.cpu(), ref, "encoder T=375")
+    vids, auds = zip(*[synth.make_inputs(1234 + i, 375) for i in range(4)])
+    xb = gpu_model.encoder(input_features=torch.cat(auds, 0).cuda(), video=torch.cat(vids, 0).cuda()).last_hidden_state
+    _check_enc(xb[0].cpu(), ref, "encoder T=375, batch of 4")
+
+
 def _check_nbest(nbest, golden, T, beam):
     yseq, score = golden[f"nbest_T{T}_b{beam}_yseq"], golden[f"nbest_T{T}_b{beam}_score"]
     n = int((score > -1e8).sum())
