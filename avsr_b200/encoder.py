@@ -46,6 +46,8 @@ class Encoder:
         # 2D convolutions of the ResNet trunk as implicit GEMMs (im2col-mode TMA); AVSR_IMPLICIT_CONV=0 = explicit im2col + GEMM
         # (dev A/B switch)
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
+        # frontend 3D conv as an implicit GEMM (csrc/frontend_conv.cu); AVSR_IMPLICIT_FRONTEND=0 = explicit patch matrix + GEMM
+        self.implicit_frontend = os.environ.get("AVSR_IMPLICIT_FRONTEND", "1") != "0"
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
@@ -113,11 +115,16 @@ class Encoder:
                 cur.wait_event(ready[ci])
                 cur.wait_event(ready[min(ci + 1, len(ready) - 1)])
             M0 = nf * 44 * 44
-            col = self._buf("col", (M0, 256), torch.bfloat16)
-            L.check(lib.avsr_im2col_frontend(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(col), L.stream()),
-                    "avsr_im2col_frontend")
             c0 = self._buf("front_conv", (M0, 64), torch.bfloat16)
-            self._conv_gemm(col, w.front_w, M0, 64, 256, bias=w.front_b, act=L.ACT_PRELU, prelu=w.front_prelu, out_bf16=c0, ld_bf16=64)
+            if self.implicit_frontend:
+                # 3D conv + BN + PReLU as an implicit GEMM: the 5x7x7 patches are gathered inside the kernel
+                L.check(lib.avsr_frontend_conv3d(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(w.front_w8), L.ptr(w.front_b),
+                                                 L.ptr(w.front_prelu), L.ptr(c0), L.stream()), "avsr_frontend_conv3d")
+            else:
+                col = self._buf("col", (M0, 256), torch.bfloat16)
+                L.check(lib.avsr_im2col_frontend(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(col), L.stream()),
+                        "avsr_im2col_frontend")
+                self._conv_gemm(col, w.front_w, M0, 64, 256, bias=w.front_b, act=L.ACT_PRELU, prelu=w.front_prelu, out_bf16=c0, ld_bf16=64)
             x = self._buf("front_pool", (nf, 22, 22, 64), torch.bfloat16)
             L.check(lib.avsr_maxpool3x3s2(L.ptr(c0), L.ptr(x), L.ll(nf), 44, 44, 64, L.stream()), "avsr_maxpool3x3s2")
             if taps is not None:

@@ -50,6 +50,10 @@ class EncoderWeights:
         wpad = torch.zeros(64, 256, dtype=torch.float64)
         wpad[:, :245] = w                                   # k = (dt*7 + dy)*7 + dx, matches im2col_frontend
         self.front_w, self.front_b = bf(wpad), f32(b)
+        # implicit-GEMM layout (csrc/frontend_conv.cu): k = (dt*7 + dy)*8 + dx, the eighth dx and k >= 280 are zero
+        w8 = torch.zeros(64, 40, 8, dtype=torch.float64)
+        w8[:, :35, :7] = w.reshape(64, 35, 7)
+        self.front_w8 = bf(w8.reshape(64, 320))
         self.front_prelu = f32(sd[r + "frontend3D.2.weight"])
         self.blocks = []
         for li in (1, 2, 3, 4):

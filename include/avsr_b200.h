@@ -164,6 +164,13 @@ int avsr_layernorm(const float* x, long long ldx, long long rows, int N, const f
                    void* out_bf16, long long ld_bf16, float* out_f32, long long ld_f32, avsr_stream_t stream);
 /* Conv3d(1->64, 5x7x7, s 1x2x2, p 2x3x3) patches of packed frames (resnet.py:132). */
 int avsr_im2col_frontend(const float* video, const int* frame_t, const int* frame_T, int f0, int nf, void* out, avsr_stream_t stream);
+/* Conv3d(1 -> 64, 5x7x7, stride 1x2x2, pad 2x3x3, no bias) + BatchNorm3d (eval, folded into w / bias) + PReLU(64) of frames
+ * [f0, f0 + nf) of the packed video as an IMPLICIT GEMM on the tensor cores (csrc/frontend_conv.cu): the patch matrix of
+ * avsr_im2col_frontend is never written.  src/nets/backend/backbones/resnet.py:132-135.  w = [64][320] bf16 with
+ * k = (dt*7 + dy)*8 + dx (dx = 7 and k >= 280 are zero), bias / prelu [64]; out = [nf][44][44][64] bf16 (NHWC); temporal zero
+ * padding stops at utterance boundaries (frame_t / frame_T as in avsr_im2col_frontend). */
+int avsr_frontend_conv3d(const float* video, const int* frame_t, const int* frame_T, int f0, int nf, const void* w, const float* bias,
+                         const float* prelu, void* out, avsr_stream_t stream);
 /* Conv2d 3x3 / 1x1 patches, channels-last bf16 (resnet.py:10-19). */
 int avsr_im2col2d(const void* in, void* out, long long F, int H, int W, int C, int ks, int stride, avsr_stream_t stream);
 /* MaxPool3d (1,3,3)/(1,2,2)/(0,1,1) (resnet.py:136) and AdaptiveAvgPool2d(1) (resnet.py:76). */

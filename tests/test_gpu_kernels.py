@@ -670,3 +670,39 @@ def test_dec_proj_folded_layernorm(L, R, N, mode):
     assert not torch.isnan(got).any()
     err = (got - ref).abs().max().item()
     assert err < max(4e-5 * (K ** 0.5), 6 * fp32_err + 1e-6), (err, fp32_err)
+
+
+@pytest.mark.parametrize("lengths", [[4, 3], [1], [9, 1, 2]])
+def test_frontend_conv3d_implicit_gemm(L, lengths):
+    """avsr_frontend_conv3d (csrc/frontend_conv.cu): Conv3d 5x7x7 / stride 1x2x2 / pad 2x3x3 + bias + PReLU as an implicit GEMM
+    against F.conv3d per utterance (the temporal halo must not reach into the neighbouring utterance of the packed batch)."""
+    lib = L.load()
+    Fr = sum(lengths)
+    video = _rand(Fr, 88, 88, seed=1)
+    w = _rand(64, 1, 5, 7, 7, seed=2, scale=0.05)
+    bias, slope = _rand(64, seed=3, scale=0.2), torch.rand(64, device="cuda") * 0.3 + 0.1
+    w8 = torch.zeros(64, 40, 8, device="cuda")
+    w8[:, :35, :7] = w.reshape(64, 35, 7)
+    w8 = w8.reshape(64, 320).bfloat16().contiguous()
+    ft = torch.cat([torch.arange(t) for t in lengths]).int().cuda()
+    fT = torch.cat([torch.full((t,), t) for t in lengths]).int().cuda()
+    out = torch.full((Fr, 44, 44, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_frontend_conv3d(L.ptr(video), L.ptr(ft), L.ptr(fT), 0, Fr, L.ptr(w8), L.ptr(bias), L.ptr(slope), L.ptr(out), L.stream()),
+            "avsr_frontend_conv3d")
+    torch.cuda.synchronize()
+    vb, wb = video.bfloat16().float(), w.bfloat16().float()
+    o = 0
+    for t in lengths:
+        ref = F.conv3d(vb[o:o + t].view(1, 1, t, 88, 88), wb, None, stride=(1, 2, 2), padding=(2, 3, 3))[0]      # [64, t, 44, 44]
+        ref = ref + bias.view(64, 1, 1, 1)
+        ref = torch.where(ref >= 0, ref, ref * slope.view(64, 1, 1, 1)).permute(1, 2, 3, 0)                      # [t, 44, 44, 64]
+        got = out[o:o + t].float()
+        assert not torch.isnan(got).any()
+        assert (got - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 1e-2, (lengths, o)
+        o += t
+    # a second call on a sub-range of the frames writes the same values (f0 / nf chunking of the encoder)
+    if Fr >= 3:
+        sub = torch.zeros(2, 44, 44, 64, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.avsr_frontend_conv3d(L.ptr(video), L.ptr(ft), L.ptr(fT), 1, 2, L.ptr(w8), L.ptr(bias), L.ptr(slope), L.ptr(sub), L.stream()),
+                "avsr_frontend_conv3d")
+        assert torch.equal(sub, out[1:3])
