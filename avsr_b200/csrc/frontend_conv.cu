@@ -125,25 +125,39 @@ frontend_conv_kernel(const FrontArgs a) {
         // ------------------------------------------------------------------------------------------------ producers
         const int pt = tid - 32;                               // 0 .. 255
         const int p = pt & 127, half = pt >> 7;                // pixel of the tile, which four chunks of a k block
-        // input window of a tile: frames f-2 .. f+2, input rows iy0 .. iy0 + 12, x = -3 .. 92 (zero outside the image / utterance)
+        // input window of a tile: frames f-2 .. f+2, input rows iy0 .. iy0 + 12, x = -3 .. 92 (zero outside the image / utterance).
+        // A thread always fetches the same WIN_PER_THREAD element pairs of the window: their (dt, row, column) are unpacked once.
+        int wdesc[WIN_PER_THREAD];                             // dt | row << 8 | xx << 16, or -1 past the end of the window
+#pragma unroll
+        for (int u = 0; u < WIN_PER_THREAD; ++u) {
+            const int e = (pt + u * N_PROD) * 2;
+            wdesc[u] = e < WIN_ELEMS ? ((e / (WROWS * WPITCH)) | (((e / WPITCH) % WROWS) << 8) | ((e % WPITCH) << 16)) : -1;
+        }
+        // shared-memory word offset of the (dt, dy) pair behind each of this thread's 20 chunks (tile independent)
+        int coff[KB][4];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int q = kb * 8 + half * 4 + cc;
+                coff[kb][cc] = q < 35 ? ((q / 7) * WROWS + (q % 7)) * (WPITCH / 2) : -1;
+            }
         float2 wreg[WIN_PER_THREAD];
-        auto window_fetch = [&](int item) {
-            const int fl = item / TILES_PER_FRAME, ti = item % TILES_PER_FRAME;
+        auto window_fetch = [&](int item, int t, int T) {
+            const int fl = item / TILES_PER_FRAME, ti = item - fl * TILES_PER_FRAME;
             const int f = a.f0 + fl;
-            const int t = __ldg(a.frame_t + f), T = __ldg(a.frame_T + f);
             const int iy0 = 2 * ((ti * TILE) / OUT) - 3;
+            const float* fbase = a.video + (long long)(f - 2) * IMG * IMG - 3;
 #pragma unroll
             for (int u = 0; u < WIN_PER_THREAD; ++u) {
-                const int e = (pt + u * N_PROD) * 2;            // element pair (e, e + 1) of the window
+                const int d = wdesc[u];
+                const int dt = d & 0xff, r = (d >> 8) & 0xff, xx = d >> 16;
+                const int tt = t + dt - 2, y = iy0 + r;
                 float2 v = make_float2(0.f, 0.f);
-                if (e < WIN_ELEMS) {
-                    const int dt = e / (WROWS * WPITCH), r = (e / WPITCH) % WROWS, xx = e % WPITCH;
-                    const int tt = t + dt - 2, y = iy0 + r, x = xx - 3;
-                    if (tt >= 0 && tt < T && y >= 0 && y < IMG) {
-                        const float* src = a.video + ((long long)(f + dt - 2) * IMG + y) * IMG;
-                        if (x >= 0 && x < IMG) v.x = __ldg(src + x);
-                        if (x + 1 >= 0 && x + 1 < IMG) v.y = __ldg(src + x + 1);
-                    }
+                if (d >= 0 && tt >= 0 && tt < T && y >= 0 && y < IMG) {
+                    const float* src = fbase + (dt * IMG + y) * IMG + xx;       // &video[f + dt - 2][y][xx - 3]
+                    if (xx >= 3 && xx < IMG + 3) v.x = __ldg(src);
+                    if (xx >= 2 && xx < IMG + 2) v.y = __ldg(src + 1);
                 }
                 wreg[u] = v;
             }
@@ -151,43 +165,54 @@ frontend_conv_kernel(const FrontArgs a) {
         auto window_store = [&](int buf) {
             __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(win + buf * WIN_ELEMS);
 #pragma unroll
-            for (int u = 0; u < WIN_PER_THREAD; ++u) {
-                const int e2 = pt + u * N_PROD;
-                if (e2 * 2 < WIN_ELEMS) w2[e2] = __floats2bfloat162_rn(wreg[u].x, wreg[u].y);
+            for (int u = 0; u < WIN_PER_THREAD; ++u)
+                if (wdesc[u] >= 0) w2[pt + u * N_PROD] = __floats2bfloat162_rn(wreg[u].x, wreg[u].y);
+        };
+        // a frame's position / utterance length are fetched TWO items ahead, so that no tile waits for them
+        auto frame_info = [&](int item, int& t, int& T) {
+            t = 0; T = 1;
+            if (item < n_items) {
+                const int f = a.f0 + item / TILES_PER_FRAME;
+                t = __ldg(a.frame_t + f);
+                T = __ldg(a.frame_T + f);
             }
         };
         int item = blockIdx.x;
         uint32_t ph_a = 0;
         int buf = 0;
+        int t0, T0, t1, T1;
+        frame_info(item, t0, T0);
+        frame_info(item + gridDim.x, t1, T1);
         if (item < n_items) {
-            window_fetch(item);
+            window_fetch(item, t0, T0);
             window_store(0);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(N_PROD) : "memory");
         for (; item < n_items; item += gridDim.x) {
             const int nxt = item + gridDim.x;
-            if (nxt < n_items) window_fetch(nxt);              // in flight while this tile's A is built
+            int t2, T2;
+            frame_info(nxt + gridDim.x, t2, T2);
+            if (nxt < n_items) window_fetch(nxt, t1, T1);      // in flight while this tile's A is built
+            t1 = t2; T1 = T2;
             const int ti = item % TILES_PER_FRAME;
             const int P = ti * TILE + p;                       // pixel of the frame
             const bool pok = P < PIX;
             const int oy = P / OUT, ox = P - oy * OUT;
             const int oy0 = (ti * TILE) / OUT;
             // word (2 bf16) index of this pixel's first input column inside a window row: x = 2 ox - 3 -> xx = 2 ox
-            const uint32_t* wwin = reinterpret_cast<const uint32_t*>(win + buf * WIN_ELEMS);
-            const int base_word = (2 * (oy - oy0)) * (WPITCH / 2) + ox;        // + (dt * 13 + dy) * 48
+            const uint32_t* wpix = reinterpret_cast<const uint32_t*>(win + buf * WIN_ELEMS) + (2 * (oy - oy0)) * (WPITCH / 2) + ox;
+            const uint32_t swz = (uint32_t)(p & 7);
+#pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(&aempty[kb], ph_a ^ 1);
                 uint8_t* dst = sA + kb * A_KB_BYTES + p * 128;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int c = half * 4 + cc;               // chunk of the k block
-                    const int q = kb * 8 + c;                  // (dt, dy) pair
-                    if (q < 35 && pok) {
-                        const int dt = q / 7, dy = q - dt * 7;
-                        const uint32_t* src = wwin + (dt * WROWS + dy) * (WPITCH / 2) + base_word;
+                    if (coff[kb][cc] >= 0 && pok) {
+                        const uint32_t* src = wpix + coff[kb][cc];
                         uint4 v;
                         v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
-                        *reinterpret_cast<uint4*>(dst + ((c ^ (p & 7)) << 4)) = v;
+                        *reinterpret_cast<uint4*>(dst + (((uint32_t)(half * 4 + cc) ^ swz) << 4)) = v;
                     }
                 }
                 tc::fence_proxy_async();
@@ -224,19 +249,23 @@ frontend_conv_kernel(const FrontArgs a) {
                 for (int h = 0; h < 2; ++h) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
+                        const int c0 = h * 32 + j;
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+                        const float4 s0 = *reinterpret_cast<const float4*>(s_prelu + c0), s1 = *reinterpret_cast<const float4*>(s_prelu + c0 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                         float v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const int c = h * 32 + j + u;
-                            float t = __uint_as_float(h == 0 ? r0[j + u] : r1[j + u]) + s_bias[c];
-                            v[u] = t >= 0.f ? t : t * s_prelu[c];
+                            const float t = __uint_as_float(h == 0 ? r0[j + u] : r1[j + u]) + bb[u];
+                            v[u] = fmaxf(t, 0.f) + ss[u] * fminf(t, 0.f);        // PReLU without a branch
                         }
                         __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
                         __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
                         uint4 pk;
                         pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
                         pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
-                        *reinterpret_cast<uint4*>(o + h * 32 + j) = pk;
+                        *reinterpret_cast<uint4*>(o + c0) = pk;
                     }
                 }
             }

@@ -50,6 +50,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// Arrival without memory ordering: the barrier before exit only keeps a CTA's shared memory alive while peers may read it.
+// (arrive.release compiles to MEMBAR.ALL.GPU + ERRBAR: after the epilogue's global stores that is a ~1 us wait per launch.)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_relaxed() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
@@ -318,8 +322,10 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             uint32_t r[32];
             tc::tmem_ld_32x32(taddr + c * 32, r);
             tc::tmem_ld_wait();
+            const uint32_t rs = tc::smem_u32(red) + (uint32_t)((c * 32) * BM + f) * 4u;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) red[(c * 32 + j) * BM + f] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j)                  // explicit st.shared: the compiler only sees a generic pointer here
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(rs + (uint32_t)(j * BM * 4)), "r"(r[j]) : "memory");
         }
         tc::tc_fence_before();
     }
@@ -419,8 +425,8 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     // ---- nobody leaves while a peer may still read its shared memory
     __syncwarp();
-    cluster_arrive();
-    cluster_wait();
+    cluster_arrive_relaxed();
+    cluster_wait_relaxed();
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);
