@@ -81,13 +81,15 @@ def pad_batch(samples: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[tor
 def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int], Tuple[torch.Tensor, torch.Tensor]],
                      references: Optional[Sequence[str]] = None, ids_to_text: Optional[Callable[[Sequence[int]], str]] = None,
                      normalize: Optional[Callable[[str], str]] = None, max_utts: Optional[int] = None, max_frames: int = 12288,
-                     device="cpu", fps: float = 25.0, group=None) -> EvalResult:
+                     device="cpu", fps: float = 25.0, group=None, collate: Optional[Callable] = None) -> EvalResult:
     """Decode utterances 0..N-1 (``lengths[i]`` frames each, inputs from ``load_sample(i)``) on all ranks of the default
     process group and return the corpus result on every rank.
 
     references / ids_to_text / normalize: label strings, the tokenizer's ``post_process`` and ``norm_string``; when any is
     missing the WER is computed on token ids written as decimal words (references then are token-id strings too).
-    ``device``: where the gather / reduce tensors live ("cuda" under nccl, "cpu" under gloo)."""
+    ``device``: where the gather / reduce tensors live ("cuda" under nccl, "cpu" under gloo).
+    ``collate``: optional replacement for ``pad_batch``: ``collate(samples) -> (videos [B,1,T,88,88], audios [B,104,T], lengths)``,
+    e.g. the GPU input pipeline on raw (uint8 frames, waveform) samples (avsr_b200.input_pipeline.DataCollator)."""
     rank, world = S._world(group)
     mine = S.shard_utterances(lengths, world)[rank]
     # max_utts=None: cost-optimal cuts (few utterances per rank -> small batches, many -> 100+); an int: fixed-size buckets
@@ -97,7 +99,7 @@ def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int],
     ids, toks = [], []
     for batch in batches:
         samples = [load_sample(i) for i in batch]
-        videos, audios, lens = pad_batch(samples)
+        videos, audios, lens = pad_batch(samples) if collate is None else collate(samples)
         if lens != [int(lengths[i]) for i in batch]:
             raise RuntimeError("load_sample returned utterances whose lengths differ from `lengths`")
         nbest = model.infer_batch(videos, audios, lens)

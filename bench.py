@@ -612,6 +612,80 @@ def run_cfg2(args):
         dist.destroy_process_group()
 
 
+def run_cfg3(args):
+    """--workload cfg3: BASELINE.json configs[3], AVCocktail-shaped: 512 fixed 10 s chunks (T = 250 frames), beam 5, the audio of
+    every chunk mixed with 1-2 synthetic interferer waveforms at SNR in {-5, 0, 5, 10} dB (SURVEY.md 8d "Cfg 4").  The whole
+    chain is on the GPU and inside the timed region: uint8 frames + waveforms in pinned host memory -> interferer mixing
+    (avsr_add_noise, what AddMultiSpk does, avhubert_dataset.py:160-222) -> log-fbank / video transform (DataCollator) ->
+    encoder -> beam search; chunks sharded over the ranks, 32 per batch; NCCL gather of the token ids at the end."""
+    import torch.distributed as dist
+    from avsr_b200 import evaluation as E
+    from avsr_b200 import input_pipeline as P
+    from avsr_b200 import sharding as S
+    from avsr_b200 import synth
+    from avsr_b200.model import AVSRCocktailB200
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, T, beam = args.cfg3_chunks, 250, 5
+    lengths = [T] * n
+    model = AVSRCocktailB200(synth.make_state_dict(0), device=dev, beam_size=beam)
+    mine = S.shard_utterances(lengths, world)[rank]
+    snrs = (-5.0, 0.0, 5.0, 10.0)
+    raw = {}
+    for i in mine:
+        g = torch.Generator().manual_seed(20_000 + i)
+        frames = torch.randint(0, 256, (T, 1, 96, 96), generator=g, dtype=torch.uint8).pin_memory()
+        k = 1 + (i % 2)                                    # 1 or 2 interferers
+        waves = (0.1 * torch.randn(1 + k, T * 640, generator=g)).pin_memory()
+        raw[i] = (frames, waves, [snrs[(i + j) % 4] for j in range(k)])
+    collator = P.DataCollator(device=str(dev))
+
+    def collate(samples):
+        feats = []
+        for frames, waves, snr in samples:
+            w = waves.to(dev, non_blocking=True)
+            mix = w[0]
+            for j, s_db in enumerate(snr):                 # AddMultiSpk: interferers are added one after the other
+                mix = P.add_noise(mix, w[1 + j], torch.tensor([s_db]))
+            feats.append({"video": frames, "audio": mix[:, None]})
+        b = collator(feats)
+        return b["videos"], b["audios"], b["video_lengths"].tolist()
+
+    times, res = [], None
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = E.evaluate_sharded(model, lengths, lambda i: raw[i], max_utts=32, max_frames=32 * T, device=dev, collate=collate)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if it >= args.warmup:
+            times.append(float(ms.item()))
+    if rank == 0:
+        ms = float(np.mean(times))
+        print(json.dumps({
+            "metric": METRIC, "value": res.audio_seconds / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 encoder GEMMs / f32 decode",
+            "data": "synthetic",
+            "config": {"workload": f"configs[3]: {n} AVCocktail-shaped 10 s chunks (T=250), beam 5, 1-2 interferer waveforms mixed at -5/0/5/10 dB on the "
+                                   f"GPU, uint8 frames + waveforms from pinned host memory through the GPU input pipeline, sharded over {world} GPU(s), "
+                                   f"32 chunks per batch", "chunks": n, "audio_s": res.audio_seconds, "batches_rank0": res.n_batches,
+                       "parallelism": f"chunk-sharded x{world}"},
+            "ms_all_steps": times, "hyps": len(res.hyp_tokens)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     global BEAM, T_FRAMES, BATCH, CTC_WEIGHT
     ap = argparse.ArgumentParser()
@@ -628,8 +702,10 @@ def main():
     ap.add_argument("--rooflines-only", action="store_true", help="dev aid: only the isolated kernel timings (not a bench line)")
     ap.add_argument("--profile-decode-steps", type=int, default=0,
                     help="profiling aid: run ONE pass with the decode truncated to this many positions and exit (not a bench value)")
-    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2"],
-                    help="cfg1 (default) = the headline configs[1] batch per GPU; cfg2 = the sharded LRS2-shaped set (configs[2], strong scaling)")
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg2", "cfg3"],
+                    help="cfg1 (default) = the headline configs[1] batch per GPU; cfg2 = the sharded LRS2-shaped set (configs[2], strong scaling); "
+                         "cfg3 = AVCocktail-shaped 10 s chunks, beam 5, interferer mixes (configs[3])")
+    ap.add_argument("--cfg3-chunks", type=int, default=512)
     ap.add_argument("--cfg2-utts", type=int, default=1243)
     ap.add_argument("--max-frames", type=int, default=12288, help="cfg2: packed frames per batch")
     ap.add_argument("--host-inputs", action="store_true", help="cfg2: features in host memory (pad + upload timed)")
@@ -639,6 +715,8 @@ def main():
         run_reference(args)
     elif args.workload == "cfg2":
         run_cfg2(args)
+    elif args.workload == "cfg3":
+        run_cfg3(args)
     else:
         run_b200(args)
 
