@@ -124,8 +124,10 @@ class BatchedBeamSearch:
 
     # ------------------------------------------------------------------------------------------ session buffers
     T_BUCKET = 16        # sessions (buffers + the captured graphs) are shared by all batches whose longest utterance rounds up to the same multiple
-    B_BUCKETS = (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024)
-    SESSION_BYTES = int(os.environ.get("AVSR_SESSION_GB", "48")) << 30     # retained sessions are evicted least-recently-used beyond this
+    # utterance slots per session: fine enough that a batch wastes < 15 % of its rows on parked slots (every projection works on
+    # all rows of the session), coarse enough that the batches of an evaluation plan share a handful of sessions
+    B_BUCKETS = (1, 2, 4, 8, 12, 16, 24, 32, 40, 48, 64, 80, 96, 112, 128, 144, 160, 192, 224, 256, 288, 320, 384, 448, 512, 640, 768, 1024)
+    SESSION_BYTES = int(os.environ.get("AVSR_SESSION_GB", "96")) << 30     # retained sessions are evicted least-recently-used beyond this
 
     @classmethod
     def bucket_B(cls, B: int) -> int:
@@ -533,7 +535,10 @@ class BatchedBeamSearch:
         """Decoder.forward_one_step up to the output layer (decoder.py:153-181) for the rows of the session: embedding +
         positional encoding, six layers, after_norm, output projection.  Returns (partial logits [ns][R][V], ns).
         dense=False: no converged-prefix caches (the scorer plug-in API drives the kernels without the beam bookkeeping)."""
-        if self.precision == "bf16x3" and self.proj == "cluster" and not self._skip and not self.fuse_epilogue:
+        # cluster projections serve up to 128 hypothesis rows (one row tile per cluster, everything co-resident in one wave);
+        # larger batches (configs[2]-style batches of 100+ short utterances) amortise the launch chain over several row tiles
+        # and run the persistent split-K kernels instead (measured on configs[2]: 792 vs 1090 ms per pass)
+        if self.precision == "bf16x3" and self.proj == "cluster" and s["R"] <= 128 and not self._skip and not self.fuse_epilogue:
             return self._decoder_layers_cluster(s, dense)
         lib = L.load()
         w = self.w
