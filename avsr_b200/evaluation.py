@@ -122,3 +122,88 @@ def evaluate_sharded(model, lengths: Sequence[int], load_sample: Callable[[int],
     wer, e, n = S.reduce_wer(edits, nref, device=device, group=group)
     return EvalResult(wer=wer, edits=e, ref_words=n, hyp_tokens=all_toks, hyp_text=text,
                       audio_seconds=sum(int(t) for t in lengths) / fps, n_batches=len(batches))
+
+
+# ---------------------------------------------------------------------------------------------------- AVCocktail loop
+def parse_vtt(vtt_text: str) -> List[Tuple[float, float, str]]:
+    """Cues of a WebVTT document as (start seconds, end seconds, text): what ``webvtt.read`` yields to ``eval_avcocktail``
+    (script/evaluation.py:411-433; the ``webvtt`` package is not a dependency here).  Cue text lines are joined with "\\n"."""
+    import re
+    ts = re.compile(r"(?:(\d+):)?(\d{2}):(\d{2})[.,](\d{3})\s*-->\s*(?:(\d+):)?(\d{2}):(\d{2})[.,](\d{3})")
+    cues, cur = [], None
+    for line in vtt_text.replace("\r\n", "\n").split("\n"):
+        m = ts.search(line)
+        if m:
+            g = m.groups()
+            start = int(g[0] or 0) * 3600 + int(g[1]) * 60 + int(g[2]) + int(g[3]) / 1000
+            end = int(g[4] or 0) * 3600 + int(g[5]) * 60 + int(g[6]) + int(g[7]) / 1000
+            cur = [start, end, []]
+            cues.append(cur)
+        elif line.strip() == "":
+            cur = None
+        elif cur is not None:
+            cur[2].append(line.strip())
+    return [(s, e, "\n".join(t)) for s, e, t in cues]
+
+
+def avcocktail_label(vtt_text: str, normalize: Callable[[str], str]) -> Tuple[str, float, float]:
+    """The label side of ``eval_avcocktail`` (script/evaluation.py:411-433): non-empty cues sorted by start time, joined with
+    spaces and normalised; plus the earliest start / latest end of the cues (the window chunks are filtered against)."""
+    cues = [c for c in parse_vtt(vtt_text) if c[2] != ""]
+    if not cues:
+        raise ValueError("label VTT holds no cue")
+    start, end = min(c[0] for c in cues), max(c[1] for c in cues)
+    ordered = [t for _, t in sorted((c[0], c[2]) for c in cues)]
+    return normalize(" ".join(ordered)), start, end
+
+
+CHUNK_TYPES = ("asd_chunk", "fixed_chunk", "gold_chunk")
+
+
+def evaluate_avcocktail(model, videos: Dict[str, dict], ids_to_text: Callable[[Sequence[int]], str],
+                        normalize: Optional[Callable[[str], str]] = None, max_utts: Optional[int] = 32, max_frames: int = 12288,
+                        device="cpu", group=None, collate: Optional[Callable] = None):
+    """``eval_avcocktail`` over a set of videos (script/evaluation.py:406-453 and the ``*`` branch of ``main``, :556-570), sharded.
+
+    videos: ``{set_id: {"label": <VTT text>, "asd_chunk" | "fixed_chunk" | "gold_chunk": [{"start_time", "end_time",
+    "frames": T, "load": callable -> sample}]}}``.  As in the reference, a chunk is skipped when it starts more than 1 s before
+    the first label cue or ends more than 1 s after the last one; the outputs of a (video, chunk type) are concatenated in
+    start-time order, normalised and scored against the video's label with a word error rate; per chunk type the scores are
+    averaged with the labels' word counts as weights.  All kept chunks of all videos and chunk types form ONE utterance list
+    that ``evaluate_sharded`` deals over the ranks (chunks are independent; no collective on the hot path), every rank then
+    stitches and scores locally from the gathered token ids.
+
+    Returns ``(per_video {set_id: {chunk_type: wer}}, num_words {set_id: n}, average {chunk_type: wer})``."""
+    from .text import norm_string, stitch_outputs
+    norm = normalize or norm_string
+    labels, flat = {}, []
+    for set_id in sorted(videos):
+        v = videos[set_id]
+        label_text, t0, t1 = avcocktail_label(v["label"], norm)
+        labels[set_id] = label_text
+        for ct in CHUNK_TYPES:
+            for ch in v.get(ct, []):
+                s, e = float(ch["start_time"]), float(ch["end_time"])
+                if s + 1 < t0 or e - 1 > t1:                   # :441-442
+                    continue
+                flat.append((set_id, ct, s, ch))
+    lengths = [int(ch["frames"]) for _, _, _, ch in flat]
+    res = evaluate_sharded(model, lengths, lambda i: flat[i][3]["load"](), ids_to_text=ids_to_text, normalize=lambda s: s,
+                           max_utts=max_utts, max_frames=max_frames, device=device, group=group, collate=collate) if flat else None
+    per_video: Dict[str, Dict[str, float]] = {}
+    num_words = {k: len(t.split()) for k, t in labels.items()}
+    for set_id in labels:
+        per_video[set_id] = {}
+        for ct in CHUNK_TYPES:
+            idx = [i for i, f in enumerate(flat) if f[0] == set_id and f[1] == ct]
+            if ct not in videos[set_id]:
+                continue
+            out_text = stitch_outputs([flat[i][2] for i in idx], [res.hyp_text[i] for i in idx], normalize=norm) if idx else ""
+            e, n = S.corpus_wer([labels[set_id]], [out_text])
+            per_video[set_id][ct] = e / n if n else float("nan")
+    average = {}
+    for ct in CHUNK_TYPES:
+        pairs = [(per_video[k][ct], num_words[k]) for k in per_video if ct in per_video[k]]
+        if pairs:
+            average[ct] = sum(w * n for w, n in pairs) / max(1, sum(n for _, n in pairs))       # [wer] * num_words, then the mean (:564-570)
+    return per_video, num_words, average

@@ -218,3 +218,49 @@ def test_plan_batches_is_optimal_on_small_sets():
         plan = S.plan_batches(range(n), lengths, max_utts=max_utts, max_frames=max_frames)
         got = sum(S.batch_cost_ms(max(lengths[i] for i in b), len(b)) for b in plan)
         assert best is not None and abs(got - best) < 1e-9, (lengths, max_utts, max_frames, plan)
+
+
+def test_avcocktail_loop_matches_a_sequential_restatement():
+    """evaluate_avcocktail (script/evaluation.py:406-453, :556-570) with the stand-in model: label parsing from VTT, the 1 s
+    window filter, time-ordered stitching per (video, chunk type), WER per chunk type and the word-count-weighted average."""
+    from avsr_b200 import text
+    vtt = ("WEBVTT\n\n00:00:02.000 --> 00:00:04.000\nsecond cue\n\n00:00:00.500 --> 00:00:01.500\nfirst cue here\n\n"
+           "00:00:05.000 --> 00:00:05.500\n\n")
+    assert E.parse_vtt(vtt)[0] == (2.0, 4.0, "second cue") and len(E.parse_vtt(vtt)) == 3
+    label, t0, t1 = E.avcocktail_label(vtt, text.norm_string)
+    assert label == "FIRST CUE HERE SECOND CUE" and (t0, t1) == (0.5, 4.0)
+    lengths = {}
+
+    def chunk(start, end, seed, T):
+        g = torch.Generator().manual_seed(seed)
+        smp = (torch.randint(0, 3, (1, T, 88, 88), generator=g).float(), torch.randint(0, 5, (104, T), generator=g).float())
+        return {"start_time": start, "end_time": end, "frames": T, "load": (lambda s=smp: s)}
+
+    videos = {"video_0": {"label": vtt, "asd_chunk": [chunk(2.0, 4.0, 1, 9), chunk(0.5, 2.0, 2, 7), chunk(9.0, 12.0, 3, 5)],
+                          "fixed_chunk": [chunk(0.0, 4.5, 4, 11)], "gold_chunk": []},
+              "video_1": {"label": vtt.replace("first", "other words in"), "fixed_chunk": [chunk(0.0, 3.0, 5, 6), chunk(3.0, 4.9, 6, 8)]}}
+    to_text = lambda ids: " ".join(f"w{int(t)}" for t in ids)
+    per_video, nw, avg = E.evaluate_avcocktail(_StandInModel(), videos, to_text, max_utts=2, max_frames=64)
+    # sequential restatement: one inference per kept chunk, stitched by start time
+    m = _StandInModel()
+    for set_id, v in videos.items():
+        lab, a, b = E.avcocktail_label(v["label"], text.norm_string)
+        assert nw[set_id] == len(lab.split())
+        for ct in E.CHUNK_TYPES:
+            if ct not in v:
+                assert ct not in per_video[set_id]
+                continue
+            outs, starts = [], []
+            for ch in v[ct]:
+                if ch["start_time"] + 1 < a or ch["end_time"] - 1 > b:
+                    continue
+                vid, aud = ch["load"]()
+                hyp = m.infer_batch(vid.unsqueeze(0), aud.unsqueeze(0), [ch["frames"]])[0][0]
+                outs.append(to_text(E.strip_sos_eos(hyp.yseq, m.eos)))
+                starts.append(ch["start_time"])
+            want = text.stitch_outputs(starts, outs) if outs else ""
+            e, n = S.corpus_wer([lab], [want])
+            assert per_video[set_id][ct] == pytest.approx(e / n)
+    assert set(per_video["video_0"]) == {"asd_chunk", "fixed_chunk", "gold_chunk"} and per_video["video_0"]["gold_chunk"] == 1.0
+    assert avg["fixed_chunk"] == pytest.approx((per_video["video_0"]["fixed_chunk"] * nw["video_0"] + per_video["video_1"]["fixed_chunk"] * nw["video_1"])
+                                               / (nw["video_0"] + nw["video_1"]))
