@@ -12,6 +12,7 @@
 //   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator (double-buffered in TMEM), fused bias / activation /
 //                              residual / row-mask, bf16 and/or fp32 stores
 // Pipelines: smem ring full[]/empty[] (TMA <-> MMA) and TMEM tfull[]/tempty[] (MMA <-> epilogue), all mbarriers.
+#include <string.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -171,12 +172,23 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 // Ho x Wo output and k block kb = (filter tap, 64-channel slice), fetched by an im2col-mode TMA load of the activation tensor.
 struct ConvA {
     int on, Ho, Wo, C, ks, stride;
+    // Positional-conv mode (avsr_posconv_bf16_tc): grouped Conv1d(k = 128, pad = 64, 16 groups of 64 channels) over the packed
+    // frames as an implicit banded GEMM.  Tile = (work item w = 128 frames of one utterance, group g); k block j = filter tap j:
+    // the A tile is rows [q0 + j - 64, +128) x columns [64 g, +64) of THAT utterance's frames, a plain 2D TMA load through the
+    // utterance's own tensor map (rows outside the utterance are zero-filled by the TMA unit); B = W[64 g .., 64 j ..].
+    int pc_on, pc_nwork;
+    const CUtensorMap* pc_maps;      // [utterances] tensor maps in global memory
+    const int* pc_utt;               // [n_work] utterance of the work item
+    const int* pc_off;               // [n_work] first packed frame of that utterance
+    const int* pc_T;                 // [n_work] its length
+    const int* pc_q0;                // [n_work] first frame (within the utterance) of the work item
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M_in, int N_in, int K,
                const AvsrEpilogue ep_in, int splits, int kb_per_split, const ConvA conv) {
+    const int M = M_in, N = N_in;
     using C = Cfg<BN>;
     constexpr int STAGES = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -191,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
     const int tiles_m = (M + BM - 1) / BM;
-    const int tiles_mn = tiles_m * tiles_n;
+    const int tiles_mn = conv.pc_on ? conv.pc_nwork * 16 : tiles_m * tiles_n;
     const int num_tiles = tiles_mn * splits;
     const int num_kb_total = (K + BK - 1) / BK;
 
@@ -225,6 +237,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
                 const int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
                 const int kb0 = z * kb_per_split, kb1 = min(num_kb_total, kb0 + kb_per_split);
+                if (conv.pc_on) {
+                    const int w = t2 >> 4, g = t2 & 15;
+                    const CUtensorMap* um = conv.pc_maps + conv.pc_utt[w];
+                    const int q0 = conv.pc_q0[w];
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        tc::mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                        tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                        tc::tma_load_2d(sa, um, &full[stage], g * 64, q0 + kb - 64);
+                        tc::tma_load_2d(sa + A_TILE_BYTES, &tmB, &full[stage], kb * BK, g * 64);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 int cn = 0, cy = 0, cx = 0, cpb = 1;
                 if (conv.on) {
                     const int hw = conv.Ho * conv.Wo, pad = conv.ks / 2;
@@ -290,7 +316,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int z = tile / tiles_mn, t2 = tile - z * tiles_mn;
-            const int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
+            int m0 = (t2 / tiles_n) * BM, n0 = (t2 % tiles_n) * BN;
+            int M = M_in, N = N_in;
+            if (conv.pc_on) {                           // rows = packed frames of the work item's utterance, columns = the group's 64 channels
+                const int w = t2 >> 4;
+                m0 = conv.pc_off[w] + conv.pc_q0[w];
+                M = conv.pc_off[w] + conv.pc_T[w];
+                n0 = (t2 & 15) * 64;
+                N = 1024;
+            }
             AvsrEpilogue ep = ep_in;
             if (splits > 1) ep.out_f32 = ep_in.out_f32 + (long long)z * M * ep_in.ld_f32;
             const int row = m0 + quad * 32 + lane;
@@ -345,7 +379,7 @@ int g_sm_count = 0;
 
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, int splits, cudaStream_t stream,
-           const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0}) {
+           const ConvA& conv = ConvA{0, 0, 0, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}) {
     using C = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -354,7 +388,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
     }
     const int num_kb = cdiv(K, BK);
     const int kbps = cdiv(num_kb, splits);
-    const int tiles = cdiv(M, BM) * cdiv(N, BN) * splits;
+    const int tiles = conv.pc_on ? conv.pc_nwork * 16 : cdiv(M, BM) * cdiv(N, BN) * splits;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
     gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, splits, kbps, conv);
     AVSR_LAUNCH_CHECK();
@@ -470,7 +504,7 @@ extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, 
     if (rc != AVSR_OK) return rc;
     rc = tc::make_tmap_2d_bf16(&tb, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
     if (rc != AVSR_OK) return rc;
-    const ConvA conv = {1, Ho, Wo, C, ks, stride};
+    const ConvA conv = {1, Ho, Wo, C, ks, stride, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (bn == 64) return launch<64>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     if (bn == 128) return launch<128>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     return launch<256>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
@@ -521,4 +555,45 @@ extern "C" int avsr_gemm_bf16_tc_splitk(const void* A, long long lda, const void
     const int num_kb = cdiv(K, BK), kbps = cdiv(num_kb, splits);
     AVSR_REQUIRE((splits - 1) * kbps < num_kb, "avsr_gemm_bf16_tc_splitk: %d splits leave an empty split for K=%d", splits, K);
     return gemm_entry(A, lda, B, ldb, M, N, K, &ep, bn_hint, splits, stream);
+}
+
+// ---- positional convolution as an implicit banded GEMM -----------------------------------------------------------------
+// Host helper (no GPU work): one tensor map per utterance over its frames of the packed bf16 activations x [F, 1024]
+// (utterance b = rows utt_off[b] .. + utt_T[b]), written to maps_host [B][128 bytes]; the caller uploads them.  Rows a load
+// asks for outside [0, utt_T[b]) come back as zeros: the convolution's zero padding at the UTTERANCE boundary.
+extern "C" int avsr_posconv_encode_maps(const void* x, const long long* utt_off, const int* utt_T, int B, void* maps_host) {
+    AVSR_REQUIRE(x && utt_off && utt_T && maps_host && B > 0, "avsr_posconv_encode_maps: bad arguments");
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    CUtensorMap* out = reinterpret_cast<CUtensorMap*>(maps_host);
+    for (int b = 0; b < B; ++b) {
+        AVSR_REQUIRE(utt_T[b] > 0 && utt_off[b] >= 0, "avsr_posconv_encode_maps: utterance %d has no frames", b);
+        CUtensorMap m;
+        int rc = tc::make_tmap_2d_bf16(&m, reinterpret_cast<const __nv_bfloat16*>(x) + utt_off[b] * 1024, (uint64_t)utt_T[b], 1024, 1024, BM, BK);
+        if (rc != AVSR_OK) return rc;
+        memcpy(out + b, &m, sizeof(m));
+    }
+    return AVSR_OK;
+}
+
+// x + GELU(Conv1d_{k=128, pad=64, groups=16}(x)[..., :-1] + bias) of HF Wav2Vec2PositionalConvEmbedding (modeling_wav2vec2.py:326-379,
+// called from src/nets/backend/backbones/avhubert.py:698-699) as ONE launch over all 16 groups: out tile (128 frames of an
+// utterance x the 64 channels of a group) = sum over the 128 taps of A_j W_j^T with A_j = frames [q0 + j - 64, +128) of the
+// utterance (TMA load through utt_maps[utterance], zero outside it).  The patch matrix (128 x the input) is never written.
+// W = [1024][8192] bf16 with k = tap * 64 + channel-in-group (the explicit path's layout); work arrays as avsr_attention_varlen
+// plus work_utt (utterance index); ep = bias [1024] per column, GELU, residual / output rows indexed by PACKED frame.
+extern "C" int avsr_posconv_bf16_tc(const void* utt_maps, const void* W, int n_work, const int* work_utt, const int* work_off, const int* work_T,
+                                    const int* work_q0, const AvsrEpilogue* ep, cudaStream_t stream) {
+    AVSR_REQUIRE(utt_maps && W && work_utt && work_off && work_T && work_q0 && ep && n_work > 0, "avsr_posconv_bf16_tc: bad arguments");
+    AVSR_REQUIRE(((uintptr_t)utt_maps & 63) == 0, "avsr_posconv_bf16_tc: tensor maps must be 64-byte aligned");
+    AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_posconv_bf16_tc: no output buffer");
+    if (g_sm_count == 0) {
+        int dev = 0;
+        AVSR_CHECK_CUDA(cudaGetDevice(&dev));
+        AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap tb;
+    int rc = tc::make_tmap_2d_bf16(&tb, W, 1024, 8192, 8192, 64, BK);
+    if (rc != AVSR_OK) return rc;
+    const ConvA conv = {0, 0, 0, 0, 0, 0, 1, n_work, reinterpret_cast<const CUtensorMap*>(utt_maps), work_utt, work_off, work_T, work_q0};
+    return launch<64>(tb, tb, n_work * 128, 1024, 8192, *ep, 1, stream, conv);
 }

@@ -48,6 +48,8 @@ class Encoder:
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
         # frontend 3D conv as an implicit GEMM (csrc/frontend_conv.cu); AVSR_IMPLICIT_FRONTEND=0 = explicit patch matrix + GEMM
         self.implicit_frontend = os.environ.get("AVSR_IMPLICIT_FRONTEND", "1") != "0"
+        # positional conv as an implicit banded GEMM (avsr_posconv_bf16_tc); AVSR_IMPLICIT_POSCONV=0 = explicit patches + 16 GEMMs
+        self.implicit_posconv = os.environ.get("AVSR_IMPLICIT_POSCONV", "1") != "0"
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
@@ -163,11 +165,13 @@ class Encoder:
             offs_t = torch.cumsum(ln, 0) - ln
             fb_t = torch.repeat_interleave(torch.arange(B, dtype=torch.int64), ln)
             ft_t = torch.arange(F, dtype=torch.int64) - offs_t[fb_t]
-            work = [(int(offs_t[b]), t, q0) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
+            work = [(int(offs_t[b]), t, q0, b) for b, t in enumerate(lengths) for q0 in range(0, t, 128)]
             idx = dict(frame_b=fb_t.to(torch.int32).to(dev), frame_t=ft_t.to(torch.int32).to(dev), frame_T=ln[fb_t].to(torch.int32).to(dev),
                        n_work=len(work), work_off=torch.tensor([x[0] for x in work], dtype=torch.int32, device=dev),
                        work_T=torch.tensor([x[1] for x in work], dtype=torch.int32, device=dev),
-                       work_q0=torch.tensor([x[2] for x in work], dtype=torch.int32, device=dev))
+                       work_q0=torch.tensor([x[2] for x in work], dtype=torch.int32, device=dev),
+                       work_utt=torch.tensor([x[3] for x in work], dtype=torch.int32, device=dev),
+                       utt_off=offs_t.clone(), utt_T=ln.to(torch.int32), pos_maps={})
             self._idx_cache[key] = idx
         frame_b, frame_t, frame_T = idx["frame_b"], idx["frame_t"], idx["frame_T"]
 
@@ -189,13 +193,28 @@ class Encoder:
             taps["fused"] = h.clone()
 
         # --- positional conv (k=128, groups=16) + GELU + residual (avhubert.py:698-699)
-        pcol = self._buf("col", (16, F, 8192), torch.bfloat16)
-        L.check(lib.avsr_posconv_im2col(L.ptr(hb), L.ptr(pcol), L.ptr(frame_t), L.ptr(frame_T), L.ll(F), 0, 16, L.stream()), "avsr_posconv_im2col")
-        for g in range(16):
-            hg = h[:, g * 64:]
-            L.gemm_bf16(pcol[g], w.pos_w[g], F, 64, 8192,
-                        L.make_epilogue(bias=w.pos_b[g * 64:], act=L.ACT_GELU, residual=hg, ldr=1024, out_f32=hg, ld_f32=1024),
-                        lda=8192, ldb=8192, bn_hint=64)
+        if self.implicit_posconv:
+            # implicit banded GEMM, one launch over all groups: every filter tap is a TMA load of the utterance's own frames
+            # (one tensor map per utterance: rows outside it come back as zeros); maps are cached per (lengths, buffer)
+            maps = idx["pos_maps"].get(hb.data_ptr())
+            if maps is None:
+                host = torch.zeros(B, 128, dtype=torch.uint8)
+                L.check(lib.avsr_posconv_encode_maps(L.ptr(hb), C.c_void_p(idx["utt_off"].data_ptr()), C.c_void_p(idx["utt_T"].data_ptr()), B,
+                                                     C.c_void_p(host.data_ptr())), "avsr_posconv_encode_maps")
+                L.launch_count -= 1
+                maps = host.to(dev)
+                idx["pos_maps"] = {hb.data_ptr(): maps}
+            ep = L.make_epilogue(bias=w.pos_b, act=L.ACT_GELU, residual=h, ldr=1024, out_f32=h, ld_f32=1024)
+            L.check(lib.avsr_posconv_bf16_tc(L.ptr(maps), L.ptr(w.pos_w), idx["n_work"], L.ptr(idx["work_utt"]), L.ptr(idx["work_off"]),
+                                             L.ptr(idx["work_T"]), L.ptr(idx["work_q0"]), C.byref(ep), L.stream()), "avsr_posconv_bf16_tc")
+        else:
+            pcol = self._buf("col", (16, F, 8192), torch.bfloat16)
+            L.check(lib.avsr_posconv_im2col(L.ptr(hb), L.ptr(pcol), L.ptr(frame_t), L.ptr(frame_T), L.ll(F), 0, 16, L.stream()), "avsr_posconv_im2col")
+            for g in range(16):
+                hg = h[:, g * 64:]
+                L.gemm_bf16(pcol[g], w.pos_w[g], F, 64, 8192,
+                            L.make_epilogue(bias=w.pos_b[g * 64:], act=L.ACT_GELU, residual=hg, ldr=1024, out_f32=hg, ld_f32=1024),
+                            lda=8192, ldb=8192, bn_hint=64)
         if taps is not None:
             taps["posconv"] = h.clone()
 

@@ -182,6 +182,16 @@ int avsr_audio_pack(const float* audio, void* out, const int* frame_b, const int
 /* patches of the grouped positional Conv1d (k=128, pad=64, g=16), zero outside the utterance. */
 int avsr_posconv_im2col(const void* x, void* out, const int* frame_t, const int* frame_T, long long F, int g0, int ng,
                         avsr_stream_t stream);
+/* Positional convolution x + GELU(Conv1d_{k=128, pad=64, groups=16}(x)[..., :-1] + bias) (HF Wav2Vec2PositionalConvEmbedding,
+ * modeling_wav2vec2.py:326-379, called from backbones/avhubert.py:698-699) as an IMPLICIT banded GEMM, one launch over all 16
+ * groups: tap j of an output tile reads frames [q0 + j - 64, +128) of the tile's utterance through that utterance's own tensor
+ * map (zero outside the utterance).  avsr_posconv_encode_maps (host only) writes the B tensor maps (128 bytes each) for the
+ * packed bf16 activations x [F, 1024] into maps_host; the caller uploads them (64-byte aligned) and passes them as utt_maps.
+ * W [1024][8192] bf16, k = tap * 64 + channel-in-group; work_* = 128-frame work items (utterance index, first packed frame of
+ * the utterance, its length, first frame of the item); ep = per-column bias [1024], GELU, residual / outputs by packed frame. */
+int avsr_posconv_encode_maps(const void* x, const long long* utt_off, const int* utt_T, int B, void* maps_host);
+int avsr_posconv_bf16_tc(const void* utt_maps, const void* W, int n_work, const int* work_utt, const int* work_off, const int* work_T,
+                         const int* work_q0, const AvsrEpilogue* ep, avsr_stream_t stream);
 int avsr_cast_bf16(const float* in, long long ldi, void* out, long long ldo, long long rows, int cols, avsr_stream_t stream);
 
 /* ---- fp32 decode-side ops ----------------------------------------------------------------------------------------- */

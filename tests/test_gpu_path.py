@@ -54,6 +54,32 @@ def test_encoder_vs_reference_cfg0_T375(gpu_model, golden_cfg0):
     _check_enc(xb[0].cpu(), ref, "encoder T=375, batch of 4")
 
 
+def test_implicit_posconv_and_frontend_equal_explicit_paths(gpu_model):
+    """The implicit-GEMM forms of the positional conv (one launch, per-utterance tensor maps) and of the 3D-conv frontend give
+    the results of the explicit patch-matrix paths on a mixed-length batch that spans several 128-frame work items."""
+    enc = gpu_model.encoder
+    lengths = [200, 3, 131]
+    vids, auds = zip(*[synth.make_inputs(60 + i, t) for i, t in enumerate(lengths)])
+    video = torch.cat([v[0, 0] for v in vids], 0).cuda().contiguous()
+    audio = torch.zeros(3, 104, max(lengths))
+    for b, a in enumerate(auds):
+        audio[b, :, :lengths[b]] = a[0]
+    audio = audio.cuda()
+    outs = {}
+    for imp in (True, False):
+        enc.implicit_posconv = enc.implicit_frontend = imp
+        taps = {}
+        x = enc.forward_packed(video, audio, lengths, taps)
+        outs[imp] = (taps["trunk"].clone(), taps["fused"].clone(), taps["posconv"].clone(), x.clone())
+    enc.implicit_posconv = enc.implicit_frontend = True
+    for a, b, name in zip(outs[True], outs[False], ("trunk", "fused", "posconv", "output")):
+        d = (a - b).abs().max().item()
+        assert d <= 2e-2 * max(1.0, b.abs().max().item()), (name, d)
+    # the two forms accumulate in a different order but from the same bf16 operands: the positional conv itself agrees tightly
+    pc_t, pc_f = outs[True][2] - outs[True][1], outs[False][2] - outs[False][1]
+    assert (pc_t - pc_f).abs().max().item() < 5e-3 * max(1.0, pc_f.abs().max().item())
+
+
 def _check_nbest(nbest, golden, T, beam):
     yseq, score = golden[f"nbest_T{T}_b{beam}_yseq"], golden[f"nbest_T{T}_b{beam}_score"]
     n = int((score > -1e8).sum())
