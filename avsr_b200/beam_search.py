@@ -442,6 +442,8 @@ class BatchedBeamSearch:
                nxt=None):
         """One cluster projection (avsr_dec_proj): operand = compact bf16x3 rows `a3` or LayerNorm(x) with ln = (gamma, beta).
         nxt: the weights the NEXT projection of the chain streams; this launch asks the L2 to fetch them."""
+        if "gemm" in self._skip:
+            return
         lib = L.load()
         R = s["R"]
         g, b = ln if ln is not None else (None, None)
@@ -454,6 +456,8 @@ class BatchedBeamSearch:
 
     def _cattn(self, s, mode, q, ldq, kc, vc, dense, li, nxt):
         """Self (mode 0) / source (mode 1) attention of the position; also starts the L2 fetch of the next projection's weights."""
+        if ("self" if mode == 0 else "cross") in self._skip:
+            return
         lib = L.load()
         beam, R, lmax = self.beam_size, s["R"], s["lmax"]
         pf = nxt if self.weight_prefetch else None
@@ -467,6 +471,8 @@ class BatchedBeamSearch:
 
     def _cfold(self, s, W3g, u, c, N, act=L.ACT_NONE, out=None, ldo=None, split=None, nxt=None):
         """Projection of LayerNorm(x) with the LayerNorm folded in (avsr_dec_proj_folded): operand = the raw rows s['x3']."""
+        if "gemm" in self._skip:
+            return
         lib = L.load()
         pf = nxt if (nxt is not None and self.weight_prefetch) else None
         L.check(lib.avsr_dec_proj_folded(L.ptr(s["x3"]), L.ll(3 * 1024), L.ptr(s["stats"]), C.c_float(1e-12), L.ptr(u), L.ptr(c), L.ptr(W3g),
@@ -538,7 +544,7 @@ class BatchedBeamSearch:
         # cluster projections serve up to 128 hypothesis rows (one row tile per cluster, everything co-resident in one wave);
         # larger batches (configs[2]-style batches of 100+ short utterances) amortise the launch chain over several row tiles
         # and run the persistent split-K kernels instead (measured on configs[2]: 792 vs 1090 ms per pass)
-        if self.precision == "bf16x3" and self.proj == "cluster" and s["R"] <= 128 and not self._skip and not self.fuse_epilogue:
+        if self.precision == "bf16x3" and self.proj == "cluster" and s["R"] <= 128 and not ("epi" in self._skip) and not self.fuse_epilogue:
             return self._decoder_layers_cluster(s, dense)
         lib = L.load()
         w = self.w

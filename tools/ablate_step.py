@@ -61,10 +61,14 @@ def time_step(skip, n=8, reps=6):
 
 full = time_step(set())
 print(f"full position (without fusion/advance): {full:8.1f} us")
-for name, skip in (("self-attention x6", {"self"}), ("source attention x6", {"cross"}), ("both attentions", {"self", "cross"}),
-                   ("row epilogues x24", {"epi"}), ("projections x37", {"gemm"}), ("projections + epilogues", {"gemm", "epi"}),
-                   ("softmax/top-S + CTC", {"tail"}), ("everything but projections+epilogues", {"self", "cross", "tail"}),
-                   ("everything but attention", {"gemm", "epi", "tail"})):
+cluster = bs.proj == "cluster" and s["R"] <= 128
+groups = [("self-attention x6", {"self"}), ("source attention x6", {"cross"}), ("both attentions", {"self", "cross"}),
+          ("projections x37", {"gemm"}), ("softmax/top-S + CTC", {"tail"}), ("everything but projections", {"self", "cross", "tail"}),
+          ("everything but attention", {"gemm", "tail"})]
+if not cluster:
+    groups += [("row epilogues x24", {"epi"}), ("projections + epilogues", {"gemm", "epi"})]
+print("projection path:", "cluster (54 launches per position)" if cluster else "split-K + row epilogues (78 launches)")
+for name, skip in groups:
     t = time_step(skip)
     print(f"  without {name:40s}: {t:8.1f} us   (group costs {full - t:7.1f} us in place)")
 bs._skip = frozenset()
