@@ -102,6 +102,11 @@ class BatchedBeamSearch:
         # LayerNorm folded into the consuming projection (avsr_dec_proj_folded: raw rows through TMA, mean / rstd applied to the
         # finished sums) instead of normalising while the operand is staged; AVSR_LN_FOLD=0 keeps the staged form (A/B switch)
         self.ln_fold = os.environ.get("AVSR_LN_FOLD", "1") != "0"
+        # MB of the layer's cross-attention K/V that the self-attention output projection (two launches before the source
+        # attention) asks the L2 to fetch (0 = off); the HBM stream then overlaps the latency-bound projections in between
+        self.kv_prefetch_mb = float(os.environ.get("AVSR_KV_PREFETCH_MB", "0"))
+        # the projection two launches before a self-attention asks the L2 for that layer's dense K/V history (AVSR_SELF_KV_PREFETCH)
+        self.self_kv_prefetch = os.environ.get("AVSR_SELF_KV_PREFETCH", "0") == "1"
         if self.proj not in ("cluster", "splitk"):
             raise RuntimeError(f"AVSR_PROJ must be cluster or splitk, got {self.proj!r}")
         self.graph_launches = 0       # kernels launched through graph replays (bench.py adds them to gpu_launches)
@@ -509,6 +514,11 @@ class BatchedBeamSearch:
             else:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, ln=(lay["n1_g"], lay["n1_b"]), bias=lay["bqkv"], out=s["qkv"])
             self._cattn(s, 0, s["qkv"], 3072, s["kc"][li], s["vc"][li], dense, li, lay["wo3"])
+            if self.kv_prefetch_mb > 0:
+                ckv = s["ckv_t"][li]
+                nbytes = min(int(self.kv_prefetch_mb * (1 << 20)), ckv.numel() * 4) // 16 * 16
+                L.check(lib.avsr_dec_proj_also_prefetch(L.ptr(ckv), L.ll(nbytes)), "avsr_dec_proj_also_prefetch")
+                L.launch_count -= 1
             self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
                         nxt=lay["wq23g"] if fold else lay["wq23"])
             # source attention (decoder_layer.py:97-107)
@@ -528,6 +538,10 @@ class BatchedBeamSearch:
                 nxt = w.layers[li + 1]["wqkv3g"] if fold else w.layers[li + 1]["wqkv3"]
             else:
                 nxt = w.out_w3g if fold else w.out_w3
+            if self.self_kv_prefetch and dense and li + 1 < nl:
+                L.check(lib.avsr_dec_proj_prefetch_self_kv(L.ptr(s["kd"][li + 1]), L.ptr(s["vd"][li + 1]), lmax, s["B"] * 16, L.ptr(s["step"])),
+                        "avsr_dec_proj_prefetch_self_kv")
+                L.launch_count -= 1
             self._cproj(s, lay["w23"], 1024, 3072, a3=s["ffn3"], bias=lay["b2"], residual=s["x"], out=s["x"], split=x3, stats_out=True, nxt=nxt)
         # after_norm + output layer (decoder.py:176-181); the output bias is added by the softmax kernel that follows.  It
         # fetches the first projection of the NEXT position (only small kernels run in between)

@@ -42,6 +42,19 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_s
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Dev aid (avsr_dec_attn_debug): phase timestamps of CTA (0, 0) of the self-attention kernel, globaltimer nanoseconds.
+__device__ unsigned long long* g_attn_dbg = nullptr;
+#ifndef AVSR_ATTN_DEBUG
+#define AVSR_ATTN_DEBUG 0
+#endif
+__device__ __forceinline__ void dbg_stamp(int k) {
+    if (AVSR_ATTN_DEBUG && g_attn_dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_attn_dbg[k] = t;
+    }
+}
+
 struct AttnArgs {
     const float* q_in; long long ldq; int nsplit; const float* q_bias;
     float* kc; float* vc; const unsigned char* anc; int lmax;
@@ -81,7 +94,8 @@ __device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbas
 // Everything after griddepcontrol.wait, for exactly NHT live hyps (NH = hyp slots of the beam).
 template <int MODE, int NH, int NHT>
 __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, unsigned* rlist, float* vtile, float4 (&kreg)[DH / 4],
-                                          const float* kbase, const float* vbase, long long nr, int T_utt, int step, int conv) {
+                                          const float* kbase, const float* vbase, long long nr, int T_utt, int step, int conv,
+                                          const float4 (&pre)[3]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y;
@@ -113,6 +127,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         for (int i = 0; i < VR; ++i) cp_async16(vt_s + i * DH * 4, vdb + (long long)(hw * VR + i) * DH + 4 * l16);
     }
 
+    if (MODE == 0) dbg_stamp(2);
     // ---- query: 16-byte groups, all split-K terms of a group requested at once (two threads share a group when there are
     //      few hyps); the current k / v of the chunk that owns this position go straight to the cache
     const long long zstride = (long long)R * ldq;
@@ -137,10 +152,9 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     const bool two = nsplit > 1 && 2 * G <= CK;      // two threads per group: splits [0, zh) and [zh, nsplit)
     const int zh = two ? (nsplit + 1) / 2 : nsplit;
     if (nsplit <= 0) {
-        for (int g = tid; g < G; g += CK) {
-            const int h = g / (DH / 4), j = g % (DH / 4);
-            *reinterpret_cast<float4*>(&sm.qs[h][4 * j]) = *reinterpret_cast<const float4*>(q_in + (long long)(row0 + h) * ldq + head * DH + 4 * j);
-        }
+        // finished projections: q (and k | v) of the NH hypothesis slots were requested together with the beam state, right
+        // after griddepcontrol.wait (thread = (slot, 16-byte group)); one round trip instead of two
+        if (tid < G) *reinterpret_cast<float4*>(&sm.qs[tid / (DH / 4)][4 * (tid % (DH / 4))]) = pre[0];
     } else {
         for (int g = tid; g < (two ? 2 * G : G); g += CK) {
             const int sub = g / G, gg = g % G;
@@ -149,7 +163,15 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
             *reinterpret_cast<float4*>(sub == 0 ? &sm.qs[h][4 * j] : &sm.qpart[h][4 * j]) = v;
         }
     }
-    if (MODE == 0) {
+    if (MODE == 0 && nsplit <= 0) {
+        if (tid < G) {
+            const int h = tid / (DH / 4), j = tid % (DH / 4);
+            const long long rr = (long long)step * beam + h;
+            const long long cb = (long long)(utt * HEADS + head) * nr * DH;
+            *reinterpret_cast<float4*>(a.kc + cb + ((long long)(j >> 1) * nr + rr) * KG + (j & 1) * 4) = pre[1];
+            *reinterpret_cast<float4*>(a.vc + cb + rr * DH + 4 * j) = pre[2];
+        }
+    } else if (MODE == 0) {
         for (int g = tid; g < 2 * G; g += CK) {
             const int kv = g / G, gg = g % G;
             const int h = gg / (DH / 4), j = gg % (DH / 4);
@@ -167,6 +189,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
             else *reinterpret_cast<float4*>(a.vc + cb + rr * DH + 4 * j) = v;
         }
     }
+    if (MODE == 0) dbg_stamp(3);
     // ---- mode 0: list of the distinct (pos, slot) rows referenced by the live hyps, in (pos, slot) order
     int nrows = (MODE == 1) ? T_utt : 0;
     if (MODE == 0) {
@@ -207,6 +230,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     }
     if (tid < NHT) { sm.s_run[0][tid] = -INFINITY; sm.s_run[1][tid] = 0.f; }
     __syncthreads();                                 // qs / qpart, rlist, s_run ready
+    if (MODE == 0) dbg_stamp(4);
     if (nsplit > 0) {                                // finish the query: (first half + second half) + bias
         for (int g = tid; g < G; g += CK) {
             const int h = g / (DH / 4), j = g % (DH / 4);
@@ -257,6 +281,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     };
     if (MODE == 0 && !early) { request_k(0); request_v(0); }  // mode 1: tile 0 was requested before griddepcontrol.wait
     __syncthreads();                                 // finished query visible (the loads above are already in flight)
+    if (MODE == 0) dbg_stamp(5);
     for (int tile = 0; tile < ntiles; ++tile) {
         const int t0 = tile * CK;
         const bool kvalid = t0 + tid < nrows;
@@ -264,16 +289,23 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         const int nv = min(VR, nrows - t0 - hw * VR);                // valid V rows of this half-warp in this tile (may be <= 0)
         // ---- scores of this thread's key against every live hyp
         float s[NHT];
+        {
+            // four independent partial sums per hyp: the 64-term dot product is 4 chains of 16 dependent FMAs, not one of 64
+            // (the kernel runs at 3-4 warps per scheduler: dependent-issue latency, not throughput, paces it)
+            float p0[NHT], p1[NHT], p2[NHT], p3[NHT];
 #pragma unroll
-        for (int h = 0; h < NHT; ++h) s[h] = 0.f;
+            for (int h = 0; h < NHT; ++h) p0[h] = p1[h] = p2[h] = p3[h] = 0.f;
 #pragma unroll
-        for (int j = 0; j < DH / 4; ++j) {
+            for (int j = 0; j < DH / 4; ++j) {
 #pragma unroll
-            for (int h = 0; h < NHT; ++h) {
-                const float4 q = *reinterpret_cast<const float4*>(&sm.qs[h][4 * j]);
-                s[h] = fmaf(q.x, kreg[j].x, s[h]); s[h] = fmaf(q.y, kreg[j].y, s[h]);
-                s[h] = fmaf(q.z, kreg[j].z, s[h]); s[h] = fmaf(q.w, kreg[j].w, s[h]);
+                for (int h = 0; h < NHT; ++h) {
+                    const float4 q = *reinterpret_cast<const float4*>(&sm.qs[h][4 * j]);
+                    p0[h] = fmaf(q.x, kreg[j].x, p0[h]); p1[h] = fmaf(q.y, kreg[j].y, p1[h]);
+                    p2[h] = fmaf(q.z, kreg[j].z, p2[h]); p3[h] = fmaf(q.w, kreg[j].w, p3[h]);
+                }
             }
+#pragma unroll
+            for (int h = 0; h < NHT; ++h) s[h] = (p0[h] + p1[h]) + (p2[h] + p3[h]);
         }
         if (tile + 1 < ntiles) request_k(t0 + CK);   // the key registers are free: next tile's keys fly during softmax and P.V
 #pragma unroll
@@ -292,8 +324,9 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
             float e = 0.f;
             scale[h] = 1.f;
             if (mn > -INFINITY) {
-                e = expf(s[h] - mn);                 // masked / invalid keys: exp(-inf) = 0
-                scale[h] = expf(mo - mn);            // mo = -inf -> 0 (nothing accumulated yet)
+                // ex2.approx (2^-22 relative): far below the fp32 rounding of the 64-term scores themselves
+                e = __expf(s[h] - mn);               // masked / invalid keys: exp(-inf) = 0
+                scale[h] = __expf(mo - mn);          // mo = -inf -> 0 (nothing accumulated yet)
             }
             mnew[h] = mn;
             sm.sc[h][tid] = e;
@@ -339,6 +372,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         }
         if (tile + 1 < ntiles) request_v(t0 + CK);   // this thread's V slots are free again
     }
+    if (MODE == 0) dbg_stamp(6);
     // ---- merge the eight half-warp accumulators (fixed order); they all refer to the same running max
 #pragma unroll
     for (int h = 0; h < NHT; ++h) *reinterpret_cast<float4*>(&sm.s_o[hw][h][4 * l16]) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
@@ -356,6 +390,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
         for (int w = 0; w < NHW; ++w) o += sm.s_o[w][h][d];
         store_out(h, d, o / sm.s_run[1][h]);
     }
+    if (MODE == 0) dbg_stamp(7);
 }
 
 template <int MODE, int NH>
@@ -367,6 +402,7 @@ dec_attn_stream_kernel(const AttnArgs a) {
     const int tid = threadIdx.x;
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y;
+    if (MODE == 0) dbg_stamp(0);
     pdl_trigger();
     if (a.pf != nullptr && tid == 0) {
         constexpr long long PIECE = 16 * 1024;
@@ -405,6 +441,7 @@ dec_attn_stream_kernel(const AttnArgs a) {
         vbase = a.vc + (long long)(utt * HEADS + head) * nr * DH;
     }
     pdl_wait();
+    if (MODE == 0) dbg_stamp(1);
     // everything the body needs from the beam state is requested in ONE round trip (both parities of conv_len: which one
     // applies depends on *step)
     const int nh = a.n_run[utt];
@@ -414,9 +451,19 @@ dec_attn_stream_kernel(const AttnArgs a) {
         conv0 = a.conv_len[utt];
         conv1 = a.conv_len[a.R / a.beam + utt];
     }
+    float4 pre[3];
+    pre[0] = pre[1] = pre[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.nsplit <= 0 && tid < NH * (DH / 4)) {
+        // same round trip as the beam state: this position's query (self-attention: and key, value) of all NH slots
+        const float* qp = a.q_in + (long long)(utt * a.beam + tid / (DH / 4)) * a.ldq + head * DH + 4 * (tid % (DH / 4));
+        if (tid / (DH / 4) < a.beam) {
+            pre[0] = *reinterpret_cast<const float4*>(qp);
+            if (MODE == 0) { pre[1] = *reinterpret_cast<const float4*>(qp + D); pre[2] = *reinterpret_cast<const float4*>(qp + 2 * D); }
+        }
+    }
     if (nh == 0) { cp_async_wait_all(); return; }
     const int conv = ((step + 1) & 1) ? conv1 : conv0;
-#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step, conv)
+#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step, conv, pre)
     if (NH <= 4) {
         switch (nh) {
             case 1: AVSR_BODY(1); break;
@@ -583,5 +630,13 @@ extern "C" int avsr_dec_cache_promote(const float* kc, const float* vc, float* k
     const long long sls = B * HEADS * (long long)lmax * beam * DH, dls = B * HEADS * (long long)lmax * DH;
     AVSR_CHECK_CUDA(avsr_launch_pdl(dec_cache_promote_kernel, dim3((unsigned)B, n_layers), dim3(256), 0, stream, kc, vc, kd, vd, sls, dls, anc,
                                     lmax, n_run, beam, R, step, conv_len));
+    return AVSR_OK;
+}
+
+// Dev aid: buf = 8 uint64 in device memory (or NULL to switch off); CTA (0, 0) of every self-attention launch then records
+// globaltimer stamps at: kernel entry, after griddepcontrol.wait, query gather start, row list start, row list done, tile loop
+// start, tile loop done, output stored.
+extern "C" int avsr_dec_attn_debug(unsigned long long* buf) {
+    AVSR_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_dbg, &buf, sizeof(buf)));
     return AVSR_OK;
 }

@@ -82,6 +82,10 @@ struct ProjArgs {
     __nv_bfloat16* split_out;           // compact bf16x3 rows [R][3 N]
     float* stats_out;                   // [N / 128][R][2]
     const char* pf; long long pf_bytes;  // span the NEXT kernel of the chain streams (its weights): fetched into L2 from here
+    const char* pf2; long long pf2_bytes;  // a second span (K/V a later attention kernel streams), same treatment
+    // dense self-attention caches of the layer whose attention runs two launches from now (avsr_dec_proj_prefetch_self_kv):
+    // positions [0, *step) of every (utterance, head) are fetched into L2 after this kernel's griddepcontrol.wait
+    const float* skd; const float* svd; int s_lmax, s_nuh; const int* s_step;
 };
 
 // three bf16 terms of 8 consecutive fp32 values -> one 16-byte chunk per term
@@ -160,6 +164,26 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     for (int j = 0; j < 3; ++j) tc::tma_load_2d(sa + j * A_TILE, &tmA, &full[i], (kb0 + i) * BK + j * K, n0);
                 }
             }
+            if (p.skd != nullptr) {
+                // (utterance, head) spans of the dense caches: K = 8 planes of [pos][8] floats, V = [pos][64] floats
+                const int L = *p.s_step;                   // positions 0 .. L-1 exist (read after the wait: the chain wrote it)
+                if (L > 0) {
+                    const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
+                    const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                    const unsigned kb_bytes = (unsigned)L * 32u, v_bytes = (unsigned)L * 256u;
+                    for (long long uh = cta; uh < p.s_nuh; uh += ncta) {
+                        const float* kbase = p.skd + uh * (long long)p.s_lmax * 64;
+                        const float* vbase = p.svd + uh * (long long)p.s_lmax * 64;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kbase + (long long)j * p.s_lmax * 8), "r"(kb_bytes) : "memory");
+                        for (unsigned o = 0; o < v_bytes; o += 32768u) {
+                            const unsigned n = min(32768u, v_bytes - o);
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(vbase) + o), "r"(n) : "memory");
+                        }
+                    }
+                }
+            }
             int stage = npre % STAGES;
             uint32_t phase = (npre == STAGES) ? 1u : 0u;
             for (int kb = kb0 + npre; kb < kb1; ++kb) {
@@ -177,17 +201,21 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            if (p.pf != nullptr) {
-                // the weights of the next projection do not depend on anything: ask the L2 for this CTA's share now (fire and
-                // forget), so that the next kernel's TMA loads find them on chip instead of paying the HBM latency after its wait
+            // the weights of the next projection (and K/V a later attention streams) do not depend on anything: ask the L2 for
+            // this CTA's share now (fire and forget), so that their consumers find them on chip instead of paying HBM latency
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                const char* pfp = which == 0 ? p.pf : p.pf2;
+                const long long pfb = which == 0 ? p.pf_bytes : p.pf2_bytes;
+                if (pfp == nullptr) continue;
                 constexpr long long PIECE = 16 * 1024;
                 const long long ncta = (long long)gridDim.x * gridDim.y * gridDim.z;
                 const long long cta = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-                const long long share = ((p.pf_bytes + ncta - 1) / ncta + PIECE - 1) / PIECE * PIECE;
-                const long long lo = cta * share, hi = min(p.pf_bytes, lo + share);
+                const long long share = ((pfb + ncta - 1) / ncta + PIECE - 1) / PIECE * PIECE;
+                const long long lo = cta * share, hi = min(pfb, lo + share);
                 for (long long o = lo; o < hi; o += PIECE) {
                     const unsigned n = (unsigned)min(PIECE, hi - o) & ~15u;
-                    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf + o), "r"(n) : "memory");
+                    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pfp + o), "r"(n) : "memory");
                 }
             }
             const uint32_t idesc = tc::umma_idesc_bf16(BM, (uint32_t)NB);
@@ -445,6 +473,12 @@ int sm_count() {
 
 size_t smem_bytes(int nb) { return (size_t)STAGES * (3 * W_TILE + 3 * nb * BK * 2) + 1024 + 256 + 2 * MAX_NB * sizeof(float); }
 
+const float* g_skd = nullptr;
+const float* g_svd = nullptr;
+int g_slmax = 0, g_snuh = 0;
+const int* g_sstep = nullptr;
+const char* g_pf2 = nullptr;
+long long g_pf2_bytes = 0;
 int g_force_splits = 0;
 int g_sm_budget = 0;                                   // SMs one projection may occupy (0 = all): concurrent decode chains share the GPU
 bool g_configured = false;
@@ -543,6 +577,25 @@ extern "C" int avsr_dec_proj_set_sm_budget(int sms) {
     return AVSR_OK;
 }
 
+// A second L2 fetch-ahead span for the NEXT avsr_dec_proj / avsr_dec_proj_folded launch only (e.g. the cross-attention K/V
+// that an attention kernel two launches later streams); cleared by that launch.
+extern "C" int avsr_dec_proj_also_prefetch(const void* span, long long bytes) {
+    if ((span != nullptr && (((uintptr_t)span & 15) != 0 || bytes <= 0))) return AVSR_ERR_ARG;
+    g_pf2 = (const char*)span;
+    g_pf2_bytes = bytes;
+    return AVSR_OK;
+}
+
+// The NEXT avsr_dec_proj* launch also asks the L2 for positions [0, *step) of the dense self-attention caches kd / vd of one
+// layer (layouts of avsr_dec_cache_promote; n_utt_heads = utterances x 16 spans, lmax positions each): issued after that
+// launch's griddepcontrol.wait, so the history streams from HBM while the latency-bound projections in between run and the
+// self-attention two launches later reads it from L2.  One-shot.
+extern "C" int avsr_dec_proj_prefetch_self_kv(const float* kd, const float* vd, int lmax, int n_utt_heads, const int* step) {
+    if (kd != nullptr && (vd == nullptr || step == nullptr || lmax <= 0 || n_utt_heads <= 0 || ((uintptr_t)kd & 31) || ((uintptr_t)vd & 15))) return AVSR_ERR_ARG;
+    g_skd = kd; g_svd = vd; g_slmax = lmax; g_snuh = n_utt_heads; g_sstep = step;
+    return AVSR_OK;
+}
+
 // One decoder-step projection with its glue:  y = act(a W^T + bias) + residual  for R rows.
 //   operand a:  A3 != NULL: compact bf16x3 rows [R, 3K] (pitch lda elements), loaded with TMA; else a = LayerNorm(x) with
 //               x [R, K] fp32 (pitch ldx), stats_in [K/128][R][2] = (mean, M2) of every 128-column tile of x as a previous call
@@ -586,7 +639,9 @@ static int dec_proj_launch(const void* A3, long long lda, const float* x, long l
         ta = tw;
     }
     ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, fold_u, bias, act, residual, ldr, out, ldo,
-                  (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
+                  (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, g_pf2, g_pf2 ? g_pf2_bytes : 0, g_skd, g_svd, g_slmax, g_snuh, g_sstep};
+    g_pf2 = nullptr;                                   // one-shot (avsr_dec_proj_also_prefetch)
+    g_skd = g_svd = nullptr;                           // one-shot (avsr_dec_proj_prefetch_self_kv)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles_m, splits, tiles_n);
     cfg.blockDim = dim3(NUM_THREADS);

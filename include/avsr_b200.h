@@ -139,6 +139,8 @@ int avsr_gemm_x3_chain(const void* A3, long long lda, const void* W3, long long 
  * avsr_dec_proj_splits: the cluster size (= K splits) chosen for a shape on the current device. */
 int avsr_dec_proj_splits(int R, int N, int K);
 int avsr_dec_proj_force_splits(int splits);                /* dev knob: 0 = automatic */
+int avsr_dec_proj_prefetch_self_kv(const float* kd, const float* vd, int lmax, int n_utt_heads, const int* step);   /* one-shot: the next launch fetches [0, *step) of a layer's dense self-attention caches into L2 */
+int avsr_dec_proj_also_prefetch(const void* span, long long bytes);   /* one-shot second L2 fetch-ahead span of the next avsr_dec_proj* launch */
 int avsr_dec_proj_set_sm_budget(int sms);                  /* SMs one launch is planned for (0 = all): concurrent decode chains */
 int avsr_dec_proj_max_clusters(int cluster_size, int nb);   /* resident clusters of that size (operand tiles of nb rows) */
 int avsr_dec_proj(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
@@ -236,6 +238,7 @@ int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq, int nsplit
                           const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
                           const int* step, float* out, long long n_frames, void* out_split, const float* kd, const float* vd,
                           const int* conv_len, const void* l2_prefetch, long long l2_prefetch_bytes, avsr_stream_t stream);
+int avsr_dec_attn_debug(unsigned long long* buf);   /* dev aid: phase timestamps of one self-attention CTA (8 uint64, NULL = off) */
 /* Dense copy of the CONVERGED history prefix (positions where all live hyps of an utterance share their ancestor): copies the
  * newly converged rows of all layers from the per-slot caches to kd / vd (key element (layer, utt, head, pos, d) at
  * layer*B*16*lmax*64 + ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at layer*B*16*lmax*64 +
