@@ -284,9 +284,34 @@ __device__ __forceinline__ void fv_stream(const float* __restrict__ lpc, int ldp
     }
 }
 
-// exact log-domain value of one cell (the reference's formula): logsumexp over t of phi[t-1] + x[t][c], plus r[start-1,0]
+// exact log-domain value of one cell (the reference's formula): logsumexp over t of phi[t-1] + x[t][c], plus r[start-1,0].
+// The column is read ONCE: every lane requests all of its (strided, one sector each) posteriors before the first use and
+// keeps the terms in registers for the second pass - one memory round trip instead of ~2 T / 32 partly serialised ones; this
+// warp runs after the streaming pass, when the rest of its CTA is idle, so its latency is the tail of the kernel.
+constexpr int FV_XR = 16;                 // terms per lane kept in registers (T <= 512); longer utterances loop in chunks
 __device__ __forceinline__ float fv_exact_warp(const float* __restrict__ lp, int ldp, int c, int start, int T, const float* phi, int nh,
                                                int h, float x0, int lane) {
+    if (T - start <= 32 * FV_XR) {
+        float v[FV_XR];
+#pragma unroll
+        for (int u = 0; u < FV_XR; ++u) {
+            const int t = start + lane + 32 * u;
+            v[u] = (t < T) ? __ldg(lp + (long long)t * ldp + c) : 0.f;
+        }
+        float mx = x0;
+#pragma unroll
+        for (int u = 0; u < FV_XR; ++u) {
+            const int t = start + lane + 32 * u;
+            v[u] = (t < T) ? phi[(t - 1) * nh + h] + v[u] : -INFINITY;
+            mx = fmaxf(mx, v[u]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < FV_XR; ++u) sum += expf(v[u] - mx);          // exp(-inf) = 0 for the slots past the end
+        sum = warp_sum(sum);
+        return mx + logf(sum + expf(x0 - mx));
+    }
     float mx = x0;
     for (int t = start + lane; t < T; t += 32) mx = fmaxf(mx, phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c]);
     mx = warp_max(mx);
