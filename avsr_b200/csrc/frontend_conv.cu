@@ -13,11 +13,14 @@
 // tile = 8 consecutive input pixels, and a chunk is copied with four aligned 32-bit shared-memory loads and one 16-byte
 // store.  One persistent CTA per SM:
 //   warp 0      : MMA issuer (tcgen05.mma M128 x N64 x K16, 20 per tile), owns TMEM (2 accumulators x 64 columns)
-//   warps 1-8   : producers.  Per tile: the fp32 input window (5 frames x <= 13 rows x 88) is fetched one tile AHEAD into
-//                 registers, converted to bf16 in shared memory (zero borders), and the A tile is built k block by k block
-//                 in the 128-byte-swizzled UMMA layout.  The five k blocks of A are a ring (slot j = k block j): block j of the
+//   warps 1-8   : builders.  Per tile the A operand is built k block by k block in the 128-byte-swizzled UMMA layout from the
+//                 bf16 input window in shared memory.  The five k blocks of A are a ring (slot j = k block j): block j of the
 //                 next tile is rebuilt as soon as the MMAs that read block j of this tile have retired.
 //   warps 9-12  : epilogue.  tcgen05.ld (thread = pixel), bias + PReLU, 64 bf16 channels = one 128-byte store per pixel (NHWC).
+//   warps 13-16 : loaders.  The fp32 input window of a tile (5 frames x <= 13 rows x 88, zero borders) is fetched one tile
+//                 ahead into registers and stored as bf16 into a three-slot ring of windows (mbarrier hand-off to the builders).
+//                 They are separate warps because the builders execute fence.proxy.async (MEMBAR.ALL.CTA) after every k
+//                 block, which would wait for global loads in flight in the same thread (measured: 3.3 -> ? us per tile).
 // The 40 KB of weights stay in shared memory for the whole kernel.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -34,10 +37,20 @@ constexpr int WROWS = 13, WPITCH = 96;                        // input window ro
 constexpr int WIN_ELEMS = 5 * WROWS * WPITCH;                 // 6240
 constexpr int A_KB_BYTES = TILE * 128;                        // 16 KB per k block
 constexpr int B_KB_BYTES = NCH * 128;                         // 8 KB per k block
-constexpr int N_PROD = 256, N_EPI = 128;
-constexpr int NUM_THREADS = 32 + N_PROD + N_EPI;
-constexpr int WIN_PER_THREAD = (WIN_ELEMS / 2 + N_PROD - 1) / N_PROD;      // bf16 pairs per producer thread: 13
-constexpr int SMEM_BYTES = KB * A_KB_BYTES + KB * B_KB_BYTES + 2 * WIN_ELEMS * 2 + 2 * NCH * 4 + 256 + 1024;
+constexpr int N_PROD = 256, N_EPI = 128, N_LOAD = 128;
+constexpr int NUM_THREADS = 32 + N_PROD + N_EPI + N_LOAD;
+constexpr int WIN_SLOTS = 3;
+constexpr int WIN_PER_THREAD = (WIN_ELEMS / 2 + N_LOAD - 1) / N_LOAD;      // bf16 pairs per loader thread: 25
+constexpr int SMEM_BYTES = KB * A_KB_BYTES + KB * B_KB_BYTES + WIN_SLOTS * WIN_ELEMS * 2 + 2 * NCH * 4 + 256 + 1024;
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t i = 0; !tc::mbar_try_wait(bar, parity); ++i)
@@ -61,14 +74,16 @@ frontend_conv_kernel(const FrontArgs a) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                            // [KB][128 rows][128 B]
     uint8_t* sB = sA + KB * A_KB_BYTES;                            // [KB][64 rows][128 B]
-    __nv_bfloat16* win = reinterpret_cast<__nv_bfloat16*>(sB + KB * B_KB_BYTES);       // [2][5][13][96]
-    float* s_bias = reinterpret_cast<float*>(win + 2 * WIN_ELEMS);
+    __nv_bfloat16* win = reinterpret_cast<__nv_bfloat16*>(sB + KB * B_KB_BYTES);       // [WIN_SLOTS][5][13][96]
+    float* s_bias = reinterpret_cast<float*>(win + WIN_SLOTS * WIN_ELEMS);
     float* s_prelu = s_bias + NCH;
     uint64_t* afull = reinterpret_cast<uint64_t*>(s_prelu + NCH);
     uint64_t* aempty = afull + KB;
     uint64_t* tfull = aempty + KB;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* wfull = tempty + 2;
+    uint64_t* wempty = wfull + WIN_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + WIN_SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_items = a.nf * TILES_PER_FRAME;
@@ -76,6 +91,7 @@ frontend_conv_kernel(const FrontArgs a) {
     if (tid == 0) {
         for (int j = 0; j < KB; ++j) { tc::mbar_init(&afull[j], N_PROD / 32); tc::mbar_init(&aempty[j], 1); }
         for (int j = 0; j < 2; ++j) { tc::mbar_init(&tfull[j], 1); tc::mbar_init(&tempty[j], N_EPI / 32); }
+        for (int j = 0; j < WIN_SLOTS; ++j) { tc::mbar_init(&wfull[j], N_LOAD / 32); tc::mbar_init(&wempty[j], N_PROD / 32); }
         tc::fence_barrier_init();
     }
     if (warp == 0) {
@@ -122,17 +138,9 @@ frontend_conv_kernel(const FrontArgs a) {
             }
         }
     } else if (warp <= N_PROD / 32) {
-        // ------------------------------------------------------------------------------------------------ producers
+        // ------------------------------------------------------------------------------------------------ builders
         const int pt = tid - 32;                               // 0 .. 255
         const int p = pt & 127, half = pt >> 7;                // pixel of the tile, which four chunks of a k block
-        // input window of a tile: frames f-2 .. f+2, input rows iy0 .. iy0 + 12, x = -3 .. 92 (zero outside the image / utterance).
-        // A thread always fetches the same WIN_PER_THREAD element pairs of the window: their (dt, row, column) are unpacked once.
-        int wdesc[WIN_PER_THREAD];                             // dt | row << 8 | xx << 16, or -1 past the end of the window
-#pragma unroll
-        for (int u = 0; u < WIN_PER_THREAD; ++u) {
-            const int e = (pt + u * N_PROD) * 2;
-            wdesc[u] = e < WIN_ELEMS ? ((e / (WROWS * WPITCH)) | (((e / WPITCH) % WROWS) << 8) | ((e % WPITCH) << 16)) : -1;
-        }
         // shared-memory word offset of the (dt, dy) pair behind each of this thread's 20 chunks (tile independent)
         int coff[KB][4];
 #pragma unroll
@@ -140,8 +148,52 @@ frontend_conv_kernel(const FrontArgs a) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const int q = kb * 8 + half * 4 + cc;
-                coff[kb][cc] = q < 35 ? ((q / 7) * WROWS + (q % 7)) * (WPITCH / 2) : -1;
+                coff[kb][cc] = q < 35 ? ((q / 7) * WROWS + (q % 7)) * (WPITCH / 2) * 4 : -1;       // bytes
             }
+        const uint32_t sA_s = tc::smem_u32(sA) + (uint32_t)p * 128u, win_s = tc::smem_u32(win);
+        const uint32_t swz = (uint32_t)(p & 7);
+        uint32_t ph_a = 0, ph_w = 0;
+        int slot = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int ti = item % TILES_PER_FRAME;
+            const int P = ti * TILE + p;                       // pixel of the frame
+            const bool pok = P < PIX;
+            const int oy = P / OUT, ox = P - oy * OUT;
+            const int oy0 = (ti * TILE) / OUT;
+            // byte address of this pixel's first input column inside a window row: x = 2 ox - 3 -> xx = 2 ox -> word ox
+            const uint32_t wpix = win_s + (uint32_t)(slot * WIN_ELEMS * 2) + (uint32_t)(((2 * (oy - oy0)) * (WPITCH / 2) + ox) * 4);
+            mbar_wait(&wfull[slot], ph_w);                     // the loaders have finished this tile's window
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(&aempty[kb], ph_a ^ 1);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (coff[kb][cc] >= 0 && pok) {
+                        const uint32_t src = wpix + (uint32_t)coff[kb][cc];
+                        const uint32_t v0 = lds32(src), v1 = lds32(src + 4), v2 = lds32(src + 8), v3 = lds32(src + 12);
+                        sts128(sA_s + (uint32_t)(kb * A_KB_BYTES) + ((((uint32_t)(half * 4 + cc)) ^ swz) << 4), v0, v1, v2, v3);
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&afull[kb]);
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&wempty[slot]);     // this window slot may be refilled
+            ph_a ^= 1;
+            if (++slot == WIN_SLOTS) { slot = 0; ph_w ^= 1; }
+        }
+    } else if (warp > (N_PROD + N_EPI) / 32) {
+        // ------------------------------------------------------------------------------------------------ loaders
+        const int lt = tid - 32 - N_PROD - N_EPI;              // 0 .. 127
+        // input window of a tile: frames f-2 .. f+2, input rows iy0 .. iy0 + 12, x = -3 .. 92 (zero outside the image / utterance).
+        // A thread always fetches the same WIN_PER_THREAD element pairs of the window: their (dt, row, column) are unpacked once.
+        int wdesc[WIN_PER_THREAD];                             // dt | row << 8 | xx << 16, or -1 past the end of the window
+#pragma unroll
+        for (int u = 0; u < WIN_PER_THREAD; ++u) {
+            const int e = (lt + u * N_LOAD) * 2;
+            wdesc[u] = e < WIN_ELEMS ? ((e / (WROWS * WPITCH)) | (((e / WPITCH) % WROWS) << 8) | ((e % WPITCH) << 16)) : -1;
+        }
         float2 wreg[WIN_PER_THREAD];
         auto window_fetch = [&](int item, int t, int T) {
             const int fl = item / TILES_PER_FRAME, ti = item - fl * TILES_PER_FRAME;
@@ -162,12 +214,6 @@ frontend_conv_kernel(const FrontArgs a) {
                 wreg[u] = v;
             }
         };
-        auto window_store = [&](int buf) {
-            __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(win + buf * WIN_ELEMS);
-#pragma unroll
-            for (int u = 0; u < WIN_PER_THREAD; ++u)
-                if (wdesc[u] >= 0) w2[pt + u * N_PROD] = __floats2bfloat162_rn(wreg[u].x, wreg[u].y);
-        };
         // a frame's position / utterance length are fetched TWO items ahead, so that no tile waits for them
         auto frame_info = [&](int item, int& t, int& T) {
             t = 0; T = 1;
@@ -178,51 +224,26 @@ frontend_conv_kernel(const FrontArgs a) {
             }
         };
         int item = blockIdx.x;
-        uint32_t ph_a = 0;
-        int buf = 0;
         int t0, T0, t1, T1;
         frame_info(item, t0, T0);
         frame_info(item + gridDim.x, t1, T1);
-        if (item < n_items) {
-            window_fetch(item, t0, T0);
-            window_store(0);
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(N_PROD) : "memory");
+        if (item < n_items) window_fetch(item, t0, T0);
+        uint32_t ph_w = 0;
+        int slot = 0;
         for (; item < n_items; item += gridDim.x) {
+            mbar_wait(&wempty[slot], ph_w ^ 1);                // the builders are done with the tile that used this slot
+            __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(win + slot * WIN_ELEMS);
+#pragma unroll
+            for (int u = 0; u < WIN_PER_THREAD; ++u)
+                if (wdesc[u] >= 0) w2[lt + u * N_LOAD] = __floats2bfloat162_rn(wreg[u].x, wreg[u].y);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&wfull[slot]);      // release: the stores above are visible to the waiting builders
+            if (++slot == WIN_SLOTS) { slot = 0; ph_w ^= 1; }
             const int nxt = item + gridDim.x;
             int t2, T2;
             frame_info(nxt + gridDim.x, t2, T2);
-            if (nxt < n_items) window_fetch(nxt, t1, T1);      // in flight while this tile's A is built
+            if (nxt < n_items) window_fetch(nxt, t1, T1);      // in flight until the next slot is free
             t1 = t2; T1 = T2;
-            const int ti = item % TILES_PER_FRAME;
-            const int P = ti * TILE + p;                       // pixel of the frame
-            const bool pok = P < PIX;
-            const int oy = P / OUT, ox = P - oy * OUT;
-            const int oy0 = (ti * TILE) / OUT;
-            // word (2 bf16) index of this pixel's first input column inside a window row: x = 2 ox - 3 -> xx = 2 ox
-            const uint32_t* wpix = reinterpret_cast<const uint32_t*>(win + buf * WIN_ELEMS) + (2 * (oy - oy0)) * (WPITCH / 2) + ox;
-            const uint32_t swz = (uint32_t)(p & 7);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(&aempty[kb], ph_a ^ 1);
-                uint8_t* dst = sA + kb * A_KB_BYTES + p * 128;
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    if (coff[kb][cc] >= 0 && pok) {
-                        const uint32_t* src = wpix + coff[kb][cc];
-                        uint4 v;
-                        v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
-                        *reinterpret_cast<uint4*>(dst + (((uint32_t)(half * 4 + cc) ^ swz) << 4)) = v;
-                    }
-                }
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&afull[kb]);
-            }
-            ph_a ^= 1;
-            buf ^= 1;
-            if (nxt < n_items) window_store(buf);
-            asm volatile("bar.sync 1, %0;" ::"n"(N_PROD) : "memory");      // the next window is complete; this one may be overwritten
         }
     } else {
         // ------------------------------------------------------------------------------------------------ epilogue
