@@ -103,6 +103,10 @@ __device__ __forceinline__ void split3_chunk(const float (&v)[8], uint4& c1, uin
     c3 = *reinterpret_cast<const uint4*>(t3);
 }
 
+// LN = the operand is LayerNorm(x) staged by the epilogue warps (its own instantiation: the staging code is a third of the
+// kernel's instructions and the decode position never runs it with the LayerNorm folded - a smaller kernel spends less of a
+// ~8 us launch on instruction fetch, ncu: no_instruction 21-26 % of the stall samples)
+template <bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const ProjArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -127,13 +131,13 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(&full[s], p.ln_mode ? 1 + 4 : 1);      // producer's expect_tx arrival (+ one per staging warp)
+            tc::mbar_init(&full[s], LN ? 1 + 4 : 1);      // producer's expect_tx arrival (+ one per staging warp)
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmW);
-        if (!p.ln_mode) tc::tma_prefetch_desc(&tmA);
+        if (!LN) tc::tma_prefetch_desc(&tmA);
     }
     if (warp == 1) {
         tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -152,12 +156,12 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const int npre = min(STAGES, kb1 - kb0);
             for (int i = 0; i < npre; ++i) {
                 uint8_t* sw = smem + i * STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[i], p.ln_mode ? w_tx : w_tx + a_tx);
+                tc::mbar_arrive_expect_tx(&full[i], LN ? w_tx : w_tx + a_tx);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) tc::tma_load_2d(sw + j * W_TILE, &tmW, &full[i], (kb0 + i) * BK + j * K, m0);
             }
             pdl_wait();
-            if (!p.ln_mode) {
+            if (!LN) {
                 for (int i = 0; i < npre; ++i) {
                     uint8_t* sa = smem + i * STAGE_BYTES + 3 * W_TILE;
 #pragma unroll
@@ -189,10 +193,10 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             for (int kb = kb0 + npre; kb < kb1; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sw = smem + stage * STAGE_BYTES;
-                tc::mbar_arrive_expect_tx(&full[stage], p.ln_mode ? w_tx : w_tx + a_tx);
+                tc::mbar_arrive_expect_tx(&full[stage], LN ? w_tx : w_tx + a_tx);
 #pragma unroll
                 for (int j = 0; j < 3; ++j) tc::tma_load_2d(sw + j * W_TILE, &tmW, &full[stage], kb * BK + j * K, m0);
-                if (!p.ln_mode) {
+                if (!LN) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) tc::tma_load_2d(sw + 3 * W_TILE + j * A_TILE, &tmA, &full[stage], kb * BK + j * K, n0);
                 }
@@ -247,7 +251,7 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const int et = threadIdx.x - 64;               // 0 .. 127
         const int quad = warp & 3;
         pdl_wait();                                    // x / stats / residual are written by the previous kernels of the chain
-        if (p.ln_mode) {
+        if (LN) {
             // Everything this phase needs from global memory is requested in as few dependent round trips as possible: the
             // fp32 rows of the first k block and the row statistics go out together; the rows of k block i + 1 are requested
             // before k block i is converted and stored.
@@ -484,8 +488,10 @@ int g_sm_budget = 0;                                   // SMs one projection may
 bool g_configured = false;
 int configure() {
     if (!g_configured) {
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_NB)));
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_NB)));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MAX_NB)));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         const char* e = getenv("AVSR_X3C_SPLITS");
         if (e) g_force_splits = atoi(e);
         g_configured = true;
@@ -515,7 +521,7 @@ int max_active_clusters(int cs, int nb) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, dec_proj_kernel, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, dec_proj_kernel<false>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         n = 0;
     }
@@ -656,7 +662,8 @@ static int dec_proj_launch(const void* A3, long long lda, const float* x, long l
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_proj_kernel, tw, ta, p));
+    if (x != nullptr) AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_proj_kernel<true>, tw, ta, p));
+    else AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_proj_kernel<false>, tw, ta, p));
     return AVSR_OK;
 }
 

@@ -14,7 +14,7 @@ from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
-which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "skinny"}
+which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "proj", "front", "posconv"}
 B, beam, T, V = 32, 3, 375, 5049
 R = B * beam
 i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
@@ -79,5 +79,50 @@ if "skinny" in which:
     for i in range(3):
         flush.zero_()
         L.check(lib.avsr_gemm_x3_splitk(L.ptr(a3), L.ll(3 * K), L.ptr(ws[i]), L.ll(3 * K), R, N, K, L.ptr(part), L.stream()), "g")
+    torch.cuda.synchronize()
+if "proj" in which:
+    # the cluster projections of a decode position: q|k|v / w_1 shape, attention-output shape, w_2 shape (weights cycled: cold HBM)
+    x = torch.randn(R, 1024, device=dev)
+    stats = torch.zeros(8, R, 2, device=dev)
+    bias = torch.zeros(3072, device=dev)
+    a3 = {k: torch.randn(R, 3 * k, device=dev).bfloat16() for k in (1024, 3072)}
+    out = torch.zeros(R, 3072, device=dev)
+    for rep in range(2):
+        for (N, K), res in (((1024, 1024), True), ((1024, 3072), True), ((3072, 1024), False)):
+            w = split3_weight_compact(torch.randn(N, K, device=dev) * 0.03)
+            flush.zero_()
+            L.check(lib.avsr_dec_proj(L.ptr(a3[K]), L.ll(3 * K), None, L.ll(0), None, None, None, C.c_float(1e-12), L.ptr(w), L.ll(3 * K), R, N, K,
+                                      L.ptr(bias), 0, L.ptr(x) if res else None, L.ll(1024), L.ptr(x) if res else L.ptr(out), L.ll(N), None,
+                                      L.ptr(stats) if res else None, None, L.ll(0), L.stream()), "proj")
+    torch.cuda.synchronize()
+
+if "front" in which:
+    nf = 2048
+    video = torch.randn(nf, 88, 88, device=dev)
+    w8 = (torch.randn(64, 320, device=dev) * 0.05).bfloat16()
+    fb, fs = torch.randn(64, device=dev), torch.rand(64, device=dev)
+    ft = (torch.arange(nf, device=dev) % 375).int()
+    fT = torch.full((nf,), 375, dtype=torch.int32, device=dev)
+    fo = torch.empty(nf, 44, 44, 64, dtype=torch.bfloat16, device=dev)
+    for _ in range(2):
+        L.check(lib.avsr_frontend_conv3d(L.ptr(video), L.ptr(ft), L.ptr(fT), 0, nf, L.ptr(w8), L.ptr(fb), L.ptr(fs), L.ptr(fo), L.stream()), "front")
+    torch.cuda.synchronize()
+
+if "posconv" in which:
+    Fr = B * T
+    hb = torch.randn(Fr, 1024, device=dev).bfloat16()
+    h = torch.randn(Fr, 1024, device=dev)
+    pw = (torch.randn(1024, 8192, device=dev) * 0.01).bfloat16()
+    pb = torch.randn(1024, device=dev)
+    offs = torch.arange(B, dtype=torch.int64) * T
+    lens = torch.full((B,), T, dtype=torch.int32)
+    host = torch.zeros(B, 128, dtype=torch.uint8)
+    L.check(lib.avsr_posconv_encode_maps(L.ptr(hb), C.c_void_p(offs.data_ptr()), C.c_void_p(lens.data_ptr()), B, C.c_void_p(host.data_ptr())), "maps")
+    maps = host.to(dev)
+    work = [(b, b * T, T, q0) for b in range(B) for q0 in range(0, T, 128)]
+    wu, wo_, wT, wq = (i32([x[j] for x in work]) for j in range(4))
+    ep = L.make_epilogue(bias=pb, act=L.ACT_GELU, residual=h, ldr=1024, out_f32=h, ld_f32=1024)
+    for _ in range(2):
+        L.check(lib.avsr_posconv_bf16_tc(L.ptr(maps), L.ptr(pw), len(work), L.ptr(wu), L.ptr(wo_), L.ptr(wT), L.ptr(wq), C.byref(ep), L.stream()), "posconv")
     torch.cuda.synchronize()
 print("ok")
