@@ -92,14 +92,14 @@ __device__ __forceinline__ void load_k(float4 (&kreg)[DH / 4], const float* kbas
 }
 
 // Everything after griddepcontrol.wait, for exactly NHT live hyps (NH = hyp slots of the beam).
-template <int MODE, int NH, int NHT>
+template <int MODE, int NH, int NHT, bool SPLITQ>
 __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, unsigned* rlist, float* vtile, float4 (&kreg)[DH / 4],
                                           const float* kbase, const float* vbase, long long nr, int T_utt, int step, int conv,
                                           const float4 (&pre)[3]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = tid >> 4, l16 = tid & 15;
     const int utt = blockIdx.x, head = blockIdx.y;
-    const int beam = a.beam, R = a.R, nsplit = a.nsplit;
+    const int beam = a.beam, R = a.R, nsplit = SPLITQ ? a.nsplit : 0;       // SPLITQ = false: the instantiation without the split-K gather code
     const int row0 = utt * beam;
     const int n = (MODE == 1) ? T_utt : step + 1;    // keys (mode 1) / positions (mode 0)
     const float* q_in = a.q_in;
@@ -393,7 +393,10 @@ __device__ __forceinline__ void attn_body(const AttnArgs& a, AttnSmem<NH>& sm, u
     if (MODE == 0) dbg_stamp(7);
 }
 
-template <int MODE, int NH>
+// SPLITQ: q (| k | v) arrive as split-K partial sums (round 1's projections) instead of finished rows.  The decode position
+// with the cluster projections always passes finished rows; its instantiation leaves the gather code out (instruction
+// fetch is a measurable part of these ~20 us launches: ncu no_instruction 25 % of the stall samples).
+template <int MODE, int NH, bool SPLITQ>
 __global__ void __launch_bounds__(CK, (NH <= 4) ? 4 : 2)
 dec_attn_stream_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float vtile[];                 // [CK][64] V rows of the current tile (cp.async target), then rlist
@@ -453,7 +456,7 @@ dec_attn_stream_kernel(const AttnArgs a) {
     }
     float4 pre[3];
     pre[0] = pre[1] = pre[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.nsplit <= 0 && tid < NH * (DH / 4)) {
+    if ((!SPLITQ || a.nsplit <= 0) && tid < NH * (DH / 4)) {
         // same round trip as the beam state: this position's query (self-attention: and key, value) of all NH slots
         const float* qp = a.q_in + (long long)(utt * a.beam + tid / (DH / 4)) * a.ldq + head * DH + 4 * (tid % (DH / 4));
         if (tid / (DH / 4) < a.beam) {
@@ -463,7 +466,7 @@ dec_attn_stream_kernel(const AttnArgs a) {
     }
     if (nh == 0) { cp_async_wait_all(); return; }
     const int conv = ((step + 1) & 1) ? conv1 : conv0;
-#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step, conv, pre)
+#define AVSR_BODY(NHT) attn_body<MODE, NH, NHT, SPLITQ>(a, sm, rlist, vtile, kreg, kbase, vbase, nr, T_utt, step, conv, pre)
     if (NH <= 4) {
         switch (nh) {
             case 1: AVSR_BODY(1); break;
@@ -585,28 +588,28 @@ extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq,
     // V tile + (self-attention) the list of distinct history rows, at most lmax * beam entries
     const size_t smem = (size_t)CK * DH * sizeof(float) + (mode == 0 ? (size_t)lmax * nslots * sizeof(unsigned) : 0);
     AVSR_REQUIRE(smem <= 160 * 1024, "avsr_dec_attn_step: %d positions do not fit the shared-memory row list", lmax);
-    static size_t configured[4] = {0, 0, 0, 0};
-    const int ki = (mode == 0 ? 0 : 2) + (nslots == 4 ? 0 : 1);
+    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ki = ((mode == 0 ? 0 : 2) + (nslots == 4 ? 0 : 1)) * 2 + (nsplit > 0 ? 1 : 0);
+    void (*kern)(const AttnArgs) = nullptr;
+    switch (ki) {
+        case 0: kern = dec_attn_stream_kernel<0, 4, false>; break;
+        case 1: kern = dec_attn_stream_kernel<0, 4, true>; break;
+        case 2: kern = dec_attn_stream_kernel<0, 8, false>; break;
+        case 3: kern = dec_attn_stream_kernel<0, 8, true>; break;
+        case 4: kern = dec_attn_stream_kernel<1, 4, false>; break;
+        case 5: kern = dec_attn_stream_kernel<1, 4, true>; break;
+        case 6: kern = dec_attn_stream_kernel<1, 8, false>; break;
+        default: kern = dec_attn_stream_kernel<1, 8, true>; break;
+    }
     if (smem > configured[ki]) {
         const int lim = 160 * 1024;
-        cudaError_t e = cudaSuccess;
-        if (ki == 0) e = cudaFuncSetAttribute(dec_attn_stream_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        else if (ki == 1) e = cudaFuncSetAttribute(dec_attn_stream_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        else if (ki == 2) e = cudaFuncSetAttribute(dec_attn_stream_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        else e = cudaFuncSetAttribute(dec_attn_stream_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        AVSR_CHECK_CUDA(e);
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
         configured[ki] = lim;
     }
     const dim3 grid(R / beam, HEADS);
     const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, kd, vd, conv_len, n_run, utt_off, utt_T, beam, R, step, out,
                         n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
-    if (mode == 0) {
-        if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 4>, grid, dim3(CK), smem, stream, a));
-        else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<0, 8>, grid, dim3(CK), smem, stream, a));
-    } else {
-        if (beam <= 4) AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 4>, grid, dim3(CK), smem, stream, a));
-        else AVSR_CHECK_CUDA(avsr_launch_pdl(dec_attn_stream_kernel<1, 8>, grid, dim3(CK), smem, stream, a));
-    }
+    AVSR_CHECK_CUDA(avsr_launch_pdl(kern, grid, dim3(CK), smem, stream, a));
     return AVSR_OK;
 }
 

@@ -542,7 +542,13 @@ int plan_splits(int R, int N, int K, int nb) {
     if (smax < 1) smax = 1;
     if (force > 0) return force < smax ? force : smax;
     for (int s = smax; s > 1; --s)
-        if (max_active_clusters(s, nb) >= tiles * share) return s;
+        if (max_active_clusters(s, nb) >= tiles * share) {
+            // the critical path is the CTA with the most k blocks: take the SMALLEST cluster that has the same maximum (fewer
+            // peers to reduce over and fewer CTAs to place; K = 1024: 8 x 2 k blocks instead of 10 x {1, 2})
+            const int worst = cdiv(nkb, s);
+            while (s > 1 && cdiv(nkb, s - 1) == worst) --s;
+            return s;
+        }
     return 1;
 }
 
