@@ -215,7 +215,8 @@ def decoder_batch_score(sd: SD, ys: torch.Tensor, caches: Optional[List[torch.Te
 class KVDecoder:
     """Mathematically equal KV-cache form of the decoder step, used to keep the oracle
     fast at large T.  Cross-attention K/V are projected once per utterance; self-attention K/V are cached
-    per hyp.  Checked against ``decoder_batch_score`` in tests/test_oracle_internal.py."""
+    per hyp.  Checked against ``decoder_batch_score`` and the reference's ``Decoder.batch_score`` output in
+    tests/test_oracle_golden.py::test_decoder_step_matches_reference."""
 
     def __init__(self, sd: SD, memory: torch.Tensor, heads: int = 16):
         self.sd, self.heads = sd, heads
