@@ -121,8 +121,9 @@ class BatchedBeamSearch:
         # projection launches of the chains each want one CTA with ~200 KB of shared memory on every SM and serialise.
         self.n_groups = max(1, int(os.environ.get("AVSR_DECODE_GROUPS", "1")))
         L.load()
-        if self.n_groups > 1 and self.proj == "cluster":
+        if self.proj == "cluster" and (self.n_groups > 1 or "AVSR_SM_BUDGET" in os.environ):
             # concurrent chains: plan every projection for its share of the SMs so that the chains' clusters are co-resident
+            # (AVSR_SM_BUDGET with one chain: consecutive launches of the chain co-resident, dev experiment)
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             L.check(L.load().avsr_dec_proj_set_sm_budget(int(os.environ.get("AVSR_SM_BUDGET", sms // self.n_groups))), "avsr_dec_proj_set_sm_budget")
             L.launch_count -= 1
@@ -196,6 +197,7 @@ class BatchedBeamSearch:
             L.check(lib0.avsr_ctc_prefix_full_plan(B, V, C.byref(ncg), C.byref(ts)), "avsr_ctc_prefix_full_plan")
             s["fpart"] = torch.empty(B, ts.value, beam, V, dtype=torch.float32, device=dev)
             s["ftick"] = i32(B, ncg.value)
+            s["want_probs"] = True
         # self-attention caches, one contiguous span per (utterance, head): keys transposed in 32-byte groups
         # [layer][utt][head][8][pos*beam+slot][8], values [layer][utt][head][pos*beam+slot][64] (csrc/dec_attn.cu)
         s["kc"] = torch.empty(nl, B, 16, 8, lmax * beam, 8, dtype=torch.float32, device=dev)
@@ -235,6 +237,9 @@ class BatchedBeamSearch:
         # per-utterance precomputed tensors
         s["ldp"] = (V + 31) // 32 * 32              # posterior row pitch: 128-byte aligned rows (V = 5049 -> 5056)
         s["logp"] = torch.zeros(F, s["ldp"], dtype=torch.float32, device=dev)
+        # CTC-only search: the posteriors themselves, exp(logp) once per batch, so that the full-vocabulary kernel (run at every
+        # position over the whole block) streams them without an exponential per element
+        s["probs"] = torch.zeros(F, s["ldp"], dtype=torch.float32, device=dev) if s.get("want_probs") else None
         s["ckv"] = torch.empty(F, nl * 2 * 1024, dtype=torch.float32, device=dev)
         # cross-attention K/V, head-major: [layer][k|v][head][frame][64] (one contiguous span per (utterance, head))
         s["ckv_t"] = torch.empty(nl, 2, 16, F, 64, dtype=torch.float32, device=dev)
@@ -402,10 +407,10 @@ class BatchedBeamSearch:
         w = self.w
         R, beam, V = s["R"], self.beam_size, self.n_vocab
         st = L.stream
-        L.check(lib.avsr_ctc_prefix_full(L.ptr(s["logp"]), V, s["ldp"], w.blank, self.eos, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]),
+        L.check(lib.avsr_ctc_prefix_full_probs(L.ptr(s["logp"]), L.ptr(s["probs"]), V, s["ldp"], w.blank, self.eos, L.ptr(s["utt_off"]), L.ptr(s["utt_T"]),
                                          L.ptr(s["n_run"]), beam, s["B"], 1, L.ptr(s["last_tok"]), L.ptr(s["iota"]), L.ptr(s["r_buf"]),
                                          s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]), L.ptr(s["ctc_full"]), L.ptr(s["fpart"]),
-                                         L.ptr(s["ftick"]), st()), "avsr_ctc_prefix_full")
+                                         L.ptr(s["ftick"]), st()), "avsr_ctc_prefix_full_probs")
         L.check(lib.avsr_beam_fuse_topk_advance_full(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["ctc_full"]), C.c_float(0.0),
                                                      C.c_float(1.0), L.ptr(s["rc_last"]), L.ptr(s["rc_chain"]), L.ptr(s["rc_tok"]), st()),
                 "avsr_beam_fuse_topk_advance_full")
@@ -630,6 +635,8 @@ class BatchedBeamSearch:
                 L.sgemm(x_packed, w.ckv_w, F, n, 1024, L.make_epilogue(bias=w.ckv_b, out_f32=s["ckv"], ld_f32=n))
         if ctc:
             L.check(lib.avsr_log_softmax_rows(L.ptr(s["logp"]), L.ll(s["ldp"]), L.ll(F), V, L.stream()), "avsr_log_softmax_rows")
+            if s.get("probs") is not None:
+                L.check(lib.avsr_ctc_exp_posteriors(L.ptr(s["logp"]), L.ll(F * s["ldp"]), L.ptr(s["probs"]), L.stream()), "avsr_ctc_exp_posteriors")
         if cross_kv:
             L.check(lib.avsr_kv_head_major(L.ptr(s["ckv"]), L.ptr(s["ckv_t"]), L.ll(F), L.ll(s["F"]), n, 1, L.stream()), "avsr_kv_head_major")
         B, beam = s["B"], self.beam_size

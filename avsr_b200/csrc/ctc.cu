@@ -218,16 +218,21 @@ dec_tail_kernel(const float* __restrict__ part, int nsplit, const float* __restr
 // exactly in the log domain by a warp each, so every cell matches the reference to fp32 rounding.
 //
 // Work decomposition (HBM-bound streaming): the log-posteriors of an utterance are one dense [T][ldp] block whose rows are
-// 16-byte aligned (ldp % 4 == 0; the producer pads V = 5049 to 5056).  CTA = (utterance, group of FV_CG columns, time
-// split); a thread owns four consecutive columns, reads them with one 16-byte load per row and keeps 2 x FV_UT rows in
-// flight (a form with 4-byte loads of 5 strided columns had too few bytes in flight per SM and stalled at 45 % of HBM
-// peak; before that, ~27 instructions per posterior made it issue-bound at 37 %).  The sums for up to FV_NHP hyps live in
-// registers.  With more than one time split the partial sums are published and the last CTA of a (utterance, column
-// group) to finish (ticket) adds them in split order, takes the logarithm and writes the scores.
+// 16-byte aligned (ldp % 4 == 0; the producer pads V = 5049 to 5056).  CTA = (utterance, group of up to FV_CG columns, time
+// split).  Warp 5's elected thread streams the CTA's row segments into a shared-memory ring with bulk async copies
+// (cp.async.bulk + mbarrier transaction counts: ~70 KB per CTA in flight, requested before the preamble runs); the 160
+// consumer threads own four consecutive columns each, read them back with one 16-byte shared-memory load per row and keep
+// the sums for up to FV_NHP hyps in registers.  (History: 4-byte loads of 5 strided columns, too few bytes in flight, 45 %
+// of the HBM peak; ~27 instructions per posterior, issue-bound, 37 %; 16-byte loads double-buffered in registers, 2 x 12
+// rows per thread, 62 %.)  Warp 6 evaluates the c == last-token cells exactly while the stream runs.  With more than one
+// time split the partial sums are published and the last CTA of a (utterance, column group) to finish (ticket) adds them in
+// split order, takes the logarithm and writes the scores.
 constexpr int FV_MAXH = 8;
-constexpr int FV_THREADS = 160;
+constexpr int FV_THREADS = 160;           // consumer threads: a thread owns four consecutive columns
 constexpr int FV_CG = FV_THREADS * 4;     // most columns a group can have (the plan sizes the groups to fill the SMs)
-constexpr int FV_UT = 12;                 // rows per batch (two batches in flight)
+constexpr int FV_ALL = FV_THREADS + 64;   // + warp 5: row-stream producer, warp 6: exact evaluation of the c == last-token cells
+constexpr int FV_FR = 8;                  // rows per ring slot (fewer rows per slot measured slower: 4 rows 70 us, 2 rows 111 us against 55 us)
+constexpr int FV_MAXST = 4;               // ring slots (the host takes fewer when the tables of a long utterance need the room; 2 .. 4 measure the same)
 constexpr int FV_NHP = 5;                 // hyps accumulated per pass over the block (beam <= 5: the block is read once)
 constexpr int FV_ES = 8;                  // row stride of the E table in shared memory (floats): one or two 16-byte reads per row
 constexpr int FV_NSPECIAL = 1024;
@@ -239,48 +244,64 @@ __device__ __forceinline__ float fv_exp(float x) {
     return r;
 }
 
-// rows t .. t+FV_UT-1 of this thread's four columns; rows past the end are clamped (their weight is skipped by the consumer)
-__device__ __forceinline__ void fv_load(const float* __restrict__ lpc, int ldp, int t, int t_last, float4 (&x)[FV_UT]) {
-#pragma unroll
-    for (int u = 0; u < FV_UT; ++u) x[u] = __ldg(reinterpret_cast<const float4*>(lpc + (long long)min(t + u, t_last) * ldp));
+// ---- the row stream: shared-memory ring filled by bulk async copies (one per row segment), consumed with 16-byte reads.
+// A chunk = FV_FR consecutive rows of this CTA's column group; a ring slot holds one chunk.  The producer (one elected
+// thread) keeps every slot of the ring requested, so a CTA has nst * FV_FR rows (~70 KB) in flight without holding them in
+// registers - the register-staged form (2 x 12 rows per thread) stalled at 62 % of the HBM peak.
+__device__ __forceinline__ void fv_bulk_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-
-template <int NH>
-__device__ __forceinline__ void fv_consume(const float* __restrict__ s_E, int t, int t_hi, const float4 (&x)[FV_UT], float (&acc)[4][FV_NHP]) {
-#pragma unroll
-    for (int u = 0; u < FV_UT; ++u) {
-        if (t + u < t_hi) {                          // uniform across the CTA
-            float ev[8];
-            const float4 e0 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES);
-            ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w;
-            if (NH > 4) {
-                const float4 e1 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES + 4);
-                ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
-            }
-            // ex2.approx.ftz(x * log2 e): one FMUL + one MUFU per posterior (__expf adds a denormal-range fix-up: a compare and
-            // two more multiplies).  Relative error ~2^-21, far below the rounding of the fp32 sum itself; posteriors below
-            // e^-87 flush to zero, where the IEEE result (< 1e-38) could not change a sum that is checked against 1e-30.
-            const float pr[4] = {fv_exp(x[u].x), fv_exp(x[u].y), fv_exp(x[u].z), fv_exp(x[u].w)};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int h = 0; h < NH; ++h) acc[k][h] = fmaf(ev[h], pr[k], acc[k][h]);
-        }
+__device__ __forceinline__ void fv_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t i = 0; !ok; ++i) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (i > (1u << 28)) __trap();                // seconds, not a hung GPU, if a byte count was ever wrong
     }
 }
 
-// acc[k][h] += sum_{t in [t_lo, t_hi)} E[h][t-1] * exp(x[t][c0 + k]); the next batch is requested before the current one is
-// consumed (two register buffers, loop unrolled by two so that no values are moved).
-template <int NH>
-__device__ __forceinline__ void fv_stream(const float* __restrict__ lpc, int ldp, int t_lo, int t_hi, const float* __restrict__ s_E,
-                                          float4 (&xa)[FV_UT], float (&acc)[4][FV_NHP]) {
-    const int t_last = t_hi - 1;
-    float4 xb[FV_UT];
-    for (int t = t_lo; t < t_hi; t += 2 * FV_UT) {
-        fv_load(lpc, ldp, t + FV_UT, t_last, xb);
-        fv_consume<NH>(s_E, t, t_hi, xa, acc);
-        fv_load(lpc, ldp, t + 2 * FV_UT, t_last, xa);
-        fv_consume<NH>(s_E, t + FV_UT, t_hi, xb, acc);
+// rows [t, t + nr) of the chunk at shared-memory address xs: acc[k][h] += E[h][t'-1] * exp(x[t'][c0 + k]).
+// FULL = all FV_FR rows, no per-row branch: the rows of a chunk are independent until the final FMAs, and with ~2.5 warps per
+// scheduler it is this instruction-level parallelism (8 rows of LDS -> ex2 -> FMA in flight) that hides the latencies; with
+// a (uniform) branch per row every row paid its own LDS + MUFU latency chain, ~185 cycles, and the CONSUMERS, not HBM, paced
+// the kernel (measured: time = 0.40 us per chunk + 0.097 us per row, whatever the ring depth).
+template <int NH, bool FULL, bool PRE>
+__device__ __forceinline__ void fv_consume_chunk(const float* __restrict__ s_E, int t, int nr, uint32_t xs, uint32_t row_bytes,
+                                                 float (&acc)[4][FV_NHP]) {
+    constexpr int G = FULL ? 4 : 1;                  // rows in flight together (registers: 2 CTAs of 7 warps leave 128 per thread)
+#pragma unroll(FULL ? FV_FR / G : 1)
+    for (int u0 = 0; u0 < (FULL ? FV_FR : nr); u0 += G) {
+        float4 x[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+            if (FULL || u0 + i < nr)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(xs + (uint32_t)(u0 + i) * row_bytes));
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if (FULL || u0 + i < nr) {               // uniform across the CTA
+                const int u = u0 + i;
+                float ev[8];
+                const float4 e0 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES);
+                ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w;
+                if (NH > 4) {
+                    const float4 e1 = *reinterpret_cast<const float4*>(s_E + (t + u - 1) * FV_ES + 4);
+                    ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
+                }
+                // ex2.approx.ftz(x * log2 e): one FMUL + one MUFU per posterior (__expf adds a denormal-range fix-up: a compare
+                // and two more multiplies).  Relative error ~2^-21, far below the rounding of the fp32 sum itself; posteriors
+                // below e^-87 flush to zero, where the IEEE result (< 1e-38) could not change a sum that is checked against 1e-30.
+                // PRE: the stream already holds the posteriors (avsr_ctc_exp_posteriors: the same ex2 of the same inputs, done once
+                // per utterance instead of once per decode position)
+                const float pr[4] = {PRE ? x[i].x : fv_exp(x[i].x), PRE ? x[i].y : fv_exp(x[i].y), PRE ? x[i].z : fv_exp(x[i].z),
+                                     PRE ? x[i].w : fv_exp(x[i].w)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) acc[k][h] = fmaf(ev[h], pr[k], acc[k][h]);
+            }
+        }
     }
 }
 
@@ -321,26 +342,60 @@ __device__ __forceinline__ float fv_exact_warp(const float* __restrict__ lp, int
     return mx + logf(sum + expf(x0 - mx));
 }
 
-__global__ void __launch_bounds__(FV_THREADS, 2)
-ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank, int eos, const int* __restrict__ utt_off,
+// One pass of the consumers over the CTA's rows: chunk g of the ring sequence (g runs on across passes), slot g % nst.
+template <int NH, bool PRE>
+__device__ __forceinline__ void fv_stream_ring(const float* __restrict__ s_E, int t_lo, int t_hi, int nch, int nst, int& g, uint32_t bar_s,
+                                               uint32_t ring_s, uint32_t slot_bytes, uint32_t row_bytes, bool active, int tid, int lane,
+                                               float (&acc)[4][FV_NHP]) {
+    for (int ch = 0; ch < nch; ++ch, ++g) {
+        const int slot = g % nst;
+        fv_mbar_wait(bar_s + 8u * slot, (uint32_t)(g / nst) & 1u);                       // full[slot] (all lanes poll: one poller per warp + __syncwarp measured 45 % slower)
+        const int t = t_lo + ch * FV_FR, nr = min(FV_FR, t_hi - t);
+        if (active) {
+            if (nr == FV_FR) fv_consume_chunk<NH, true, PRE>(s_E, t, nr, ring_s + slot * slot_bytes + 16u * tid, row_bytes, acc);
+            else fv_consume_chunk<NH, false, PRE>(s_E, t, nr, ring_s + slot * slot_bytes + 16u * tid, row_bytes, acc);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s + 8u * (FV_MAXST + slot)) : "memory");   // empty[slot]
+    }
+}
+
+template <bool PRE>
+__global__ void __launch_bounds__(FV_ALL, 2)
+ctc_prefix_full_kernel(const float* __restrict__ logp, const float* __restrict__ probs, int V, int ldp, int blank, int eos, const int* __restrict__ utt_off,
                        const int* __restrict__ utt_T, const int* __restrict__ n_run, int beam, int R, int S,
                        const int* __restrict__ last_tok, const int* __restrict__ rprev_idx, const float* __restrict__ r_buf,
                        int tmax, const int* __restrict__ step_p, const float* __restrict__ s_prev, float* __restrict__ scores,
-                       int ncg, int cgw, int tsplit, float* __restrict__ part, int* __restrict__ tickets) {
-    extern __shared__ __align__(16) float sm[];     // s_E [T][FV_ES], s_rs [T][nh] (r_sum), s_pb [T][nh] (blank-ending)
+                       int ncg, int cgw, int tsplit, float* __restrict__ part, int* __restrict__ tickets, int nst, int tab_bytes, int pdl) {
+    extern __shared__ __align__(128) float sm[];    // s_E [T][FV_ES], s_rs [T][nh] (r_sum), s_pb [T][nh] (blank-ending); ring at tab_bytes
     __shared__ float s_M[FV_MAXH];
-    __shared__ float s_red[FV_THREADS / 32][FV_MAXH];
+    __shared__ float s_red[FV_ALL / 32][FV_MAXH];
     __shared__ int s_nspecial, s_last;
     __shared__ int s_special[FV_NSPECIAL];
+    __shared__ __align__(8) uint64_t s_bar[2 * FV_MAXST];        // full[FV_MAXST], empty[FV_MAXST]
     const int utt = blockIdx.y;
     const int cg = blockIdx.x % ncg, z = blockIdx.x / ncg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(s_bar);
+    if (tid == 0) {
+        s_nspecial = 0;
+        for (int i = 0; i < FV_MAXST; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8u * i), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s + 8u * (FV_MAXST + i)), "r"(FV_THREADS / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // programmatic dependent launch: the next kernel of the stream may place its CTAs as ours retire; nothing written by an
+    // earlier kernel (posteriors, beam state, forward variables) is read before the wait
+    if (pdl) pdl_trigger();
+    pdl_wait();
     const int nh = n_run[utt];
     const int step = *step_p;
     const int T = utt_T[utt];
     const long long uoff = utt_off[utt];
     if (nh == 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* lp = logp + uoff * ldp;
+    const float* src = (PRE ? probs : logp) + uoff * ldp;        // what the ring streams
     float* s_E = sm;
     float* s_rs = sm + (size_t)T * FV_ES;
     float* s_pb = s_rs + (size_t)T * nh;
@@ -348,24 +403,44 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
     const int start = step > 1 ? step : 1;
     const int per = (T - start + tsplit - 1) / tsplit;
     const int t_lo = start + z * per, t_hi = min(T, t_lo + per);
-    if (tid == 0) s_nspecial = 0;
-    // this thread's columns c0 .. c0+3 (columns >= V lie in the row padding or are clamped; they are dropped at the end)
-    const int c0 = (4 * tid < cgw) ? cg * cgw + 4 * tid : ldp;    // cgw = columns per group (multiple of 4); spare threads idle
-    const float* lpc = lp + min(c0, ldp - 4);
-    // ---- first batch of log-posteriors: requested now, consumed after the preamble below (its latency is hidden)
-    float4 xa[FV_UT];
-    if (t_lo < t_hi) fv_load(lpc, ldp, t_lo, t_hi - 1, xa);
+    // ---- the row stream of this CTA: columns [cbase, cbase + width) of rows [t_lo, t_hi), in chunks of FV_FR rows
+    const int cbase = cg * cgw;
+    const int width = min(cgw, ldp - cbase);         // > 0: the plan never makes an empty group; a multiple of 4 (ldp, cgw are)
+    const uint32_t row_bytes = (uint32_t)cgw * 4u, seg_bytes = (uint32_t)width * 4u, slot_bytes = FV_FR * row_bytes;
+    const int nch = t_hi > t_lo ? (t_hi - t_lo + FV_FR - 1) / FV_FR : 0;
+    const int total = nch * ((nh + FV_NHP - 1) / FV_NHP);        // the block is streamed once per FV_NHP hyps
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(sm) + (uint32_t)tab_bytes;
+    __syncthreads();
+    auto issue = [&](int g) {                        // producer thread only (one copy per lane of a warp measured slower)
+        const int slot = g % nst, t = t_lo + (g % nch) * FV_FR, nr = min(FV_FR, t_hi - t);
+        const uint32_t fb = bar_s + 8u * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)nr * seg_bytes) : "memory");
+        for (int u = 0; u < nr; ++u)
+            fv_bulk_row(ring_s + slot * slot_bytes + (uint32_t)u * row_bytes, src + (long long)(t + u) * ldp + cbase, seg_bytes, fb);
+    };
+    // the whole ring is requested now: its latency is hidden by the preamble below
+    if (tid == FV_THREADS)
+        for (int g = 0; g < min(nst, total); ++g) issue(g);
+    // this thread's columns c0 .. c0+3 (columns >= V lie in the row padding; they are dropped at the end)
+    const bool active = tid < FV_THREADS && 4 * tid < width;
+    const int c0 = active ? cbase + 4 * tid : ldp;
     // ---- parent forward variables -> r_sum, blank-ending part, per-hyp maximum over the time range that is used
     if (step == 0) {
-        if (tid == 0) {                             // r_prev[:,1] = cumsum(x[:, blank]) (ctc_prefix_score.py:58-63), r_prev[:,0] = logzero
+        // r_prev[:,1] = cumsum(x[:, blank]) (ctc_prefix_score.py:58-63), r_prev[:,0] = logzero: the column is fetched by all
+        // threads, summed in frame order by one (the order of the reference's CPU cumsum), finished by all
+        for (int t = tid; t < T; t += FV_ALL) s_pb[t * nh] = lp[(long long)t * ldp + blank];
+        __syncthreads();
+        if (tid == 0) {
             float cs = 0.f;
             for (int t = 0; t < T; ++t) {
-                cs += lp[(long long)t * ldp + blank];
-                for (int h = 0; h < nh; ++h) { s_pb[t * nh + h] = cs; s_rs[t * nh + h] = lse2(LOGZERO, cs); }
+                cs += s_pb[t * nh];
+                for (int h = 0; h < nh; ++h) s_pb[t * nh + h] = cs;
             }
         }
+        __syncthreads();
+        for (int i = tid; i < T * nh; i += FV_ALL) s_rs[i] = lse2(LOGZERO, s_pb[i]);
     } else {
-        for (int i = tid; i < T * nh; i += FV_THREADS) {
+        for (int i = tid; i < T * nh; i += FV_ALL) {
             const int t = i / nh, h = i % nh;
             const float2 v = (reinterpret_cast<const float2*>(r_buf) + ((long long)cur * R * S + rprev_idx[utt * beam + h]) * tmax)[t];
             s_pb[i] = v.y;
@@ -375,27 +450,33 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
     __syncthreads();
     for (int h = 0; h < nh; ++h) {
         float mx = -INFINITY;
-        for (int t = start - 1 + tid; t <= T - 2; t += FV_THREADS) mx = fmaxf(mx, s_rs[t * nh + h]);
+        for (int t = start - 1 + tid; t <= T - 2; t += FV_ALL) mx = fmaxf(mx, s_rs[t * nh + h]);
         mx = warp_max(mx);
         if (lane == 0) s_red[warp][h] = mx;
     }
     __syncthreads();
     if (tid < nh) {
         float mx = -INFINITY;
-        for (int w = 0; w < FV_THREADS / 32; ++w) mx = fmaxf(mx, s_red[w][tid]);
+        for (int w = 0; w < FV_ALL / 32; ++w) mx = fmaxf(mx, s_red[w][tid]);
         s_M[tid] = (mx == -INFINITY) ? 0.f : mx;    // T == 1: no recursion term at all
+    }
+    __syncthreads();
+    for (int i = tid; i < T * FV_ES; i += FV_ALL) {              // E table of the first pass: hyp j in column j
+        const int t = i / FV_ES, j = i % FV_ES;
+        s_E[i] = j < min(FV_NHP, nh) ? expf(s_rs[t * nh + j] - s_M[j]) : 0.f;
     }
     __syncthreads();
 
     // ---- finalisation of one cell from its linear-domain sum `a` (all time splits added)
     auto finish = [&](int h, int c, float a) {
         const int row = utt * beam + h;
+        if (c == last_tok[row]) return;                          // evaluated exactly by warp 6 of the z == 0 CTA
         const float x0 = (step == 0) ? lp[c] : LOGZERO;          // r[start-1, 0]: x[0][c] for the empty prefix, else logzero
         a += expf(x0 - s_M[h]);
-        if (c == last_tok[row] || !(a > FV_TINY) || !(a < 1e30f)) {
+        if (!(a > FV_TINY) || !(a < 1e30f)) {
             const int slot = atomicAdd(&s_nspecial, 1);          // exact log-domain evaluation by a warp below
             if (slot < FV_NSPECIAL) { s_special[slot] = c * FV_MAXH + h; return; }
-            const float* phi = (c == last_tok[row]) ? s_pb : s_rs;   // list full (pathological input): this thread does it alone
+            const float* phi = s_rs;                             // list full (pathological input): this thread does it alone
             float mx = x0;
             for (int t = start; t < T; ++t) mx = fmaxf(mx, phi[(t - 1) * nh + h] + lp[(long long)t * ldp + c]);
             float sum = expf(x0 - mx);
@@ -412,39 +493,66 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
         scores[(long long)row * V + c] = lpsi - s_prev[row];
     };
 
-    // ---- main pass(es): stream this CTA's rows, FV_NHP hyps at a time
-    for (int h0 = 0; h0 < nh; h0 += FV_NHP) {
-        const int ng = min(FV_NHP, nh - h0);
-        float acc[4][FV_NHP];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int h = 0; h < FV_NHP; ++h) acc[k][h] = 0.f;
-        if (h0 > 0) __syncthreads();                 // the previous pass is done with the table
-        for (int i = tid; i < T * FV_ES; i += FV_THREADS) {          // E table of this pass: hyp h0 + j in column j
-            const int t = i / FV_ES, j = i % FV_ES;
-            s_E[i] = j < ng ? expf(s_rs[t * nh + h0 + j] - s_M[h0 + j]) : 0.f;
-        }
-        __syncthreads();
-        if (h0 > 0 && t_lo < t_hi) fv_load(lpc, ldp, t_lo, t_hi - 1, xa);
-        if (c0 < V) {
-            switch (ng) {
-                case 1: fv_stream<1>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
-                case 2: fv_stream<2>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
-                case 3: fv_stream<3>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
-                case 4: fv_stream<4>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
-                default: fv_stream<5>(lpc, ldp, t_lo, t_hi, s_E, xa, acc); break;
+    if (warp == FV_THREADS / 32) {
+        // ---- producer: refill a slot as soon as the five consumer warps have released it
+        if (lane == 0) {
+            for (int g = nst; g < total; ++g) {
+                fv_mbar_wait(bar_s + 8u * (FV_MAXST + g % nst), (uint32_t)(g / nst - 1) & 1u);
+                issue(g);
             }
         }
+    } else if (warp == FV_THREADS / 32 + 1) {
+        // ---- the c == last-token cell of every hyp (its phi is the blank-ending forward variable): always exact, and known
+        //      up front, so it is evaluated while the stream runs instead of after it
+        if (z == 0) {
+            for (int h = 0; h < nh; ++h) {
+                const int row = utt * beam + h;
+                const int cx = last_tok[row];
+                if (cx < cbase || cx >= cbase + cgw || cx >= V) continue;                // warp-uniform
+                const float x0 = (step == 0) ? lp[cx] : LOGZERO;
+                float lpsi = fv_exact_warp(lp, ldp, cx, start, T, s_pb, nh, h, x0, lane);
+                if (lane == 0) {
+                    if (cx == eos) lpsi = s_rs[(T - 1) * nh + h];
+                    if (cx == blank) lpsi = LOGZERO;
+                    scores[(long long)row * V + cx] = lpsi - s_prev[row];
+                }
+            }
+        }
+    } else {
+        // ---- consumers: stream this CTA's rows, FV_NHP hyps at a time
+        int g = 0;
+        for (int h0 = 0; h0 < nh; h0 += FV_NHP) {
+            const int ng = min(FV_NHP, nh - h0);
+            float acc[4][FV_NHP];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = c0 + k;
-            if (c < V) {
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int h = 0; h < FV_NHP; ++h) {
-                    if (h < ng) {
-                        if (tsplit == 1) finish(h0 + h, c, acc[k][h]);
-                        else part[(((long long)utt * tsplit + z) * beam + h0 + h) * V + c] = acc[k][h];
+                for (int h = 0; h < FV_NHP; ++h) acc[k][h] = 0.f;
+            if (h0 > 0) {
+                asm volatile("bar.sync 1, %0;" ::"n"(FV_THREADS) : "memory");              // the previous pass is done with the table
+                for (int i = tid; i < T * FV_ES; i += FV_THREADS) {                        // E table of this pass: hyp h0 + j in column j
+                    const int t = i / FV_ES, j = i % FV_ES;
+                    s_E[i] = j < ng ? expf(s_rs[t * nh + h0 + j] - s_M[h0 + j]) : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(FV_THREADS) : "memory");
+            }
+            switch (ng) {
+                case 1: fv_stream_ring<1, PRE>(s_E, t_lo, t_hi, nch, nst, g, bar_s, ring_s, slot_bytes, row_bytes, active, tid, lane, acc); break;
+                case 2: fv_stream_ring<2, PRE>(s_E, t_lo, t_hi, nch, nst, g, bar_s, ring_s, slot_bytes, row_bytes, active, tid, lane, acc); break;
+                case 3: fv_stream_ring<3, PRE>(s_E, t_lo, t_hi, nch, nst, g, bar_s, ring_s, slot_bytes, row_bytes, active, tid, lane, acc); break;
+                case 4: fv_stream_ring<4, PRE>(s_E, t_lo, t_hi, nch, nst, g, bar_s, ring_s, slot_bytes, row_bytes, active, tid, lane, acc); break;
+                default: fv_stream_ring<5, PRE>(s_E, t_lo, t_hi, nch, nst, g, bar_s, ring_s, slot_bytes, row_bytes, active, tid, lane, acc); break;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                if (c < V) {
+#pragma unroll
+                    for (int h = 0; h < FV_NHP; ++h) {
+                        if (h < ng) {
+                            if (tsplit == 1) finish(h0 + h, c, acc[k][h]);
+                            else part[(((long long)utt * tsplit + z) * beam + h0 + h) * V + c] = acc[k][h];
+                        }
                     }
                 }
             }
@@ -474,18 +582,26 @@ ctc_prefix_full_kernel(const float* __restrict__ logp, int V, int ldp, int blank
         }
     }
     __syncthreads();
-    // ---- exact path: one warp per special cell
+    // ---- exact path: one warp per cell whose linear-domain sum left the fp32 range
     const int nsp = min(s_nspecial, FV_NSPECIAL);
-    for (int i = warp; i < nsp; i += FV_THREADS / 32) {
+    for (int i = warp; i < nsp; i += FV_ALL / 32) {
         const int cx = s_special[i] / FV_MAXH, h = s_special[i] % FV_MAXH;
         const int row = utt * beam + h;
         const float x0 = (step == 0) ? lp[cx] : LOGZERO;
-        float lpsi = fv_exact_warp(lp, ldp, cx, start, T, (cx == last_tok[row]) ? s_pb : s_rs, nh, h, x0, lane);
+        float lpsi = fv_exact_warp(lp, ldp, cx, start, T, s_rs, nh, h, x0, lane);
         if (lane == 0) {
             if (cx == eos) lpsi = s_rs[(T - 1) * nh + h];
             if (cx == blank) lpsi = LOGZERO;
             scores[(long long)row * V + cx] = lpsi - s_prev[row];
         }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ctc_exp_posteriors_kernel(const float4* __restrict__ logp, long long n4, float4* __restrict__ probs) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 x = __ldg(logp + i);
+        probs[i] = make_float4(fv_exp(x.x), fv_exp(x.y), fv_exp(x.z), fv_exp(x.w));
     }
 }
 
@@ -849,30 +965,69 @@ extern "C" int avsr_ctc_prefix_full_plan(int B, int V, int* ncg, int* tsplit) {
     return AVSR_OK;
 }
 
-extern "C" int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
-                                    int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
-                                    const int* step, const float* s_prev, float* scores, float* part, int* tickets, cudaStream_t stream) {
+// probs (optional) = exp(logp) as avsr_ctc_exp_posteriors wrote it, same pitch: the kernel then streams the posteriors
+// themselves and its inner loop is pure FMA (the ex2 per posterior, 60 M MUFU operations per launch at 16 per clock and SM,
+// paced the kernel more than HBM did: 63 us with, 47 us without).  The log-posteriors are still needed (exact path, eos /
+// empty-prefix terms).  Results are bit-identical with and without probs.
+extern "C" int avsr_ctc_prefix_full_probs(const float* logp, const float* probs, int V, int ldp, int blank, int eos, const int* utt_off,
+                                          const int* utt_T, const int* n_run, int beam, int B, int S, const int* last_tok, const int* rprev_idx,
+                                          const float* r_buf, int tmax, const int* step, const float* s_prev, float* scores, float* part,
+                                          int* tickets, cudaStream_t stream) {
     AVSR_REQUIRE(logp && utt_off && utt_T && n_run && last_tok && rprev_idx && r_buf && step && s_prev && scores,
                  "avsr_ctc_prefix_full: null argument");
     AVSR_REQUIRE(beam >= 1 && beam <= FV_MAXH, "avsr_ctc_prefix_full: beam %d exceeds %d", beam, FV_MAXH);
     AVSR_REQUIRE(B > 0 && B <= 65535 && V > 0 && tmax > 0, "avsr_ctc_prefix_full: bad sizes");
-    AVSR_REQUIRE(ldp >= V && (ldp & 3) == 0 && (reinterpret_cast<uintptr_t>(logp) & 15) == 0,
+    AVSR_REQUIRE(ldp >= V && (ldp & 3) == 0 && (reinterpret_cast<uintptr_t>(logp) & 15) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0,
                  "avsr_ctc_prefix_full: posterior rows must be 16-byte aligned (pitch %d floats, base %p)", ldp, (const void*)logp);
     int ncg = 0, tsplit = 0;
     int rc = avsr_ctc_prefix_full_plan(B, V, &ncg, &tsplit);
     if (rc != AVSR_OK) return rc;
     AVSR_REQUIRE(tsplit == 1 || (part && tickets), "avsr_ctc_prefix_full: %d time splits need the scratch buffers", tsplit);
-    const size_t smem = ((size_t)tmax * FV_ES + (size_t)2 * tmax * beam) * sizeof(float);
-    AVSR_REQUIRE(smem <= 160 * 1024, "avsr_ctc_prefix_full: T*beam too large for shared memory");
-    static size_t configured = 0;
-    if (smem > 32 * 1024 && smem > configured) {
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = 160 * 1024;
+    const int cgw = cdiv(cdiv(V, 4), ncg) * 4;       // columns per group
+    // shared memory: the tables of the utterance, then the row ring (as many slots as leave room for two CTAs per SM)
+    const size_t tab = (((size_t)tmax * FV_ES + (size_t)2 * tmax * beam) * sizeof(float) + 127) / 128 * 128;
+    const size_t slot = (size_t)FV_FR * cgw * sizeof(float);
+    const size_t lim = 200 * 1024, two = 108 * 1024;
+    AVSR_REQUIRE(tab + 2 * slot <= lim, "avsr_ctc_prefix_full: T*beam too large for shared memory");
+    int nst = tab + 2 * slot <= two ? (int)((two - tab) / slot) : (int)((lim - tab) / slot);
+    nst = nst > FV_MAXST ? FV_MAXST : nst;
+    const size_t smem = tab + nst * slot;
+    static bool configured = false;
+    static int k_pdl = 0;                             // dev knob AVSR_CTC_PDL: let the next kernel's CTAs in early (measured neutral)
+    if (!configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_full_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_full_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        const char* e = getenv("AVSR_CTC_PDL");
+        k_pdl = e ? atoi(e) : 0;
+        configured = true;
     }
     dim3 grid(ncg * tsplit, B);
-    const int cgw = cdiv(cdiv(V, 4), ncg) * 4;       // columns per group
-    ctc_prefix_full_kernel<<<grid, FV_THREADS, smem, stream>>>(logp, V, ldp, blank, eos, utt_off, utt_T, n_run, beam, B * beam, S, last_tok,
-                                                               rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, cgw, tsplit, part, tickets);
+    if (probs != nullptr)
+        AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_full_kernel<true>, grid, dim3(FV_ALL), smem, stream, logp, probs, V, ldp, blank, eos, utt_off,
+                                        utt_T, n_run, beam, B * beam, S, last_tok, rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, cgw,
+                                        tsplit, part, tickets, nst, (int)tab, k_pdl));
+    else
+        AVSR_CHECK_CUDA(avsr_launch_pdl(ctc_prefix_full_kernel<false>, grid, dim3(FV_ALL), smem, stream, logp, probs, V, ldp, blank, eos, utt_off,
+                                        utt_T, n_run, beam, B * beam, S, last_tok, rprev_idx, r_buf, tmax, step, s_prev, scores, ncg, cgw,
+                                        tsplit, part, tickets, nst, (int)tab, k_pdl));
+    return AVSR_OK;
+}
+
+extern "C" int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
+                                    int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
+                                    const int* step, const float* s_prev, float* scores, float* part, int* tickets, cudaStream_t stream) {
+    return avsr_ctc_prefix_full_probs(logp, nullptr, V, ldp, blank, eos, utt_off, utt_T, n_run, beam, B, S, last_tok, rprev_idx, r_buf, tmax, step,
+                                      s_prev, scores, part, tickets, stream);
+}
+
+// probs[i] = exp(logp[i]) for the n floats of a posterior block (padding included), with the very ex2.approx.ftz the
+// full-vocabulary kernel applies when it is given log-posteriors only.  Once per utterance batch (n % 4 == 0, 16-byte aligned).
+extern "C" int avsr_ctc_exp_posteriors(const float* logp, long long n, float* probs, cudaStream_t stream) {
+    AVSR_REQUIRE(logp && probs && n > 0 && (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(logp) | reinterpret_cast<uintptr_t>(probs)) & 15) == 0,
+                 "avsr_ctc_exp_posteriors: bad arguments");
+    const long long n4 = n / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    ctc_exp_posteriors_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(logp), n4, reinterpret_cast<float4*>(probs));
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

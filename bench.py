@@ -362,11 +362,16 @@ def _kernel_rooflines(model, peaks):
     # three independent posterior blocks (3 x 242 MB) used in turn: every launch streams its block from HBM (the 126 MB L2
     # only holds clean lines of the previous block), no flush kernel whose dirty lines the timed kernel would have to evict
     ldp = (V + 31) // 32 * 32
-    logps = []
+    logps, probs = [], []
     for _ in range(3):
         lp = torch.zeros(BATCH * T, ldp, device=dev)
         lp[:, :V] = torch.log_softmax(torch.randn(BATCH * T, V, device=dev), -1)
         logps.append(lp)
+        # the posteriors themselves, computed once per batch as the CTC-only search does (beam_search.prepare); the kernel
+        # streams THEM at every position (same bytes as the log-posteriors, no exponential in the inner loop)
+        pr = torch.empty_like(lp)
+        L.check(lib.avsr_ctc_exp_posteriors(L.ptr(lp), L.ll(lp.numel()), L.ptr(pr), L.stream()), "ctc_exp")
+        probs.append(pr)
     i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
     utt_off, utt_T = i32([b * T for b in range(BATCH)]), i32([T] * BATCH)
     n_run, last = i32([nh] * BATCH), i32([7] * (BATCH * nh))
@@ -382,9 +387,9 @@ def _kernel_rooflines(model, peaks):
     cnt = {"i": 0}
 
     def ctc_full():
-        lp = logps[cnt["i"] % 3]
+        lp, pr = logps[cnt["i"] % 3], probs[cnt["i"] % 3]
         cnt["i"] += 1
-        L.check(lib.avsr_ctc_prefix_full(L.ptr(lp), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), nh, BATCH, 1,
+        L.check(lib.avsr_ctc_prefix_full_probs(L.ptr(lp), L.ptr(pr), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), nh, BATCH, 1,
                                          L.ptr(last), L.ptr(rprev), L.ptr(r_buf), T, L.ptr(step_t), L.ptr(s_prev), L.ptr(scores),
                                          L.ptr(fpart), L.ptr(ftick), L.stream()), "ctc_full")
     t = timeit(ctc_full, n=12)
@@ -393,7 +398,7 @@ def _kernel_rooflines(model, peaks):
                                     "frac": byts / t / 1e9 / peaks["hbm"], "traffic": traffic.get("ctc_prefix_full_vocab"), "us_per_launch": t * 1e6,
                                     "shape": f"{BATCH} utt x {nh} hyps x T={T} x V={V}, {ncg.value} column groups x {ts.value} time splits per "
                                              f"utterance; 3 posterior blocks of 242 MB used in turn (each launch reads from HBM)"}
-    del logps
+    del logps, probs
     # (4) source attention of one decode position (csrc/dec_attn.cu): the K/V of all 32 utterances, 6 layers used in turn
     #     (590 MB > L2).  Algorithmic bytes per launch = 2 * sum(T) * 1024 * 4 (every frame's K and V row read once).
     R = BATCH * BEAM

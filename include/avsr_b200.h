@@ -277,6 +277,15 @@ int avsr_ctc_prefix_full_plan(int B, int V, int* ncg, int* tsplit);
 int avsr_ctc_prefix_full(const float* logp, int V, int ldp, int blank, int eos, const int* utt_off, const int* utt_T, const int* n_run,
                          int beam, int B, int S, const int* last_tok, const int* rprev_idx, const float* r_buf, int tmax,
                          const int* step, const float* s_prev, float* scores, float* part, int* tickets, avsr_stream_t stream);
+/* The same with the posteriors themselves given as well: probs = exp(logp) as avsr_ctc_exp_posteriors writes it (same pitch);
+ * the kernel streams probs and its inner loop needs no exponential.  The search calls avsr_ctc_exp_posteriors once per batch
+ * of utterances and this entry point at every position.  probs == NULL: identical to avsr_ctc_prefix_full.  Results are
+ * bit-identical either way. */
+int avsr_ctc_prefix_full_probs(const float* logp, const float* probs, int V, int ldp, int blank, int eos, const int* utt_off,
+                               const int* utt_T, const int* n_run, int beam, int B, int S, const int* last_tok, const int* rprev_idx,
+                               const float* r_buf, int tmax, const int* step, const float* s_prev, float* scores, float* part,
+                               int* tickets, cudaStream_t stream);
+int avsr_ctc_exp_posteriors(const float* logp, long long n, float* probs, cudaStream_t stream);
 /* BatchBeamSearch.search fusion + batch_beam top-k + post_process + end_detect
  * (src/nets/batch_beam_search.py:86-110,222-349; src/nets/e2e_asr_common.py:18-48). */
 int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,

@@ -484,6 +484,16 @@ def test_ctc_prefix_full_vs_torch(L, B, beam, V, step):
                                      L.ptr(scores), L.ptr(part), L.ptr(tick), L.stream()), "ctc_full")
     torch.cuda.synchronize()
     assert int(tick.abs().sum().item()) == 0
+    # the same with the posteriors precomputed once (what the CTC-only search does at every position): bit-identical
+    probs = torch.empty_like(logp_p)
+    scores_p = torch.full((R, V), 123.0, device="cuda")
+    L.check(lib.avsr_ctc_exp_posteriors(L.ptr(logp_p), L.ll(logp_p.numel()), L.ptr(probs), L.stream()), "ctc_exp")
+    L.check(lib.avsr_ctc_prefix_full_probs(L.ptr(logp_p), L.ptr(probs), V, ldp, blank, eos, L.ptr(d_off), L.ptr(d_T), L.ptr(d_run), beam, B, 1,
+                                           L.ptr(d_last), L.ptr(rprev), L.ptr(r_buf), tmax, L.ptr(d_step), L.ptr(s_prev),
+                                           L.ptr(scores_p), L.ptr(part), L.ptr(tick), L.stream()), "ctc_full_probs")
+    torch.cuda.synchronize()
+    assert int(tick.abs().sum().item()) == 0
+    assert torch.equal(scores, scores_p)
     start = max(step, 1)
     for b in range(B):
         T = lengths[b]
