@@ -12,6 +12,7 @@
 //   warps 2-5: epilogue      - tcgen05.ld the fp32 accumulator (double-buffered in TMEM), fused bias / activation /
 //                              residual / row-mask, bf16 and/or fp32 stores
 // Pipelines: smem ring full[]/empty[] (TMA <-> MMA) and TMEM tfull[]/tempty[] (MMA <-> epilogue), all mbarriers.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -32,16 +33,13 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + COLPAR_BYTES;
 };
 
-// One 32-column chunk of one accumulator row.  `cb` / `cp` point at this chunk's per-column bias / PReLU slopes staged in
-// shared memory by the epilogue warps BEFORE they wait for the accumulator (a global load here would expose a full memory
-// latency per chunk: with two epilogue warps per scheduler nothing hides it).  `rbias` is the per-row bias (bias_mode 2),
-// `res` the residual values of this chunk already in registers (has_res), both fetched ahead of use as well.
-__device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, int col0, int M, int N, const uint32_t (&r)[32],
-                                               const float* cb, const float* cp, float rbias, const float (&res)[32], bool has_res) {
-    if (row >= M) return;
-    const int ncols = min(32, N - col0);
-    if (ncols <= 0) return;
-    float v[32];
+// Row-wise arithmetic of one 32-column chunk of one accumulator row: v = act(acc + bias) + residual (or act after the residual),
+// row mask.  `cb` / `cp` point at this chunk's per-column bias / PReLU slopes staged in shared memory by the epilogue warps
+// BEFORE they wait for the accumulator (a global load here would expose a full memory latency per chunk: with two epilogue
+// warps per scheduler nothing hides it).  `rbias` is the per-row bias (bias_mode 2), `res` the residual values of this chunk
+// already in registers (has_res), both fetched ahead of use as well.
+__device__ __forceinline__ void epilogue_math(const AvsrEpilogue& ep, int row, int M, const uint32_t (&r)[32], const float* cb, const float* cp,
+                                              float rbias, const float (&res)[32], bool has_res, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (ep.bias != nullptr) {
@@ -84,10 +82,17 @@ __device__ __forceinline__ void epilogue_chunk(const AvsrEpilogue& ep, int row, 
             for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * cp[j];
         }
     }
-    if (ep.row_mask != nullptr && ep.row_mask[row] == 0) {
+    if (ep.row_mask != nullptr && row < M && ep.row_mask[row] == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
+}
+
+// Stores of one finished chunk: thread = row, 32 consecutive columns.
+__device__ __forceinline__ void epilogue_store_direct(const AvsrEpilogue& ep, int row, int col0, int M, int N, const float (&v)[32]) {
+    if (row >= M) return;
+    const int ncols = min(32, N - col0);
+    if (ncols <= 0) return;
     if (ep.out_f32 != nullptr) {
         float* op = ep.out_f32 + (long long)row * ep.ld_f32 + col0;
         if (ncols == 32 && (ep.ld_f32 & 3) == 0) {
@@ -159,6 +164,47 @@ __device__ __forceinline__ void load_residual(const AvsrEpilogue& ep, int row, i
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) res[j] = (j < ncols) ? __bfloat162float(rp[j]) : 0.f;
+        }
+    }
+}
+
+// (Round 2 negative result: transposing every chunk through a per-warp shared-memory tile so that global accesses are 4 rows x
+// 128 contiguous bytes per instruction instead of 32 rows x 16 bytes was measured SLOWER for the whole encoder, 32.8 ms against
+// 30.2 ms per 32 x 375-frame batch: the two shared-memory round trips and warp barriers per chunk cost more than the 32-line
+// store instructions they replace.  The direct stores stay.)
+
+// Epilogue of one accumulator tile for one epilogue warp (TMEM lane quadrant `quad`, column half `half`): the first chunk's
+// residual is requested BEFORE the wait for the accumulator, the next chunk's while the current one is processed.
+template <int BN, bool BOUNDED>
+__device__ __forceinline__ void epilogue_tile(const AvsrEpilogue& ep, uint32_t taddr, int m0, int n0, int M, int N, int quad, int half, int lane,
+                                              const float* cpar, float rbias, uint64_t* tfull_bar, uint32_t tfull_parity) {
+    constexpr int CHUNKS = BN / 32 / 2 > 0 ? BN / 32 / 2 : 1;
+    const bool has_res = ep.residual != nullptr;
+    const int row = m0 + quad * 32 + lane;
+    const int c_first = half * CHUNKS;
+    float res[32];
+    if (has_res) load_residual(ep, row, n0 + c_first * 32, M, N, res);
+    if (BOUNDED) {
+        for (uint32_t i = 0; !tc::mbar_try_wait(tfull_bar, tfull_parity); ++i)
+            if (i > (1u << 27)) __trap();
+    } else {
+        tc::mbar_wait(tfull_bar, tfull_parity);
+    }
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < CHUNKS; ++cc) {
+        const int c = c_first + cc, col0 = n0 + c * 32;
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c * 32, r);
+        const bool more = has_res && cc + 1 < CHUNKS;
+        float v[32], res_next[32];
+        if (more) load_residual(ep, row, col0 + 32, M, N, res_next);       // in flight while this chunk is processed
+        tc::tmem_ld_wait();
+        epilogue_math(ep, row, M, r, cpar + c * 32, cpar + BN + c * 32, rbias, res, has_res, v);
+        epilogue_store_direct(ep, row, col0, M, N, v);
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) res[j] = res_next[j];
         }
     }
 }
@@ -308,10 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may touch
         const int half = (warp - 2) >> 2;               // which half of the tile's columns
         const int etid = threadIdx.x - 64;              // 0 .. 32 * NUM_EPI_WARPS - 1
-        constexpr int CHUNKS = BN / 32 / 2 > 0 ? BN / 32 / 2 : 1;
         const bool col_bias = ep_in.bias != nullptr && ep_in.bias_mode != 2;
         const bool has_prelu = ep_in.act == AVSR_ACT_PRELU && ep_in.prelu != nullptr;
-        const bool has_res = ep_in.residual != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -338,29 +382,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             const float rbias = (ep_in.bias != nullptr && ep_in.bias_mode == 2 && row < M) ? __ldg(ep_in.bias + row) : 0.f;
-            float res[32];
-            const int c_first = half * CHUNKS;
-            if (has_res && !(BN == 32 && half == 1)) load_residual(ep, row, n0 + c_first * 32, M, N, res);
             if (col_bias || has_prelu) asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-            tc::mbar_wait(&tfull[acc], acc_phase);
-            tc::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int cc = 0; cc < CHUNKS; ++cc) {
-                const int c = c_first + cc;
-                if (BN == 32 && half == 1) break;
-                uint32_t r[32];
-                tc::tmem_ld_32x32(taddr + c * 32, r);
-                float res_next[32];
-                const bool more = has_res && cc + 1 < CHUNKS;
-                if (more) load_residual(ep, row, n0 + (c + 1) * 32, M, N, res_next);      // in flight while this chunk is processed
-                tc::tmem_ld_wait();
-                epilogue_chunk(ep, row, n0 + c * 32, M, N, r, cpar + c * 32, cpar + BN + c * 32, rbias, res, has_res);
-                if (more) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) res[j] = res_next[j];
-                }
-            }
+            epilogue_tile<BN, false>(ep, taddr, m0, n0, M, N, quad, half, lane, cpar, rbias, &tfull[acc], acc_phase);
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
@@ -375,7 +399,189 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (tcgen05 cta_group::2) for the big encoder GEMMs.  Why: the single-CTA kernel above streams 48 KB per k
+// block (A 128x64 + B 256x64) for 512 tensor-pipe clocks = 96 B/clk per SM; the L2 delivers ~12 TB/s chip-wide (ncu r02:
+// lts 1.26 GB per FFN launch in 102 us, the ~6300 B/clk cap of B300_MICROARCH.md), i.e. ~43 B/clk per SM, so the tensor pipe
+// waits for operands half of the time (51.7 % active).  A pair of CTAs on the two SMs of a TPC computes a 256 x 256 tile with
+// ONE MMA stream: each CTA stages its own 128 A rows and HALF of the B tile (128 of the 256 rows), the leader's
+// tcgen05.mma.cta_group::2 reads both halves out of both shared memories and writes each CTA's 128 x 256 accumulator into
+// that CTA's own TMEM.  Per CTA and k block: 32 KB for the same 512 clocks = 64 B/clk, and the smaller stage doubles the
+// pipeline depth (6 stages instead of 3).
+//   * both CTAs' producers signal the LEADER's full barrier (peer bit of the shared::cluster address cleared);
+//   * the leader's commits are multicast to both CTAs' empty / accumulator-full barriers;
+//   * both CTAs' epilogue warps release the accumulator buffer on the leader's barrier (remote mbarrier arrive).
+// Epilogue, persistent tile loop and TMEM double buffering are those of the single-CTA kernel.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the pair's even CTA
+constexpr int BN2 = 256;
+constexpr int B_HALF_BYTES = (BN2 / 2) * BK * 2;
+constexpr int STAGE2_BYTES = A_TILE_BYTES + B_HALF_BYTES;     // 32 KB
+constexpr int STAGES2 = 6;
+constexpr int COLPAR2_BYTES = 2 * 2 * BN2 * 4;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256 + COLPAR2_BYTES;
+
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; !tc::mbar_try_wait(bar, parity); ++i)
+        if (i > (1u << 27)) __trap();                 // a protocol error ends the kernel instead of hanging the GPU
+}
+__device__ __forceinline__ uint32_t pair_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pair_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(tc::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tc::smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                    const AvsrEpilogue ep) {
+    constexpr int BN = BN2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* empty = full + STAGES2;
+    uint64_t* tfull = empty + STAGES2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* colpar = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES + 256);        // [2 acc][bias BN | prelu BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = pair_rank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            tc::mbar_init(&full[s], 1);               // the leader's expect_tx arrival; bytes come from both CTAs
+            tc::mbar_init(&empty[s], 1);              // the leader's commit, multicast
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull[a], 1);
+            tc::mbar_init(&tempty[a], 2 * NUM_EPI_WARPS);     // the epilogue warps of both CTAs (leader's copy is the one waited on)
+        }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc::tc_fence_before();
+    pair_sync();                                      // barriers of both CTAs initialised before anybody signals the peer
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                const int m0 = (tile / tiles_n) * 2 * BM + (int)rank * BM, n0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_bounded(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE2_BYTES;
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    tma_load_2d_pair(sa, &tmA, &full[stage], kb * BK, m0);
+                    tma_load_2d_pair(sa + A_TILE_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += npairs) {
+                mbar_wait_bounded(&tempty[acc], acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_bounded(&full[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint64_t adesc = tc::umma_desc_sw128(sa);
+                    const uint64_t bdesc = tc::umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k != 0) ? 1u : 0u);
+                    umma_commit_pair(&empty[stage]);        // frees the slot in both CTAs when these MMAs retire
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull[acc]);              // accumulators of both CTAs complete -> both epilogues
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int etid = threadIdx.x - 64;
+        const bool col_bias = ep.bias != nullptr && ep.bias_mode != 2;
+        const bool has_prelu = ep.act == AVSR_ACT_PRELU && ep.prelu != nullptr;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += npairs) {
+            const int m0 = (tile / tiles_n) * 2 * BM + (int)rank * BM, n0 = (tile % tiles_n) * BN;
+            const int row = m0 + quad * 32 + lane;
+            float* cpar = colpar + acc * 2 * BN;
+            if (col_bias || has_prelu) {
+                for (int i = etid; i < BN; i += 32 * NUM_EPI_WARPS) {
+                    const int col = n0 + i;
+                    if (col_bias) cpar[i] = col < N ? __ldg(ep.bias + col) : 0.f;
+                    if (has_prelu) cpar[BN + i] = col < N ? __ldg(ep.prelu + col) : 0.f;
+                }
+            }
+            const float rbias = (ep.bias != nullptr && ep.bias_mode == 2 && row < M) ? __ldg(ep.bias + row) : 0.f;
+            if (col_bias || has_prelu) asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            epilogue_tile<BN, true>(ep, taddr, m0, n0, M, N, quad, half, lane, cpar, rbias, &tfull[acc], acc_phase);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc::tc_fence_before();
+    pair_sync();                                      // nobody frees TMEM / leaves while the peer may still use this CTA's memory
+    if (warp == 1) {
+        tc::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 int g_sm_count = 0;
+int g_pair_on = -1;                                  // dev knob, read once: AVSR_GEMM_PAIR=0 (no CTA-pair kernel)
+bool pair_enabled() {
+    if (g_pair_on < 0) {
+        const char* e = getenv("AVSR_GEMM_PAIR");
+        g_pair_on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    }
+    return g_pair_on == 1;
+}
 
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const AvsrEpilogue& ep, int splits, cudaStream_t stream,
@@ -510,6 +716,37 @@ extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, 
     return launch<256>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
 }
 
+// The CTA-pair kernel takes plain GEMMs that fill the device with 256 x 256 tiles (the transformer's QKV / out / FFN
+// projections at batch sizes worth the launch); AVSR_GEMM_PAIR=0 switches it off (dev knob).
+static int launch_pair(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue& ep, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        configured = true;
+    }
+    CUtensorMap ta, tb;
+    int rc = tc::make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (rc != AVSR_OK) return rc;
+    rc = tc::make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN2 / 2, BK);
+    if (rc != AVSR_OK) return rc;
+    const int tiles = cdiv(M, 2 * BM) * cdiv(N, BN2);
+    const int pairs = tiles < g_sm_count / 2 ? tiles : g_sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel, ta, tb, M, N, K, ep));
+    return AVSR_OK;
+}
+
 static int gemm_entry(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, const AvsrEpilogue* ep,
                       int bn_hint, int splits, cudaStream_t stream) {
     AVSR_REQUIRE(A && B && ep, "avsr_gemm_bf16_tc: null operand");
@@ -527,6 +764,8 @@ static int gemm_entry(const void* A, long long lda, const void* B, long long ldb
         else bn = (cdiv(M, BM) * cdiv(N, 256) * splits >= 2 * g_sm_count) ? 256 : 128;
     }
     AVSR_REQUIRE(bn == 64 || bn == 128 || bn == 256, "avsr_gemm_bf16_tc: bad bn_hint %d", bn_hint);
+    if (bn == 256 && bn_hint == 0 && splits == 1 && pair_enabled() && cdiv(M, 2 * BM) * cdiv(N, BN2) >= g_sm_count)
+        return launch_pair(A, lda, B, ldb, M, N, K, *ep, stream);
     CUtensorMap ta, tb;
     int rc = tc::make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (rc != AVSR_OK) return rc;

@@ -443,6 +443,41 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
             assert (out[row] - want).abs().max().item() < tol, (b, h)
 
 
+@pytest.mark.parametrize("M,N,K,mode", [(12000, 1024, 1024, "res"), (9000, 4096, 512, "gelu"), (5000, 5049, 384, "f32"),
+                                        (37889, 1024, 128, "prelu")])
+def test_gemm_cta_pair_kernel(L, M, N, K, mode):
+    """The CTA-pair (tcgen05 cta_group::2) GEMM the big encoder projections dispatch to (>= 148 tiles of 256 x 256): ragged M
+    (last pair half / fully out of range), N not a multiple of 256, every epilogue flavour, against torch fp32 on the same
+    bf16 operands; and bit-identical to the single-CTA kernel (same k order, same fp32 accumulation)."""
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().cuda()
+    b = (torch.randn(N, K, generator=g) * 0.5).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = a.float() @ b.float().t() + bias
+    kw = dict(bias=bias)
+    if mode == "res":
+        res = torch.randn(M, N, generator=g).cuda()
+        kw.update(residual=res, ldr=N)
+        ref = ref + res
+    elif mode == "gelu":
+        kw.update(act=L.ACT_GELU)
+        ref = torch.nn.functional.gelu(ref)
+    elif mode == "prelu":
+        slope = torch.rand(N, generator=g).cuda()
+        kw.update(act=L.ACT_PRELU, prelu=slope)
+        ref = torch.where(ref > 0, ref, ref * slope)
+    outs = []
+    for bn in (0, 256):                           # 0: automatic (the pair kernel at these sizes), 256: the single-CTA kernel
+        o32 = torch.full((M, N), 7.0, device="cuda")
+        o16 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        L.gemm_bf16(a, b, M, N, K, L.make_epilogue(out_f32=o32, ld_f32=N, out_bf16=o16, ld_bf16=N, **kw), bn_hint=bn)
+        torch.cuda.synchronize()
+        outs.append((o32, o16))
+    err = (outs[0][0] - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("B,beam,V,step", [(1, 3, 5049, 2), (5, 5, 5049, 7), (80, 3, 700, 3), (3, 8, 2600, 1), (2, 3, 5049, 0)])
 def test_ctc_prefix_full_vs_torch(L, B, beam, V, step):
     """Full-vocabulary CTC prefix scores (ctc_prefix_score.py:68-187 with scoring_ids=None) against the log-domain formula in
