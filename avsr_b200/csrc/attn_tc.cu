@@ -5,8 +5,10 @@
 // One CTA = one (utterance, head, 128-query tile).  Exact two-pass softmax over 128-key blocks:
 //   pass A: S = Q K_j^T (tcgen05.mma, fp32 in TMEM) -> row max
 //   pass B: S = Q K_j^T again, P = exp(S - max) -> bf16 into swizzled smem, O += P V_j (tcgen05.mma, O in TMEM)
-// Q (pre-scaled by 1/8 at weight-pack time) and all K blocks stay resident in shared memory; V^T blocks are
-// double-buffered TMA loads.  Inputs: qk [F, 2048] bf16 (q | k), vt [1024, F] bf16 (V transposed: d-major rows),
+// Q (pre-scaled by 1/8 at weight-pack time) and all K blocks stay resident in shared memory; V^T blocks are TMA loads into
+// one or two buffers.  The CTA is one dependent chain (load -> MMA -> TMEM read -> softmax -> MMA ...), so the kernel is
+// latency-bound per CTA: the shared-memory layout is sized by the longest utterance of the batch (kcap key blocks) and, up to
+// 384 keys, two CTAs share an SM (one V buffer, 112 KB each) so that one's softmax overlaps the other's MMAs and loads.  Inputs: qk [F, 2048] bf16 (q | k), vt [1024, F] bf16 (V transposed: d-major rows),
 // output [F, 1024] bf16.  Thread i owns query row i (TMEM lane i).
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -17,17 +19,18 @@ constexpr int QT = 128;          // queries per CTA
 constexpr int KB = 128;          // keys per block
 constexpr int MAX_KB = 6;        // T <= 768 frames (30.7 s)
 constexpr int TILE16K = 16384;
-constexpr int ATT_SMEM = TILE16K /*Q*/ + MAX_KB * TILE16K /*K*/ + 2 * TILE16K /*V x2*/ + 2 * TILE16K /*P*/ + 1024 + 256;
+constexpr int ATT_TWO_PER_SM = 7 * TILE16K + 256;      // largest footprint that still lets two CTAs share an SM
+__host__ __device__ constexpr int att_smem(int kcap, int nvb) { return (1 /*Q*/ + kcap /*K*/ + nvb /*V*/ + 2 /*P*/) * TILE16K + 256; }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const int* __restrict__ work_off,
-               const int* __restrict__ work_T, const int* __restrict__ work_q0, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+               const int* __restrict__ work_T, const int* __restrict__ work_q0, __nv_bfloat16* __restrict__ out, int kcap, int nvb) {
+    extern __shared__ __align__(1024) uint8_t smem[];          // the 128-byte swizzle needs 1024-byte aligned tiles
+    if ((reinterpret_cast<uintptr_t>(smem) & 1023) != 0) __trap();
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE16K;
-    uint8_t* sV = sK + MAX_KB * TILE16K;
-    uint8_t* sP = sV + 2 * TILE16K;
+    uint8_t* sV = sK + kcap * TILE16K;
+    uint8_t* sP = sV + nvb * TILE16K;
     uint64_t* bar_qk = reinterpret_cast<uint64_t*>(sP + 2 * TILE16K);
     uint64_t* bar_v = bar_qk + 1;      // [2]
     uint64_t* bar_s = bar_v + 2;       // S ready
@@ -121,11 +124,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
             tc::mbar_wait(bar_o, ph_o);
             ph_o ^= 1;
         }
-        if (tid == 0 && kb + 1 < nkb) {     // prefetch V^T of the next block
-            uint8_t* dst = sV + ((kb + 1) & 1) * TILE16K;
-            tc::mbar_arrive_expect_tx(&bar_v[(kb + 1) & 1], TILE16K);
-            tc::tma_load_2d(dst, &tmV, &bar_v[(kb + 1) & 1], koff + (kb + 1) * KB, h * 64);
-            tc::tma_load_2d(dst + 8192, &tmV, &bar_v[(kb + 1) & 1], koff + (kb + 1) * KB + 64, h * 64);
+        // V^T of block kb + nvb - 1: into the other buffer one block ahead (two buffers), or into the single buffer now that the
+        // product that read it has retired (it then lands while this block's scores and exponentials are computed)
+        const int nxt = kb + nvb - 1;
+        if (tid == 0 && nxt > 0 && nxt < nkb) {
+            uint8_t* dst = sV + (nxt % nvb) * TILE16K;
+            tc::mbar_arrive_expect_tx(&bar_v[nxt % nvb], TILE16K);
+            tc::tma_load_2d(dst, &tmV, &bar_v[nxt % nvb], koff + nxt * KB, h * 64);
+            tc::tma_load_2d(dst + 8192, &tmV, &bar_v[nxt % nvb], koff + nxt * KB + 64, h * 64);
         }
         tc::mbar_wait(bar_s, ph_s);
         ph_s ^= 1;
@@ -159,8 +165,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
-            tc::mbar_wait(&bar_v[kb & 1], (kb >> 1) & 1);
-            const uint32_t pv = tc::smem_u32(sV + (kb & 1) * TILE16K);
+            tc::mbar_wait(&bar_v[kb % nvb], (kb / nvb) & 1);
+            const uint32_t pv = tc::smem_u32(sV + (kb % nvb) * TILE16K);
             const uint32_t pp = tc::smem_u32(sP);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -214,15 +220,20 @@ extern "C" int avsr_attention_varlen(const void* qk, const void* vt, long long l
     AVSR_REQUIRE(max_T + 7 <= MAX_KB * KB, "avsr_attention_varlen: utterance of %d frames exceeds the supported %d", max_T, MAX_KB * KB - 7);
     static bool configured = false;
     if (!configured) {
-        AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, att_smem(MAX_KB, 2)));
         configured = true;
     }
+    // key blocks the longest utterance needs (7 = worst-case alignment shift of the first key); two V buffers when they still
+    // leave room for a second CTA on the SM (or when one CTA per SM is all that fits anyway), else one
+    const int kcap = (max_T + 7 + KB - 1) / KB;
+    const int nvb = (att_smem(kcap, 2) <= ATT_TWO_PER_SM || att_smem(kcap, 1) > ATT_TWO_PER_SM) ? 2 : 1;
+    const int smem = att_smem(kcap, nvb);
     CUtensorMap tq, tv;
     int rc = tc::make_tmap_2d_bf16(&tq, qk, (uint64_t)F, 2048, 2048, 128, 64);
     if (rc != AVSR_OK) return rc;
     rc = tc::make_tmap_2d_bf16(&tv, vt, 1024, (uint64_t)F, (uint64_t)ld_vt, 64, 64);
     if (rc != AVSR_OK) return rc;
-    attn_tc_kernel<<<dim3(n_work, 16), 128, ATT_SMEM, stream>>>(tq, tv, work_off, work_T, work_q0, (__nv_bfloat16*)out);
+    attn_tc_kernel<<<dim3(n_work, 16), 128, smem, stream>>>(tq, tv, work_off, work_T, work_q0, (__nv_bfloat16*)out, kcap, nvb);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }
