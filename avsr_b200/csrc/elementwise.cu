@@ -115,7 +115,7 @@ im2col2d_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict_
 // ------------------------------------------------------------------ max pool 3x3 s2 p1 (NHWC bf16), 8 channels/thread
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long total_vec, int H, int W, int C,
-                    int Ho, int Wo) {
+                    int Ho, int Wo, long long out_row_pitch, long long out_frame_pitch) {
     const int cv = C / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
         const int c8 = (int)(i % cv);
@@ -141,7 +141,7 @@ maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restr
         __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(m[j]);
-        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(out + ((f * out_frame_pitch + (long long)oy * out_row_pitch + ox) * C + c8 * 8)) = *reinterpret_cast<const uint4*>(o);
     }
 }
 
@@ -262,13 +262,22 @@ extern "C" int avsr_im2col2d(const void* in, void* out, long long F, int H, int 
     return AVSR_OK;
 }
 
-extern "C" int avsr_maxpool3x3s2(const void* in, void* out, long long F, int H, int W, int C, cudaStream_t stream) {
+// out_row_pitch_px / out_frame_pitch_px: pixel pitches of the output rows / frames (0 = dense); only the Ho x Wo valid pixels of
+// a frame are written (a padded layout keeps its zero pads).
+extern "C" int avsr_maxpool3x3s2_pitched(const void* in, void* out, long long F, int H, int W, int C, long long out_row_pitch_px,
+                                         long long out_frame_pitch_px, cudaStream_t stream) {
     AVSR_REQUIRE(in && out && F > 0 && (C & 7) == 0, "avsr_maxpool3x3s2: bad arguments");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long rp = out_row_pitch_px > 0 ? out_row_pitch_px : Wo, fp = out_frame_pitch_px > 0 ? out_frame_pitch_px : rp * Ho;
+    AVSR_REQUIRE(rp >= Wo && fp >= rp * (Ho - 1) + Wo, "avsr_maxpool3x3s2: output pitches too small");
     const long long total = F * Ho * Wo * (C / 8);
-    maxpool3x3s2_kernel<<<GRID1D(total), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C, Ho, Wo);
+    maxpool3x3s2_kernel<<<GRID1D(total), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C, Ho, Wo, rp, fp);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
+}
+
+extern "C" int avsr_maxpool3x3s2(const void* in, void* out, long long F, int H, int W, int C, cudaStream_t stream) {
+    return avsr_maxpool3x3s2_pitched(in, out, F, H, W, C, 0, 0, stream);
 }
 
 extern "C" int avsr_avgpool(const void* in, void* out, long long F, int HW, int C, cudaStream_t stream) {

@@ -573,6 +573,148 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / 64 -> 64 convolution with the input HALO staged once (ResNet layer1: four convolutions on 22 x 22 x 64
+// maps, resnet.py:30-69).  The generic implicit GEMM above fetches one 128-pixel x 64-channel operand tile per filter tap:
+// 9 x 16 KB of activations + 9 x 8 KB of weights per 128 x 64 output tile whose MMAs last 1152 clocks - 190 B/clk per SM
+// against the ~43 B/clk the L2 delivers, so the tensor pipe idled 3/4 of the time (ncu r02: 25 % active, 292 us per launch).
+// Here the activations live in a PADDED pixel layout (Wp = W + 2 columns, Hp = H + 1 rows per frame, pads are zero and are
+// never written): the nine taps of an output pixel p are the pixels p + dy * Wp + dx of the same linear array, so a tile of
+// 128 consecutive (padded) pixels needs ONE contiguous halo of 128 + 2 (Wp + 1) pixels = 23 KB, loaded by one TMA request,
+// and the A operand of tap (dy, dx) is the SAME shared-memory tile read from row (Wp + 1) + dy * Wp + dx on: a UMMA descriptor
+// whose start address is moved by whole 128-byte rows.  (The 128-byte swizzle is a function of the absolute shared-memory
+// address bits, and every stage starts on a 1024-byte boundary as the TMA write assumed, so the matrix-base-offset field of
+// the descriptor stays 0: setting it to the row phase was measured WRONG, leaving it 0 is bit-exact.)  The weights of all nine taps (72 KB) stay resident in shared memory for the whole persistent CTA.  L2 traffic per
+// tile: 23 KB instead of 216 KB; 8 % of the rows computed are pad pixels whose results are dropped.
+constexpr int HL_ROWS = 184;                          // halo rows per tile (128 + 2 * 25 = 178 used), a multiple of 8
+constexpr int HL_BYTES = HL_ROWS * 128;               // 23 x 1024: every stage starts on a swizzle-pattern boundary
+constexpr int HL_STAGES = 4;
+constexpr int HL_W_BYTES = 9 * 64 * 128;              // 9 taps x [64 output channels][64 input channels] bf16
+constexpr int HL_SMEM = HL_W_BYTES + HL_STAGES * HL_BYTES + 1024 + 256 + 2 * 2 * 64 * 4;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const AvsrEpilogue ep, int W, int H,
+                    long long total_px) {
+    constexpr int BN = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW = smem;
+    uint8_t* sH = smem + HL_W_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sH + HL_STAGES * HL_BYTES);
+    uint64_t* empty = full + HL_STAGES;
+    uint64_t* tfull = empty + HL_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    float* colpar = reinterpret_cast<float*>(sH + HL_STAGES * HL_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Wp = W + 2, Hp = H + 1, fpx = Wp * Hp;   // padded row / frame pitches in pixels
+    const int num_tiles = (int)((total_px + BM - 1) / BM);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HL_STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(&tfull[a], 1);
+            tc::mbar_init(&tempty[a], NUM_EPI_WARPS);
+        }
+        tc::mbar_init(wfull, 1);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmX);
+        tc::tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, 2 * BN);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(wfull, HL_W_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tc::tma_load_2d(sW + tap * 8192, &tmW, wfull, tap * 64, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait_bounded(&empty[stage], phase ^ 1);
+                tc::mbar_arrive_expect_tx(&full[stage], HL_BYTES);
+                // rows before the first / after the last pixel are zero-filled by the TMA unit (the pads of the first frame)
+                tc::tma_load_2d(sH + stage * HL_BYTES, &tmX, &full[stage], 0, tile * BM - (Wp + 1));
+                if (++stage == HL_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            mbar_wait_bounded(wfull, 0);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait_bounded(&tempty[acc], acc_phase ^ 1);
+                mbar_wait_bounded(&full[stage], phase);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t sh = tc::smem_u32(sH + stage * HL_BYTES);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int off = (Wp + 1) + (tap / 3 - 1) * Wp + (tap % 3 - 1);          // first halo row of this tap's operand
+                    const uint64_t adesc = tc::umma_desc_sw128(sh + (uint32_t)off * 128u);
+                    const uint64_t bdesc = tc::umma_desc_sw128(tc::smem_u32(sW + tap * 8192));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) tc::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (tap | k) != 0 ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[stage]);
+                tc::umma_commit(&tfull[acc]);
+                if (++stage == HL_STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int etid = threadIdx.x - 64;
+        const bool col_bias = ep.bias != nullptr && ep.bias_mode != 2;
+        const bool has_prelu = ep.act == AVSR_ACT_PRELU && ep.prelu != nullptr;
+        // bias / PReLU slopes of the 64 output channels are the same for every tile: staged once (both accumulator slots)
+        for (int i = etid; i < 2 * BN; i += 32 * NUM_EPI_WARPS) {
+            const int a = i / BN, col = i % BN;
+            colpar[a * 2 * BN + col] = col_bias ? __ldg(ep.bias + col) : 0.f;
+            colpar[a * 2 * BN + BN + col] = has_prelu ? __ldg(ep.prelu + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = tile * BM;
+            const long long px = (long long)m0 + quad * 32 + lane;      // this thread's padded pixel
+            const int q = (int)(px % fpx);
+            const bool valid = px < total_px && q / Wp < H && q % Wp < W;
+            // pad pixels: nothing is read or written (they must stay zero: they are the halo of their neighbours)
+            const int M_eff = valid ? (int)total_px : 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            epilogue_tile<BN, true>(ep, taddr, m0, 0, M_eff, BN, quad, half, lane, colpar + acc * 2 * BN, 0.f, &tfull[acc], acc_phase);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
 int g_sm_count = 0;
 int g_pair_on = -1;                                  // dev knob, read once: AVSR_GEMM_PAIR=0 (no CTA-pair kernel)
 bool pair_enabled() {
@@ -650,7 +792,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, int ks, int stride,
-                          uint32_t pixels, uint32_t channels) {
+                          uint32_t pixels, uint32_t channels, uint64_t row_pitch_px, uint64_t frame_pitch_px) {
     static EncodeIm2colFn fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;
@@ -668,7 +810,9 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64
         return AVSR_ERR_ARG;
     }
     cuuint64_t gdim[4] = {c, w, h, n};
-    cuuint64_t gstr[3] = {c * 2, w * c * 2, h * w * c * 2};
+    if (row_pitch_px == 0) row_pitch_px = w;          // dense image rows / frames unless the caller says otherwise
+    if (frame_pitch_px == 0) frame_pitch_px = h * row_pitch_px;
+    cuuint64_t gstr[3] = {c * 2, row_pitch_px * c * 2, frame_pitch_px * c * 2};
     const int pad = ks / 2;
     int lower[2] = {-pad, -pad};             // {W, H}: the filter's base pixel starts `pad` pixels outside the image ...
     int upper[2] = {-pad, -pad};             // ... and stops pad - (ks - 1) = -pad from the far edge
@@ -689,8 +833,11 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64
 // (BasicBlock and downsample convs, src/nets/backend/backbones/resnet.py:30-69): out[(f, y, x), :] = epilogue(sum_{ky,kx,c}
 // in[f, y*s+ky-pad, x*s+kx-pad, c] * Wt[:, (ky*ks + kx)*C + c]).  in [F, H, W, C] bf16, Wt [Cout, ks*ks*C] bf16 (the layout the
 // explicit im2col path uses), the epilogue's outputs are [F*Ho*Wo, Cout].  C % 64 == 0.  The patch matrix is never written.
-extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
-                                   const AvsrEpilogue* ep, cudaStream_t stream) {
+// in_row_pitch_px / in_frame_pitch_px: pixel pitches of the input image rows / frames (0 = dense); a padded layout such as the
+// one avsr_conv3x3_halo_bf16 works on is read in place.
+extern "C" int avsr_conv2d_bf16_tc_pitched(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
+                                           long long in_row_pitch_px, long long in_frame_pitch_px, const AvsrEpilogue* ep,
+                                           cudaStream_t stream) {
     AVSR_REQUIRE(in && Wt && ep && F > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "avsr_conv2d_bf16_tc: bad arguments");
     AVSR_REQUIRE((ks == 1 || ks == 3) && (stride == 1 || stride == 2), "avsr_conv2d_bf16_tc: ks %d / stride %d unsupported", ks, stride);
     AVSR_REQUIRE((C % BK) == 0, "avsr_conv2d_bf16_tc: C = %d must be a multiple of %d", C, BK);
@@ -706,7 +853,9 @@ extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, 
     const int M = (int)(F * Ho * Wo), K = ks * ks * C;
     const int bn = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : ((cdiv(M, BM) * cdiv(Cout, 256) >= 2 * g_sm_count) ? 256 : 128));
     CUtensorMap ta, tb;
-    int rc = tc::make_tmap_im2col_bf16(&ta, in, (uint64_t)F, (uint64_t)H, (uint64_t)W, (uint64_t)C, ks, stride, BM, BK);
+    AVSR_REQUIRE(in_row_pitch_px >= 0 && in_frame_pitch_px >= 0 && (in_row_pitch_px == 0 || in_row_pitch_px >= W), "avsr_conv2d_bf16_tc: bad input pitches");
+    int rc = tc::make_tmap_im2col_bf16(&ta, in, (uint64_t)F, (uint64_t)H, (uint64_t)W, (uint64_t)C, ks, stride, BM, BK, (uint64_t)in_row_pitch_px,
+                                       (uint64_t)in_frame_pitch_px);
     if (rc != AVSR_OK) return rc;
     rc = tc::make_tmap_2d_bf16(&tb, Wt, (uint64_t)Cout, (uint64_t)K, (uint64_t)K, (uint32_t)bn, BK);
     if (rc != AVSR_OK) return rc;
@@ -714,6 +863,43 @@ extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, 
     if (bn == 64) return launch<64>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     if (bn == 128) return launch<128>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
     return launch<256>(ta, tb, M, Cout, K, *ep, 1, stream, conv);
+}
+
+extern "C" int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
+                                   const AvsrEpilogue* ep, cudaStream_t stream) {
+    return avsr_conv2d_bf16_tc_pitched(in, Wt, F, H, W, C, Cout, ks, stride, 0, 0, ep, stream);
+}
+
+// 3x3 / stride 1 / pad 1 convolution, 64 -> 64 channels, on the PADDED layout: activations [F][H + 1][W + 2][64] bf16 whose pad
+// cells (columns W, W + 1 of every row; row H of every frame) are zero.  ep.out_bf16 / ep.out_f32 / ep.residual use the same
+// layout (row = padded pixel index, 64 columns); pad cells of the output are not written (allocate it zeroed once).
+// Wt [64][9 * 64] bf16, k = (ky * 3 + kx) * 64 + cin (the layout avsr_conv2d_bf16_tc takes).
+extern "C" int avsr_conv3x3_halo_bf16(const void* in, const void* Wt, long long F, int H, int W, const AvsrEpilogue* ep, cudaStream_t stream) {
+    AVSR_REQUIRE(in && Wt && ep && F > 0 && H > 0 && W > 0, "avsr_conv3x3_halo_bf16: bad arguments");
+    AVSR_REQUIRE(ep->out_bf16 || ep->out_f32, "avsr_conv3x3_halo_bf16: no output buffer");
+    AVSR_REQUIRE(2 * (W + 3) + BM <= HL_ROWS, "avsr_conv3x3_halo_bf16: rows of %d pixels do not fit the halo tile", W);
+    const long long total_px = F * (long long)(H + 1) * (W + 2);
+    AVSR_REQUIRE(total_px < (1ll << 31) - HL_ROWS, "avsr_conv3x3_halo_bf16: too many pixels");
+    if (g_sm_count == 0) {
+        int dev = 0;
+        AVSR_CHECK_CUDA(cudaGetDevice(&dev));
+        AVSR_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static bool configured = false;
+    if (!configured) {
+        AVSR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
+        configured = true;
+    }
+    CUtensorMap tx, tw;
+    int rc = tc::make_tmap_2d_bf16(&tx, in, (uint64_t)total_px, 64, 64, HL_ROWS, 64);
+    if (rc != AVSR_OK) return rc;
+    rc = tc::make_tmap_2d_bf16(&tw, Wt, 64, 576, 576, 64, 64);
+    if (rc != AVSR_OK) return rc;
+    const long long tiles = cdiv(total_px, BM);
+    const int grid = tiles < g_sm_count ? (int)tiles : g_sm_count;
+    conv3x3_halo_kernel<<<grid, NUM_THREADS, HL_SMEM, stream>>>(tx, tw, *ep, W, H, total_px);
+    AVSR_LAUNCH_CHECK();
+    return AVSR_OK;
 }
 
 // The CTA-pair kernel takes plain GEMMs that fill the device with 256 x 256 tiles (the transformer's QKV / out / FFN

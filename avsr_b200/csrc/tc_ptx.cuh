@@ -142,5 +142,5 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 // im2col map of a bf16 NHWC tensor [n, h, w, c] for a ks x ks / stride / pad ks/2 convolution: boxes of `pixels` output pixels
 // x `channels` input channels; 128B swizzle; out-of-image -> 0.
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, uint64_t n, uint64_t h, uint64_t w, uint64_t c, int ks, int stride,
-                          uint32_t pixels, uint32_t channels);
+                          uint32_t pixels, uint32_t channels, uint64_t row_pitch_px = 0, uint64_t frame_pitch_px = 0);
 }  // namespace tc

@@ -48,6 +48,9 @@ class Encoder:
         self.implicit_conv = os.environ.get("AVSR_IMPLICIT_CONV", "1") != "0"
         # frontend 3D conv as an implicit GEMM (csrc/frontend_conv.cu); AVSR_IMPLICIT_FRONTEND=0 = explicit patch matrix + GEMM
         self.implicit_frontend = os.environ.get("AVSR_IMPLICIT_FRONTEND", "1") != "0"
+        # ResNet layer1 (four 3x3 / 64 -> 64 convolutions on 22 x 22 maps) on the padded pixel layout with the halo staged once
+        # per tile (csrc/gemm_tc.cu, conv3x3_halo_kernel); AVSR_HALO_CONV=0 = the generic implicit GEMM on the dense layout
+        self.halo_conv = os.environ.get("AVSR_HALO_CONV", "1") != "0"
         # positional conv as an implicit banded GEMM (avsr_posconv_bf16_tc); AVSR_IMPLICIT_POSCONV=0 = explicit patches + 16 GEMMs
         self.implicit_posconv = os.environ.get("AVSR_IMPLICIT_POSCONV", "1") != "0"
 
@@ -62,21 +65,57 @@ class Encoder:
             self._ws[name] = t
         return t[:n].view(*shape)
 
+    def _zbuf(self, name, shape, dtype):
+        """Workspace that is ZERO when first handed out and that only its owner writes: the padded activation layout of layer1
+        relies on pad cells that nobody ever touches."""
+        n = 1
+        for d in shape:
+            n *= d
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.zeros(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
     # ------------------------------------------------------------------ pieces
     def _conv_gemm(self, col, w, M, N, K, **ep):
         L.gemm_bf16(col, w, M, N, K, L.make_epilogue(**ep), lda=K, ldb=K)
 
-    def _basic_block(self, x, nf, H, C_in, blk, tag):
-        """x: [nf,H,H,C_in] bf16 -> [nf,Ho,Ho,C_out] bf16 (resnet.py:56-69)."""
+    def _basic_block_halo(self, xp, nf, H, blk, tag):
+        """Identity BasicBlock of layer1 on the padded layout: xp [nf,H+1,H+2,64] bf16 (zero pads) -> same layout."""
+        lib = L.load()
+        shape = (nf, H + 1, H + 2, 64)
+        t1 = self._zbuf("l1_t1", shape, torch.bfloat16)
+        out = self._zbuf("l1_out_" + tag, shape, torch.bfloat16)
+        ep1 = L.make_epilogue(bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"], out_bf16=t1, ld_bf16=64)
+        L.check(lib.avsr_conv3x3_halo_bf16(L.ptr(xp), L.ptr(blk["conv1_w"]), L.ll(nf), H, H, C.byref(ep1), L.stream()), "avsr_conv3x3_halo_bf16")
+        ep2 = L.make_epilogue(bias=blk["conv2_b"], act=L.ACT_PRELU, prelu=blk["prelu2"], residual=xp, ldr=64, act_after_residual=True,
+                              out_bf16=out, ld_bf16=64)
+        L.check(lib.avsr_conv3x3_halo_bf16(L.ptr(t1), L.ptr(blk["conv2_w"]), L.ll(nf), H, H, C.byref(ep2), L.stream()), "avsr_conv3x3_halo_bf16")
+        return out
+
+    def _basic_block(self, x, nf, H, C_in, blk, tag, padded=False):
+        """x: [nf,H,H,C_in] bf16 -> [nf,Ho,Ho,C_out] bf16 (resnet.py:56-69).  padded: x is in the padded layout
+        [nf,H+1,H+2,C_in] of layer1 (read in place through pitched tensor maps)."""
         lib = L.load()
         s, C_out = blk["stride"], blk["cout"]
         Ho = (H + 2 - 3) // s + 1
         M = nf * Ho * Ho
         t1 = self._buf("blk_t1", (M, C_out), torch.bfloat16)
         ep1 = dict(bias=blk["conv1_b"], act=L.ACT_PRELU, prelu=blk["prelu1"], out_bf16=t1, ld_bf16=C_out)
+
+        def conv_in(wt, ks, ep):
+            e = L.make_epilogue(**ep)
+            if padded:
+                L.check(lib.avsr_conv2d_bf16_tc_pitched(L.ptr(x), L.ptr(wt), L.ll(nf), H, H, C_in, C_out, ks, s, L.ll(H + 2), L.ll((H + 1) * (H + 2)),
+                                                        C.byref(e), L.stream()), "avsr_conv2d_bf16_tc_pitched")
+            else:
+                L.conv2d_bf16(x, wt, nf, H, H, C_in, C_out, ks, s, e)
+
+        assert not padded or (self.implicit_conv and "down_w" in blk), "the padded layout is only read by the implicit convolutions of a down-sampling block"
         if self.implicit_conv:
             # the convolutions run as implicit GEMMs: the TMA unit gathers the patches, nothing is materialised
-            L.conv2d_bf16(x, blk["conv1_w"], nf, H, H, C_in, C_out, 3, s, L.make_epilogue(**ep1))
+            conv_in(blk["conv1_w"], 3, ep1)
         else:
             col = self._buf("col", (M, 9 * C_in), torch.bfloat16)
             L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(col), L.ll(nf), H, H, C_in, 3, s, L.stream()), "avsr_im2col2d")
@@ -85,7 +124,7 @@ class Encoder:
             res = self._buf("blk_res", (M, C_out), torch.bfloat16)
             epd = dict(bias=blk["down_b"], out_bf16=res, ld_bf16=C_out)
             if self.implicit_conv:
-                L.conv2d_bf16(x, blk["down_w"], nf, H, H, C_in, C_out, 1, s, L.make_epilogue(**epd))
+                conv_in(blk["down_w"], 1, epd)
             else:
                 colr = self._buf("col", (M, C_in), torch.bfloat16)
                 L.check(lib.avsr_im2col2d(L.ptr(x), L.ptr(colr), L.ll(nf), H, H, C_in, 1, s, L.stream()), "avsr_im2col2d")
@@ -127,13 +166,25 @@ class Encoder:
                 L.check(lib.avsr_im2col_frontend(L.ptr(video_packed), L.ptr(frame_t), L.ptr(frame_T), f0, nf, L.ptr(col), L.stream()),
                         "avsr_im2col_frontend")
                 self._conv_gemm(col, w.front_w, M0, 64, 256, bias=w.front_b, act=L.ACT_PRELU, prelu=w.front_prelu, out_bf16=c0, ld_bf16=64)
-            x = self._buf("front_pool", (nf, 22, 22, 64), torch.bfloat16)
-            L.check(lib.avsr_maxpool3x3s2(L.ptr(c0), L.ptr(x), L.ll(nf), 44, 44, 64, L.stream()), "avsr_maxpool3x3s2")
+            halo = self.halo_conv and self.implicit_conv
+            if halo:
+                # padded layout [nf, 23, 24, 64]: the pooled 22 x 22 pixels of a frame, two zero columns per row, one zero row
+                x = self._zbuf("l1_pool", (nf, 23, 24, 64), torch.bfloat16)
+                L.check(lib.avsr_maxpool3x3s2_pitched(L.ptr(c0), L.ptr(x), L.ll(nf), 44, 44, 64, L.ll(24), L.ll(23 * 24), L.stream()),
+                        "avsr_maxpool3x3s2_pitched")
+            else:
+                x = self._buf("front_pool", (nf, 22, 22, 64), torch.bfloat16)
+                L.check(lib.avsr_maxpool3x3s2(L.ptr(c0), L.ptr(x), L.ll(nf), 44, 44, 64, L.stream()), "avsr_maxpool3x3s2")
             if taps is not None:
-                taps.setdefault("frontend3d", []).append(x.clone())
+                taps.setdefault("frontend3d", []).append(x[:, :22, :22].clone())
             H, Cc = 22, 64
+            padded = halo
             for i, blk in enumerate(w.blocks):
-                x, H = self._basic_block(x, nf, H, Cc, blk, str(i & 1))
+                if padded and blk["stride"] == 1 and Cc == 64 and blk["cout"] == 64 and "down_w" not in blk:
+                    x = self._basic_block_halo(x, nf, H, blk, str(i & 1))
+                    continue
+                x, H = self._basic_block(x, nf, H, Cc, blk, str(i & 1), padded=padded)
+                padded = False
                 Cc = blk["cout"]
             L.check(lib.avsr_avgpool(L.ptr(x), L.ptr(feat[f0:]), L.ll(nf), H * H, 512, L.stream()), "avsr_avgpool")
         return feat

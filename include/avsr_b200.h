@@ -98,6 +98,15 @@ int avsr_gemm_bf16_tc(const void* A, long long lda, const void* B, long long ldb
  * src/nets/backend/backbones/resnet.py:30-69. */
 int avsr_conv2d_bf16_tc(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
                         const AvsrEpilogue* ep, avsr_stream_t stream);
+/* The same reading the input image rows / frames at the given pixel pitches (0 = dense), e.g. in place from the padded layout
+ * below. */
+int avsr_conv2d_bf16_tc_pitched(const void* in, const void* Wt, long long F, int H, int W, int C, int Cout, int ks, int stride,
+                                long long in_row_pitch_px, long long in_frame_pitch_px, const AvsrEpilogue* ep, avsr_stream_t stream);
+/* 3x3 / stride 1 / pad 1 convolution 64 -> 64 channels (ResNet layer1, src/nets/backend/backbones/resnet.py:30-69) on the PADDED
+ * layout [F][H + 1][W + 2][64] bf16 whose pad cells are zero: the halo of a 128-pixel tile is one contiguous run of the array,
+ * staged in shared memory once and read by all nine filter taps.  Output / residual of `ep` use the same layout (ld = 64); pad
+ * cells of the output are left untouched.  Wt as for avsr_conv2d_bf16_tc.  Bit-identical to it on the valid pixels. */
+int avsr_conv3x3_halo_bf16(const void* in, const void* Wt, long long F, int H, int W, const AvsrEpilogue* ep, avsr_stream_t stream);
 /* Split-K form for skinny operands: part[z][M][N] fp32 raw partial sums (reduced by avsr_splitk_epilogue). With the
  * "bf16x3" operand layout (avsr_split3 / *_split outputs: [a1|a1|a2|a1|a2|a3] x [w1|w2|w1|w3|w2|w1]) this gives
  * fp32-accurate decoder projections on the tensor cores (src/nets/backend/transformer/decoder_layer.py:58-121). */
@@ -177,6 +186,9 @@ int avsr_frontend_conv3d(const float* video, const int* frame_t, const int* fram
 int avsr_im2col2d(const void* in, void* out, long long F, int H, int W, int C, int ks, int stride, avsr_stream_t stream);
 /* MaxPool3d (1,3,3)/(1,2,2)/(0,1,1) (resnet.py:136) and AdaptiveAvgPool2d(1) (resnet.py:76). */
 int avsr_maxpool3x3s2(const void* in, void* out, long long F, int H, int W, int C, avsr_stream_t stream);
+/* ... writing the Ho x Wo pooled pixels of every frame at the given output pixel pitches (0 = dense). */
+int avsr_maxpool3x3s2_pitched(const void* in, void* out, long long F, int H, int W, int C, long long out_row_pitch_px,
+                              long long out_frame_pitch_px, avsr_stream_t stream);
 int avsr_avgpool(const void* in, void* out, long long F, int HW, int C, avsr_stream_t stream);
 /* audio [B,104,Tpad] fp32 -> packed [F,104] bf16 (the transpose of avhubert.py:196). */
 int avsr_audio_pack(const float* audio, void* out, const int* frame_b, const int* frame_t, long long F, int Cin, int Tpad,

@@ -443,6 +443,53 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
             assert (out[row] - want).abs().max().item() < tol, (b, h)
 
 
+@pytest.mark.parametrize("nf,with_res", [(3, False), (37, True), (300, True)])
+def test_conv3x3_halo_equals_implicit_gemm(L, nf, with_res):
+    """ResNet layer1 convolution on the padded layout (halo staged once, nine taps = nine shifted descriptors of the same tile)
+    against the generic implicit-GEMM convolution on the dense layout: bit-identical on the valid pixels (same tap / k order),
+    pad cells of the output untouched; the pitched max-pool and the pitched convolution read / write that layout in place."""
+    lib = L.load()
+    H = W = 22
+    Hp, Wp = H + 1, W + 2
+    g = torch.Generator().manual_seed(nf)
+    x = torch.randn(nf, H, W, 64, generator=g).bfloat16().cuda()
+    w = (torch.randn(64, 576, generator=g) * 0.05).bfloat16().cuda()
+    bias, slope = torch.randn(64, generator=g).cuda(), torch.rand(64, generator=g).cuda()
+    res = torch.randn(nf, H, W, 64, generator=g).bfloat16().cuda()
+    xp = torch.zeros(nf, Hp, Wp, 64, dtype=torch.bfloat16, device="cuda")
+    xp[:, :H, :W] = x
+    rp = torch.zeros_like(xp)
+    rp[:, :H, :W] = res
+    want = torch.empty(nf * H * W, 64, dtype=torch.bfloat16, device="cuda")
+    kw = dict(bias=bias, act=L.ACT_PRELU, prelu=slope)
+    kw_d = dict(kw, residual=res.view(-1, 64), ldr=64, act_after_residual=True) if with_res else kw
+    kw_p = dict(kw, residual=rp.view(-1, 64), ldr=64, act_after_residual=True) if with_res else kw
+    L.conv2d_bf16(x, w, nf, H, W, 64, 64, 3, 1, L.make_epilogue(out_bf16=want, ld_bf16=64, **kw_d))
+    got = torch.full((nf, Hp, Wp, 64), 3.0, dtype=torch.bfloat16, device="cuda")
+    epp = L.make_epilogue(out_bf16=got.view(-1, 64), ld_bf16=64, **kw_p)
+    L.check(lib.avsr_conv3x3_halo_bf16(L.ptr(xp), L.ptr(w), L.ll(nf), H, W, C.byref(epp), L.stream()), "halo conv")
+    torch.cuda.synchronize()
+    assert torch.equal(got[:, :H, :W].reshape(-1, 64), want)
+    assert (got[:, H] == 3.0).all() and (got[:, :, W:] == 3.0).all()
+    # pitched max-pool writes the padded layout in place; pitched convolution (stride 2, the entry of layer2) reads it in place
+    c0 = torch.randn(nf, 44, 44, 64, generator=g).bfloat16().cuda()
+    dense = torch.empty(nf, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    padded = torch.zeros(nf, Hp, Wp, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.avsr_maxpool3x3s2(L.ptr(c0), L.ptr(dense), L.ll(nf), 44, 44, 64, L.stream()), "maxpool")
+    L.check(lib.avsr_maxpool3x3s2_pitched(L.ptr(c0), L.ptr(padded), L.ll(nf), 44, 44, 64, L.ll(Wp), L.ll(Hp * Wp), L.stream()), "maxpool pitched")
+    torch.cuda.synchronize()
+    assert torch.equal(padded[:, :H, :W], dense) and (padded[:, H] == 0).all() and (padded[:, :, W:] == 0).all()
+    w2 = (torch.randn(128, 576, generator=g) * 0.05).bfloat16().cuda()
+    o_d = torch.empty(nf * 121, 128, dtype=torch.bfloat16, device="cuda")
+    o_p = torch.empty_like(o_d)
+    L.conv2d_bf16(dense, w2, nf, H, W, 64, 128, 3, 2, L.make_epilogue(out_bf16=o_d, ld_bf16=128))
+    ep2 = L.make_epilogue(out_bf16=o_p, ld_bf16=128)
+    L.check(lib.avsr_conv2d_bf16_tc_pitched(L.ptr(padded), L.ptr(w2), L.ll(nf), H, W, 64, 128, 3, 2, L.ll(Wp), L.ll(Hp * Wp), C.byref(ep2), L.stream()),
+            "conv pitched")
+    torch.cuda.synchronize()
+    assert torch.equal(o_d, o_p)
+
+
 @pytest.mark.parametrize("M,N,K,mode", [(12000, 1024, 1024, "res"), (9000, 4096, 512, "gelu"), (5000, 5049, 384, "f32"),
                                         (37889, 1024, 128, "prelu")])
 def test_gemm_cta_pair_kernel(L, M, N, K, mode):

@@ -80,6 +80,30 @@ def test_implicit_posconv_and_frontend_equal_explicit_paths(gpu_model):
     assert (pc_t - pc_f).abs().max().item() < 5e-3 * max(1.0, pc_f.abs().max().item())
 
 
+def test_halo_layer1_equals_dense_layer1(gpu_model):
+    """ResNet layer1 on the padded layout (halo convolution, pitched max-pool, pitched entry of layer2) gives bit-identical trunk
+    features to the dense implicit-GEMM path, on a batch that is not a multiple of anything."""
+    enc = gpu_model.encoder
+    lengths = [77, 5, 40]
+    vids, auds = zip(*[synth.make_inputs(80 + i, t) for i, t in enumerate(lengths)])
+    video = torch.cat([v[0, 0] for v in vids], 0).cuda().contiguous()
+    audio = torch.zeros(3, 104, max(lengths))
+    for b, a in enumerate(auds):
+        audio[b, :, :lengths[b]] = a[0]
+    audio = audio.cuda()
+    outs = {}
+    try:
+        for halo in (True, False):
+            enc.halo_conv = halo
+            taps = {}
+            x = enc.forward_packed(video, audio, lengths, taps)
+            outs[halo] = (torch.cat(taps["frontend3d"], 0).clone(), taps["trunk"].clone(), x.clone())
+    finally:
+        enc.halo_conv = True
+    for a, b, name in zip(outs[True], outs[False], ("pooled frontend", "trunk", "output")):
+        assert torch.equal(a, b), name
+
+
 def _check_nbest(nbest, golden, T, beam):
     yseq, score = golden[f"nbest_T{T}_b{beam}_yseq"], golden[f"nbest_T{T}_b{beam}_score"]
     n = int((score > -1e8).sum())
