@@ -692,15 +692,44 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = tile * BM;
-            const long long px = (long long)m0 + quad * 32 + lane;      // this thread's padded pixel
+        const bool has_res = ep.residual != nullptr;
+        const int col0 = half * 32;                    // BN = 64: one 32-column chunk per warp
+        // this thread's padded pixel of a tile, or -1 for a pad pixel: nothing is read or written there (the pads must stay
+        // zero: they are the halo of their neighbours)
+        auto pixel_of = [&](int tile) -> long long {
+            const long long px = (long long)tile * BM + quad * 32 + lane;
             const int q = (int)(px % fpx);
-            const bool valid = px < total_px && q / Wp < H && q % Wp < W;
-            // pad pixels: nothing is read or written (they must stay zero: they are the halo of their neighbours)
-            const int M_eff = valid ? (int)total_px : 0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-            epilogue_tile<BN, true>(ep, taddr, m0, 0, M_eff, BN, quad, half, lane, colpar + acc * 2 * BN, 0.f, &tfull[acc], acc_phase);
+            return (px < total_px && q / Wp < H && q % Wp < W) ? px : -1;
+        };
+        // the residual of tile i + 1 is requested before tile i is finished: its latency would otherwise be paid once per tile
+        // (one warp finishes one tile at a time; measured 149 us per launch with the residual against 110 us without)
+        float res[32], res_next[32];
+        {
+            const long long px = blockIdx.x < num_tiles ? pixel_of(blockIdx.x) : -1;
+            if (has_res) load_residual(ep, px >= 0 ? (int)px : 0, col0, px >= 0 ? (int)total_px : 0, BN, res);
+        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const long long px = pixel_of(tile);
+            const int M_eff = px >= 0 ? (int)total_px : 0;
+            const int row = px >= 0 ? (int)px : 0;
+            const int nt = tile + gridDim.x;
+            if (has_res && nt < num_tiles) {
+                const long long pn = pixel_of(nt);
+                load_residual(ep, pn >= 0 ? (int)pn : 0, col0, pn >= 0 ? (int)total_px : 0, BN, res_next);
+            }
+            mbar_wait_bounded(&tfull[acc], acc_phase);
+            tc::tc_fence_after();
+            uint32_t r[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + col0, r);
+            tc::tmem_ld_wait();
+            float v[32];
+            const float* cpar = colpar + acc * 2 * BN;
+            epilogue_math(ep, row, M_eff, r, cpar + col0, cpar + BN + col0, 0.f, res, has_res, v);
+            epilogue_store_direct(ep, row, col0, M_eff, BN, v);
+            if (has_res) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) res[j] = res_next[j];
+            }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tempty[acc]);
