@@ -1,6 +1,6 @@
 """Dev aid for ncu: a few launches of the kernels the roofline names, at the bench workload's shapes (no timing claims).
 
-    python tools/profile_kernels.py [ctc] [attn] [gemm] [skinny]
+    python tools/profile_kernels.py [ctc] [attn] [gemm] [skinny] [proj] [front] [posconv] [halo] [encattn]
 """
 import ctypes as C
 import os
@@ -14,7 +14,7 @@ from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
-which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "proj", "front", "posconv"}
+which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "proj", "front", "posconv", "halo", "encattn"}
 B, beam, T, V = 32, 3, 375, 5049
 R = B * beam
 i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
@@ -35,9 +35,11 @@ if "ctc" in which:
     L.check(lib.avsr_ctc_prefix_full_plan(B, V, C.byref(ncg), C.byref(ts)), "plan")
     fpart = torch.empty(B, ts.value, beam, V, device=dev)
     ftick = torch.zeros(B, ncg.value, dtype=torch.int32, device=dev)
+    probs = torch.empty_like(logp)
+    L.check(lib.avsr_ctc_exp_posteriors(L.ptr(logp), L.ll(logp.numel()), L.ptr(probs), L.stream()), "exp")
     for _ in range(3):
         flush.zero_()
-        L.check(lib.avsr_ctc_prefix_full(L.ptr(logp), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, B, 1, L.ptr(last),
+        L.check(lib.avsr_ctc_prefix_full_probs(L.ptr(logp), L.ptr(probs), V, ldp, 0, V - 1, L.ptr(utt_off), L.ptr(utt_T), L.ptr(n_run), beam, B, 1, L.ptr(last),
                                          L.ptr(rprev), L.ptr(r_buf), T, L.ptr(st2), L.ptr(s_prev), L.ptr(scores), L.ptr(fpart),
                                          L.ptr(ftick), L.stream()), "ctc_full")
     torch.cuda.synchronize()
@@ -67,7 +69,9 @@ if "gemm" in which:
     o16 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     ep = L.make_epilogue(bias=bias, act=L.ACT_GELU, out_bf16=o16, ld_bf16=N)
     for _ in range(3):
-        L.gemm_bf16(a, w, M, N, K, ep)
+        L.gemm_bf16(a, w, M, N, K, ep)                     # automatic: the CTA-pair kernel at this size
+    for _ in range(2):
+        L.gemm_bf16(a, w, M, N, K, ep, bn_hint=256)        # the single-CTA kernel, for comparison
     torch.cuda.synchronize()
 
 if "skinny" in which:
@@ -124,5 +128,33 @@ if "posconv" in which:
     ep = L.make_epilogue(bias=pb, act=L.ACT_GELU, residual=h, ldr=1024, out_f32=h, ld_f32=1024)
     for _ in range(2):
         L.check(lib.avsr_posconv_bf16_tc(L.ptr(maps), L.ptr(pw), len(work), L.ptr(wu), L.ptr(wo_), L.ptr(wT), L.ptr(wq), C.byref(ep), L.stream()), "posconv")
+    torch.cuda.synchronize()
+if "halo" in which:
+    nf, H = 2048, 22
+    xp = torch.zeros(nf, H + 1, H + 2, 64, dtype=torch.bfloat16, device=dev)
+    xp[:, :H, :H] = torch.randn(nf, H, H, 64, device=dev).bfloat16()
+    w9 = (torch.randn(64, 576, device=dev) * 0.05).bfloat16()
+    hb, hs = torch.randn(64, device=dev), torch.rand(64, device=dev)
+    out = torch.zeros_like(xp)
+    ep1 = L.make_epilogue(bias=hb, act=L.ACT_PRELU, prelu=hs, out_bf16=out.view(-1, 64), ld_bf16=64)
+    ep2 = L.make_epilogue(bias=hb, act=L.ACT_PRELU, prelu=hs, residual=xp.view(-1, 64), ldr=64, act_after_residual=True, out_bf16=out.view(-1, 64), ld_bf16=64)
+    for ep in (ep1, ep2, ep1, ep2):
+        L.check(lib.avsr_conv3x3_halo_bf16(L.ptr(xp), L.ptr(w9), L.ll(nf), H, H, C.byref(ep), L.stream()), "halo")
+    xd = torch.randn(nf, H, H, 64, device=dev).bfloat16()
+    od = torch.empty(nf * H * H, 64, dtype=torch.bfloat16, device=dev)
+    for _ in range(2):                                     # the generic implicit GEMM on the dense layout, for comparison
+        L.conv2d_bf16(xd, w9, nf, H, H, 64, 64, 3, 1, L.make_epilogue(bias=hb, act=L.ACT_PRELU, prelu=hs, out_bf16=od, ld_bf16=64))
+    torch.cuda.synchronize()
+
+if "encattn" in which:
+    Fr = B * T
+    qk = torch.randn(Fr, 2048, device=dev).bfloat16()
+    vt = torch.randn(1024, Fr + 8, device=dev).bfloat16()
+    o = torch.empty(Fr, 1024, dtype=torch.bfloat16, device=dev)
+    work = [(b * T, T, q0) for b in range(B) for q0 in range(0, T, 128)]
+    wo2, wT2, wq2 = (i32([x[j] for x in work]) for j in range(3))
+    for _ in range(2):
+        L.check(lib.avsr_attention_varlen(L.ptr(qk), L.ptr(vt), L.ll(Fr + 8), L.ptr(o), L.ll(Fr), L.ptr(wo2), L.ptr(wT2), L.ptr(wq2), len(work), T,
+                                          L.stream()), "attention")
     torch.cuda.synchronize()
 print("ok")
