@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "avsr_b200", "libavsr_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-pats = {"UTCHMMA": r"\bUTCHMMA", "LDTM": r"\bLDTM", "UTMALDG": r"\bUTMALDG", "UTMAPF(L2 prefetch)": r"\bUBLKPF|\bUTMAPF", "UTCBAR/commit": r"\bUTCBAR",
+pats = {"UTCHMMA": r"\bUTCHMMA", "LDTM": r"\bLDTM", "UTMALDG": r"\bUTMALDG", "UBLKCP(bulk copy)": r"\bUBLKCP", "UTMAPF(L2 prefetch)": r"\bUBLKPF|\bUTMAPF", "UTCBAR/commit": r"\bUTCBAR",
         "UCGABAR(cluster barrier)": r"\bUCGABAR", "SYNCS(mbarrier)": r"\bSYNCS", "LDGSTS(cp.async)": r"\bLDGSTS",
         "instructions": r"^\s+/\*[0-9a-f]{4,}\*/"}
 cur, counts = None, collections.OrderedDict()
