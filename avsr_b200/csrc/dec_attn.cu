@@ -25,6 +25,7 @@
 //   * The query (and the current k, v) can be taken straight from the split-K partial sums of the projection that produced
 //     them (sum over splits in a fixed order + bias), which saves one epilogue launch per attention.
 //   * The body is instantiated for the exact number of live hyps: no per-hyp guards in the inner loops.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -62,6 +63,7 @@ struct AttnArgs {
     const int* n_run; const int* utt_off; const int* utt_T; int beam; int R; const int* step_p;
     float* out; long long n_frames; __nv_bfloat16* out_split;
     const char* pf; long long pf_bytes;      // span the next kernel of the chain streams (its weights): fetched into L2 from here
+    int kv_ahead;                            // fetch this CTA's remaining K / V into L2 before griddepcontrol.wait (dev knob)
 };
 
 template <int NH>
@@ -438,10 +440,41 @@ dec_attn_stream_kernel(const AttnArgs a) {
 #pragma unroll
         for (int i = 0; i < VR; ++i)
             if (i < nv) cp_async16(vt_s + i * DH * 4, vsrc + i * DH);
+        // the rest of this (utterance, head)'s K / V does not depend on the query either: ask the L2 for it now, while the
+        // query projection this launch waits for is still running and HBM is idle (its weights are a few MB)
+        if (a.kv_ahead && tid < 9 && T_utt > CK) {
+            const unsigned rows = (unsigned)(T_utt - CK);
+            if (tid < 8) {
+                const unsigned n = (rows * 32u) & ~15u;
+                if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kbase + ((long long)tid * nr + CK) * KG), "r"(n) : "memory");
+            } else {
+                for (unsigned o = 0; o < rows * 256u; o += 32768u) {
+                    const unsigned n = min(32768u, rows * 256u - o);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(vbase + (long long)CK * DH) + o), "r"(n) : "memory");
+                }
+            }
+        }
     } else {
         nr = (long long)a.lmax * a.beam;
         kbase = a.kc + (long long)(utt * HEADS + head) * nr * DH;
         vbase = a.vc + (long long)(utt * HEADS + head) * nr * DH;
+        // self-attention: the dense copy of the converged history.  *step_p may still be one position old here (the chain that
+        // advances it is upstream of the wait); it only sizes a prefetch hint
+        if (a.kv_ahead && a.conv_len != nullptr && tid < 9) {
+            const int L = min(*a.step_p, a.lmax);
+            if (L > 0) {
+                const float* kdb0 = a.kd + (long long)(utt * HEADS + head) * a.lmax * DH;
+                const float* vdb0 = a.vd + (long long)(utt * HEADS + head) * a.lmax * DH;
+                if (tid < 8) {
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kdb0 + (long long)tid * a.lmax * KG), "r"((unsigned)L * 32u) : "memory");
+                } else {
+                    for (unsigned o = 0; o < (unsigned)L * 256u; o += 32768u) {
+                        const unsigned n = min(32768u, (unsigned)L * 256u - o);
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(vdb0) + o), "r"(n) : "memory");
+                    }
+                }
+            }
+        }
     }
     pdl_wait();
     if (MODE == 0) dbg_stamp(1);
@@ -584,6 +617,8 @@ extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq,
                      ((uintptr_t)vc & 15) == 0,
                  "avsr_dec_attn_step: q_in / q_bias / vc must be 16-byte aligned, kc 32-byte aligned and ldq a multiple of 4");
     AVSR_REQUIRE(mode == 1 || (long long)lmax * beam < (1 << 24), "avsr_dec_attn_step: cache too long");
+    static int kv_ahead = -1;                // dev knob AVSR_ATTN_KV_AHEAD: bit 0 = source attention, bit 1 = self-attention
+    if (kv_ahead < 0) { const char* e = getenv("AVSR_ATTN_KV_AHEAD"); kv_ahead = e ? atoi(e) : 0; }
     const int nslots = beam <= 4 ? 4 : 8;
     // V tile + (self-attention) the list of distinct history rows, at most lmax * beam entries
     const size_t smem = (size_t)CK * DH * sizeof(float) + (mode == 0 ? (size_t)lmax * nslots * sizeof(unsigned) : 0);
@@ -608,7 +643,7 @@ extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq,
     }
     const dim3 grid(R / beam, HEADS);
     const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, kd, vd, conv_len, n_run, utt_off, utt_T, beam, R, step, out,
-                        n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0};
+                        n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, (kv_ahead >> (mode == 1 ? 0 : 1)) & 1};
     AVSR_CHECK_CUDA(avsr_launch_pdl(kern, grid, dim3(CK), smem, stream, a));
     return AVSR_OK;
 }

@@ -48,6 +48,48 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, int N, const float*
     }
 }
 
+// N = 1024 (every LayerNorm of the transformer): one WARP per row, the row lives in registers (8 float4 per lane), both
+// reductions are warp shuffles: no shared memory, no block barriers.  The one-CTA-per-row kernel below pays three barrier phases
+// per row and ran at 26 us per 12 000 rows (74 MB: 2.8 TB/s); this one is a plain streaming kernel.
+__global__ void __launch_bounds__(256)
+layernorm1024_kernel(const float* __restrict__ x, long long ldx, long long rows, const float* __restrict__ g, const float* __restrict__ b,
+                     float eps, __nv_bfloat16* __restrict__ out_bf16, long long ld_bf16, float* __restrict__ out_f32, long long ld_f32) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * ldx;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(xr + i * 128 + lane * 4));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.f / 1024.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / 1024.f) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = i * 128 + lane * 4;
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+        const float o0 = (v[i].x - mean) * rstd * gg.x + bb.x, o1 = (v[i].y - mean) * rstd * gg.y + bb.y;
+        const float o2 = (v[i].z - mean) * rstd * gg.z + bb.z, o3 = (v[i].w - mean) * rstd * gg.w + bb.w;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * ld_f32 + c) = make_float4(o0, o1, o2, o3);
+        if (out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(out_bf16 + row * ld_bf16 + c) = pk;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ frontend 3D conv im2col
 // video fp32 [F,88,88] (packed frames) -> A [F*44*44, 256] bf16, k = (dt*7 + dy)*7 + dx for the 5x7x7 patch
 // (stride 1x2x2, pad 2x3x3), columns 245..255 zero.  One CTA per (frame, output row).
@@ -236,8 +278,15 @@ extern "C" int avsr_layernorm(const float* x, long long ldx, long long rows, int
     AVSR_REQUIRE(x && gamma && beta && rows > 0 && N > 0 && (N & 3) == 0 && (ldx & 3) == 0 && N * 4 <= 48 * 1024,
                  "avsr_layernorm: bad arguments (rows=%lld N=%d)", rows, N);
     AVSR_REQUIRE(out_bf16 || out_f32, "avsr_layernorm: no output");
-    layernorm_kernel<<<(unsigned)rows, 256, (size_t)N * 4, stream>>>(x, ldx, N, gamma, beta, eps, (__nv_bfloat16*)out_bf16, ld_bf16,
-                                                                    out_f32, ld_f32);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                           reinterpret_cast<uintptr_t>(out_f32)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 &&
+                         (ld_f32 & 3) == 0 && (ld_bf16 & 3) == 0;
+    if (N == 1024 && aligned)
+        layernorm1024_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, ldx, rows, gamma, beta, eps, (__nv_bfloat16*)out_bf16, ld_bf16,
+                                                                           out_f32, ld_f32);
+    else
+        layernorm_kernel<<<(unsigned)rows, 256, (size_t)N * 4, stream>>>(x, ldx, N, gamma, beta, eps, (__nv_bfloat16*)out_bf16, ld_bf16,
+                                                                        out_f32, ld_f32);
     AVSR_LAUNCH_CHECK();
     return AVSR_OK;
 }

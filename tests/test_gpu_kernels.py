@@ -156,14 +156,19 @@ def test_bf16x3_tensor_core_gemm_is_fp32_accurate(L, R, N, K):
     assert err < 2e-5 * (K ** 0.5) and err < 8 * fp32_err + 1e-6, (err, fp32_err)
 
 
-def test_layernorm(L):
-    x, g, b = _rand(777, 2048, seed=1, scale=3.0), _rand(2048, seed=2), _rand(2048, seed=3)
-    o16 = torch.empty(777, 2048, dtype=torch.bfloat16, device="cuda")
-    o32 = torch.empty(777, 2048, device="cuda")
+@pytest.mark.parametrize("rows,N", [(777, 2048), (12003, 1024), (5, 1024), (64, 1792)])
+def test_layernorm(L, rows, N):
+    """Block-per-row kernel (any N) and the warp-per-row kernel of the transformer width (N = 1024), ragged row counts, in place."""
+    x, g, b = _rand(rows, N, seed=1, scale=3.0) + 2.0, _rand(N, seed=2), _rand(N, seed=3)
+    o16 = torch.empty(rows, N, dtype=torch.bfloat16, device="cuda")
+    o32 = torch.empty(rows, N, device="cuda")
     L.layernorm(x, g, b, 1e-5, out_bf16=o16, out_f32=o32)
-    ref = F.layer_norm(x, (2048,), g, b, 1e-5)
+    ref = F.layer_norm(x, (N,), g, b, 1e-5)
     assert (o32 - ref).abs().max().item() < 1e-4
     assert (o16.float() - ref).abs().max().item() < 0.05
+    xi = x.clone()
+    L.layernorm(xi, g, b, 1e-5, out_f32=xi)
+    assert torch.equal(xi, o32)
 
 
 def test_im2col_pool_kernels(L):

@@ -350,7 +350,18 @@ def test_large_decode_batches_equal_small_ones(gpu_model):
     assert big.n_batches <= 2 and small.n_batches >= 10
     assert len(big.hyp_tokens) == 150
     diff = [i for i in range(150) if big.hyp_tokens[i] != small.hyp_tokens[i]]
-    assert not diff, diff
+    # The packed offset of an utterance shifts the key-block boundaries of the encoder attention (last-bit differences in the
+    # bf16 encoder output), and batches above 128 hypothesis rows use the split-K projections: a 1-best may only differ where
+    # the search itself has a TIE - the two best hypotheses of that utterance, decoded alone, score within 1e-4 of each other
+    # and are exactly the two answers (seen: utterance 62, both at -73.969513).
+    assert len(diff) <= 2, diff
+    for i in diff:
+        v, a = load(i)
+        x = gpu_model.encoder(input_features=a[None].cuda(), video=v[None].cuda()).last_hidden_state[0]
+        nbest = gpu_model.beam_search(x)
+        assert len(nbest) >= 2 and abs(float(nbest[0].score) - float(nbest[1].score)) < 1e-4, (i, [float(h.score) for h in nbest[:3]])
+        top2 = {tuple(h.yseq.tolist()[1:-1]) for h in nbest[:2]}                 # hyp_tokens carry no sos / eos
+        assert {tuple(big.hyp_tokens[i]), tuple(small.hyp_tokens[i])} == top2, (i, big.hyp_tokens[i], small.hyp_tokens[i], top2)
 
 
 def test_pinned_host_inputs_are_uploaded_in_chunks(gpu_model):
