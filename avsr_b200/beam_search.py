@@ -120,6 +120,10 @@ class BatchedBeamSearch:
         # two concurrent chains measured SLOWER (449 vs 373 ms per 32-utterance pass; 3 groups 524, 4 groups 587): the
         # projection launches of the chains each want one CTA with ~200 KB of shared memory on every SM and serialise.
         self.n_groups = max(1, int(os.environ.get("AVSR_DECODE_GROUPS", "1")))
+        # AVSR_FUSE_STEP=1: the fusion kernel also closes the position (53 launches per position instead of 54).  Measured neutral
+        # (295.0 vs 294.6 ms per pass): the one-thread step kernel already overlaps its neighbours through programmatic dependent
+        # launch, so the default stays the separate launch.
+        self.fuse_step = os.environ.get("AVSR_FUSE_STEP", "0") != "0"
         L.load()
         if self.proj == "cluster" and (self.n_groups > 1 or "AVSR_SM_BUDGET" in os.environ):
             # concurrent chains: plan every projection for its share of the SMs so that the chains' clusters are co-resident
@@ -166,6 +170,7 @@ class BatchedBeamSearch:
         s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
         s["utt_T"], s["utt_off"], s["utt_maxlen"] = i32(B), i32(B), i32(B)
         s["step"], s["any_running"] = i32(1), i32(1)
+        s["ticket"] = i32(1)                       # avsr_beam_fuse_topk_advance_step: CTAs that have finished the position
         # host copies of any_running (asynchronous poll, double-buffered: a flag is read one replay late)
         s["poll"] = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
         s["poll_event"] = [torch.cuda.Event(), torch.cuda.Event()]
@@ -391,6 +396,12 @@ class BatchedBeamSearch:
                                   L.ptr(s["rprev_idx"]), L.ptr(s["r_buf"]), s["tmax"], L.ptr(s["step"]), L.ptr(s["psi"]),
                                   L.ptr(s["rsum_last"]), st()), "avsr_dec_tail")
         if "advance" in self._skip:
+            return
+        if self.fuse_step:
+            # fusion / top-k / bookkeeping AND the end of the position (liveness count, step + 1) in one launch
+            L.check(lib.avsr_beam_fuse_topk_advance_step(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
+                                                         L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc),
+                                                         L.ptr(s["any_running"]), L.ptr(s["ticket"]), st()), "avsr_beam_fuse_topk_advance_step")
             return
         L.check(lib.avsr_beam_fuse_topk_advance(C.byref(s["state"]), L.ptr(s["dec_logp"]), L.ptr(s["part_ids"]), L.ptr(s["psi"]),
                                                 L.ptr(s["rsum_last"]), C.c_float(self.w_dec), C.c_float(self.w_ctc), st()),
@@ -652,7 +663,7 @@ class BatchedBeamSearch:
             ml[:nb] = maxlens
         s["utt_maxlen"].copy_(torch.from_numpy(ml))
         s["n_utts"] = nb
-        for k in ("step", "any_running", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev", "conv_len"):
+        for k in ("step", "any_running", "ticket", "rprev_idx", "n_ended", "done", "overflow", "score", "dec_sc", "ctc_sc", "s_prev", "conv_len"):
             s[k].zero_()
         if self.ctc_only:
             s["psi"].zero_()                          # log_psi of the empty prefix

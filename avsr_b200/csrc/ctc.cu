@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(256)
 beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ dec_logp, const int* __restrict__ part_ids,
                               const float* __restrict__ psi, const float* __restrict__ rsum_last, float w_dec, float w_ctc,
                               const float* __restrict__ ctc_full, int* __restrict__ rc_last, int* __restrict__ rc_chain,
-                              int* __restrict__ rc_tok) {
+                              int* __restrict__ rc_tok, int* __restrict__ any_running, int* __restrict__ ticket) {
     __shared__ float cval[256 * MAXB];
     __shared__ int cidx[256 * MAXB];
     __shared__ float redv[8];
@@ -639,10 +639,24 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
     pdl_trigger();
     pdl_wait();
     const int nrun = st.n_run[b];
-    if (nrun == 0) return;
+    const int step = *st.step;
+    // any_running != NULL: this launch also closes the position (what avsr_beam_step_advance does in a launch of its own): the
+    // LAST CTA to get here counts the utterances that still run and advances *step; every CTA has read *step by then
+    auto close_position = [&]() {
+        if (any_running == nullptr || threadIdx.x != 0) return;
+        __threadfence();                               // this CTA's n_run is visible before its ticket
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            *ticket = 0;                               // re-armed for the next position
+            __threadfence();
+            int live = 0;
+            for (int u = 0; u < st.B; ++u) live += __ldcg(st.n_run + u) > 0;
+            *any_running = live;
+            *const_cast<int*>(st.step) = step + 1;      // the struct carries it read-only for everybody else
+        }
+    };
+    if (nrun == 0) { close_position(); return; }
     const int beam = st.beam, V = st.V, S = st.S;
     const int base = b * beam;
-    const int step = *st.step;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- fast path.  Only the pre-beam candidates and eos have a CTC score other than logzero (batch_beam_search.py:229-247:
@@ -852,6 +866,7 @@ beam_fuse_topk_advance_kernel(const AvsrBeamState st, const float* __restrict__ 
         if (tid == 0) a_new[(long long)(base + r) * st.lmax + step] = (unsigned char)par;
     }
     for (int r = tid; r < beam; r += 256) st.row_active[base + r] = r < cnt ? 1 : 0;
+    close_position();                                  // thread 0 wrote n_run[b] above, in program order
 }
 
 // Dense score matrix of one CTCPrefixScoreTH.__call__ in pre-beam mode, as the scorer plug-in API has to return it
@@ -1038,7 +1053,22 @@ extern "C" int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float*
     AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0, "avsr_beam_fuse_topk_advance: beam %d unsupported (max %d)", st->beam, MAXB);
     AVSR_REQUIRE(st->beam <= 255, "avsr_beam_fuse_topk_advance: ancestry slots are 8-bit");
     AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, part_ids, psi, rsum_last,
-                                    w_dec, w_ctc, (const float*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr));
+                                    w_dec, w_ctc, (const float*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr,
+                                    (int*)nullptr));
+    return AVSR_OK;
+}
+
+// The same, also closing the position in this launch (avsr_beam_step_advance folded in: one launch less per position):
+// *any_running = utterances still running, *st->step += 1, done by the last CTA to finish; `ticket` = one int32, zero before the
+// first call (the kernel re-arms it).
+extern "C" int avsr_beam_fuse_topk_advance_step(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,
+                                                const float* rsum_last, float w_dec, float w_ctc, int* any_running, int* ticket,
+                                                cudaStream_t stream) {
+    AVSR_REQUIRE(st && dec_logp && part_ids && psi && rsum_last && any_running && ticket, "avsr_beam_fuse_topk_advance_step: null argument");
+    AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0, "avsr_beam_fuse_topk_advance: beam %d unsupported (max %d)", st->beam, MAXB);
+    AVSR_REQUIRE(st->beam <= 255, "avsr_beam_fuse_topk_advance: ancestry slots are 8-bit");
+    AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, part_ids, psi, rsum_last,
+                                    w_dec, w_ctc, (const float*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, any_running, ticket));
     return AVSR_OK;
 }
 
@@ -1054,7 +1084,8 @@ extern "C" int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const f
     AVSR_REQUIRE(st->beam >= 1 && st->beam <= MAXB && st->B > 0 && st->S == 1, "avsr_beam_fuse_topk_advance_full: beam %d / S %d unsupported",
                  st->beam, st->S);
     AVSR_CHECK_CUDA(avsr_launch_pdl(beam_fuse_topk_advance_kernel, dim3(st->B), dim3(256), 0, stream, *st, dec_logp, (const int*)nullptr,
-                                    (const float*)nullptr, (const float*)nullptr, w_dec, w_ctc, ctc_full, rc_last, rc_chain, rc_tok));
+                                    (const float*)nullptr, (const float*)nullptr, w_dec, w_ctc, ctc_full, rc_last, rc_chain, rc_tok,
+                                    (int*)nullptr, (int*)nullptr));
     return AVSR_OK;
 }
 

@@ -307,6 +307,11 @@ int avsr_beam_fuse_topk_advance(const AvsrBeamState* st, const float* dec_logp, 
  * inputs of the avsr_ctc_prefix_prebeam (S = 1) call that recomputes its forward variables.  The state must have S = 1. */
 int avsr_beam_fuse_topk_advance_full(const AvsrBeamState* st, const float* dec_logp, const float* ctc_full, float w_dec, float w_ctc,
                                      int* rc_last, int* rc_chain, int* rc_tok, avsr_stream_t stream);
+/* avsr_beam_fuse_topk_advance + avsr_beam_step_advance in one launch: the last CTA to finish sets *any_running and advances
+ * *st->step.  ticket: one int32 in device memory, zero before the first call. */
+int avsr_beam_fuse_topk_advance_step(const AvsrBeamState* st, const float* dec_logp, const int* part_ids, const float* psi,
+                                     const float* rsum_last, float w_dec, float w_ctc, int* any_running, int* ticket,
+                                     avsr_stream_t stream);
 int avsr_beam_step_advance(int* step, const int* n_run, int B, int* any_running, avsr_stream_t stream);
 
 /* ---- input pipeline: the data format on the input side of the path (src/dataset/avhubert_dataset.py) -------------- */
