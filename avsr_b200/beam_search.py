@@ -124,6 +124,9 @@ class BatchedBeamSearch:
         # (295.0 vs 294.6 ms per pass): the one-thread step kernel already overlaps its neighbours through programmatic dependent
         # launch, so the default stays the separate launch.
         self.fuse_step = os.environ.get("AVSR_FUSE_STEP", "0") != "0"
+        # query merge: the source-attention query projection of layers 1 .. 5 rides along with q | k | v and the attention-output
+        # projection (7 launches per layer instead of 8); AVSR_QUERY_MERGE=0 = its own launch
+        self.query_merge = os.environ.get("AVSR_QUERY_MERGE", "1") != "0"
         L.load()
         if self.proj == "cluster" and (self.n_groups > 1 or "AVSR_SM_BUDGET" in os.environ):
             # concurrent chains: plan every projection for its share of the SMs so that the chains' clusters are co-resident
@@ -170,7 +173,8 @@ class BatchedBeamSearch:
         s = dict(B=B, R=R, tmax=tmax, lmax=lmax, F=F)
         s["utt_T"], s["utt_off"], s["utt_maxlen"] = i32(B), i32(B), i32(B)
         s["step"], s["any_running"] = i32(1), i32(1)
-        s["ticket"] = i32(1)                       # avsr_beam_fuse_topk_advance_step: CTAs that have finished the position
+        s["ticket"] = i32(1)
+        s["tq"] = f32(R, 1024)                     # query merge: x (g2 . Wq)^T of the layer input, waiting for the attention-output projection                       # avsr_beam_fuse_topk_advance_step: CTAs that have finished the position
         # host copies of any_running (asynchronous poll, double-buffered: a flag is read one replay late)
         s["poll"] = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
         s["poll_event"] = [torch.cuda.Event(), torch.cuda.Event()]
@@ -523,25 +527,46 @@ class BatchedBeamSearch:
                 "avsr_dec_embed_ln")
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93): q | k | v finished by the projection, bias included
-            if li == 0:
+            merge = fold and self.query_merge and li > 0 and "gemm" not in self._skip
+            if merge:
+                # q | k | v of LayerNorm1(x) and, riding along, tq = x (g2 . Wq)^T for the source-attention query
+                pf = lay["wcat2_3"] if self.weight_prefetch else None
+                L.check(lib.avsr_dec_proj_dual(L.ptr(s["x3"]), L.ll(3 * 1024), L.ptr(s["stats"]), C.c_float(1e-12), L.ptr(lay["ucat1"]),
+                                               L.ptr(lay["ccat1"]), L.ptr(lay["wcat1_3"]), L.ll(3 * 1024), R, 4096, 1024, 3072, L.ACT_NONE,
+                                               None, L.ll(1024), L.ptr(s["qkv"]), L.ll(3072), None, L.ll(1024), L.ptr(s["tq"]), L.ll(1024),
+                                               None, L.ptr(pf), L.ll(pf.numel() * pf.element_size() if pf is not None else 0), st()),
+                        "avsr_dec_proj_dual(qkv)")
+            elif li == 0:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, a3=s["a3"], bias=lay["bqkv"], out=s["qkv"])
             elif fold:
                 self._cfold(s, lay["wqkv3g"], lay["uqkv"], lay["cqkv"], 3072, out=s["qkv"])
             else:
                 self._cproj(s, lay["wqkv3"], 3072, 1024, ln=(lay["n1_g"], lay["n1_b"]), bias=lay["bqkv"], out=s["qkv"])
-            self._cattn(s, 0, s["qkv"], 3072, s["kc"][li], s["vc"][li], dense, li, lay["wo3"])
+            self._cattn(s, 0, s["qkv"], 3072, s["kc"][li], s["vc"][li], dense, li, lay["wcat2_3"] if merge else lay["wo3"])
             if self.kv_prefetch_mb > 0:
                 ckv = s["ckv_t"][li]
                 nbytes = min(int(self.kv_prefetch_mb * (1 << 20)), ckv.numel() * 4) // 16 * 16
                 L.check(lib.avsr_dec_proj_also_prefetch(L.ptr(ckv), L.ll(nbytes)), "avsr_dec_proj_also_prefetch")
                 L.launch_count -= 1
-            self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
-                        nxt=lay["wq23g"] if fold else lay["wq23"])
-            # source attention (decoder_layer.py:97-107)
-            if fold:
-                self._cfold(s, lay["wq23g"], lay["uq2"], lay["cq2"], 1024, out=s["q2"])
+            if merge:
+                # x += att Wo^T + bo (with the LayerNorm2 statistics) and q2raw = tq + att ((g2 . Wq) Wo)^T + (g2 . Wq) bo; the
+                # source attention applies the LayerNorm's rstd / mean to q2raw itself
+                L.check(lib.avsr_dec_proj_dual(L.ptr(s["att3"]), L.ll(3 * 1024), None, C.c_float(1e-12), None, L.ptr(lay["bcat2"]),
+                                               L.ptr(lay["wcat2_3"]), L.ll(3 * 1024), R, 2048, 1024, 1024, L.ACT_NONE, L.ptr(s["x"]), L.ll(1024),
+                                               L.ptr(s["x"]), L.ll(1024), L.ptr(s["tq"]), L.ll(1024), L.ptr(s["q2"]), L.ll(1024),
+                                               L.ptr(s["stats"]), None, L.ll(0), st()), "avsr_dec_proj_dual(out)")
+                if "cross" not in self._skip:
+                    L.check(lib.avsr_dec_attn_fold_query(L.ptr(s["stats"]), L.ptr(lay["uq2"]), L.ptr(lay["cq2"]), C.c_float(1e-12)),
+                            "avsr_dec_attn_fold_query")
+                    L.launch_count -= 1
             else:
-                self._cproj(s, lay["wq23"], 1024, 1024, ln=(lay["n2_g"], lay["n2_b"]), bias=lay["bq2"], out=s["q2"])
+                self._cproj(s, lay["wo3"], 1024, 1024, a3=s["att3"], bias=lay["bo"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
+                            nxt=lay["wq23g"] if fold else lay["wq23"])
+                # source attention (decoder_layer.py:97-107)
+                if fold:
+                    self._cfold(s, lay["wq23g"], lay["uq2"], lay["cq2"], 1024, out=s["q2"])
+                else:
+                    self._cproj(s, lay["wq23"], 1024, 1024, ln=(lay["n2_g"], lay["n2_b"]), bias=lay["bq2"], out=s["q2"])
             self._cattn(s, 1, s["q2"], 1024, s["ckv_t"][li, 0], s["ckv_t"][li, 1], dense, li, lay["wo23"])
             self._cproj(s, lay["wo23"], 1024, 1024, a3=s["att3"], bias=lay["bo2"], residual=s["x"], out=s["x"], split=x3, stats_out=True,
                         nxt=lay["w13g"] if fold else lay["w13"])
@@ -552,6 +577,8 @@ class BatchedBeamSearch:
                 self._cproj(s, lay["w13"], 3072, 1024, ln=(lay["n3_g"], lay["n3_b"]), bias=lay["b1"], act=L.ACT_RELU, split=s["ffn3"], nxt=lay["w23"])
             if li + 1 < nl:
                 nxt = w.layers[li + 1]["wqkv3g"] if fold else w.layers[li + 1]["wqkv3"]
+                if fold and self.query_merge:
+                    nxt = w.layers[li + 1]["wcat1_3"]
             else:
                 nxt = w.out_w3g if fold else w.out_w3
             if self.self_kv_prefetch and dense and li + 1 < nl:

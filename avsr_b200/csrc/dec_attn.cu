@@ -64,6 +64,10 @@ struct AttnArgs {
     float* out; long long n_frames; __nv_bfloat16* out_split;
     const char* pf; long long pf_bytes;      // span the next kernel of the chain streams (its weights): fetched into L2 from here
     int kv_ahead;                            // fetch this CTA's remaining K / V into L2 before griddepcontrol.wait (dev knob)
+    // source attention whose query projection was merged into the previous projections ("query merge"): q_in holds
+    // x (gamma . Wq)^T of the layer-normed row WITHOUT the LayerNorm; the kernel finishes it, q = rstd (q_in - mean u) + c, from
+    // the row's tile statistics q_stats [8][R][2] (mean, M2 per 128 columns, as avsr_dec_proj writes them)
+    const float* q_stats; const float* q_u; const float* q_c; float q_eps;
 };
 
 template <int NH>
@@ -495,6 +499,25 @@ dec_attn_stream_kernel(const AttnArgs a) {
         if (tid / (DH / 4) < a.beam) {
             pre[0] = *reinterpret_cast<const float4*>(qp);
             if (MODE == 0) { pre[1] = *reinterpret_cast<const float4*>(qp + D); pre[2] = *reinterpret_cast<const float4*>(qp + 2 * D); }
+            if (MODE == 1 && a.q_stats != nullptr) {
+                // same round trip: the row's eight tile statistics and this group's fold vectors
+                const int row = utt * a.beam + tid / (DH / 4), col = head * DH + 4 * (tid % (DH / 4));
+                float2 st[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) st[u] = __ldcg(reinterpret_cast<const float2*>(a.q_stats + ((long long)u * a.R + row) * 2));
+                const float4 u4 = __ldg(reinterpret_cast<const float4*>(a.q_u + col));
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.q_c + col));
+                float ms = 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ms += st[u].x;
+                const float mean = ms * 0.125f;
+                float m2 = 0.f;                      // Chan's merge of the equal-sized tiles, in tile order
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const float d = st[u].x - mean; m2 += st[u].y + 128.f * d * d; }
+                const float rstd = rsqrtf(m2 * (1.f / 1024.f) + a.q_eps);
+                pre[0].x = rstd * (pre[0].x - mean * u4.x) + c4.x; pre[0].y = rstd * (pre[0].y - mean * u4.y) + c4.y;
+                pre[0].z = rstd * (pre[0].z - mean * u4.z) + c4.z; pre[0].w = rstd * (pre[0].w - mean * u4.w) + c4.w;
+            }
         }
     }
     if (nh == 0) { cp_async_wait_all(); return; }
@@ -600,6 +623,22 @@ dec_cache_promote_kernel(const float* __restrict__ kc, const float* __restrict__
 // kd / vd / conv_len (mode 0, optional): dense caches of the converged history prefix maintained by avsr_dec_cache_promote,
 //   key element (utt, head, pos, d) at ((utt*16 + head)*8 + d/8)*lmax*8 + pos*8 + d%8, value element at
 //   ((utt*16 + head)*lmax + pos)*64 + d; conv_len [2][R/beam], the kernel reads conv_len[(*step + 1) & 1][utt].
+namespace {
+const float* g_q_stats = nullptr;
+const float* g_q_u = nullptr;
+const float* g_q_c = nullptr;
+float g_q_eps = 0.f;
+}  // namespace
+
+// The NEXT source-attention launch (mode 1, finished-row query) receives its query WITHOUT the LayerNorm of the row it was
+// projected from and finishes it itself: q = rstd (q_in - mean u) + c with (mean, rstd) from stats [8][R][2] (tile statistics of
+// the 1024-wide row, avsr_dec_proj's stats_out), u / c [1024] = weights.fold_layernorm's vectors.  One-shot.
+extern "C" int avsr_dec_attn_fold_query(const float* stats, const float* u, const float* c, float eps) {
+    if (stats != nullptr && (!u || !c || (((uintptr_t)stats & 7) | ((uintptr_t)u & 15) | ((uintptr_t)c & 15)) != 0)) return AVSR_ERR_ARG;
+    g_q_stats = stats; g_q_u = u; g_q_c = c; g_q_eps = eps;
+    return AVSR_OK;
+}
+
 extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                                      const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam,
                                      int R, const int* step, float* out, long long n_frames, void* out_split, const float* kd,
@@ -643,7 +682,9 @@ extern "C" int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq,
     }
     const dim3 grid(R / beam, HEADS);
     const AttnArgs a = {q_in, ldq, nsplit, q_bias, kc, vc, anc, lmax, kd, vd, conv_len, n_run, utt_off, utt_T, beam, R, step, out,
-                        n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, (kv_ahead >> (mode == 1 ? 0 : 1)) & 1};
+                        n_frames, (__nv_bfloat16*)out_split, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, (kv_ahead >> (mode == 1 ? 0 : 1)) & 1,
+                        g_q_stats, g_q_u, g_q_c, g_q_eps};
+    g_q_stats = nullptr;                              // one-shot (avsr_dec_attn_fold_query)
     AVSR_CHECK_CUDA(avsr_launch_pdl(kern, grid, dim3(CK), smem, stream, a));
     return AVSR_OK;
 }

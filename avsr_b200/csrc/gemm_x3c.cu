@@ -86,6 +86,9 @@ struct ProjArgs {
     // dense self-attention caches of the layer whose attention runs two launches from now (avsr_dec_proj_prefetch_self_kv):
     // positions [0, *step) of every (utterance, head) are fetched into L2 after this kernel's griddepcontrol.wait
     const float* skd; const float* svd; int s_lmax, s_nuh; const int* s_step;
+    // second column range (avsr_dec_proj_dual): output features [n1, N) go to out2 / take residual2 (both indexed from column
+    // n1 on) and get neither the folded LayerNorm nor statistics / a bf16x3 copy; n1 = 0: one range.  n1 % 128 == 0.
+    int n1; const float* residual2; long long ldr2; float* out2; long long ldo2;
 };
 
 // three bf16 terms of 8 consecutive fp32 values -> one 16-byte chunk per term
@@ -373,17 +376,27 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const int fcol = m0 + lane * 4;                // this lane's four output features
         // vector path: N and the pitches are multiples of 4, so a group of four features is in or out as a whole; otherwise
         // (the output layer, N = 5049 with dense rows) every element is guarded and stored on its own
-        const bool vec = (N & 3) == 0 && (p.ldo & 3) == 0 && (p.ldr & 3) == 0;
+        const bool second = p.n1 > 0 && m0 >= p.n1;    // tile-uniform: which column range this tile belongs to
+        const float* const residual = second ? p.residual2 : p.residual;
+        const long long ldr = second ? p.ldr2 : p.ldr;
+        float* const out = second ? p.out2 : p.out;
+        const long long ldo = second ? p.ldo2 : p.ldo;
+        const int cb = second ? p.n1 : 0;              // first column of the range's own buffers
+        const int nsw = p.n1 > 0 ? p.n1 : N;           // row width of the bf16x3 copy (first range only)
+        const float* const fold_u = second ? nullptr : p.fold_u;
+        __nv_bfloat16* const split_out = second ? nullptr : p.split_out;
+        float* const stats_out = second ? nullptr : p.stats_out;
+        const bool vec = (N & 3) == 0 && (ldo & 3) == 0 && (ldr & 3) == 0;
         const bool fok = fcol < N;
         const uint32_t red_s = tc::smem_u32(red);
         float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.fold_u != nullptr && fok) {
-            if (vec) u4 = __ldg(reinterpret_cast<const float4*>(p.fold_u + fcol));
+        if (fold_u != nullptr && fok) {
+            if (vec) u4 = __ldg(reinterpret_cast<const float4*>(fold_u + fcol));
             else {
-                u4.x = __ldg(p.fold_u + fcol);
-                if (fcol + 1 < N) u4.y = __ldg(p.fold_u + fcol + 1);
-                if (fcol + 2 < N) u4.z = __ldg(p.fold_u + fcol + 2);
-                if (fcol + 3 < N) u4.w = __ldg(p.fold_u + fcol + 3);
+                u4.x = __ldg(fold_u + fcol);
+                if (fcol + 1 < N) u4.y = __ldg(fold_u + fcol + 1);
+                if (fcol + 2 < N) u4.z = __ldg(fold_u + fcol + 2);
+                if (fcol + 3 < N) u4.w = __ldg(fold_u + fcol + 3);
             }
         }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -399,8 +412,8 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         for (int r = r_lo + ew; r < r_hi; r += 4) {
             const int row = n0 + r;
             float4 res4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.residual != nullptr && fok) {
-                const float* rp = p.residual + (long long)row * p.ldr + fcol;
+            if (residual != nullptr && fok) {
+                const float* rp = residual + (long long)row * ldr + (fcol - cb);
                 if (vec) res4 = __ldcg(reinterpret_cast<const float4*>(rp));
                 else {
                     res4.x = __ldcg(rp);
@@ -418,7 +431,7 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
             for (int z = 0; z < MAX_CLUSTER; ++z)
                 if (z < (int)csize) { v.x += t[z].x; v.y += t[z].y; v.z += t[z].z; v.w += t[z].w; }       // split order: deterministic
-            if (p.fold_u != nullptr) {
+            if (fold_u != nullptr) {
                 // LayerNorm of the operand row, applied to the finished sums (see ProjArgs): merge the row's tile statistics
                 // in tile order (lanes 0 .. K/128-1 hold one tile each; xor-shuffle trees are order-independent per lane count)
                 const int nt = K / 128;
@@ -435,8 +448,8 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (p.act == AVSR_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             v.x += res4.x; v.y += res4.y; v.z += res4.z; v.w += res4.w;
             if (fok) {
-                if (p.out != nullptr) {
-                    float* op = p.out + (long long)row * p.ldo + fcol;
+                if (out != nullptr) {
+                    float* op = out + (long long)row * ldo + (fcol - cb);
                     if (vec) *reinterpret_cast<float4*>(op) = v;
                     else {
                         op[0] = v.x;
@@ -445,13 +458,13 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         if (fcol + 3 < N) op[3] = v.w;
                     }
                 }
-                if (p.split_out != nullptr) avsr_split3c_store4(p.split_out + (long long)row * 3 * N, N, fcol, v);
+                if (split_out != nullptr) avsr_split3c_store4(split_out + (long long)row * 3 * nsw, nsw, fcol, v);
             }
-            if (p.stats_out != nullptr) {              // N % 128 == 0 here: every lane holds valid features
+            if (stats_out != nullptr) {                // N % 128 == 0 here: every lane holds valid features
                 const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
                 const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
                 const float m2 = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
-                if (lane == 0) *reinterpret_cast<float2*>(p.stats_out + ((long long)blockIdx.x * R + row) * 2) = make_float2(mean, m2);
+                if (lane == 0) *reinterpret_cast<float2*>(stats_out + ((long long)blockIdx.x * R + row) * 2) = make_float2(mean, m2);
             }
         }
     }
@@ -616,10 +629,13 @@ extern "C" int avsr_dec_proj_prefetch_self_kv(const float* kd, const float* vd, 
 //   outputs:    out [R, N] fp32 (pitch ldo) and / or split_out [R, 3N] compact bf16x3; stats_out [N/128][R][2] (N % 128 == 0)
 //               for a later LayerNorm-mode call.  residual may alias out (each element is read and written by one thread).
 //   l2_prefetch: optional span (the weights of the NEXT projection of the chain) that the kernel asks the L2 to fetch.
+struct DualRange { int n1; const float* residual2; long long ldr2; float* out2; long long ldo2; };
+
 static int dec_proj_launch(const void* A3, long long lda, const float* x, long long ldx, const float* stats_in, const float* ln_g,
                              const float* ln_b, float ln_eps, const float* fold_u, const void* W3, long long ldw, int R, int N, int K, const float* bias, int act,
                              const float* residual, long long ldr, float* out, long long ldo, void* split_out, float* stats_out,
-                             const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream) {
+                             const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream,
+                             const DualRange dual = DualRange{0, nullptr, 0, nullptr, 0}) {
     AVSR_REQUIRE(W3 && R > 0 && N > 0 && K > 0 && (K % BK) == 0, "avsr_dec_proj: bad shape R=%d N=%d K=%d (K must be a multiple of 64)", R, N, K);
     AVSR_REQUIRE(!split_out || (N & 3) == 0, "avsr_dec_proj: split_out needs N %% 4 == 0");
     AVSR_REQUIRE((A3 != nullptr) != (x != nullptr), "avsr_dec_proj: exactly one of A3 (bf16x3 rows) and x (LayerNorm mode) must be given");
@@ -632,6 +648,9 @@ static int dec_proj_launch(const void* A3, long long lda, const float* x, long l
     AVSR_REQUIRE(!l2_prefetch || (((uintptr_t)l2_prefetch & 15) == 0 && l2_prefetch_bytes > 0), "avsr_dec_proj: prefetch span must be 16-byte aligned");
     AVSR_REQUIRE(act == AVSR_ACT_NONE || act == AVSR_ACT_RELU, "avsr_dec_proj: activation %d unsupported", act);
     AVSR_REQUIRE(!stats_out || (N % 128) == 0, "avsr_dec_proj: stats_out needs N %% 128 == 0");
+    AVSR_REQUIRE(dual.n1 == 0 || (dual.n1 > 0 && dual.n1 < N && (dual.n1 % BM) == 0 && (N & 3) == 0 && dual.out2 && (dual.ldo2 & 3) == 0 &&
+                                  ((uintptr_t)dual.out2 & 15) == 0 && (!dual.residual2 || ((dual.ldr2 & 3) == 0 && ((uintptr_t)dual.residual2 & 15) == 0))),
+                 "avsr_dec_proj_dual: the second range starts on a 128-column boundary and needs an aligned output");
     AVSR_REQUIRE((!out || ((uintptr_t)out & 15) == 0) && (!residual || ((uintptr_t)residual & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0) &&
                      (!split_out || ((uintptr_t)split_out & 7) == 0) && (!stats_out || ((uintptr_t)stats_out & 7) == 0),
                  "avsr_dec_proj: outputs / residual / bias must be 16-byte aligned");
@@ -651,7 +670,8 @@ static int dec_proj_launch(const void* A3, long long lda, const float* x, long l
         ta = tw;
     }
     ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, fold_u, bias, act, residual, ldr, out, ldo,
-                  (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, g_pf2, g_pf2 ? g_pf2_bytes : 0, g_skd, g_svd, g_slmax, g_snuh, g_sstep};
+                  (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, g_pf2, g_pf2 ? g_pf2_bytes : 0, g_skd, g_svd, g_slmax, g_snuh, g_sstep,
+                  dual.n1, dual.residual2, dual.ldr2, dual.out2, dual.ldo2};
     g_pf2 = nullptr;                                   // one-shot (avsr_dec_proj_also_prefetch)
     g_skd = g_svd = nullptr;                           // one-shot (avsr_dec_proj_prefetch_self_kv)
     cudaLaunchConfig_t cfg = {};
@@ -694,4 +714,19 @@ extern "C" int avsr_dec_proj_folded(const void* X3, long long lda, const float* 
     AVSR_REQUIRE(fold_u && fold_c, "avsr_dec_proj_folded: fold_u / fold_c missing");
     return dec_proj_launch(X3, lda, nullptr, 0, stats_in, nullptr, nullptr, ln_eps, fold_u, W3g, ldw, R, N, K, fold_c, act, residual, ldr, out, ldo,
                            split_out, stats_out, l2_prefetch, l2_prefetch_bytes, stream);
+}
+
+// Two projections of the SAME operand in one launch: the weight rows [0, n1) and [n1, N) are two matrices stacked on top of each
+// other; output features of the first range behave as in avsr_dec_proj_folded / avsr_dec_proj (folded LayerNorm when fold_u is
+// given, bias, activation, residual, out, statistics), those of the second range get bias[n] + residual2 and go to out2
+// (both indexed from column n1 on), without LayerNorm.  bias covers all N features.  n1 % 128 == 0.
+// Use: the source-attention query of a decoder layer without a launch of its own ("query merge").
+extern "C" int avsr_dec_proj_dual(const void* A3, long long lda, const float* stats_in, float ln_eps, const float* fold_u, const float* bias,
+                                  const void* W3, long long ldw, int R, int N, int K, int n1, int act, const float* residual, long long ldr,
+                                  float* out, long long ldo, const float* residual2, long long ldr2, float* out2, long long ldo2,
+                                  float* stats_out, const void* l2_prefetch, long long l2_prefetch_bytes, cudaStream_t stream) {
+    AVSR_REQUIRE(A3 && bias && out && out2 && n1 > 0, "avsr_dec_proj_dual: missing argument");
+    const DualRange dual = {n1, residual2, ldr2, out2, ldo2};
+    return dec_proj_launch(A3, lda, nullptr, 0, stats_in, nullptr, nullptr, ln_eps, fold_u, W3, ldw, R, N, K, bias, act, residual, ldr, out, ldo,
+                           nullptr, stats_out, l2_prefetch, l2_prefetch_bytes, stream, dual);
 }

@@ -217,5 +217,19 @@ class DecoderWeights:
             lay["wq23g"], lay["uq2"], lay["cq2"] = fold_layernorm(lay["wq2"], lay["bq2"], lay["n2_g"], lay["n2_b"])
             lay["w13g"], lay["u1"], lay["c1"] = fold_layernorm(lay["w1"], lay["b1"], lay["n3_g"], lay["n3_b"])
         self.out_w3g, self.out_u, self.out_c = fold_layernorm(self.out_w, None, self.after_g, self.after_b)     # out_b is added by the softmax kernel
+        # "Query merge" (csrc/gemm_x3c.cu avsr_dec_proj_dual, csrc/dec_attn.cu avsr_dec_attn_fold_query): the source-attention
+        # query LayerNorm2(x1) Wq^T + bq, x1 = x + att Wo^T + bo, needs x1 (g2 . Wq)^T = x (g2 . Wq)^T + att ((g2 . Wq) Wo)^T +
+        # (g2 . Wq) bo: the first product rides along with q | k | v (operand: the raw row x), the second with the attention-output
+        # projection (operand: att), and the attention kernel applies the LayerNorm's rstd / mean itself (uq2, cq2 above).
+        for lay in self.layers:
+            wg = lay["wq2"].double().cpu() * lay["n2_g"].double().cpu().unsqueeze(0)              # g2 . Wq   [1024, 1024]
+            wprime = (wg @ lay["wo"].double().cpu()).float().to(device)                             # (g2 . Wq) Wo
+            dvec = (wg @ lay["bo"].double().cpu()).float().to(device)                               # (g2 . Wq) bo
+            zeros = torch.zeros(1024, dtype=torch.float32, device=device)
+            lay["wcat1_3"] = torch.cat([lay["wqkv3g"], lay["wq23g"]], 0).contiguous()               # [3072 + 1024, 3 K]
+            lay["ucat1"] = torch.cat([lay["uqkv"], zeros]).contiguous()
+            lay["ccat1"] = torch.cat([lay["cqkv"], zeros]).contiguous()
+            lay["wcat2_3"] = torch.cat([lay["wo3"], split3_weight_compact(wprime)], 0).contiguous()  # [1024 + 1024, 3 K]
+            lay["bcat2"] = torch.cat([lay["bo"], dvec]).contiguous()
         self.ctc_w6 = split3_weight(self.ctc_w)                         # once-per-utterance projections (generic GEMM, K' = 6K)
         self.ckv_w6 = split3_weight(self.ckv_w)

@@ -246,6 +246,17 @@ int avsr_dec_attn_step(int mode, const float* q_in, long long ldq, int nsplit, c
                        const int* conv_len, avsr_stream_t stream);
 /* The same, and every CTA first asks the L2 to fetch its share of [l2_prefetch, +l2_prefetch_bytes): the weights of the
  * projection that follows the attention in the chain (must not be written by the chain). */
+/* "Query merge": the source-attention query of a decoder layer, LayerNorm(x1) Wq^T + bq with x1 = x + att Wo^T + bo, is linear in
+ * (x, att) up to the LayerNorm's row statistics: x1 (gamma . Wq)^T = x (gamma . Wq)^T + att ((gamma . Wq) Wo)^T + const.  The two
+ * products ride along in the projections that have x and att as their operand anyway (avsr_dec_proj_dual: extra output columns),
+ * and the source-attention kernel applies rstd (. - mean u) + c itself.  One projection launch less per layer. */
+int avsr_dec_proj_dual(const void* A3, long long lda, const float* stats_in, float ln_eps, const float* fold_u, const float* bias,
+                       const void* W3, long long ldw, int R, int N, int K, int n1, int act, const float* residual, long long ldr,
+                       float* out, long long ldo, const float* residual2, long long ldr2, float* out2, long long ldo2,
+                       float* stats_out, const void* l2_prefetch, long long l2_prefetch_bytes, avsr_stream_t stream);
+/* One-shot: the next mode-1 avsr_dec_attn_step* launch finishes its query q = rstd (q_in - mean u) + c from the tile statistics
+ * stats [8][R][2] of the row the query was projected from (u, c [1024] as weights.fold_layernorm builds them). */
+int avsr_dec_attn_fold_query(const float* stats, const float* u, const float* c, float eps);
 int avsr_dec_attn_step_pf(int mode, const float* q_in, long long ldq, int nsplit, const float* q_bias, float* kc, float* vc,
                           const unsigned char* anc, int lmax, const int* n_run, const int* utt_off, const int* utt_T, int beam, int R,
                           const int* step, float* out, long long n_frames, void* out_split, const float* kd, const float* vd,

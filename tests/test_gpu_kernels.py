@@ -448,6 +448,64 @@ def test_dec_attn_step_cross(L, beam, lengths, nsplit):
             assert (out[row] - want).abs().max().item() < tol, (b, h)
 
 
+@pytest.mark.parametrize("R", [3, 96, 128])
+def test_query_merge_equals_separate_projection(L, R):
+    """avsr_dec_proj_dual + avsr_dec_attn_fold_query: the source-attention query computed as extra output columns of the
+    q|k|v projection (operand x) and of the attention-output projection (operand att), finished by the attention kernel from
+    the row statistics, against LayerNorm2(x + att Wo^T + bo) Wq^T + bq in float64; and the first column ranges (q|k|v with the
+    folded LayerNorm1, x1 with its statistics) against the single-range launches they replace."""
+    from avsr_b200.weights import fold_layernorm, split3_weight_compact
+    lib = L.load()
+    g = torch.Generator().manual_seed(R)
+    D = 1024
+    rnd = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g) * sc).cuda()
+    x, att = rnd(R, D) + 0.7, rnd(R, D)
+    wqkv, bqkv, wo, bo, wq2, bq2 = rnd(3 * D, D, sc=0.04), rnd(3 * D, sc=0.1), rnd(D, D, sc=0.04), rnd(D, sc=0.1), rnd(D, D, sc=0.04), rnd(D, sc=0.1)
+    g1, b1, g2, b2 = 1 + rnd(D, sc=0.2), rnd(D, sc=0.2), 1 + rnd(D, sc=0.2), rnd(D, sc=0.2)
+    wqkv3g, uqkv, cqkv = fold_layernorm(wqkv, bqkv, g1, b1)
+    wq23g, uq2, cq2 = fold_layernorm(wq2, bq2, g2, b2)
+    wg = wq2.double().cpu() * g2.double().cpu().unsqueeze(0)
+    wcat1 = torch.cat([wqkv3g, wq23g], 0).contiguous()
+    ucat1, ccat1 = torch.cat([uqkv, torch.zeros(D, device="cuda")]).contiguous(), torch.cat([cqkv, torch.zeros(D, device="cuda")]).contiguous()
+    wo3 = split3_weight_compact(wo)
+    wcat2 = torch.cat([wo3, split3_weight_compact((wg @ wo.double().cpu()).float().cuda())], 0).contiguous()
+    bcat2 = torch.cat([bo, (wg @ bo.double().cpu()).float().cuda()]).contiguous()
+    # operands as the chain has them: x3 / att3 = compact bf16x3 rows, stats of x in the tile format
+    x3, att3 = split3_weight_compact(x), split3_weight_compact(att)
+    xt = x.view(R, 8, 128)
+    stats = torch.stack([xt.mean(-1), ((xt - xt.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).permute(1, 0, 2).contiguous()      # [8][R][2]
+    qkv_d, tq = torch.empty(R, 3 * D, device="cuda"), torch.empty(R, D, device="cuda")
+    L.check(lib.avsr_dec_proj_dual(L.ptr(x3), L.ll(3 * D), L.ptr(stats), C.c_float(1e-12), L.ptr(ucat1), L.ptr(ccat1), L.ptr(wcat1), L.ll(3 * D),
+                                   R, 4 * D, D, 3 * D, L.ACT_NONE, None, L.ll(D), L.ptr(qkv_d), L.ll(3 * D), None, L.ll(D), L.ptr(tq), L.ll(D),
+                                   None, None, L.ll(0), L.stream()), "dual qkv")
+    qkv_s = torch.empty(R, 3 * D, device="cuda")
+    L.check(lib.avsr_dec_proj_folded(L.ptr(x3), L.ll(3 * D), L.ptr(stats), C.c_float(1e-12), L.ptr(uqkv), L.ptr(cqkv), L.ptr(wqkv3g), L.ll(3 * D),
+                                     R, 3 * D, D, L.ACT_NONE, None, L.ll(D), L.ptr(qkv_s), L.ll(3 * D), None, None, None, L.ll(0), L.stream()), "folded qkv")
+    x1_d, q2raw, stats2 = x.clone(), torch.empty(R, D, device="cuda"), torch.zeros(8, R, 2, device="cuda")
+    L.check(lib.avsr_dec_proj_dual(L.ptr(att3), L.ll(3 * D), None, C.c_float(1e-12), None, L.ptr(bcat2), L.ptr(wcat2), L.ll(3 * D), R, 2 * D, D, D,
+                                   L.ACT_NONE, L.ptr(x1_d), L.ll(D), L.ptr(x1_d), L.ll(D), L.ptr(tq), L.ll(D), L.ptr(q2raw), L.ll(D),
+                                   L.ptr(stats2), None, L.ll(0), L.stream()), "dual out")
+    x1_s, stats2_s = x.clone(), torch.zeros(8, R, 2, device="cuda")
+    L.check(lib.avsr_dec_proj(L.ptr(att3), L.ll(3 * D), None, L.ll(0), None, None, None, C.c_float(1e-12), L.ptr(wo3), L.ll(3 * D), R, D, D, L.ptr(bo), 0,
+                              L.ptr(x1_s), L.ll(D), L.ptr(x1_s), L.ll(D), None, L.ptr(stats2_s), None, L.ll(0), L.stream()), "single out")
+    torch.cuda.synchronize()
+    # the stacked launches plan a different cluster size (more output tiles): the same sums in a different split order
+    assert (x1_d - x1_s).abs().max().item() < 2e-5 * max(1.0, x1_s.abs().max().item())
+    assert (stats2 - stats2_s).abs().max().item() < 1e-3
+    assert (qkv_d - qkv_s).abs().max().item() < 2e-5 * max(1.0, qkv_s.abs().max().item())
+    # finished query: what the attention kernel computes from q2raw and the statistics of x1
+    x1 = x.double().cpu() + att.double().cpu() @ wo.double().cpu().t() + bo.double().cpu()
+    ln = torch.nn.functional.layer_norm(x1, (D,), g2.double().cpu(), b2.double().cpu(), 1e-12)
+    want = ln @ wq2.double().cpu().t() + bq2.double().cpu()
+    st = stats2.double().cpu()
+    mean = st[:, :, 0].mean(0)
+    m2 = (st[:, :, 1] + 128.0 * (st[:, :, 0] - mean) ** 2).sum(0)
+    rstd = 1.0 / torch.sqrt(m2 / D + 1e-12)
+    got = rstd[:, None] * (q2raw.double().cpu() - mean[:, None] * uq2.double().cpu()) + cq2.double().cpu()
+    err = (got - want).abs().max().item()
+    assert err < 5e-5 * max(1.0, want.abs().max().item()), err
+
+
 @pytest.mark.parametrize("nf,with_res", [(3, False), (37, True), (300, True)])
 def test_conv3x3_halo_equals_implicit_gemm(L, nf, with_res):
     """ResNet layer1 convolution on the padded layout (halo staged once, nine taps = nine shifted descriptors of the same tile)
