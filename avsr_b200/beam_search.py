@@ -124,8 +124,8 @@ class BatchedBeamSearch:
         # (295.0 vs 294.6 ms per pass): the one-thread step kernel already overlaps its neighbours through programmatic dependent
         # launch, so the default stays the separate launch.
         self.fuse_step = os.environ.get("AVSR_FUSE_STEP", "0") != "0"
-        # query merge: the source-attention query projection of layers 1 .. 5 rides along with q | k | v and the attention-output
-        # projection (7 launches per layer instead of 8); AVSR_QUERY_MERGE=0 = its own launch
+        # query merge: the source-attention query projection of every layer rides along with q | k | v and the attention-output
+        # projection (7 launches per layer instead of 8: 48 per position); AVSR_QUERY_MERGE=0 = its own launch
         self.query_merge = os.environ.get("AVSR_QUERY_MERGE", "1") != "0"
         L.load()
         if self.proj == "cluster" and (self.n_groups > 1 or "AVSR_SM_BUDGET" in os.environ):
@@ -522,12 +522,18 @@ class BatchedBeamSearch:
         if dense:
             L.check(lib.avsr_dec_cache_promote(L.ptr(s["kc"]), L.ptr(s["vc"]), L.ptr(s["kd"]), L.ptr(s["vd"]), w.n_layers, L.ptr(s["anc"]), lmax,
                                                L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]), L.ptr(s["conv_len"]), st()), "avsr_dec_cache_promote")
-        L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
-                                      L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), None, L.ptr(s["a3"]), st()),
-                "avsr_dec_embed_ln")
+        merge_all = fold and self.query_merge and "gemm" not in self._skip
+        if merge_all:
+            # layer 0 takes its LayerNorm folded like the others: the embedding is written raw, with its tile statistics
+            L.check(lib.avsr_dec_embed_raw(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
+                                           L.ptr(s["x"]), L.ptr(s["x3"]), L.ptr(s["stats"]), st()), "avsr_dec_embed_raw")
+        else:
+            L.check(lib.avsr_dec_embed_ln(L.ptr(w.embed), L.ptr(w.pe), L.ptr(s["last_tok"]), L.ptr(s["n_run"]), beam, R, L.ptr(s["step"]),
+                                          L.ptr(l0["n1_g"]), L.ptr(l0["n1_b"]), C.c_float(1e-12), L.ptr(s["x"]), None, L.ptr(s["a3"]), st()),
+                    "avsr_dec_embed_ln")
         for li, lay in enumerate(w.layers):
             # self-attention (decoder_layer.py:82-93): q | k | v finished by the projection, bias included
-            merge = fold and self.query_merge and li > 0 and "gemm" not in self._skip
+            merge = merge_all
             if merge:
                 # q | k | v of LayerNorm1(x) and, riding along, tq = x (g2 . Wq)^T for the source-attention query
                 pf = lay["wcat2_3"] if self.weight_prefetch else None
@@ -589,7 +595,7 @@ class BatchedBeamSearch:
         # after_norm + output layer (decoder.py:176-181); the output bias is added by the softmax kernel that follows.  It
         # fetches the first projection of the NEXT position (only small kernels run in between)
         if fold:
-            self._cfold(s, w.out_w3g, w.out_u, w.out_c, V, out=s["logits"], ldo=V, nxt=l0["wqkv3"])
+            self._cfold(s, w.out_w3g, w.out_u, w.out_c, V, out=s["logits"], ldo=V, nxt=l0["wcat1_3"] if merge_all else l0["wqkv3"])
         else:
             self._cproj(s, w.out_w3, V, 1024, ln=(w.after_g, w.after_b), out=s["logits"], ldo=V, nxt=l0["wqkv3"])
         return s["logits"], 1

@@ -72,6 +72,31 @@ __global__ void __launch_bounds__(256) log_softmax_rows_kernel(float* __restrict
     for (int c = threadIdx.x; c < V; c += blockDim.x) r[c] = (r[c] - mx) - lse;
 }
 
+// Embedding of the position WITHOUT the first LayerNorm (the q|k|v projection of layer 0 takes it folded, like every other
+// layer): x = emb[tok] * sqrt(d) + pe[step] (decoder.py:153-175, embedding.py:78-87) as fp32, as compact bf16x3 and the row's
+// (mean, M2) per 128-column tile in the layout avsr_dec_proj consumes (stats [8][R][2]).  Warp w owns columns [128 w, +128).
+__global__ void __launch_bounds__(256)
+dec_embed_raw_kernel(const float* __restrict__ emb, const float* __restrict__ pe, const int* __restrict__ last_tok,
+                     const int* __restrict__ n_run, int beam, int R, const int* __restrict__ step_p, float* __restrict__ x,
+                     __nv_bfloat16* __restrict__ x_split, float* __restrict__ stats) {
+    const int row = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    if ((row % beam) >= n_run[row / beam]) return;
+    const int step = *step_p;
+    const int c = threadIdx.x * 4;
+    const float4 e = *reinterpret_cast<const float4*>(emb + (long long)last_tok[row] * D + c);
+    const float4 p = *reinterpret_cast<const float4*>(pe + (long long)step * D + c);
+    float4 v;
+    v.x = e.x * 32.f + p.x; v.y = e.y * 32.f + p.y; v.z = e.z * 32.f + p.z; v.w = e.w * 32.f + p.w;
+    *reinterpret_cast<float4*>(x + (long long)row * D + c) = v;
+    avsr_split3c_store4(x_split + (long long)row * 3 * D, D, c, v);
+    const float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float m2 = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    if ((threadIdx.x & 31) == 0) *reinterpret_cast<float2*>(stats + ((long long)(threadIdx.x >> 5) * R + row) * 2) = make_float2(mean, m2);
+}
+
 }  // namespace
 
 extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R,
@@ -81,6 +106,15 @@ extern "C" int avsr_dec_embed_ln(const float* emb, const float* pe, const int* l
                  "avsr_dec_embed_ln: bad arguments");
     AVSR_CHECK_CUDA(avsr_launch_pdl(dec_embed_ln_kernel, dim3(R), dim3(256), 0, stream, emb, pe, last_tok, n_run, beam, step, gamma, beta, eps, x,
                                     a, (__nv_bfloat16*)a_split));
+    return AVSR_OK;
+}
+
+// x [R, 1024] fp32, x_split [R, 3 * 1024] compact bf16x3, stats [8][R][2]: the embedded position, not normalised.
+extern "C" int avsr_dec_embed_raw(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R,
+                                  const int* step, float* x, void* x_split, float* stats, cudaStream_t stream) {
+    AVSR_REQUIRE(emb && pe && last_tok && n_run && step && x && x_split && stats && R > 0 && beam > 0, "avsr_dec_embed_raw: bad arguments");
+    AVSR_CHECK_CUDA(avsr_launch_pdl(dec_embed_raw_kernel, dim3(R), dim3(256), 0, stream, emb, pe, last_tok, n_run, beam, R, step, x,
+                                    (__nv_bfloat16*)x_split, stats));
     return AVSR_OK;
 }
 

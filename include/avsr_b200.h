@@ -228,6 +228,10 @@ int avsr_log_softmax_rows(float* x, long long ld, long long rows, int V, avsr_st
 /* Decoder.forward_one_step pieces (src/nets/backend/transformer/decoder.py:153-183, decoder_layer.py:58-121). */
 int avsr_dec_embed_ln(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
                       const float* gamma, const float* beta, float eps, float* x, float* a, void* a_split, avsr_stream_t stream);
+/* The embedded position without the LayerNorm: fp32 rows, compact bf16x3 rows and (mean, M2) per 128-column tile
+ * (stats [8][R][2]) for a projection that takes the LayerNorm folded (avsr_dec_proj_folded / avsr_dec_proj_dual). */
+int avsr_dec_embed_raw(const float* emb, const float* pe, const int* last_tok, const int* n_run, int beam, int R, const int* step,
+                       float* x, void* x_split, float* stats, avsr_stream_t stream);
 /* One decode position of MultiHeadedAttention (transformer/attention.py:38-106, called from decoder_layer.py:82-107) with
  * cached K/V, streamed once (csrc/dec_attn.cu).  Keys are stored transposed in 32-byte groups, values row-major.
  * mode 0 = self-attention over the hypothesis' own history: query / current k / current v = columns [0,1024) / [1024,2048) /
