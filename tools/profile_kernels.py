@@ -14,7 +14,7 @@ from avsr_b200.weights import split3_weight_compact
 
 lib = L.load()
 dev = "cuda"
-which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "proj", "front", "posconv", "halo", "encattn"}
+which = set(sys.argv[1:]) or {"ctc", "attn", "gemm", "proj", "front", "posconv", "halo", "encattn", "dual", "ln"}
 B, beam, T, V = 32, 3, 375, 5049
 R = B * beam
 i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
@@ -156,5 +156,34 @@ if "encattn" in which:
     for _ in range(2):
         L.check(lib.avsr_attention_varlen(L.ptr(qk), L.ptr(vt), L.ll(Fr + 8), L.ptr(o), L.ll(Fr), L.ptr(wo2), L.ptr(wT2), L.ptr(wq2), len(work), T,
                                           L.stream()), "attention")
+    torch.cuda.synchronize()
+if "dual" in which:
+    # the two stacked projections of the query merge: q|k|v + tq (N = 4096, folded LayerNorm on the first 3072 columns) and
+    # attention output + source query (N = 2048), weights cycled (cold HBM)
+    x3 = torch.randn(R, 3 * 1024, device=dev).bfloat16()
+    stats = torch.zeros(8, R, 2, device=dev)
+    stats[..., 1] = 128.0
+    xres, tq, q2, qkv = torch.randn(R, 1024, device=dev), torch.zeros(R, 1024, device=dev), torch.zeros(R, 1024, device=dev), torch.zeros(R, 3072, device=dev)
+    u1, c1, b2 = torch.zeros(4096, device=dev), torch.zeros(4096, device=dev), torch.zeros(2048, device=dev)
+    for rep in range(2):
+        w1 = split3_weight_compact(torch.randn(4096, 1024, device=dev) * 0.03)
+        w2 = split3_weight_compact(torch.randn(2048, 1024, device=dev) * 0.03)
+        flush.zero_()
+        L.check(lib.avsr_dec_proj_dual(L.ptr(x3), L.ll(3072), L.ptr(stats), C.c_float(1e-12), L.ptr(u1), L.ptr(c1), L.ptr(w1), L.ll(3072), R, 4096, 1024,
+                                       3072, 0, None, L.ll(1024), L.ptr(qkv), L.ll(3072), None, L.ll(1024), L.ptr(tq), L.ll(1024), None, None, L.ll(0),
+                                       L.stream()), "dual qkv")
+        flush.zero_()
+        L.check(lib.avsr_dec_proj_dual(L.ptr(x3), L.ll(3072), None, C.c_float(1e-12), None, L.ptr(b2), L.ptr(w2), L.ll(3072), R, 2048, 1024, 1024, 0,
+                                       L.ptr(xres), L.ll(1024), L.ptr(xres), L.ll(1024), L.ptr(tq), L.ll(1024), L.ptr(q2), L.ll(1024), L.ptr(stats),
+                                       None, L.ll(0), L.stream()), "dual out")
+    torch.cuda.synchronize()
+
+if "ln" in which:
+    hx = torch.randn(B * T, 1024, device=dev)
+    lg, lb = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+    lo = torch.empty(B * T, 1024, dtype=torch.bfloat16, device=dev)
+    for _ in range(2):
+        flush.zero_()
+        L.layernorm(hx, lg, lb, 1e-5, out_bf16=lo)
     torch.cuda.synchronize()
 print("ok")
