@@ -89,6 +89,7 @@ struct ProjArgs {
     // second column range (avsr_dec_proj_dual): output features [n1, N) go to out2 / take residual2 (both indexed from column
     // n1 on) and get neither the folded LayerNorm nor statistics / a bf16x3 copy; n1 = 0: one range.  n1 % 128 == 0.
     int n1; const float* residual2; long long ldr2; float* out2; long long ldo2;
+    int early_trigger;                  // dev knob AVSR_PROJ_EARLY_TRIGGER: griddepcontrol.launch_dependents before the prologue
 };
 
 // three bf16 terms of 8 consecutive fp32 values -> one 16-byte chunk per term
@@ -125,6 +126,7 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     float* red = reinterpret_cast<float*>(smem);       // [NB][128] fp32 accumulator tile of this CTA (aliases the pipeline stages)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.early_trigger) pdl_trigger();
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const int m0 = blockIdx.x * BM;                    // first output feature of the tile
     const int n0 = blockIdx.z * NB;                    // first activation row of the tile
@@ -150,7 +152,7 @@ dec_proj_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_trigger();                                     // dependents may start their own prologue
+    if (!p.early_trigger) pdl_trigger();               // dependents may start their own prologue
 
     if (warp == 0) {
         if (lane == 0) {
@@ -497,6 +499,7 @@ const int* g_sstep = nullptr;
 const char* g_pf2 = nullptr;
 long long g_pf2_bytes = 0;
 int g_force_splits = 0;
+int g_early_trigger = 0;
 int g_sm_budget = 0;                                   // SMs one projection may occupy (0 = all): concurrent decode chains share the GPU
 bool g_configured = false;
 int configure() {
@@ -507,6 +510,8 @@ int configure() {
         AVSR_CHECK_CUDA(cudaFuncSetAttribute(dec_proj_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         const char* e = getenv("AVSR_X3C_SPLITS");
         if (e) g_force_splits = atoi(e);
+        e = getenv("AVSR_PROJ_EARLY_TRIGGER");
+        if (e) g_early_trigger = atoi(e);
         g_configured = true;
     }
     return AVSR_OK;
@@ -671,7 +676,7 @@ static int dec_proj_launch(const void* A3, long long lda, const float* x, long l
     }
     ProjArgs p = {R, N, K, nb, x != nullptr ? 1 : 0, x, ldx, stats_in, ln_g, ln_b, ln_eps, fold_u, bias, act, residual, ldr, out, ldo,
                   (__nv_bfloat16*)split_out, stats_out, (const char*)l2_prefetch, l2_prefetch ? l2_prefetch_bytes : 0, g_pf2, g_pf2 ? g_pf2_bytes : 0, g_skd, g_svd, g_slmax, g_snuh, g_sstep,
-                  dual.n1, dual.residual2, dual.ldr2, dual.out2, dual.ldo2};
+                  dual.n1, dual.residual2, dual.ldr2, dual.out2, dual.ldo2, g_early_trigger};
     g_pf2 = nullptr;                                   // one-shot (avsr_dec_proj_also_prefetch)
     g_skd = g_svd = nullptr;                           // one-shot (avsr_dec_proj_prefetch_self_kv)
     cudaLaunchConfig_t cfg = {};
