@@ -264,3 +264,54 @@ def test_avcocktail_loop_matches_a_sequential_restatement():
     assert set(per_video["video_0"]) == {"asd_chunk", "fixed_chunk", "gold_chunk"} and per_video["video_0"]["gold_chunk"] == 1.0
     assert avg["fixed_chunk"] == pytest.approx((per_video["video_0"]["fixed_chunk"] * nw["video_0"] + per_video["video_1"]["fixed_chunk"] * nw["video_1"])
                                                / (nw["video_0"] + nw["video_1"]))
+
+
+_AVC_VTT = ("WEBVTT\n\n00:00:02.000 --> 00:00:04.000\nsecond cue\n\n00:00:00.500 --> 00:00:01.500\nfirst cue here\n\n"
+            "00:00:05.000 --> 00:00:05.500\n\n")
+
+
+def _avc_chunk(start, end, seed, T):
+    g = torch.Generator().manual_seed(seed)
+    smp = (torch.randint(0, 3, (1, T, 88, 88), generator=g).float(), torch.randint(0, 5, (104, T), generator=g).float())
+    return {"start_time": start, "end_time": end, "frames": T, "load": (lambda s=smp: s)}
+
+
+def _avc_videos():
+    return {"video_0": {"label": _AVC_VTT, "asd_chunk": [_avc_chunk(2.0, 4.0, 1, 9), _avc_chunk(0.5, 2.0, 2, 7), _avc_chunk(9.0, 12.0, 3, 5)],
+                        "fixed_chunk": [_avc_chunk(0.0, 4.5, 4, 11)], "gold_chunk": [_avc_chunk(0.4, 1.6, 7, 6), _avc_chunk(1.9, 4.2, 8, 10)]},
+            "video_1": {"label": _AVC_VTT.replace("first", "other words in"),
+                        "fixed_chunk": [_avc_chunk(0.0, 3.0, 5, 6), _avc_chunk(3.0, 4.9, 6, 8)], "asd_chunk": [_avc_chunk(0.2, 4.4, 9, 13)]}}
+
+
+def _avc_to_text(ids):
+    return " ".join(f"w{int(t)}" for t in ids)
+
+
+def _avc_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank,) + tuple(E.evaluate_avcocktail(_StandInModel(), _avc_videos(), _avc_to_text, max_utts=2, max_frames=64)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_avcocktail_loop_world2_equals_single_process():
+    """The (video, chunk type) units of eval_avcocktail sharded over two ranks (gloo): every rank stitches and scores from the
+    gathered token ids and gets the single-process numbers (shard by chunk, per-video concatenation stays exact)."""
+    single = E.evaluate_avcocktail(_StandInModel(), _avc_videos(), _avc_to_text, max_utts=2, max_frames=64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_avc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, per_video, nw, avg in got:
+        assert nw == single[1]
+        assert {k: {c: pytest.approx(v) for c, v in d.items()} for k, d in single[0].items()} == per_video
+        assert {c: pytest.approx(v) for c, v in single[2].items()} == avg
